@@ -1,0 +1,144 @@
+/*
+ * nele_score.h -- C ABI of the B200-native batched intelligibility-scoring
+ * engine (libnele_score.so).
+ *
+ * This is the drop-in boundary for NELE-GAN's metric-labelling hot path.  The
+ * reference has no FFI: its boundary is a set of Python callables.  Each entry
+ * point below names the reference interface(s) it replaces (file:line under
+ * the reference tree); INTEGRATION.md shows the ctypes binding a maintainer
+ * adds on the reference side.
+ *
+ *   reference callable                                   replaced by
+ *   ---------------------------------------------------  ------------------
+ *   pyHASPI/pyhaspi2.py:76   haspi_v2(x, fx, y, fy, HL)   nele_score_batch, NELE_METRIC_HASPI
+ *   pysiib.SIIB(x, y, fs, gauss=True)   (intel.py:77,100) nele_score_batch, NELE_METRIC_SIIB
+ *   pystoi.stoi(x, y, fs, extended=True)(intel.py:126,133) nele_score_batch, NELE_METRIC_ESTOI
+ *   intel.py:57-140  *_Wrapper[_raw]_harvard(x, y, fs)    nele_score_batch, NELE_FLAG_MAPPED on/off
+ *   audio_util.py:145-203,281-321 read_batch_*            one nele_score_batch call per list
+ *
+ * Conventions: plain pointers and sizes, no ownership transfer.  The caller
+ * owns inputs and outputs; the engine owns a grow-only device workspace.  One
+ * engine per (process, device); calls on one engine are serialised by the
+ * caller.  Every function returns 0 on success or a negative NELE_E_* code;
+ * nele_last_error() gives the message.  Per-pair conditions that the
+ * reference reports by raising (signal below threshold, too few frames) come
+ * back in status[] and never abort the batch.
+ */
+#ifndef NELE_SCORE_H
+#define NELE_SCORE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NELE_ABI_VERSION 1
+
+/* metric mask */
+#define NELE_METRIC_HASPI 0x1u /* HASPI v2  (pyhaspi2.py:76-107)   */
+#define NELE_METRIC_SIIB  0x2u /* SIIB^Gauss with the wrapper's >=25 s tiling (intel.py:57-100) */
+#define NELE_METRIC_ESTOI 0x4u /* ESTOI     (pystoi.stoi extended=True) */
+#define NELE_METRIC_ALL   0x7u
+
+/* flags */
+#define NELE_FLAG_MAPPED        0x01u /* logistic mapping of intel.py:102-140 (norm=True); else raw scores */
+#define NELE_FLAG_DEVICE_INPUT  0x02u /* ref/deg are device pointers (offs/lens stay on the host) */
+#define NELE_FLAG_NO_DITHER     0x04u /* HASPI: zero cepstral dither (parity / deterministic mode) */
+#define NELE_FLAG_SIIB_NO_TILE  0x08u /* SIIB: plain pysiib.SIIB semantics, no wrapper tiling */
+#define NELE_FLAG_KEEP_STAGES   0x10u /* keep per-stage tensors of this call for nele_get_stage() */
+
+/* error codes (function return values) */
+#define NELE_OK              0
+#define NELE_E_ARG          -1 /* bad argument (null pointer, n < 0, unsupported fs ...) */
+#define NELE_E_CUDA         -2 /* CUDA runtime error; see nele_last_error */
+#define NELE_E_NOMEM        -3
+#define NELE_E_NODEVICE     -4 /* no CUDA device: the engine has no CPU path */
+
+/* per-pair status: one byte per metric, (status >> 8*k) & 0xff,
+ * k = 0 HASPI, 1 SIIB, 2 ESTOI */
+#define NELE_ST_OK           0
+#define NELE_ST_BELOW_THR    1 /* HASPI "Signal below threshold" (pyhaspi2.py:357-358): score = NaN */
+#define NELE_ST_TOO_SHORT    2 /* ESTOI < 30 frames: score = 1e-5 (pystoi sentinel);
+                                  SIIB < 20 s of active speech after tiling: score = NaN */
+#define NELE_ST_BAD_RATE     3 /* sampling rate not supported for this metric: score = NaN */
+#define NELE_ST_SKIPPED      0xff /* metric not requested */
+
+typedef struct nele_engine nele_engine;
+
+/* Create an engine on CUDA device `device`.  Fails with NELE_E_NODEVICE when
+ * there is no usable GPU -- there is deliberately no CPU fallback. */
+int nele_create(int device, nele_engine** out);
+void nele_destroy(nele_engine* e);
+
+/* Message of the last failure on this engine (or of the last failed
+ * nele_create when e == NULL).  Valid until the next call. */
+const char* nele_last_error(const nele_engine* e);
+int nele_abi_version(void);
+
+/*
+ * Score n (clean, degraded) pairs.
+ *
+ *   ref, deg   concatenated float32 waveforms; pair i occupies
+ *              [offs[i], offs[i] + lens[i]) in both.  x = clean reference,
+ *              y = degraded = enhanced + noise, as audio_util.py:139 forms it.
+ *              Host pointers unless NELE_FLAG_DEVICE_INPUT.
+ *   offs,lens  host arrays [n]; lens[i] is the common (already trimmed)
+ *              length -- the reference trims to min(len) in intel.py:58-60.
+ *   fs         sampling rate of every pair.  16000 for all three metrics
+ *              (audio_util.py:131 asserts it); HASPI alone accepts any
+ *              fs <= 24000 (pyhaspi2.py:810-821).
+ *   dither     NULL, or a host float32 matrix [2][dither_rows][32] of
+ *              unit-variance normals shared by all pairs: row r of matrix 0
+ *              (1) is added, scaled by 0.1 dB, to the r-th above-threshold
+ *              envelope frame of x (y) -- the injected form of
+ *              pyhaspi2.py:362-365 used for parity tests.  With NULL and no
+ *              NELE_FLAG_NO_DITHER the engine draws its own normals from a
+ *              counter-based generator keyed by (seed, pair, signal, row).
+ *   hl         NULL (normal hearing, the only configuration the reference
+ *              vouches for, pyHASPI/README.txt:14) or 6 audiogram losses in
+ *              dB at 250..6000 Hz applied to y as pyhaspi2.py:1160 does.
+ *   scores     host double [n][3], column order {SIIB, HASPI, ESTOI} -- the
+ *              order train_nele.py:320-322 computes and
+ *              audio_util.py:367-389 serialises them.
+ *   haspi_raw  NULL or host double [n][10]: the ten modulation-band
+ *              correlations haspi_v2 returns as `raw`.
+ *   status     NULL or host int32 [n] (see NELE_ST_*).
+ *   stream     cudaStream_t to run on, or NULL for the engine's own stream.
+ *              The call returns after the results are in the output arrays.
+ */
+int nele_score_batch(nele_engine* e, const float* ref, const float* deg, const int64_t* offs,
+                     const int32_t* lens, int n, int fs, uint32_t metrics, uint32_t flags,
+                     const float* dither, int64_t dither_rows, uint64_t seed, const double* hl,
+                     double* scores, double* haspi_raw, int32_t* status, void* stream);
+
+/*
+ * Parity-test access to the per-stage tensors of the last nele_score_batch
+ * call made with NELE_FLAG_KEEP_STAGES.  Copies stage `name` of pair `pair`
+ * into dst (capacity cap bytes) and reports its size; dst may be NULL to query
+ * the size.  Stages (element type, shape):
+ *   "haspi.mid"    f64 [2][n24]        middle-ear output of x and y (pyhaspi2.py:1185-1186)
+ *   "haspi.bw"     f64 [2][32]         BWx, BWy                      (pyhaspi2.py:1204-1205)
+ *   "haspi.shift"  i32 [32]            group-delay shifts            (pyhaspi2.py:1118-1122)
+ *   "haspi.envlp"  f32 [2][nsub][32]   ebm_EnvFilt output            (pyhaspi2.py:412-413)
+ *   "haspi.nsel"   i32 [1]             frames above threshold        (pyhaspi2.py:355-356)
+ *   "haspi.cep"    f32 [2][5][nsel]    de-meaned cepstra 2..6        (pyhaspi2.py:366-374)
+ *   "estoi.x10"    f64 [2][n10]        10 kHz signals
+ *   "estoi.tob"    f64 [2][nfr][15]    one-third-octave magnitudes
+ *   "siib.tile"    i32 [3]             {M, active frames (wrapper VAD), KLT frames Nf}
+ *   "siib.logspec" f32 [2][28][F]      masked, de-meaned log band energies
+ *   "siib.lambda"  f32 [420]           eigenvalues of cov(X), ascending
+ *   "siib.rho"     f32 [420]           per-component correlation
+ */
+int nele_get_stage(nele_engine* e, const char* name, int pair, void* dst, size_t cap, size_t* nbytes);
+
+/* Device-side time (ms, CUDA events on the launching stream) of the kernels of
+ * the last nele_score_batch call, excluding host<->device copies; and the
+ * number of kernel launches it made. */
+int nele_last_timing(const nele_engine* e, double* kernel_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NELE_SCORE_H */

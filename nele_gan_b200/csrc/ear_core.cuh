@@ -1,0 +1,271 @@
+// Per-band arithmetic of the HASPI ear model (one lane = one auditory band of
+// one signal).  Shared by the CUDA kernels in haspi.cu and by the host-side
+// emulation harness tests/host_emul (g++), so the band math can be checked on
+// a machine without a GPU.  Reference: pyHASPI/pyhaspi2.py (line numbers in
+// the comments).
+//
+// T is the type of the linear recurrences (gammatone poles, carrier rotation,
+// compression low-pass, IHC adaptation); the pointwise log/pow/sqrt section is
+// always single precision (|error| ~1e-5 dB, three orders below the 0.1 dB
+// dither the model itself adds).
+#pragma once
+#include <math.h>
+
+#include "common.cuh"
+
+namespace nele {
+
+// Per-band constants of one scoring call (depend on the audiogram HL only).
+// Index q: 0 = reference signal x (always normal hearing, pyhaspi2.py:1162-1167),
+//          1 = processed signal y.
+struct BandConst {
+  double cf;        // centre frequency                      (:753-777)
+  double erb;       // 24.7 + cf / 9.26449                   (:866)
+  double bw1;       // control-path bandwidth, HL = 100 dB   (:1168-1171)
+  double attn_ohc[2], bwmin[2], lowknee[2], cr[2], attn_ihc[2];  // (:779-807)
+};
+
+// Linearised IHC adaptation update (pyhaspi2.py:1040-1071):
+//   V1' = m11 V1 + m12 V2 + g1 V0,  V2' = m21 V1 + m22 V2 + g2 V0,
+//   out = max((V0 - V1') * r1inv, 0).
+struct IhcConst {
+  double m11, m12, m21, m22, g1, g2, r1inv;
+};
+
+inline IhcConst make_ihc_const(double delta = 2.0, double fs = 24000.0) {
+  if (delta < 1.0001) delta = 1.0001;
+  const double tau1 = 0.002, tau2 = 0.060, T = 1.0 / fs;
+  const double R1 = 1.0 / delta, R2 = 0.5 * (1.0 - R1), R3 = R2;
+  const double C1 = tau1 * (R1 + R2) / (R1 * R2), C2 = tau2 / ((R1 + R2) * R3);
+  const double a11 = R1 + R2 + R1 * R2 * (C1 / T), a12 = -R1, a21 = -R3,
+               a22 = R2 + R3 + R2 * R3 * (C2 / T);
+  const double denom = 1.0 / (a11 * a22 - a21 * a12);
+  const double R12C1 = R1 * R2 * (C1 / T), R23C2 = R2 * R3 * (C2 / T);
+  IhcConst k;
+  k.m11 = denom * a22 * R12C1;
+  k.m12 = -denom * a12 * R23C2;
+  k.g1 = denom * a22 * R2;
+  k.m21 = -denom * a21 * R12C1;
+  k.m22 = denom * a11 * R23C2;
+  k.g2 = -denom * a21 * R2;
+  k.r1inv = 1.0 / R1;
+  return k;
+}
+
+// 4th-order baseband gammatone (pyhaspi2.py:870-878):
+//   H(z) = gain (1 + 2a z^-1)^2 / (1 - a z^-1)^4,  a = exp(-2 pi/fs 1.019 BW ERB)
+// run as four cascaded one-pole sections followed by the numerator.
+template <typename T>
+struct GtCoef {
+  T a, c1, c2;  // pole, 4a, 4a^2
+  float gain;
+};
+
+template <typename T>
+NELE_HD GtCoef<T> make_gt(double bw, double erb) {
+  const double tpt = 2.0 * 3.14159265358979323846 / 24000.0;
+  const double a = exp(-(bw * tpt * erb * 1.019));
+  const double a1 = 4.0 * a, a2 = -6.0 * a * a, a3 = 4.0 * a * a * a, a4 = -a * a * a * a, a5 = 4.0 * a * a;
+  GtCoef<T> g;
+  g.a = (T)a;
+  g.c1 = (T)a1;
+  g.c2 = (T)a5;
+  g.gain = (float)(2.0 * (1.0 - a1 - a2 - a3 - a4) / (1.0 + a1 + a5));
+  return g;
+}
+
+// DC group delay of the filter above, rounded as np.round does
+// (scipy.signal.group_delay(..., w=1) evaluates at omega = 0; pyhaspi2.py:1117-1118).
+NELE_HD double gt_group_delay(double bw, double erb) {
+  const double tpt = 2.0 * 3.14159265358979323846 / 24000.0;
+  const double a = exp(-(bw * tpt * erb * 1.019));
+  return rint(4.0 * a / (1.0 - a) + 4.0 * a / (1.0 + 2.0 * a));
+}
+
+template <typename T>
+struct Gt4 {
+  T r1, r2, r3, r4, rp, i1, i2, i3, i4, ip;
+  NELE_HD void reset() { r1 = r2 = r3 = r4 = rp = i1 = i2 = i3 = i4 = ip = (T)0; }
+  // -> squared magnitude of the (unnormalised) complex output
+  NELE_HD T step(const GtCoef<T>& k, T xr, T xi) {
+    r1 = k.a * r1 + xr;
+    i1 = k.a * i1 + xi;
+    r2 = k.a * r2 + r1;
+    i2 = k.a * i2 + i1;
+    r3 = k.a * r3 + r2;
+    i3 = k.a * i3 + i2;
+    const T nr = k.a * r4 + r3;
+    const T ni = k.a * i4 + i3;
+    const T ur = nr + k.c1 * r4 + k.c2 * rp;
+    const T ui = ni + k.c1 * i4 + k.c2 * ip;
+    rp = r4;
+    ip = i4;
+    r4 = nr;
+    i4 = ni;
+    return ur * ur + ui * ui;
+  }
+};
+
+// carrier cos(w t), -sin(w t) (pyhaspi2.py:843-861 rotates by -w); advanced by
+// the same rotation recurrence and re-seeded from the exact phase by the
+// caller every few hundred samples so single precision cannot drift.
+template <typename T>
+struct Carrier {
+  T c, s, cn, sn;
+  double w;
+  NELE_HD void init(double cf) {
+    w = 2.0 * 3.14159265358979323846 / 24000.0 * cf;
+    cn = (T)cos(w);
+    sn = (T)sin(w);
+  }
+  // state such that the next advance() yields sample t
+  NELE_HD void seed_before(long long t) {
+    const double ph = w * (double)(t - 1);
+    c = (T)cos(ph);
+    s = (T)(-sin(ph));
+  }
+  NELE_HD void advance() {
+    const T nc = c * cn + s * sn;
+    s = s * cn - c * sn;
+    c = nc;
+  }
+};
+
+#define NELE_LOG2_10 3.3219280948873623f
+#define NELE_20_OVER_LOG2_10 6.0205999132796239f /* 20 log10(2) */
+
+NELE_HD float db20(float v) {  // 20 log10(v)
+#if defined(__CUDA_ARCH__)
+  return NELE_20_OVER_LOG2_10 * __log2f(v);
+#else
+  return NELE_20_OVER_LOG2_10 * log2f(v);
+#endif
+}
+NELE_HD float undb20(float d) {  // 10^(d/20)
+#if defined(__CUDA_ARCH__)
+  return exp2f(d * (NELE_LOG2_10 / 20.0f));
+#else
+  return exp2f(d * (NELE_LOG2_10 / 20.0f));
+#endif
+}
+
+// Control-path lane: envelope power accumulation for eb_BWadjust
+// (pyhaspi2.py:1202-1205, 917-980).
+template <typename T>
+struct ControlLane {
+  Carrier<T> car;
+  GtCoef<T> k;
+  Gt4<T> f;
+  NELE_HD void init(const BandConst& b) {
+    car.init(b.cf);
+    k = make_gt<T>(b.bw1, b.erb);
+    f.reset();
+  }
+  NELE_HD T step(T x) {
+    car.advance();
+    return f.step(k, x * car.c, x * car.s);
+  }
+};
+
+// cdB -> bandwidth (pyhaspi2.py:971-980); sumsq = sum of unnormalised |u|^2.
+NELE_HD double bw_from_control(double sumsq, double gain, int n, double bwmin, double bwmax) {
+  const double crms = gain * sqrt(sumsq / (double)n);
+  const double cdb = 20.0 * log10(crms) + 65.0;
+  if (cdb < 50.0) return bwmin;
+  if (cdb > 100.0) return bwmax;
+  return bwmin + ((cdb - 50.0) / 50.0) * (bwmax - bwmin);
+}
+
+// Main-pass lane: control + signal gammatone, OHC compression, dB SL,
+// IHC adaptation, then the 52-tap Hann FIR of ebm_EnvFilt evaluated only at
+// the kept (every 9th) positions.  The lane runs on its own time axis delayed
+// by `shift` samples so that group-delay compensation (pyhaspi2.py:1124-1129)
+// costs nothing: at loop index i it consumes input sample i - shift.
+template <typename T>
+struct EarLane {
+  Carrier<T> car;
+  GtCoef<T> kc, ks;
+  Gt4<T> fc, fs;
+  T zlp, v1, v2;
+  T m11, m12, m21, m22, g1, g2;
+  float r1inv, thr_low, crfac, attn_ohc, lvl_ihc;
+  float acc[6];
+  int shift;
+
+  NELE_HD void init(const BandConst& b, int q, double bw_sig, int shift_, const IhcConst& ih) {
+    car.init(b.cf);
+    kc = make_gt<T>(b.bw1, b.erb);
+    ks = make_gt<T>(bw_sig, b.erb);
+    fc.reset();
+    fs.reset();
+    zlp = v1 = v2 = (T)0;
+    m11 = (T)ih.m11; m12 = (T)ih.m12; m21 = (T)ih.m21; m22 = (T)ih.m22;
+    g1 = (T)ih.g1; g2 = (T)ih.g2;
+    r1inv = (float)ih.r1inv;
+    thr_low = (float)b.lowknee[q];
+    crfac = (float)(1.0 - 1.0 / b.cr[q]);
+    attn_ohc = (float)b.attn_ohc[q];
+    lvl_ihc = (float)(65.0 - b.attn_ihc[q]);
+    shift = shift_;
+    for (int d = 0; d < 6; ++d) acc[d] = 0.f;
+  }
+
+  // one input sample -> IHC-adapted envelope in dB SL (pyhaspi2.py:1207-1229)
+  NELE_HD float sample(T x) {
+    car.advance();
+    const T xr = x * car.c, xi = x * car.s;
+    const float pc = (float)fc.step(kc, xr, xi);
+    const float ps = (float)fs.step(ks, xr, xi);
+    const float ctrl = kc.gain * sqrtf(pc);
+    const float env = ks.gain * sqrtf(ps);
+    // eb_EnvCompressBM (:982-999)
+    float le = 65.0f + db20(fmaxf(ctrl, 1.0e-30f));
+    le = fminf(fmaxf(le, thr_low), 100.0f);
+    const float g = undb20(-attn_ohc - (le - thr_low) * crfac);
+    const T b0 = (T)0.095107983402496;
+    const T glp = b0 * (T)g + zlp;
+    zlp = b0 * (T)g + (T)0.809784033195007 * glp;
+    const float envc = (float)glp * env;
+    // eb_EnvSL2 (:1080-1083)
+    const float v0 = fmaxf(lvl_ihc + db20(envc + 1.0e-30f), 0.0f);
+    // eb_IHCadapt (:1065-1073)
+    const T V0 = (T)v0;
+    const T n1 = m11 * v1 + m12 * v2 + g1 * V0;
+    const T n2 = m21 * v1 + m22 * v2 + g2 * V0;
+    v1 = n1;
+    v2 = n2;
+    return fmaxf((float)(V0 - n1) * r1inv, 0.0f);
+  }
+
+  // FIR bookkeeping.  Sample at loop index i = 9 b + P contributes
+  // fir[d][P] * v to output j = b - 2 + d, d = 0..5  (fir[d][P] = h[9(d-2)+26-P]).
+  template <int P>
+  NELE_HD void accumulate(float v, const float* fir) {
+#pragma unroll
+    for (int d = 0; d < 6; ++d) acc[d] = fmaf(fir[d * 9 + P], v, acc[d]);
+  }
+  // after phase 8 of block b: returns output j = b - 2 and rotates
+  NELE_HD float emit() {
+    const float o = acc[0];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) acc[d] = acc[d + 1];
+    acc[5] = 0.f;
+    return o;
+  }
+};
+
+// h[k] = np.hanning(52)[k] / sum  -> fir[d*9 + p] = h[9(d-2) + 26 - p] (0 outside 0..51)
+inline void make_env_fir(float* fir /*[54]*/) {
+  double h[kEnvTaps], s = 0.0;
+  for (int k = 0; k < kEnvTaps; ++k) {
+    h[k] = 0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * k / (kEnvTaps - 1));
+    s += h[k];
+  }
+  for (int d = 0; d < 6; ++d)
+    for (int p = 0; p < 9; ++p) {
+      const int k = 9 * (d - 2) + kEnvHalf - p;
+      fir[d * 9 + p] = (k >= 0 && k < kEnvTaps) ? (float)(h[k] / s) : 0.f;
+    }
+}
+
+}  // namespace nele

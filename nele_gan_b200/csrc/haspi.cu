@@ -1,0 +1,580 @@
+// HASPI v2 on sm_100a: batched ear model + modulation-correlation back-end.
+//
+// Data flow for one sub-batch of pairs (reference: pyHASPI/pyhaspi2.py:76-107):
+//
+//   haspi_prep_kernel      per (pair, signal) CTA: RMS normalise (:81-84), polyphase
+//                          resampy kaiser_best to 24 kHz + RMS match (:810-821), middle
+//                          ear IIR (:833-841) as a 256-way blocked linear recurrence
+//   haspi_control_kernel   per (pair, signal) warp, lane = band: control-path gammatone
+//                          envelope power over the whole utterance -> BWx / BWy (:1202-1205)
+//   haspi_shift_kernel     group-delay shifts from BWx (:1115-1122)
+//   haspi_ear_kernel       per (pair, signal) warp, lane = band: control + signal
+//                          gammatone, compression, dB SL, IHC adaptation (:1207-1229), delay
+//                          alignment (:1238-1240) and the 52-tap Hann FIR kept at every 9th
+//                          sample (:378-414) -> envlp [nsub][32]
+//   haspi_cep_kernel       per pair CTA: loudness threshold, compaction, dither, 32->5
+//                          cosine projection, column means (:342-375)
+//   haspi_modcorr_kernel   per (pair, cepstral coef, time tile) CTA: ten real zero-phase FIR
+//                          band-pass filters (= ebm_ModFilt, :275-339) fused with the
+//                          correlation sums of ebm_ModCorr (:254-273)
+//   haspi_score_kernel     per pair thread: CM -> aveCM -> Intel (:102-104)
+//
+// The ear-model kernels run one auditory band per lane and walk the time axis
+// sequentially: a batch of thousands of pairs supplies 64 independent
+// recurrences per pair, which fills the machine without the >2x arithmetic
+// overhead of a time-parallel scan of the 4th-order complex gammatone.
+#include <stdio.h>
+
+#include "kernels.h"
+
+namespace nele {
+
+__constant__ float c_envfir[54];
+__constant__ IhcConst c_ihc;
+__constant__ float c_cepm[kBands * kNumCep];
+__constant__ int c_mod_nhalf[kNumMod];
+__constant__ int c_mod_off[kNumMod + 1];
+__device__ float g_modtaps[2880];
+
+constexpr int kModTapsTotal = 2850;
+constexpr int kModMaxHalf = 307;
+
+// ------------------------------------------------------------------ prep
+// Middle-ear filter state update, direct form II transposed exactly as
+// scipy.signal.lfilter runs the two sections (pyhaspi2.py:835-840).
+struct MidState {
+  double z0, z1, z2;
+};
+__device__ __forceinline__ double mid_step(MidState& s, double x) {
+  const double bl = 0.434173751206302, al = -0.131652497587396;
+  const double b0 = 0.937260390269893, b1 = -1.874520780539785, b2 = 0.937260390269893;
+  const double a1 = -1.870580640735279, a2 = 0.878460920344291;
+  const double y1 = bl * x + s.z0;
+  s.z0 = bl * x - al * y1;
+  const double y2 = b0 * y1 + s.z1;
+  s.z1 = b1 * y1 - a1 * y2 + s.z2;
+  s.z2 = b2 * y1 - a2 * y2;
+  return y2;
+}
+
+constexpr int kPrepThreads = 256;
+
+__global__ void __launch_bounds__(kPrepThreads) haspi_prep_kernel(PairGeom g, HaspiBuffers b) {
+  const int pair = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
+  const float* __restrict__ src = (q == 0 ? b.ref : b.deg) + g.off16[pair];
+  const int L = g.len16[pair];
+  const int N = g.n24[pair];
+  float* __restrict__ x24 = b.x24 + (int64_t)q * b.tot24 + g.off24[pair];
+  double* __restrict__ mid = b.mid + (int64_t)q * b.tot24 + g.off24[pair];
+  __shared__ double red[32];
+  __shared__ double s_loc[kPrepThreads][3];
+  __shared__ double s_M[3][3];
+
+  // 1. RMS of the input (pyhaspi2.py:81-84)
+  double ss = 0.0;
+  for (int i = tid; i < L; i += kPrepThreads) {
+    const double v = (double)src[i];
+    ss += v * v;
+  }
+  ss = block_sum(ss, red);
+  const double inv_rms = 1.0 / sqrt(ss / (double)L);
+
+  // 2. resample to 24 kHz (resampy kaiser_best, phase-tabulated) or copy
+  double ss24 = 0.0;
+  if (b.rs_up == 1 && b.rs_down == 1) {
+    for (int t = tid; t < N; t += kPrepThreads) {
+      const float v = (float)((double)src[t] * inv_rms);
+      x24[t] = v;
+      ss24 += (double)v * (double)v;
+    }
+  } else {
+    const int n_out = (int)(((int64_t)L * b.rs_up) / b.rs_down);  // int(L * ratio)
+    for (int t = tid; t < N; t += kPrepThreads) {
+      float v = 0.f;
+      if (t < n_out) {
+        const int64_t pos = (int64_t)t * b.rs_down;
+        const int n = (int)(pos / b.rs_up), r = (int)(pos % b.rs_up);
+        const double* __restrict__ tp = b.rs_taps + (size_t)r * 128;
+        double acc = 0.0;
+        const int cl = min(n + 1, 64);
+#pragma unroll 4
+        for (int i = 0; i < cl; ++i) acc = fma(__ldg(tp + i), (double)__ldg(src + n - i), acc);
+        const int cr = min(L - n - 1, 64);
+#pragma unroll 4
+        for (int k = 0; k < cr; ++k) acc = fma(__ldg(tp + 64 + k), (double)__ldg(src + n + 1 + k), acc);
+        v = (float)(acc * inv_rms);
+      }
+      x24[t] = v;
+      ss24 += (double)v * (double)v;
+    }
+  }
+  ss24 = block_sum(ss24, red);
+  // (xRMS / yRMS) * y with xRMS = 1 after the normalisation above (pyhaspi2.py:816-818)
+  const double scale = (b.rs_up == 1 && b.rs_down == 1) ? 1.0 : 1.0 / sqrt(ss24 / (double)N);
+  __syncthreads();
+
+  // 3. middle ear as a blocked linear recurrence: each thread filters one
+  //    contiguous chunk from a zero state, the chunk-to-chunk carries are
+  //    propagated with the 3x3 zero-input transition matrix, then every chunk
+  //    is re-run from its exact initial state.
+  const int Lc = (N + kPrepThreads - 1) / kPrepThreads;
+  const int t0 = min(tid * Lc, N), t1 = min(t0 + Lc, N);
+  MidState st = {0.0, 0.0, 0.0};
+  for (int t = t0; t < t1; ++t) mid_step(st, (double)(float)((double)x24[t] * scale));
+  s_loc[tid][0] = st.z0;
+  s_loc[tid][1] = st.z1;
+  s_loc[tid][2] = st.z2;
+  if (tid < 3) {
+    MidState u = {tid == 0 ? 1.0 : 0.0, tid == 1 ? 1.0 : 0.0, tid == 2 ? 1.0 : 0.0};
+    for (int k = 0; k < Lc; ++k) mid_step(u, 0.0);
+    s_M[0][tid] = u.z0;
+    s_M[1][tid] = u.z1;
+    s_M[2][tid] = u.z2;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;  // state entering chunk k
+    for (int k = 0; k < kPrepThreads; ++k) {
+      const double l0 = s_loc[k][0], l1 = s_loc[k][1], l2 = s_loc[k][2];
+      s_loc[k][0] = c0;
+      s_loc[k][1] = c1;
+      s_loc[k][2] = c2;
+      const double n0 = s_M[0][0] * c0 + s_M[0][1] * c1 + s_M[0][2] * c2 + l0;
+      const double n1 = s_M[1][0] * c0 + s_M[1][1] * c1 + s_M[1][2] * c2 + l1;
+      const double n2 = s_M[2][0] * c0 + s_M[2][1] * c1 + s_M[2][2] * c2 + l2;
+      c0 = n0;
+      c1 = n1;
+      c2 = n2;
+    }
+  }
+  __syncthreads();
+  st.z0 = s_loc[tid][0];
+  st.z1 = s_loc[tid][1];
+  st.z2 = s_loc[tid][2];
+  for (int t = t0; t < t1; ++t) {
+    const float v = (float)((double)x24[t] * scale);
+    x24[t] = v;
+    mid[t] = mid_step(st, (double)v);
+  }
+}
+
+// --------------------------------------------------------------- control
+constexpr int kEarWarps = 4;          // warps per CTA in the lane = band kernels
+constexpr int kCtlChunk = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kEarWarps * 32) haspi_control_kernel(PairGeom g, HaspiBuffers b, int n_items) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int item = blockIdx.x * kEarWarps + wib;
+  if (item >= n_items) return;
+  const int pair = item >> 1, q = item & 1;
+  const double* __restrict__ mid = b.mid + (int64_t)q * b.tot24 + g.off24[pair];
+  const int N = g.n24[pair];
+  __shared__ double s_buf[kEarWarps][kCtlChunk];
+  double* buf = s_buf[wib];
+  const BandConst bc = b.bands[lane];
+  ControlLane<T> cl;
+  cl.init(bc);
+  double acc = 0.0;
+  for (int base = 0; base < N; base += kCtlChunk) {
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kCtlChunk / 32; ++k) {
+      const int t = base + k * 32 + lane;
+      buf[k * 32 + lane] = (t < N) ? mid[t] : 0.0;
+    }
+    __syncwarp();
+    cl.car.seed_before(base);
+    const int m = min(kCtlChunk, N - base);
+    T part = (T)0;
+#pragma unroll 4
+    for (int k = 0; k < m; ++k) part += cl.step((T)buf[k]);
+    acc += (double)part;
+  }
+  b.bw[((int64_t)pair * 2 + q) * kBands + lane] =
+      bw_from_control(acc, (double)cl.k.gain, N, bc.bwmin[q], bc.bw1);
+}
+
+// group-delay shifts, always from BWx (pyhaspi2.py:1239-1240)
+__global__ void haspi_shift_kernel(HaspiBuffers b, int n) {
+  const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (pair >= n) return;
+  const double gd = gt_group_delay(b.bw[((int64_t)pair * 2 + 0) * kBands + lane], b.bands[lane].erb);
+  const double gmax = warp_max(gd);
+  b.shift[(int64_t)pair * kBands + lane] = (int)(gmax - gd);
+}
+
+// ------------------------------------------------------------------ main
+constexpr int kEarChunk = 576;  // 64 blocks of 9 samples; ring of two chunks per warp
+
+template <typename T>
+__global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_kernel(PairGeom g, HaspiBuffers b, int n_items) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int item = blockIdx.x * kEarWarps + wib;
+  if (item >= n_items) return;
+  const int pair = item >> 1, q = item & 1;
+  const double* __restrict__ mid = b.mid + (int64_t)q * b.tot24 + g.off24[pair];
+  const int N = g.n24[pair], nsub = g.nsub[pair];
+  float* __restrict__ out = b.envlp + ((int64_t)q * b.totsub + g.offsub[pair]) * kBands;
+  __shared__ T s_ring[kEarWarps][2 * kEarChunk];
+  T* ring = s_ring[wib];
+
+  EarLane<T> L;
+  {
+    const BandConst bc = b.bands[lane];
+    L.init(bc, q, b.bw[((int64_t)pair * 2 + q) * kBands + lane], b.shift[(int64_t)pair * kBands + lane], c_ihc);
+  }
+  int rp = (L.shift == 0) ? 0 : 2 * kEarChunk - L.shift;  // ring slot of sample i - shift
+  const int nblk = nsub + 2;                               // output j completes after block j + 2
+  const int nchunks = (nblk * 9 + kEarChunk - 1) / kEarChunk;
+  for (int c = 0; c < nchunks; ++c) {
+    const int i0 = c * kEarChunk;
+    T* half = ring + (c & 1) * kEarChunk;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kEarChunk / 32; ++k) {
+      const int t = i0 + k * 32 + lane;
+      half[k * 32 + lane] = (t < N) ? (T)mid[t] : (T)0;
+    }
+    __syncwarp();
+    {  // re-seed the carrier from the exact phase (lane-local time axis)
+      const int t = i0 - L.shift;
+      if (t >= 0) L.car.seed_before(t);
+      else if (t + kEarChunk > 0) L.car.seed_before(0);
+    }
+    const int blk_end = min((c + 1) * (kEarChunk / 9), nblk);
+    for (int blk = c * (kEarChunk / 9); blk < blk_end; ++blk) {
+      const int ib = blk * 9;
+      float v[9];
+#pragma unroll
+      for (int p = 0; p < 9; ++p) {
+        const int i = ib + p;
+        const T x = ring[rp];
+        rp = (rp + 1 == 2 * kEarChunk) ? 0 : rp + 1;
+        v[p] = (i >= L.shift && i < N) ? L.sample(x) : 0.f;
+      }
+      L.template accumulate<0>(v[0], c_envfir);
+      L.template accumulate<1>(v[1], c_envfir);
+      L.template accumulate<2>(v[2], c_envfir);
+      L.template accumulate<3>(v[3], c_envfir);
+      L.template accumulate<4>(v[4], c_envfir);
+      L.template accumulate<5>(v[5], c_envfir);
+      L.template accumulate<6>(v[6], c_envfir);
+      L.template accumulate<7>(v[7], c_envfir);
+      L.template accumulate<8>(v[8], c_envfir);
+      const float o = L.emit();
+      const int j = blk - 2;
+      if (j >= 0) out[(int64_t)j * kBands + lane] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------- cepstra
+__device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
+  const uint64_t p = (uint64_t)a * b;
+  *hi = (uint32_t)(p >> 32);
+  return (uint32_t)p;
+}
+// Philox4x32-10 counter-based generator (Salmon et al. 2011)
+__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t h0, h1;
+    const uint32_t l0 = mulhilo(0xD2511F53u, c[0], &h0), l1 = mulhilo(0xCD9E8D57u, c[2], &h1);
+    const uint32_t n0 = h1 ^ c[1] ^ k0, n2 = h0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = l1; c[2] = n2; c[3] = l0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+// unit normal for (seed, stream = pair*2+q, row, band)
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t stream, uint32_t row, uint32_t band) {
+  uint32_t c[4] = {row, band >> 1, (uint32_t)stream, (uint32_t)(stream >> 32)};
+  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float sn, cs;
+  __sincosf(6.283185307179586f * u2, &sn, &cs);
+  return (band & 1) ? r * sn : r * cs;
+}
+
+constexpr int kCepThreads = 256;
+
+__global__ void __launch_bounds__(kCepThreads) haspi_cep_kernel(PairGeom g, HaspiBuffers b) {
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  constexpr int NW = kCepThreads / 32;
+  const int nsub = g.nsub[pair];
+  const int64_t rbase = g.offsub[pair];
+  const float* __restrict__ ex = b.envlp + rbase * kBands;
+  const float* __restrict__ ey = b.envlp + (b.totsub + rbase) * kBands;
+  int32_t* __restrict__ rowsel = b.rowsel + rbase;
+  __shared__ int s_cnt[NW];
+  __shared__ int s_base;
+  __shared__ double s_sum[NW][2 * kNumCep];
+
+  // 1. loudness of every reference frame (pyhaspi2.py:352-355)
+  for (int r = wib; r < nsub; r += NW) {
+    const float lin = warp_sum(undb20(ex[(int64_t)r * kBands + lane]));
+    if (lane == 0) rowsel[r] = (db20(lin * (1.0f / kBands)) > 2.5f) ? 1 : 0;
+  }
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  // 2. exclusive scan of the keep flags -> compacted row index
+  for (int r0 = 0; r0 < nsub; r0 += kCepThreads) {
+    const int r = r0 + tid;
+    const int f = (r < nsub) ? rowsel[r] : 0;
+    int inc = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_cnt[wib] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wib; ++w) woff += s_cnt[w];
+    int tot = 0;
+    for (int w = 0; w < NW; ++w) tot += s_cnt[w];
+    const int base = s_base;
+    if (r < nsub) rowsel[r] = f ? (base + woff + inc - 1) : -1;
+    __syncthreads();
+    if (tid == 0) s_base = base + tot;
+    __syncthreads();
+  }
+  const int nsel = s_base;
+  if (tid == 0) b.nsel[pair] = nsel;
+
+  // 3. dither + projection of the kept frames (pyhaspi2.py:359-367), column sums
+  float cm[kNumCep];
+#pragma unroll
+  for (int j = 0; j < kNumCep; ++j) cm[j] = c_cepm[lane * kNumCep + j];
+  double sum[2 * kNumCep];
+#pragma unroll
+  for (int j = 0; j < 2 * kNumCep; ++j) sum[j] = 0.0;
+  const uint64_t gp = (uint64_t)(b.pair_base + pair);
+  for (int r = wib; r < nsub; r += NW) {
+    const int ci = rowsel[r];
+    if (ci < 0) continue;
+    float vx = ex[(int64_t)r * kBands + lane], vy = ey[(int64_t)r * kBands + lane];
+    if (!b.no_dither) {
+      if (b.dither) {
+        if (ci < b.dither_rows) {
+          vx += 0.1f * b.dither[(int64_t)ci * kBands + lane];
+          vy += 0.1f * b.dither[(b.dither_rows + ci) * kBands + lane];
+        }
+      } else {
+        vx += 0.1f * philox_normal(b.seed, gp * 2 + 0, (uint32_t)ci, (uint32_t)lane);
+        vy += 0.1f * philox_normal(b.seed, gp * 2 + 1, (uint32_t)ci, (uint32_t)lane);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kNumCep; ++j) {
+      const float px = warp_sum(vx * cm[j]), py = warp_sum(vy * cm[j]);
+      if (lane == 0) {
+        b.cep[(int64_t)(0 * kNumCep + j) * b.totsub + rbase + ci] = px;
+        b.cep[(int64_t)(1 * kNumCep + j) * b.totsub + rbase + ci] = py;
+        sum[j] += (double)px;
+        sum[kNumCep + j] += (double)py;
+      }
+    }
+  }
+  if (lane == 0)
+    for (int j = 0; j < 2 * kNumCep; ++j) s_sum[wib][j] = sum[j];
+  __syncthreads();
+  if (tid < 2 * kNumCep) {
+    double t = 0.0;
+    for (int w = 0; w < NW; ++w) t += s_sum[w][tid];
+    b.cepmean[(int64_t)pair * 2 * kNumCep + tid] = (nsel > 0) ? t / (double)nsel : 0.0;
+  }
+}
+
+// ----------------------------------------------- modulation filter + corr
+constexpr int kModThreads = 256;
+constexpr int kModPer = 8;                                // consecutive outputs per thread
+constexpr int kModTile = kModThreads * kModPer;           // 2048 outputs per CTA
+constexpr int kModFront = kModMaxHalf + 1;               // staged samples before the tile
+constexpr int kModSpan = kModTile + 2 * kModMaxHalf + 8;  // staged samples per signal
+__host__ __device__ constexpr int mod_skew(int u) { return u + (u >> 3); }  // bank-conflict-free for stride-8 lanes
+
+__global__ void __launch_bounds__(kModThreads) haspi_modcorr_kernel(PairGeom g, HaspiBuffers b) {
+  const int pair = blockIdx.x, j = blockIdx.y, tile = blockIdx.z, tid = threadIdx.x;
+  const int n = b.nsel[pair];
+  const int tbase = tile * kModTile;
+  if (tbase >= n || n <= 1) return;
+  extern __shared__ float smem[];
+  float* sx = smem;
+  float* sy = smem + mod_skew(kModSpan) + 1;
+  float* staps = sy + mod_skew(kModSpan) + 1;
+  __shared__ double red[32];
+  const int64_t rbase = g.offsub[pair];
+  const float* __restrict__ cx = b.cep + (int64_t)(0 * kNumCep + j) * b.totsub + rbase;
+  const float* __restrict__ cy = b.cep + (int64_t)(1 * kNumCep + j) * b.totsub + rbase;
+  const float mx = (float)b.cepmean[(int64_t)pair * 2 * kNumCep + j];
+  const float my = (float)b.cepmean[(int64_t)pair * 2 * kNumCep + kNumCep + j];
+  // staged index u <-> sample tbase - kModFront + u, zero outside [0, n)
+  for (int u = tid; u < kModSpan; u += kModThreads) {
+    const int t = tbase - kModFront + u;
+    const bool ok = (t >= 0 && t < n);
+    sx[mod_skew(u)] = ok ? cx[t] - mx : 0.f;
+    sy[mod_skew(u)] = ok ? cy[t] - my : 0.f;
+  }
+  for (int k = tid; k < kModTapsTotal; k += kModThreads) staps[k] = g_modtaps[k];
+  __syncthreads();
+
+  const int tl = tid * kModPer;  // first local output of this thread
+  double* dst = b.modsum + (((int64_t)pair * kNumCep + j) * kNumMod) * 5;
+  for (int m = 0; m < kNumMod; ++m) {
+    const int nh = c_mod_nhalf[m];
+    const float* __restrict__ tp = staps + c_mod_off[m];
+    float ax[kModPer], ay[kModPer], wx[kModPer], wy[kModPer];
+#pragma unroll
+    for (int r = 0; r < kModPer; ++r) ax[r] = ay[r] = 0.f;
+    // out[t] = sum_k g[k] x[t + nh - k]; window w[r] = x[tl + r + nh - k]
+    const int u0 = tl + kModFront + nh;  // staged index of x[tl + nh] (k = 0, r = 0)
+#pragma unroll
+    for (int r = 0; r < kModPer; ++r) {
+      wx[r] = sx[mod_skew(u0 + r)];
+      wy[r] = sy[mod_skew(u0 + r)];
+    }
+    const int ntap = 2 * nh + 1;
+    int k = 0;
+    for (; k + kModPer <= ntap; k += kModPer) {
+#pragma unroll
+      for (int kk = 0; kk < kModPer; ++kk) {
+        const float gk = tp[k + kk];
+        // logical window after kk shifts: w[r] = x[.. + r - kk]; element (r - kk) mod P holds it
+#pragma unroll
+        for (int r = 0; r < kModPer; ++r) {
+          ax[r] = fmaf(gk, wx[(r - kk + kModPer) % kModPer], ax[r]);
+          ay[r] = fmaf(gk, wy[(r - kk + kModPer) % kModPer], ay[r]);
+        }
+        // slide: logical w[0] for the next tap is x[u0 - (k + kk) - 1]; it replaces the
+        // slot that held logical w[P-1], i.e. physical (P - 1 - kk) mod P
+        const int un = u0 - (k + kk) - 1;
+        wx[(kModPer - 1 - kk + kModPer) % kModPer] = sx[mod_skew(un)];
+        wy[(kModPer - 1 - kk + kModPer) % kModPer] = sy[mod_skew(un)];
+      }
+    }
+    // remainder taps (ntap is odd): physical layout is back to identity here
+    for (; k < ntap; ++k) {
+      const float gk = tp[k];
+#pragma unroll
+      for (int r = 0; r < kModPer; ++r) {
+        ax[r] = fmaf(gk, wx[r], ax[r]);
+        ay[r] = fmaf(gk, wy[r], ay[r]);
+      }
+#pragma unroll
+      for (int r = kModPer - 1; r > 0; --r) {
+        wx[r] = wx[r - 1];
+        wy[r] = wy[r - 1];
+      }
+      const int un = u0 - k - 1;
+      wx[0] = sx[mod_skew(un)];
+      wy[0] = sy[mod_skew(un)];
+    }
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+#pragma unroll
+    for (int r = 0; r < kModPer; ++r) {
+      if (tbase + tl + r < n) {
+        const double vx = ax[r], vy = ay[r];
+        s0 += vx; s1 += vy; s2 += vx * vx; s3 += vy * vy; s4 += vx * vy;
+      }
+    }
+    s0 = block_sum(s0, red);
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    s3 = block_sum(s3, red);
+    s4 = block_sum(s4, red);
+    if (tid == 0) {
+      atomicAdd(dst + m * 5 + 0, s0);
+      atomicAdd(dst + m * 5 + 1, s1);
+      atomicAdd(dst + m * 5 + 2, s2);
+      atomicAdd(dst + m * 5 + 3, s3);
+      atomicAdd(dst + m * 5 + 4, s4);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- score
+__global__ void haspi_score_kernel(HaspiBuffers b, int n, double* intel, double* raw10, int32_t* status) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= n) return;
+  const double w[kNumMod] = {1.361, 1.521, 1.164, 0.492, 0.436, 0.690, 1.142, 0.816, 1.576, 2.269};
+  const int ns = b.nsel[pair];
+  if (ns <= 1) {  // pyhaspi2.py:357-358 raises; reported per pair instead
+    intel[pair] = nan("");
+    for (int m = 0; m < kNumMod; ++m) raw10[(int64_t)pair * kNumMod + m] = nan("");
+    status[pair] = 1;
+    return;
+  }
+  const double dn = (double)ns;
+  double tot = 0.0;
+  for (int m = 0; m < kNumMod; ++m) {
+    double ave = 0.0;
+    for (int j = 0; j < kNumCep; ++j) {
+      const double* s = b.modsum + ((((int64_t)pair * kNumCep + j) * kNumMod) + m) * 5;
+      const double xs = s[2] - s[0] * s[0] / dn, ys = s[3] - s[1] * s[1] / dn;
+      const double xy = s[4] - s[0] * s[1] / dn;
+      ave += (xs < 1.0e-30 || ys < 1.0e-30) ? 0.0 : fabs(xy) / sqrt(xs * ys);
+    }
+    ave /= (double)kNumCep;
+    raw10[(int64_t)pair * kNumMod + m] = ave;
+    tot += w[m] * ave;
+  }
+  intel[pair] = tot;
+  status[pair] = 0;
+}
+
+// ------------------------------------------------------------- launchers
+static size_t modcorr_smem_bytes() {
+  return (size_t)(2 * (mod_skew(kModSpan) + 1) + kModTapsTotal + 8) * sizeof(float);
+}
+
+void haspi_upload_constants(cudaStream_t s) {
+  float fir[54];
+  make_env_fir(fir);
+  cudaMemcpyToSymbolAsync(c_envfir, fir, sizeof(fir), 0, cudaMemcpyHostToDevice, s);
+  const IhcConst ih = make_ihc_const();
+  cudaMemcpyToSymbolAsync(c_ihc, &ih, sizeof(ih), 0, cudaMemcpyHostToDevice, s);
+  cudaStreamSynchronize(s);  // sources are stack temporaries
+}
+
+void haspi_upload_tables(const float* cepm, const int* nhalf, const int* off, const float* taps, int ntaps,
+                         cudaStream_t s) {
+  cudaMemcpyToSymbolAsync(c_cepm, cepm, sizeof(float) * kBands * kNumCep, 0, cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(c_mod_nhalf, nhalf, sizeof(int) * kNumMod, 0, cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(c_mod_off, off, sizeof(int) * (kNumMod + 1), 0, cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(g_modtaps, taps, sizeof(float) * ntaps, 0, cudaMemcpyHostToDevice, s);
+  cudaFuncSetAttribute(haspi_modcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)modcorr_smem_bytes());
+  cudaStreamSynchronize(s);
+}
+
+int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, bool f64, cudaStream_t s) {
+  int launches = 0;
+  haspi_prep_kernel<<<dim3(n, 2), kPrepThreads, 0, s>>>(g, b);
+  ++launches;
+  const int items = 2 * n, ctas = (items + kEarWarps - 1) / kEarWarps;
+  if (f64) haspi_control_kernel<double><<<ctas, kEarWarps * 32, 0, s>>>(g, b, items);
+  else haspi_control_kernel<float><<<ctas, kEarWarps * 32, 0, s>>>(g, b, items);
+  ++launches;
+  haspi_shift_kernel<<<(n * 32 + 127) / 128, 128, 0, s>>>(b, n);
+  ++launches;
+  if (f64) haspi_ear_kernel<double><<<ctas, kEarWarps * 32, 0, s>>>(g, b, items);
+  else haspi_ear_kernel<float><<<ctas, kEarWarps * 32, 0, s>>>(g, b, items);
+  ++launches;
+  haspi_cep_kernel<<<n, kCepThreads, 0, s>>>(g, b);
+  ++launches;
+  cudaMemsetAsync(b.modsum, 0, sizeof(double) * (size_t)n * kNumCep * kNumMod * 5, s);
+  const int tiles = (max_nsub + kModTile - 1) / kModTile;
+  haspi_modcorr_kernel<<<dim3(n, kNumCep, tiles), kModThreads, modcorr_smem_bytes(), s>>>(g, b);
+  ++launches;
+  return launches;
+}
+
+int haspi_finish(const HaspiBuffers& b, int n, double* intel, double* raw10, int32_t* status, cudaStream_t s) {
+  haspi_score_kernel<<<(n + 127) / 128, 128, 0, s>>>(b, n, intel, raw10, status);
+  return 1;
+}
+
+}  // namespace nele

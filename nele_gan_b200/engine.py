@@ -1,0 +1,224 @@
+"""ctypes binding of ``libnele_score.so`` (include/nele_score.h) and the batched
+host API.
+
+The engine has no CPU implementation: if the shared library is missing or no
+CUDA device is visible, constructing :class:`Engine` raises
+:class:`NeleError` -- it never falls back to the oracle or to numpy.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnele_score.so")
+
+METRIC_HASPI, METRIC_SIIB, METRIC_ESTOI = 1, 2, 4
+METRIC_ALL = 7
+FLAG_MAPPED, FLAG_DEVICE_INPUT, FLAG_NO_DITHER, FLAG_SIIB_NO_TILE, FLAG_KEEP_STAGES = 1, 2, 4, 8, 16
+ST_OK, ST_BELOW_THR, ST_TOO_SHORT, ST_BAD_RATE, ST_SKIPPED = 0, 1, 2, 3, 0xFF
+_METRIC_BITS = {"haspi": METRIC_HASPI, "siib": METRIC_SIIB, "estoi": METRIC_ESTOI, "stoi": METRIC_ESTOI}
+COL_SIIB, COL_HASPI, COL_ESTOI = 0, 1, 2
+
+SYMBOLS = ("nele_abi_version", "nele_create", "nele_destroy", "nele_last_error", "nele_score_batch",
+           "nele_get_stage", "nele_last_timing")
+
+
+class NeleError(RuntimeError):
+    pass
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library(path=None):
+    """dlopen the C-ABI library and declare its prototypes."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or LIB_PATH
+        if not os.path.exists(p):
+            raise NeleError("%s not found: build it with `python -m nele_gan_b200.build` "
+                            "(there is no CPU fallback)" % p)
+        lib = C.CDLL(p)
+        lib.nele_abi_version.restype = C.c_int
+        lib.nele_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        lib.nele_create.restype = C.c_int
+        lib.nele_destroy.argtypes = [C.c_void_p]
+        lib.nele_destroy.restype = None
+        lib.nele_last_error.argtypes = [C.c_void_p]
+        lib.nele_last_error.restype = C.c_char_p
+        lib.nele_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int64, C.c_uint64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.nele_score_batch.restype = C.c_int
+        lib.nele_get_stage.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t,
+                                       C.POINTER(C.c_size_t)]
+        lib.nele_get_stage.restype = C.c_int
+        lib.nele_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        lib.nele_last_timing.restype = C.c_int
+        if path is None:
+            _lib = lib
+        return lib
+
+
+def metric_mask(metrics):
+    if isinstance(metrics, int):
+        return metrics
+    m = 0
+    for name in metrics:
+        m |= _METRIC_BITS[name.lower()]
+    return m
+
+
+def pack(signals, align=4):
+    """Concatenate ragged 1-D float32 signals -> (flat float32, offs int64, lens int32)."""
+    lens = np.array([len(s) for s in signals], dtype=np.int32)
+    padded = (lens.astype(np.int64) + (align - 1)) // align * align
+    offs = np.concatenate(([0], np.cumsum(padded)[:-1])).astype(np.int64) if len(lens) else np.zeros(0, np.int64)
+    flat = np.zeros(int(padded.sum()), dtype=np.float32)
+    for s, o, n in zip(signals, offs, lens):
+        flat[o:o + n] = s
+    return flat, offs, lens
+
+
+class BatchResult:
+    """scores[n,3] in the column order {SIIB, HASPI, ESTOI} (train_nele.py:320-322),
+    haspi_raw[n,10], status[n] (one byte per metric, see include/nele_score.h)."""
+
+    def __init__(self, scores, haspi_raw, status):
+        self.scores, self.haspi_raw, self.status = scores, haspi_raw, status
+
+    siib = property(lambda self: self.scores[:, COL_SIIB])
+    haspi = property(lambda self: self.scores[:, COL_HASPI])
+    estoi = property(lambda self: self.scores[:, COL_ESTOI])
+
+    def metric_status(self, name):
+        k = {"haspi": 0, "siib": 1, "estoi": 2}[name]
+        return (self.status >> (8 * k)) & 0xFF
+
+
+class Engine:
+    """One scoring engine on one CUDA device."""
+
+    def __init__(self, device=0, lib_path=None):
+        self._lib = load_library(lib_path)
+        h = C.c_void_p()
+        rc = self._lib.nele_create(int(device), C.byref(h))
+        if rc != 0:
+            msg = self._lib.nele_last_error(None)
+            raise NeleError("nele_create(device=%d) failed (%d): %s" % (device, rc, msg.decode() if msg else "?"))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nele_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.nele_last_error(self._h)
+            raise NeleError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+    # ------------------------------------------------------------------ low level
+    def score_packed(self, ref, deg, offs, lens, fs=16000, metrics=METRIC_ALL, mapped=True, dither=None,
+                     seed=0, no_dither=False, hl=None, siib_no_tile=False, keep_stages=False,
+                     device_input=False, stream=None, out=None):
+        """``ref``/``deg``: flat float32 numpy arrays, or raw pointers (ints, e.g.
+        ``tensor.data_ptr()``; device pointers when ``device_input``).  ``offs``
+        int64[n], ``lens`` int32[n] are host numpy arrays."""
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        n = int(lens.shape[0])
+        if isinstance(ref, np.ndarray):
+            ref = np.ascontiguousarray(ref, dtype=np.float32)
+            deg = np.ascontiguousarray(deg, dtype=np.float32)
+            pref, pdeg = ref.ctypes.data, deg.ctypes.data
+        else:
+            pref, pdeg = int(ref), int(deg)
+        flags = (FLAG_MAPPED if mapped else 0) | (FLAG_NO_DITHER if no_dither else 0) | \
+                (FLAG_SIIB_NO_TILE if siib_no_tile else 0) | (FLAG_KEEP_STAGES if keep_stages else 0) | \
+                (FLAG_DEVICE_INPUT if device_input else 0)
+        pd, drows = None, 0
+        if dither is not None:
+            dither = np.ascontiguousarray(dither, dtype=np.float32)
+            assert dither.ndim == 3 and dither.shape[0] == 2 and dither.shape[2] == 32
+            pd, drows = dither.ctypes.data, dither.shape[1]
+        phl = None
+        if hl is not None:
+            hl = np.ascontiguousarray(hl, dtype=np.float64)
+            assert hl.shape == (6,)
+            phl = hl.ctypes.data
+        if out is None:
+            scores = np.empty((n, 3), dtype=np.float64)
+            raw = np.empty((n, 10), dtype=np.float64)
+            status = np.empty(n, dtype=np.int32)
+        else:
+            scores, raw, status = out
+        rc = self._lib.nele_score_batch(self._h, pref, pdeg, offs.ctypes.data, lens.ctypes.data, n, int(fs),
+                                        metric_mask(metrics), flags, pd, drows, int(seed) & (2 ** 64 - 1), phl,
+                                        scores.ctypes.data, raw.ctypes.data, status.ctypes.data,
+                                        None if stream is None else int(stream))
+        self._check(rc, "nele_score_batch")
+        return BatchResult(scores, raw, status)
+
+    # ----------------------------------------------------------------- high level
+    def score_batch(self, refs, degs, fs=16000, metrics=("siib", "haspi", "estoi"), mapped=True, **kw):
+        """``refs``/``degs``: sequences of 1-D float arrays (ragged allowed).  Each
+        pair is trimmed to its common length like intel.py:58-60 does."""
+        refs = [np.asarray(r, dtype=np.float32) for r in refs]
+        degs = [np.asarray(d, dtype=np.float32) for d in degs]
+        if len(refs) != len(degs):
+            raise ValueError("refs and degs differ in count")
+        if not refs:
+            return BatchResult(np.zeros((0, 3)), np.zeros((0, 10)), np.zeros(0, np.int32))
+        for i, (r, d) in enumerate(zip(refs, degs)):
+            m = min(len(r), len(d))
+            if m == 0:
+                raise ValueError("pair %d is empty" % i)
+            refs[i], degs[i] = r[:m], d[:m]
+        fr, offs, lens = pack(refs)
+        fd, _, _ = pack(degs)
+        return self.score_packed(fr, fd, offs, lens, fs=fs, metrics=metrics, mapped=mapped, **kw)
+
+    def last_timing(self):
+        """(kernel milliseconds, kernel launches) of the last call."""
+        ms, nl = C.c_double(), C.c_int64()
+        self._check(self._lib.nele_last_timing(self._h, C.byref(ms), C.byref(nl)), "nele_last_timing")
+        return ms.value, nl.value
+
+    _STAGE_DTYPES = {"haspi.mid": np.float64, "haspi.x24": np.float32, "haspi.bw": np.float64,
+                     "haspi.shift": np.int32, "haspi.envlp": np.float32, "haspi.nsel": np.int32,
+                     "haspi.cep": np.float32, "haspi.cepmean": np.float64, "estoi.x10": np.float64,
+                     "estoi.tob": np.float64, "estoi.info": np.int32, "siib.tile": np.int32,
+                     "siib.logspec": np.float32, "siib.lambda": np.float32, "siib.rho": np.float32,
+                     "siib.cov": np.float32}
+
+    def stage(self, name, pair=0):
+        """Flat array of stage ``name`` for ``pair`` of the last keep_stages call."""
+        nb = C.c_size_t()
+        self._check(self._lib.nele_get_stage(self._h, name.encode(), int(pair), None, 0, C.byref(nb)), "nele_get_stage")
+        buf = np.empty(nb.value, dtype=np.uint8)
+        self._check(self._lib.nele_get_stage(self._h, name.encode(), int(pair), buf.ctypes.data, nb.value, C.byref(nb)),
+                    "nele_get_stage")
+        return buf.view(self._STAGE_DTYPES[name])
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_engine(device=None):
+    """Process-wide engine per device (device defaults to $NELE_DEVICE, $LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("NELE_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _default_lock:
+        if device not in _default:
+            _default[device] = Engine(device)
+        return _default[device]
