@@ -38,7 +38,7 @@ extern "C" {
 
 /* metric mask */
 #define NELE_METRIC_HASPI 0x1u /* HASPI v2  (pyhaspi2.py:76-107)   */
-#define NELE_METRIC_SIIB  0x2u /* SIIB^Gauss with the wrapper's >=25 s tiling (intel.py:57-100) */
+#define NELE_METRIC_SIIB  0x2u /* SIIB^Gauss (pysiib.SIIB(..., gauss=True)) with the wrapper's >=25 s tiling (intel.py:57-100) */
 #define NELE_METRIC_ESTOI 0x4u /* ESTOI     (pystoi.stoi extended=True) */
 #define NELE_METRIC_ALL   0x7u
 
@@ -124,11 +124,16 @@ int nele_score_batch(nele_engine* e, const float* ref, const float* deg, const i
  *   "haspi.envlp"  f32 [2][nsub][32]   ebm_EnvFilt output            (pyhaspi2.py:412-413)
  *   "haspi.nsel"   i32 [1]             frames above threshold        (pyhaspi2.py:355-356)
  *   "haspi.cep"    f32 [2][5][nsel]    de-meaned cepstra 2..6        (pyhaspi2.py:366-374)
- *   "estoi.x10"    f64 [2][n10]        10 kHz signals
- *   "estoi.tob"    f64 [2][nfr][15]    one-third-octave magnitudes
- *   "siib.tile"    i32 [3]             {M, active frames (wrapper VAD), KLT frames Nf}
- *   "siib.logspec" f32 [2][28][F]      masked, de-meaned log band energies
- *   "siib.lambda"  f32 [420]           eigenvalues of cov(X), ascending
+ *   "estoi.x10"    f32 [2][n10]        10 kHz signals (pystoi resample_oct)
+ *   "estoi.info"   i32 [3]             {n10, analysis frames, frames kept by the 40 dB mask}
+ *   "estoi.kept"   i32 [kept]          indices of the kept frames
+ *   "estoi.tob"    f32 [2][kept-1][15] one-third-octave magnitudes of the silence-removed signals
+ *   "siib.tile"    i32 [4]             {M, active frames (wrapper VAD), frames of the tiled signal, active frames}
+ *   "siib.logspec" f32 [2][Fa][32]     masked, de-meaned log band energies (28 bands + 4 zero lanes)
+ *   "siib.sxx"     f64 [420][420]      centred scatter matrix of the stacked clean features
+ *   "siib.sxy" / "siib.syy"  f32 [420][420]
+ *   "siib.rank"    i32 [2]             {numerical rank of Sxx, Jacobi sweeps}
+ *   "siib.lambda"  f32 [420]           eigenvalues of Sxx (order of the Jacobi columns; 0 beyond the rank)
  *   "siib.rho"     f32 [420]           per-component correlation
  */
 int nele_get_stage(nele_engine* e, const char* name, int pair, void* dst, size_t cap, size_t* nbytes);
@@ -137,6 +142,14 @@ int nele_get_stage(nele_engine* e, const char* name, int pair, void* dst, size_t
  * the last nele_score_batch call, excluding host<->device copies; and the
  * number of kernel launches it made. */
 int nele_last_timing(const nele_engine* e, double* kernel_ms, int64_t* launches);
+
+/* Per-kernel device times of the last nele_score_batch call (bench.py's roofline
+ * figures).  nele_set_profiling(e, 1) makes every following call bracket each
+ * kernel launch with CUDA events on the launching stream; nele_kernel_time
+ * enumerates the kernels by idx = 0, 1, ... (NELE_E_ARG past the end): name,
+ * summed milliseconds and number of launches.  Off by default. */
+int nele_set_profiling(nele_engine* e, int on);
+int nele_kernel_time(const nele_engine* e, int idx, const char** name, double* ms, int64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -2,9 +2,9 @@
 //
 // One engine per (process, device).  A call splits the batch into sub-batches
 // ("chunks") that bound the device workspace, stages the chunk's waveforms in
-// HBM, runs the metric pipelines on one stream and copies the per-pair records
-// back.  There is no CPU implementation of any metric in this library: without
-// a CUDA device nele_create fails.
+// HBM, queues the three metric pipelines on one stream and copies the per-pair
+// records back.  There is no CPU implementation of any metric in this library:
+// without a CUDA device nele_create fails.
 #include "../../include/nele_score.h"
 
 #include <math.h>
@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -32,6 +33,12 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+struct KernelStat {
+  std::string name;
+  double ms = 0.0;
+  int64_t launches = 0;
+};
+
 struct nele_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -39,23 +46,36 @@ struct nele_engine {
   bool f64 = false;  // recurrence precision of the ear model (NELE_HASPI_F64=1)
 
   // constant tables
-  DevBuf bands, rs_taps;
+  DevBuf bands, rs_taps, st_taps;
   int rs_fs = 0, rs_up = 1, rs_down = 1;
+  int st_fs = 0, st_up = 1, st_down = 1, st_K = 0;
   double hl_cached[6] = {-1, -1, -1, -1, -1, -1};
 
   // workspace (grow-only)
-  DevBuf in_ref, in_deg, geom, x24, mid, bw, shift, envlp, rowsel, nsel, cep, cepmean, modsum, dither;
-  DevBuf out_intel, out_raw, out_status;
-  DevBuf estoi_ws, siib_ws;
+  DevBuf in_ref, in_deg, geom, sgeom, dither;
+  DevBuf x24, mid, bw, shift, envlp, rowsel, nsel, cep, cepmean, modsum;            // HASPI
+  DevBuf x10, st_energy, st_kept, st_nkept, st_tob;                                 // ESTOI
+  DevBuf sb_wrapdb, sb_M, sb_wact, sb_mean, sb_xdb, sb_act, sb_Fa, sb_logspec;      // SIIB, per chunk
+  DevBuf sb_base, sb_Sxx, sb_Sxy, sb_Syy, sb_Lc, sb_G, sb_perm;                     // SIIB, per sub-chunk
+  DevBuf sb_rank, sb_sweeps, sb_lambda, sb_rho;
+  DevBuf out_haspi, out_raw, out_hst, out_estoi, out_est, out_siib, out_sst;
+  std::vector<DevBuf*> all_bufs;
+  int32_t* h_M = nullptr;  // pinned
+  size_t h_M_cap = 0;
+  cudaEvent_t ev_M = nullptr;
 
   // geometry of the last chunk (for nele_get_stage)
   bool stages_valid = false;
-  std::vector<int64_t> g_off16, g_off24, g_offsub;
-  std::vector<int32_t> g_len16, g_n24, g_nsub;
-  int64_t tot24 = 0, totsub = 0;
-  int chunk_n = 0;
-  std::vector<int32_t> h_nsel;
+  uint32_t stage_metrics = 0;
+  std::vector<int64_t> g_off16, g_off24, g_offsub, g_off10, g_offfr, g_offW, g_offF, g_F;
+  std::vector<int32_t> g_len16, g_n24, g_nsub, g_n10, g_nfa, g_M;
+  int64_t tot24 = 0, totsub = 0, tot10 = 0, totfr = 0, totF = 0;
+  int chunk_n = 0, sub_lo = 0, sub_n = 0;
 
+  bool profiling = false;
+  KernelTimer kt;
+  bool kt_events = false;
+  std::vector<KernelStat> kstats;
   double last_kernel_ms = 0.0;
   int64_t last_launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -103,6 +123,40 @@ extern "C" int nele_abi_version(void) { return NELE_ABI_VERSION; }
 
 extern "C" const char* nele_last_error(const nele_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 
+static void upload_metric_tables(cudaStream_t s) {
+  {
+    float cepm[kBands * kNumCep];
+    host::make_cep_basis(cepm);
+    host::ModFilters mf;
+    host::make_mod_filters(mf);
+    haspi_upload_tables(cepm, mf.nhalf, mf.offset, mf.taps.data(), (int)mf.taps.size(), s);
+  }
+  {
+    float win[256], tw[512];
+    for (int i = 0; i < 256; ++i) win[i] = (float)(0.5 - 0.5 * cos(2.0 * host::kPi * (i + 1) / 257.0));  // hanning(258)[1:-1]
+    for (int k = 0; k < 256; ++k) {
+      tw[2 * k] = (float)cos(2.0 * host::kPi * k / 512.0);
+      tw[2 * k + 1] = (float)(-sin(2.0 * host::kPi * k / 512.0));
+    }
+    int lo[15], hi[15];
+    host::make_thirdoct_bins(lo, hi);
+    estoi_upload_tables(win, lo, hi, tw, s);
+  }
+  {
+    std::vector<float> win(400), decay(16), g2(host::kSiibBands * host::kSiibBins), g2t(host::kSiibBins * 32, 0.f), tw(800);
+    for (int i = 0; i < 400; ++i) win[i] = (float)(0.5 - 0.5 * cos(2.0 * host::kPi * i / 400.0));  // get_window('hann', 400)
+    for (int d = 0; d < 16; ++d) decay[d] = (float)(log((double)(d + 1)) / log(16.0));
+    host::make_siib_g2(g2.data());
+    for (int j = 0; j < host::kSiibBands; ++j)
+      for (int k = 0; k < host::kSiibBins; ++k) g2t[k * 32 + j] = g2[j * host::kSiibBins + k];
+    for (int k = 0; k < 400; ++k) {
+      tw[2 * k] = (float)cos(2.0 * host::kPi * k / 400.0);
+      tw[2 * k + 1] = (float)(-sin(2.0 * host::kPi * k / 400.0));
+    }
+    siib_upload_tables(win.data(), decay.data(), g2t.data(), tw.data(), s);
+  }
+}
+
 extern "C" int nele_create(int device, nele_engine** out) {
   if (!out) return fail(nullptr, NELE_E_ARG, "nele_create: out is NULL");
   *out = nullptr;
@@ -119,6 +173,13 @@ extern "C" int nele_create(int device, nele_engine** out) {
   e->device = device;
   const char* p = getenv("NELE_HASPI_F64");
   e->f64 = (p && p[0] == '1');
+  e->all_bufs = {&e->bands, &e->rs_taps, &e->st_taps, &e->in_ref, &e->in_deg, &e->geom, &e->sgeom, &e->dither,
+                 &e->x24, &e->mid, &e->bw, &e->shift, &e->envlp, &e->rowsel, &e->nsel, &e->cep, &e->cepmean, &e->modsum,
+                 &e->x10, &e->st_energy, &e->st_kept, &e->st_nkept, &e->st_tob,
+                 &e->sb_wrapdb, &e->sb_M, &e->sb_wact, &e->sb_mean, &e->sb_xdb, &e->sb_act, &e->sb_Fa, &e->sb_logspec,
+                 &e->sb_base, &e->sb_Sxx, &e->sb_Sxy, &e->sb_Syy, &e->sb_Lc, &e->sb_G, &e->sb_perm,
+                 &e->sb_rank, &e->sb_sweeps, &e->sb_lambda, &e->sb_rho,
+                 &e->out_haspi, &e->out_raw, &e->out_hst, &e->out_estoi, &e->out_est, &e->out_siib, &e->out_sst};
 #define CUC(call)                                                                             \
   do {                                                                                        \
     cudaError_t _r = (call);                                                                  \
@@ -132,19 +193,9 @@ extern "C" int nele_create(int device, nele_engine** out) {
   CUC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUC(cudaEventCreate(&e->ev0));
   CUC(cudaEventCreate(&e->ev1));
+  CUC(cudaEventCreateWithFlags(&e->ev_M, cudaEventDisableTiming));
   haspi_upload_constants(e->stream);
-  {
-    float cepm[kBands * kNumCep];
-    host::make_cep_basis(cepm);
-    host::ModFilters mf;
-    host::make_mod_filters(mf);
-    if ((int)mf.taps.size() != 2850) {
-      fail(nullptr, NELE_E_ARG, "modulation filter design produced %zu taps, expected 2850", mf.taps.size());
-      delete e;
-      return NELE_E_ARG;
-    }
-    haspi_upload_tables(cepm, mf.nhalf, mf.offset, mf.taps.data(), (int)mf.taps.size(), e->stream);
-  }
+  upload_metric_tables(e->stream);
   CUC(cudaGetLastError());
 #undef CUC
   *out = e;
@@ -154,18 +205,36 @@ extern "C" int nele_create(int device, nele_engine** out) {
 extern "C" void nele_destroy(nele_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  DevBuf* all[] = {&e->bands, &e->rs_taps, &e->in_ref, &e->in_deg, &e->geom, &e->x24, &e->mid, &e->bw, &e->shift,
-                   &e->envlp, &e->rowsel, &e->nsel, &e->cep, &e->cepmean, &e->modsum, &e->dither, &e->out_intel,
-                   &e->out_raw, &e->out_status, &e->estoi_ws, &e->siib_ws};
-  for (DevBuf* b : all)
+  for (DevBuf* b : e->all_bufs)
     if (b->p) cudaFree(b->p);
+  if (e->h_M) cudaFreeHost(e->h_M);
+  if (e->kt_events)
+    for (int i = 0; i < KernelTimer::kMax; ++i) {
+      cudaEventDestroy(e->kt.ev0[i]);
+      cudaEventDestroy(e->kt.ev1[i]);
+    }
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->ev_M) cudaEventDestroy(e->ev_M);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
 
-static int ensure_tables(nele_engine* e, int fs, const double* hl, cudaStream_t s) {
+extern "C" int nele_set_profiling(nele_engine* e, int on) {
+  if (!e) return NELE_E_ARG;
+  CU(e, cudaSetDevice(e->device));
+  if (on && !e->kt_events) {
+    for (int i = 0; i < KernelTimer::kMax; ++i) {
+      CU(e, cudaEventCreate(&e->kt.ev0[i]));
+      CU(e, cudaEventCreate(&e->kt.ev1[i]));
+    }
+    e->kt_events = true;
+  }
+  e->profiling = on != 0;
+  return NELE_OK;
+}
+
+static int ensure_tables(nele_engine* e, int fs, bool haspi_rate_ok, const double* hl, cudaStream_t s) {
   double h[6] = {0, 0, 0, 0, 0, 0};
   if (hl) memcpy(h, hl, sizeof(h));
   if (!e->bands.p || memcmp(h, e->hl_cached, sizeof(h)) != 0) {
@@ -176,25 +245,76 @@ static int ensure_tables(nele_engine* e, int fs, const double* hl, cudaStream_t 
     CU(e, cudaStreamSynchronize(s));
     memcpy(e->hl_cached, h, sizeof(h));
   }
-  if (e->rs_fs != fs) {
+  const int hfs = haspi_rate_ok ? fs : kFs24;
+  if (e->rs_fs != hfs) {
     host::ResampyTaps rt;
-    if (fs == kFs24) {
+    if (hfs == kFs24) {
       rt.up = rt.down = 1;
       rt.taps.assign(128, 0.0);
     } else {
-      host::make_resampy_taps(fs, kFs24, rt);
+      host::make_resampy_taps(hfs, kFs24, rt);
     }
     RESERVE(e, e->rs_taps, rt.taps.size() * sizeof(double));
     CU(e, cudaMemcpyAsync(e->rs_taps.p, rt.taps.data(), rt.taps.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     CU(e, cudaStreamSynchronize(s));
-    e->rs_fs = fs;
+    e->rs_fs = hfs;
     e->rs_up = rt.up;
     e->rs_down = rt.down;
+  }
+  if (e->st_fs != fs) {
+    host::PolyTaps pt;
+    if (fs == 10000) {
+      pt.up = pt.down = 1;
+      pt.K = 0;
+      pt.taps.assign(1, 1.0);
+    } else {
+      host::make_estoi_polytaps(fs, 10000, pt);
+    }
+    RESERVE(e, e->st_taps, pt.taps.size() * sizeof(double));
+    CU(e, cudaMemcpyAsync(e->st_taps.p, pt.taps.data(), pt.taps.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(e, cudaStreamSynchronize(s));
+    e->st_fs = fs;
+    e->st_up = pt.up;
+    e->st_down = pt.down;
+    e->st_K = pt.K;
   }
   return NELE_OK;
 }
 
 static const double kNaN = nan("");
+
+// pack per-pair host arrays into one blob -> one H2D copy
+struct GeomPacker {
+  std::vector<char> blob;
+  size_t add(const void* src, size_t bytes) {
+    const size_t off = (blob.size() + 15) & ~(size_t)15;
+    blob.resize(off + bytes);
+    memcpy(blob.data() + off, src, bytes);
+    return off;
+  }
+};
+
+static void collect_kernel_times(nele_engine* e) {
+  // called after the stream has been synchronised
+  for (int i = 0; i < e->kt.count; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->kt.ev0[i], e->kt.ev1[i]) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    KernelStat* st = nullptr;
+    for (auto& k : e->kstats)
+      if (k.name == e->kt.names[i]) st = &k;
+    if (!st) {
+      e->kstats.push_back(KernelStat());
+      st = &e->kstats.back();
+      st->name = e->kt.names[i];
+    }
+    st->ms += ms;
+    st->launches += 1;
+  }
+  e->kt.count = 0;
+}
 
 extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* deg, const int64_t* offs,
                                 const int32_t* lens, int n, int fs, uint32_t metrics, uint32_t flags,
@@ -211,14 +331,19 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
   e->last_kernel_ms = 0.0;
   e->last_launches = 0;
   e->stages_valid = false;
+  e->kstats.clear();
+  e->kt.count = 0;
+  e->kt.enabled = e->profiling && e->kt_events;
+  KernelTimer* kt = e->kt.enabled ? &e->kt : nullptr;
   if (n == 0) return NELE_OK;
   CU(e, cudaSetDevice(e->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
   const bool do_haspi = metrics & NELE_METRIC_HASPI, do_siib = metrics & NELE_METRIC_SIIB, do_estoi = metrics & NELE_METRIC_ESTOI;
   const bool haspi_rate_ok = fs <= kFs24;
+  const bool siib_rate_ok = fs == 16000;  // audio_util.py:131,159,187 assert it; the wrapper's R = fs / 200 presumes it
   const bool dev_in = flags & NELE_FLAG_DEVICE_INPUT;
   const bool mapped = flags & NELE_FLAG_MAPPED;
-  int rc = ensure_tables(e, haspi_rate_ok ? fs : kFs24, hl, s);
+  int rc = ensure_tables(e, fs, haspi_rate_ok, hl, s);
   if (rc != NELE_OK) return rc;
 
   if (dither && !(flags & NELE_FLAG_NO_DITHER)) {
@@ -232,8 +357,9 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
   }
 
   // ---- chunking: bound the workspace by pairs and by total samples
-  const int64_t kMaxChunkSamples = 80LL * 1000 * 1000;  // input-rate samples per signal
-  const int kMaxChunkPairs = 2048;
+  const int64_t kMaxChunkSamples = 256LL * 1000 * 1000;  // input-rate samples per signal
+  const int kMaxChunkPairs = 4096;
+  const int kSiibSub = 1024;                              // pairs per SIIB matrix sub-chunk
   int first = 0;
   while (first < n) {
     int last = first;
@@ -245,11 +371,12 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       ++last;
     }
     const int cn = last - first;
-    // geometry
+    // ---- geometry
     e->g_off16.resize(cn); e->g_len16.resize(cn); e->g_off24.resize(cn); e->g_n24.resize(cn);
-    e->g_offsub.resize(cn); e->g_nsub.resize(cn);
-    int64_t t24 = 0, tsub = 0;
-    int max_nsub = 0;
+    e->g_offsub.resize(cn); e->g_nsub.resize(cn); e->g_off10.resize(cn); e->g_n10.resize(cn);
+    e->g_offfr.resize(cn); e->g_nfa.resize(cn); e->g_offW.resize(cn);
+    int64_t t24 = 0, tsub = 0, t10 = 0, tfr = 0, tW = 0;
+    int max_nsub = 0, max_n10 = 0, max_nfa = 0;
     const bool span_copy = !dev_in && (hi - lo) <= 2 * tot + 4096;
     int64_t packed = 0;
     for (int i = 0; i < cn; ++i) {
@@ -266,12 +393,27 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       t24 += (n24 + 31) & ~31;
       tsub += nsub;
       max_nsub = std::max(max_nsub, nsub);
+      const int n10 = (int)(((int64_t)L * e->st_up + e->st_down - 1) / e->st_down);
+      const int nfa = n10 > 256 ? (n10 - 256 + 127) / 128 : 0;
+      e->g_n10[i] = n10;
+      e->g_nfa[i] = nfa;
+      e->g_off10[i] = t10;
+      e->g_offfr[i] = tfr;
+      t10 += (n10 + 31) & ~31;
+      tfr += nfa;
+      max_n10 = std::max(max_n10, n10);
+      max_nfa = std::max(max_nfa, nfa);
+      const int Lp = std::max(L, 401);
+      e->g_offW[i] = tW;
+      tW += (Lp - 400 + 199) / 200;
     }
     e->tot24 = t24;
     e->totsub = tsub;
+    e->tot10 = t10;
+    e->totfr = tfr;
     e->chunk_n = cn;
 
-    // inputs
+    // ---- inputs
     const float *d_ref = ref, *d_deg = deg;
     if (!dev_in) {
       const size_t in_elems = span_copy ? (size_t)(hi - lo) : (size_t)packed;
@@ -289,32 +431,80 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       d_ref = (const float*)e->in_ref.p;
       d_deg = (const float*)e->in_deg.p;
     }
-    // geometry arrays -> device (one buffer)
-    const size_t gbytes = (size_t)cn * (3 * sizeof(int64_t) + 3 * sizeof(int32_t));
-    RESERVE(e, e->geom, gbytes + 64);
-    char* gp = (char*)e->geom.p;
+    // ---- geometry arrays -> device (one blob, one copy)
+    GeomPacker gp;
+    const size_t o_off16 = gp.add(e->g_off16.data(), cn * sizeof(int64_t));
+    const size_t o_off24 = gp.add(e->g_off24.data(), cn * sizeof(int64_t));
+    const size_t o_offsub = gp.add(e->g_offsub.data(), cn * sizeof(int64_t));
+    const size_t o_off10 = gp.add(e->g_off10.data(), cn * sizeof(int64_t));
+    const size_t o_offfr = gp.add(e->g_offfr.data(), cn * sizeof(int64_t));
+    const size_t o_offW = gp.add(e->g_offW.data(), cn * sizeof(int64_t));
+    const size_t o_len16 = gp.add(e->g_len16.data(), cn * sizeof(int32_t));
+    const size_t o_n24 = gp.add(e->g_n24.data(), cn * sizeof(int32_t));
+    const size_t o_nsub = gp.add(e->g_nsub.data(), cn * sizeof(int32_t));
+    const size_t o_n10 = gp.add(e->g_n10.data(), cn * sizeof(int32_t));
+    const size_t o_nfa = gp.add(e->g_nfa.data(), cn * sizeof(int32_t));
+    RESERVE(e, e->geom, gp.blob.size());
+    CU(e, cudaMemcpyAsync(e->geom.p, gp.blob.data(), gp.blob.size(), cudaMemcpyHostToDevice, s));
+    CU(e, cudaStreamSynchronize(s));  // the blob is a stack temporary; also keeps H2D out of the kernel timing
+    const char* gb = (const char*)e->geom.p;
     PairGeom g;
-    g.off16 = (const int64_t*)gp;
-    g.off24 = g.off16 + cn;
-    g.offsub = g.off24 + cn;
-    g.len16 = (const int32_t*)(g.offsub + cn);
-    g.n24 = g.len16 + cn;
-    g.nsub = g.n24 + cn;
-    CU(e, cudaMemcpyAsync((void*)g.off16, e->g_off16.data(), cn * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    CU(e, cudaMemcpyAsync((void*)g.off24, e->g_off24.data(), cn * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    CU(e, cudaMemcpyAsync((void*)g.offsub, e->g_offsub.data(), cn * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    CU(e, cudaMemcpyAsync((void*)g.len16, e->g_len16.data(), cn * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    CU(e, cudaMemcpyAsync((void*)g.n24, e->g_n24.data(), cn * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    CU(e, cudaMemcpyAsync((void*)g.nsub, e->g_nsub.data(), cn * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    g.off16 = (const int64_t*)(gb + o_off16);
+    g.off24 = (const int64_t*)(gb + o_off24);
+    g.offsub = (const int64_t*)(gb + o_offsub);
+    g.len16 = (const int32_t*)(gb + o_len16);
+    g.n24 = (const int32_t*)(gb + o_n24);
+    g.nsub = (const int32_t*)(gb + o_nsub);
+    EstoiGeom eg;
+    eg.off16 = g.off16;
+    eg.len16 = g.len16;
+    eg.off10 = (const int64_t*)(gb + o_off10);
+    eg.n10 = (const int32_t*)(gb + o_n10);
+    eg.offfr = (const int64_t*)(gb + o_offfr);
+    eg.nfa = (const int32_t*)(gb + o_nfa);
+    SiibGeom sg;
+    sg.off16 = g.off16;
+    sg.len16 = g.len16;
+    sg.offW = (const int64_t*)(gb + o_offW);
+    sg.offF = nullptr;
+    sg.F = nullptr;
 
-    RESERVE(e, e->out_intel, cn * sizeof(double));
+    const bool run_haspi = do_haspi && haspi_rate_ok, run_siib = do_siib && siib_rate_ok, run_estoi = do_estoi;
+    RESERVE(e, e->out_haspi, cn * sizeof(double));
     RESERVE(e, e->out_raw, (size_t)cn * kNumMod * sizeof(double));
-    RESERVE(e, e->out_status, (size_t)cn * 3 * sizeof(int32_t));
+    RESERVE(e, e->out_hst, (size_t)cn * sizeof(int32_t));
+    RESERVE(e, e->out_estoi, cn * sizeof(double));
+    RESERVE(e, e->out_est, (size_t)cn * sizeof(int32_t));
+    RESERVE(e, e->out_siib, cn * sizeof(double));
+    RESERVE(e, e->out_sst, (size_t)cn * sizeof(int32_t));
 
     CU(e, cudaEventRecord(e->ev0, s));
+    // ---- SIIB stage 0: wrapper VAD -> tiling factors (the host needs them to size the rest)
+    SiibBuffers sb;
+    memset(&sb, 0, sizeof(sb));
+    if (run_siib) {
+      RESERVE(e, e->sb_wrapdb, (size_t)tW * sizeof(double));
+      RESERVE(e, e->sb_M, (size_t)cn * sizeof(int32_t));
+      RESERVE(e, e->sb_wact, (size_t)cn * sizeof(int32_t));
+      if (e->h_M_cap < (size_t)cn) {
+        if (e->h_M) cudaFreeHost(e->h_M);
+        e->h_M = nullptr;
+        CU(e, cudaMallocHost((void**)&e->h_M, (size_t)cn * sizeof(int32_t)));
+        e->h_M_cap = cn;
+      }
+      sb.ref = d_ref;
+      sb.deg = d_deg;
+      sb.wrapdb = (double*)e->sb_wrapdb.p;
+      sb.M = (int32_t*)e->sb_M.p;
+      sb.wrap_active = (int32_t*)e->sb_wact.p;
+      e->last_launches += siib_run_wrapvad(sg, sb, cn, flags & NELE_FLAG_SIIB_NO_TILE, kt, s);
+      CU(e, cudaMemcpyAsync(e->h_M, sb.M, (size_t)cn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      CU(e, cudaEventRecord(e->ev_M, s));
+    }
+    // ---- HASPI
     HaspiBuffers hb;
     memset(&hb, 0, sizeof(hb));
-    if (do_haspi && haspi_rate_ok) {
+    if (run_haspi) {
       RESERVE(e, e->x24, (size_t)2 * t24 * sizeof(float));
       RESERVE(e, e->mid, (size_t)2 * t24 * sizeof(double));
       RESERVE(e, e->bw, (size_t)cn * 2 * kBands * sizeof(double));
@@ -348,47 +538,177 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       hb.seed = seed;
       hb.no_dither = (flags & NELE_FLAG_NO_DITHER) ? 1 : 0;
       hb.pair_base = first;
-      e->last_launches += haspi_run(g, hb, cn, max_nsub, e->f64, s);
-      e->last_launches += haspi_finish(hb, cn, (double*)e->out_intel.p, (double*)e->out_raw.p, (int32_t*)e->out_status.p, s);
+      e->last_launches += haspi_run(g, hb, cn, max_nsub, e->f64, kt, s);
+      e->last_launches += haspi_finish(hb, cn, (double*)e->out_haspi.p, (double*)e->out_raw.p, (int32_t*)e->out_hst.p, kt, s);
+    }
+    // ---- ESTOI
+    if (run_estoi) {
+      RESERVE(e, e->x10, (size_t)2 * t10 * sizeof(float));
+      RESERVE(e, e->st_energy, (size_t)std::max<int64_t>(tfr, 1) * sizeof(double));
+      RESERVE(e, e->st_kept, (size_t)std::max<int64_t>(tfr, 1) * sizeof(int32_t));
+      RESERVE(e, e->st_nkept, (size_t)cn * sizeof(int32_t));
+      RESERVE(e, e->st_tob, (size_t)2 * std::max<int64_t>(tfr, 1) * 15 * sizeof(float));
+      EstoiBuffers eb;
+      memset(&eb, 0, sizeof(eb));
+      eb.ref = d_ref;
+      eb.deg = d_deg;
+      eb.x10 = (float*)e->x10.p;
+      eb.tot10 = t10;
+      eb.energy = (double*)e->st_energy.p;
+      eb.kept = (int32_t*)e->st_kept.p;
+      eb.nkept = (int32_t*)e->st_nkept.p;
+      eb.tob = (float*)e->st_tob.p;
+      eb.totfr = tfr;
+      eb.taps = (const double*)e->st_taps.p;
+      eb.up = e->st_up;
+      eb.down = e->st_down;
+      eb.K = e->st_K;
+      eb.score = (double*)e->out_estoi.p;
+      eb.status = (int32_t*)e->out_est.p;
+      e->last_launches += estoi_run(eg, eb, cn, max_n10, max_nfa, kt, s);
+    }
+    // ---- SIIB main pipeline
+    e->g_M.assign(cn, 0);
+    e->g_offF.assign(cn, 0);
+    e->g_F.assign(cn, 0);
+    if (run_siib) {
+      CU(e, cudaEventSynchronize(e->ev_M));
+      int64_t tF = 0;
+      const int64_t kMaxF = 400000;  // frames of one tiled signal (M is unbounded when almost nothing is active)
+      for (int i = 0; i < cn; ++i) {
+        const int M = e->h_M[i];
+        e->g_M[i] = M;
+        int64_t F = 0;
+        if (M > 0) {
+          const int64_t tl = std::max<int64_t>((int64_t)M * lens[first + i], 401);
+          F = (tl - 400 + 199) / 200;
+          if (F > kMaxF) F = 0;  // reported as too short
+        }
+        e->g_F[i] = F;
+        e->g_offF[i] = tF;
+        tF += F;
+      }
+      e->totF = std::max<int64_t>(tF, 1);
+      GeomPacker sp;
+      const size_t o_offF = sp.add(e->g_offF.data(), cn * sizeof(int64_t));
+      const size_t o_F = sp.add(e->g_F.data(), cn * sizeof(int64_t));
+      RESERVE(e, e->sgeom, sp.blob.size());
+      CU(e, cudaMemcpyAsync(e->sgeom.p, sp.blob.data(), sp.blob.size(), cudaMemcpyHostToDevice, s));
+      sg.offF = (const int64_t*)((const char*)e->sgeom.p + o_offF);
+      sg.F = (const int64_t*)((const char*)e->sgeom.p + o_F);
+      const int64_t tFa = std::max<int64_t>(tF, 1);
+      const int sub = std::min(cn, kSiibSub);
+      RESERVE(e, e->sb_mean, (size_t)cn * 2 * sizeof(double));
+      RESERVE(e, e->sb_xdb, (size_t)tFa * sizeof(double));
+      RESERVE(e, e->sb_act, (size_t)tFa * sizeof(int32_t));
+      RESERVE(e, e->sb_Fa, (size_t)cn * sizeof(int32_t));
+      RESERVE(e, e->sb_logspec, (size_t)2 * (tFa + 1) * 32 * sizeof(float));
+      RESERVE(e, e->sb_base, (size_t)sub * 59 * 1024 * sizeof(double));
+      RESERVE(e, e->sb_Sxx, (size_t)sub * 420 * 420 * sizeof(double));
+      RESERVE(e, e->sb_Sxy, (size_t)sub * 420 * 420 * sizeof(float));
+      RESERVE(e, e->sb_Syy, (size_t)sub * 420 * 420 * sizeof(float));
+      RESERVE(e, e->sb_Lc, (size_t)sub * 420 * 420 * sizeof(double));
+      RESERVE(e, e->sb_G, (size_t)sub * 420 * 448 * sizeof(float));
+      RESERVE(e, e->sb_perm, (size_t)sub * 420 * sizeof(int32_t));
+      RESERVE(e, e->sb_rank, (size_t)cn * sizeof(int32_t));
+      RESERVE(e, e->sb_sweeps, (size_t)cn * 17 * sizeof(int32_t));
+      RESERVE(e, e->sb_lambda, (size_t)cn * 420 * sizeof(float));
+      RESERVE(e, e->sb_rho, (size_t)cn * 420 * sizeof(float));
+      CU(e, cudaStreamSynchronize(s));  // sp.blob is a stack temporary
+      sb.mean = (double*)e->sb_mean.p;
+      sb.xdb = (double*)e->sb_xdb.p;
+      sb.act = (int32_t*)e->sb_act.p;
+      sb.Fa = (int32_t*)e->sb_Fa.p;
+      sb.logspec = (float*)e->sb_logspec.p;
+      sb.totF = tFa + 1;
+      sb.base = (double*)e->sb_base.p;
+      sb.Sxx = (double*)e->sb_Sxx.p;
+      sb.Sxy = (float*)e->sb_Sxy.p;
+      sb.Syy = (float*)e->sb_Syy.p;
+      sb.Lc = (double*)e->sb_Lc.p;
+      sb.G = (float*)e->sb_G.p;
+      sb.perm = (int32_t*)e->sb_perm.p;
+      sb.rank = (int32_t*)e->sb_rank.p;
+      sb.sweeps = (int32_t*)e->sb_sweeps.p;
+      sb.sweep_rot = (int32_t*)e->sb_sweeps.p + cn;
+      sb.lambda = (float*)e->sb_lambda.p;
+      sb.rho = (float*)e->sb_rho.p;
+      sb.score = (double*)e->out_siib.p;
+      sb.status = (int32_t*)e->out_sst.p;
+      CU(e, cudaMemsetAsync(e->sb_sweeps.p, 0, (size_t)cn * 17 * sizeof(int32_t), s));
+      for (int lo_p = 0; lo_p < cn; lo_p += sub) {
+        const int sn = std::min(sub, cn - lo_p);
+        int64_t maxF = 0;
+        for (int i = 0; i < sn; ++i) maxF = std::max(maxF, e->g_F[lo_p + i]);
+        sb.pair_lo = lo_p;
+        e->last_launches += siib_run(sg, sb, sn, maxF, kt, s);
+        e->sub_lo = lo_p;
+        e->sub_n = sn;
+      }
     }
     CU(e, cudaEventRecord(e->ev1, s));
     CU(e, cudaGetLastError());
 
-    // results
-    std::vector<double> h_intel(cn), h_raw((size_t)cn * kNumMod);
-    std::vector<int32_t> h_st((size_t)cn * 3);
-    if (do_haspi && haspi_rate_ok) {
-      CU(e, cudaMemcpyAsync(h_intel.data(), e->out_intel.p, cn * sizeof(double), cudaMemcpyDeviceToHost, s));
+    // ---- results
+    std::vector<double> h_haspi(cn), h_raw((size_t)cn * kNumMod), h_estoi(cn), h_siib(cn);
+    std::vector<int32_t> h_hst(cn), h_est(cn), h_sst(cn);
+    if (run_haspi) {
+      CU(e, cudaMemcpyAsync(h_haspi.data(), e->out_haspi.p, cn * sizeof(double), cudaMemcpyDeviceToHost, s));
       CU(e, cudaMemcpyAsync(h_raw.data(), e->out_raw.p, (size_t)cn * kNumMod * sizeof(double), cudaMemcpyDeviceToHost, s));
-      CU(e, cudaMemcpyAsync(h_st.data(), e->out_status.p, cn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      CU(e, cudaMemcpyAsync(h_hst.data(), e->out_hst.p, cn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    if (run_estoi) {
+      CU(e, cudaMemcpyAsync(h_estoi.data(), e->out_estoi.p, cn * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CU(e, cudaMemcpyAsync(h_est.data(), e->out_est.p, cn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    if (run_siib) {
+      CU(e, cudaMemcpyAsync(h_siib.data(), e->out_siib.p, cn * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CU(e, cudaMemcpyAsync(h_sst.data(), e->out_sst.p, cn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
     CU(e, cudaStreamSynchronize(s));
     float ms = 0.f;
     CU(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     e->last_kernel_ms += ms;
+    if (kt) collect_kernel_times(e);
     for (int i = 0; i < cn; ++i) {
       const int gi = first + i;
       int32_t st = status ? status[gi] : 0;
       if (do_haspi) {
-        int hs;
-        double v;
-        if (!haspi_rate_ok) {
-          hs = NELE_ST_BAD_RATE;
-          v = kNaN;
-        } else {
-          hs = h_st[i];
-          v = h_intel[i];
+        int hs = NELE_ST_BAD_RATE;
+        double v = kNaN;
+        if (haspi_rate_ok) {
+          hs = h_hst[i];
+          v = h_haspi[i];
           if (mapped && hs == NELE_ST_OK) v = 1.0 / (1.0 + exp(-0.95 * (v - 2.8)));  // intel.py:116-120
           if (haspi_raw) memcpy(haspi_raw + (size_t)gi * kNumMod, h_raw.data() + (size_t)i * kNumMod, kNumMod * sizeof(double));
+        } else if (haspi_raw) {
+          for (int m = 0; m < kNumMod; ++m) haspi_raw[(size_t)gi * kNumMod + m] = kNaN;
         }
         scores[3 * gi + 1] = v;
         st = (st & ~0xff) | hs;
       }
-      (void)do_siib;
-      (void)do_estoi;
+      if (do_siib) {
+        int ss = NELE_ST_BAD_RATE;
+        double v = kNaN;
+        if (siib_rate_ok) {
+          ss = h_sst[i];
+          v = h_siib[i];
+          if (mapped && ss == NELE_ST_OK) v = 1.0 / (1.0 + exp(-0.06 * (v - 32.0)));  // intel.py:102-106
+        }
+        scores[3 * gi + 0] = v;
+        st = (st & ~0xff00) | (ss << 8);
+      }
+      if (do_estoi) {
+        const int es = h_est[i];
+        double v = h_estoi[i];
+        if (mapped) v = 1.0 / (1.0 + exp(-8.0 * (v - 0.25)));  // intel.py:136-140 (the 1e-5 sentinel is mapped too)
+        scores[3 * gi + 2] = v;
+        st = (st & ~0xff0000) | (es << 16);
+      }
       if (status) status[gi] = st;
     }
     e->stages_valid = (flags & NELE_FLAG_KEEP_STAGES) && first == 0 && last == n;
+    e->stage_metrics = (run_haspi ? NELE_METRIC_HASPI : 0) | (run_siib ? NELE_METRIC_SIIB : 0) | (run_estoi ? NELE_METRIC_ESTOI : 0);
     first = last;
   }
   return NELE_OK;
@@ -401,6 +721,14 @@ extern "C" int nele_last_timing(const nele_engine* e, double* kernel_ms, int64_t
   return NELE_OK;
 }
 
+extern "C" int nele_kernel_time(const nele_engine* e, int idx, const char** name, double* ms, int64_t* launches) {
+  if (!e || idx < 0 || idx >= (int)e->kstats.size()) return NELE_E_ARG;
+  if (name) *name = e->kstats[idx].name.c_str();
+  if (ms) *ms = e->kstats[idx].ms;
+  if (launches) *launches = e->kstats[idx].launches;
+  return NELE_OK;
+}
+
 extern "C" int nele_get_stage(nele_engine* e, const char* name, int pair, void* dst, size_t cap, size_t* nbytes) {
   if (!e || !name) return NELE_E_ARG;
   if (!e->stages_valid) return fail(e, NELE_E_ARG, "nele_get_stage: no stages kept (call nele_score_batch with NELE_FLAG_KEEP_STAGES on a single-chunk batch)");
@@ -408,13 +736,15 @@ extern "C" int nele_get_stage(nele_engine* e, const char* name, int pair, void* 
   CU(e, cudaSetDevice(e->device));
   struct Piece { const void* src; size_t bytes; };
   std::vector<Piece> pieces;
+  std::vector<int32_t> ints;  // host-side values returned as-is
   const int64_t o24 = e->g_off24[pair], osub = e->g_offsub[pair];
   const int n24 = e->g_n24[pair], nsub = e->g_nsub[pair];
   std::string nm(name);
-  int32_t nsel = 0;
-  if (nm == "haspi.cep" || nm == "haspi.nsel") {
-    CU(e, cudaMemcpy(&nsel, (int32_t*)e->nsel.p + pair, sizeof(int32_t), cudaMemcpyDeviceToHost));
-  }
+  const uint32_t need = nm.rfind("haspi.", 0) == 0 ? NELE_METRIC_HASPI : nm.rfind("estoi.", 0) == 0 ? NELE_METRIC_ESTOI : NELE_METRIC_SIIB;
+  if (!(e->stage_metrics & need)) return fail(e, NELE_E_ARG, "nele_get_stage: '%s' belongs to a metric the last call did not run", name);
+  auto dev_i32 = [&](const DevBuf& b, size_t idx, int32_t* out) -> cudaError_t {
+    return cudaMemcpy(out, (const int32_t*)b.p + idx, sizeof(int32_t), cudaMemcpyDeviceToHost);
+  };
   if (nm == "haspi.mid") {
     for (int q = 0; q < 2; ++q) pieces.push_back({(double*)e->mid.p + q * e->tot24 + o24, n24 * sizeof(double)});
   } else if (nm == "haspi.x24") {
@@ -428,22 +758,72 @@ extern "C" int nele_get_stage(nele_engine* e, const char* name, int pair, void* 
   } else if (nm == "haspi.nsel") {
     pieces.push_back({(int32_t*)e->nsel.p + pair, sizeof(int32_t)});
   } else if (nm == "haspi.cep") {
+    int32_t nsel = 0;
+    CU(e, dev_i32(e->nsel, pair, &nsel));
     for (int q = 0; q < 2; ++q)
       for (int j = 0; j < kNumCep; ++j)
         pieces.push_back({(float*)e->cep.p + (size_t)(q * kNumCep + j) * e->totsub + osub, (size_t)nsel * sizeof(float)});
   } else if (nm == "haspi.cepmean") {
     pieces.push_back({(double*)e->cepmean.p + (size_t)pair * 2 * kNumCep, 2 * kNumCep * sizeof(double)});
+  } else if (nm == "estoi.x10") {
+    for (int q = 0; q < 2; ++q) pieces.push_back({(float*)e->x10.p + q * e->tot10 + e->g_off10[pair], (size_t)e->g_n10[pair] * sizeof(float)});
+  } else if (nm == "estoi.info") {
+    int32_t nk = 0;
+    CU(e, dev_i32(e->st_nkept, pair, &nk));
+    ints = {e->g_n10[pair], e->g_nfa[pair], nk};
+  } else if (nm == "estoi.kept") {
+    int32_t nk = 0;
+    CU(e, dev_i32(e->st_nkept, pair, &nk));
+    pieces.push_back({(int32_t*)e->st_kept.p + e->g_offfr[pair], (size_t)nk * sizeof(int32_t)});
+  } else if (nm == "estoi.tob") {
+    int32_t nk = 0;
+    CU(e, dev_i32(e->st_nkept, pair, &nk));
+    const int nfr = std::max(nk - 1, 0);
+    for (int q = 0; q < 2; ++q) pieces.push_back({(float*)e->st_tob.p + (q * e->totfr + e->g_offfr[pair]) * 15, (size_t)nfr * 15 * sizeof(float)});
+  } else if (nm == "siib.tile") {
+    int32_t wa = 0, fa = 0;
+    CU(e, dev_i32(e->sb_wact, pair, &wa));
+    CU(e, dev_i32(e->sb_Fa, pair, &fa));
+    ints = {e->g_M[pair], wa, (int32_t)e->g_F[pair], fa};
+  } else if (nm == "siib.logspec") {
+    int32_t fa = 0;
+    CU(e, dev_i32(e->sb_Fa, pair, &fa));
+    for (int q = 0; q < 2; ++q) pieces.push_back({(float*)e->sb_logspec.p + (q * (e->totF + 1) + e->g_offF[pair]) * 32, (size_t)fa * 32 * sizeof(float)});
+  } else if (nm == "siib.lambda") {
+    pieces.push_back({(float*)e->sb_lambda.p + (size_t)pair * 420, 420 * sizeof(float)});
+  } else if (nm == "siib.rho") {
+    pieces.push_back({(float*)e->sb_rho.p + (size_t)pair * 420, 420 * sizeof(float)});
+  } else if (nm == "siib.rank") {
+    int32_t rk = 0, sw = 0;
+    CU(e, dev_i32(e->sb_rank, pair, &rk));
+    CU(e, dev_i32(e->sb_sweeps, pair, &sw));
+    ints = {rk, sw};
+    for (int k = 0; k < 16; ++k) {
+      int32_t v = 0;
+      CU(e, dev_i32(e->sb_sweeps, (size_t)e->chunk_n + (size_t)pair * 16 + k, &v));
+      ints.push_back(v);
+    }
+  } else if (nm == "siib.sxx" || nm == "siib.sxy" || nm == "siib.syy") {
+    if (pair < e->sub_lo || pair >= e->sub_lo + e->sub_n) return fail(e, NELE_E_ARG, "nele_get_stage: '%s' is only kept for the last SIIB sub-chunk", name);
+    const size_t lp = pair - e->sub_lo;
+    if (nm == "siib.sxx") pieces.push_back({(double*)e->sb_Sxx.p + lp * 420 * 420, (size_t)420 * 420 * sizeof(double)});
+    else if (nm == "siib.sxy") pieces.push_back({(float*)e->sb_Sxy.p + lp * 420 * 420, (size_t)420 * 420 * sizeof(float)});
+    else pieces.push_back({(float*)e->sb_Syy.p + lp * 420 * 420, (size_t)420 * 420 * sizeof(float)});
   } else {
     return fail(e, NELE_E_ARG, "nele_get_stage: unknown stage '%s'", name);
   }
-  size_t total = 0;
+  size_t total = ints.size() * sizeof(int32_t);
   for (auto& p : pieces) total += p.bytes;
   if (nbytes) *nbytes = total;
   if (!dst) return NELE_OK;
   if (cap < total) return fail(e, NELE_E_ARG, "nele_get_stage: buffer too small (%zu < %zu)", cap, total);
   char* d = (char*)dst;
+  if (!ints.empty()) {
+    memcpy(d, ints.data(), ints.size() * sizeof(int32_t));
+    d += ints.size() * sizeof(int32_t);
+  }
   for (auto& p : pieces) {
-    CU(e, cudaMemcpy(d, p.src, p.bytes, cudaMemcpyDeviceToHost));
+    if (p.bytes) CU(e, cudaMemcpy(d, p.src, p.bytes, cudaMemcpyDeviceToHost));
     d += p.bytes;
   }
   return NELE_OK;

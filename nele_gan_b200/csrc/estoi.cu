@@ -1,0 +1,323 @@
+// ESTOI on sm_100a: batched restatement of pystoi.stoi(x, y, fs, extended=True)
+// (reference call sites intel.py:126,133; algorithm: oracle/pystoi_np.py).
+//
+//   estoi_resample_kernel  per (output tile, pair, signal) CTA: Octave-style polyphase
+//                          resampler to 10 kHz (resample_poly(x, up, down, window=h)),
+//                          inputs staged in shared memory, FP64 accumulation
+//   estoi_vad_kernel       per pair CTA: Hann-windowed frame energies of x, 40 dB dynamic
+//                          range mask, ordered compaction -> list of kept frames
+//   estoi_tob_kernel       per (pair, STFT frame) warp: rebuilds the frame of the
+//                          silence-removed signal from the three kept source frames that
+//                          overlap it (the overlap-add is never materialised), one complex
+//                          512-point FFT for x + i y in shared memory, one-third-octave
+//                          band magnitudes [nfr][15] for both signals
+//   estoi_corr_kernel      per pair CTA, one thread per 30-frame segment: row then column
+//                          normalisation and the correlation sum
+#include "kernels.h"
+
+namespace nele {
+
+constexpr int kStoiFrame = 256, kStoiHop = 128, kStoiFft = 512, kStoiBands = 15, kStoiSeg = 30;
+
+__constant__ float c_stoi_win[kStoiFrame];     // MATLAB hanning(256)
+__constant__ int c_stoi_lo[kStoiBands], c_stoi_hi[kStoiBands];
+__device__ float2 g_stoi_tw[kStoiFft / 2];     // exp(-2 pi i k / 512)
+
+// ------------------------------------------------------------- resample
+constexpr int kRsTile = 1024, kRsThreads = 256;
+
+__global__ void __launch_bounds__(kRsThreads) estoi_resample_kernel(EstoiGeom g, EstoiBuffers b, int span) {
+  const int pair = blockIdx.y, q = blockIdx.z, tid = threadIdx.x;
+  const int n_out = g.n10[pair];
+  const int m0 = blockIdx.x * kRsTile;
+  if (m0 >= n_out) return;
+  const float* __restrict__ src = (q == 0 ? b.ref : b.deg) + g.off16[pair];
+  const int L = g.len16[pair];
+  float* __restrict__ dst = b.x10 + (int64_t)q * b.tot10 + g.off10[pair];
+  extern __shared__ float s_in[];
+  if (b.up == 1 && b.down == 1) {
+    for (int m = m0 + tid; m < min(m0 + kRsTile, n_out); m += kRsThreads) dst[m] = src[m];
+    return;
+  }
+  // staged index u <-> input sample base + u, base = n(m0) - K
+  const int base = (int)(((int64_t)m0 * b.down) / b.up) - b.K;
+  for (int u = tid; u < span; u += kRsThreads) {
+    const int j = base + u;
+    s_in[u] = (j >= 0 && j < L) ? src[j] : 0.f;
+  }
+  __syncthreads();
+  const int nt = 2 * b.K + 1;
+  for (int m = m0 + tid; m < min(m0 + kRsTile, n_out); m += kRsThreads) {
+    const int64_t pos = (int64_t)m * b.down;
+    const int n = (int)(pos / b.up), r = (int)(pos % b.up);
+    const double* __restrict__ tp = b.taps + (size_t)r * nt;
+    const float* xs = s_in + (n - base) + b.K;  // xs[-k'] with k' = k + K -> x[n - k]
+    double acc = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < nt; ++k) acc = fma(__ldg(tp + k), (double)xs[-k], acc);
+    dst[m] = (float)acc;
+  }
+}
+
+// ------------------------------------------------------------------ VAD
+constexpr int kVadThreads = 256;
+
+__global__ void __launch_bounds__(kVadThreads) estoi_vad_kernel(EstoiGeom g, EstoiBuffers b) {
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  constexpr int NW = kVadThreads / 32;
+  const int nfa = g.nfa[pair];
+  const float* __restrict__ x = b.x10 + g.off10[pair];
+  double* __restrict__ en = b.energy + g.offfr[pair];
+  int32_t* __restrict__ kept = b.kept + g.offfr[pair];
+  __shared__ double red[32];
+  __shared__ int s_cnt[NW];
+  __shared__ int s_base;
+  if (nfa <= 0) {
+    if (tid == 0) b.nkept[pair] = 0;
+    return;
+  }
+  double mx = -1.0e300;
+  for (int f = wib; f < nfa; f += NW) {
+    const float* fr = x + (int64_t)f * kStoiHop;
+    double ss = 0.0;
+#pragma unroll
+    for (int k = 0; k < kStoiFrame / 32; ++k) {
+      const int i = k * 32 + lane;
+      const double v = (double)c_stoi_win[i] * (double)fr[i];
+      ss += v * v;
+    }
+    ss = warp_sum(ss);
+    const double e = 20.0 * log10(sqrt(ss) + 2.220446049250313e-16);
+    if (lane == 0) en[f] = e;
+    mx = fmax(mx, e);
+  }
+  mx = block_max(mx, red);
+  const double thr = mx - 40.0;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int f0 = 0; f0 < nfa; f0 += kVadThreads) {
+    const int f = f0 + tid;
+    const int keep = (f < nfa && en[f] > thr) ? 1 : 0;
+    int inc = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_cnt[wib] = inc;
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < NW; ++w) {
+      if (w < wib) woff += s_cnt[w];
+      tot += s_cnt[w];
+    }
+    const int base = s_base;
+    if (keep) kept[base + woff + inc - 1] = f;
+    __syncthreads();
+    if (tid == 0) s_base = base + tot;
+    __syncthreads();
+  }
+  if (tid == 0) b.nkept[pair] = s_base;
+}
+
+// ------------------------------------------------- STFT + one-third octaves
+constexpr int kTobWarps = 8;
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+  return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+}
+
+__global__ void __launch_bounds__(kTobWarps * 32) estoi_tob_kernel(EstoiGeom g, EstoiBuffers b) {
+  const int pair = blockIdx.y, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nk = b.nkept[pair];
+  const int nfr = nk - 1;  // STFT frames of the silence-removed signal
+  __shared__ float2 s_z[kTobWarps][kStoiFft];
+  __shared__ float2 s_tw[kStoiFft / 2];
+  for (int k = threadIdx.x; k < kStoiFft / 2; k += kTobWarps * 32) s_tw[k] = g_stoi_tw[k];
+  __syncthreads();
+  const int m = blockIdx.x * kTobWarps + wib;
+  if (m >= nfr) return;
+  const float* __restrict__ x = b.x10 + g.off10[pair];
+  const float* __restrict__ y = b.x10 + b.tot10 + g.off10[pair];
+  const int32_t* __restrict__ kept = b.kept + g.offfr[pair];
+  float2* z = s_z[wib];
+  const int64_t sc = (int64_t)kept[m] * kStoiHop;
+  const int64_t sp = (m > 0) ? (int64_t)kept[m - 1] * kStoiHop : -1;
+  const int64_t sn = (int64_t)kept[m + 1] * kStoiHop;
+  // frame of the overlap-added signal, windowed again, bit-reversed into z
+#pragma unroll
+  for (int k = 0; k < kStoiFrame / 32; ++k) {
+    const int i = k * 32 + lane;
+    const float w = c_stoi_win[i];
+    float vx = w * x[sc + i], vy = w * y[sc + i];
+    if (i < kStoiHop) {
+      if (sp >= 0) {
+        const float w2 = c_stoi_win[i + kStoiHop];
+        vx = fmaf(w2, x[sp + i + kStoiHop], vx);
+        vy = fmaf(w2, y[sp + i + kStoiHop], vy);
+      }
+    } else {
+      const float w2 = c_stoi_win[i - kStoiHop];
+      vx = fmaf(w2, x[sn + i - kStoiHop], vx);
+      vy = fmaf(w2, y[sn + i - kStoiHop], vy);
+    }
+    const int br = (int)(__brev((unsigned)i) >> 23);  // 9-bit reversal
+    z[br] = make_float2(w * vx, w * vy);
+    z[br | 1] = make_float2(0.f, 0.f);                // i + 256 reverses to br + 1
+  }
+  __syncwarp();
+  // in-place radix-2 decimation-in-time, 9 stages, 8 butterflies per lane per stage
+#pragma unroll
+  for (int s = 0; s < 9; ++s) {
+    const int half = 1 << s;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = u * 32 + lane;
+      const int pos = j & (half - 1);
+      const int i0 = ((j >> s) << (s + 1)) + pos, i1 = i0 + half;
+      const float2 t = cmul(z[i1], s_tw[pos << (8 - s)]);
+      const float2 a = z[i0];
+      z[i0] = make_float2(a.x + t.x, a.y + t.y);
+      z[i1] = make_float2(a.x - t.x, a.y - t.y);
+    }
+    __syncwarp();
+  }
+  // spectra of the two real signals from Z = FFT(x + i y)
+  float px[8], py[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int k = u * 32 + lane;
+    const float2 a = z[k], c = z[(kStoiFft - k) & (kStoiFft - 1)];
+    const float xr = a.x + c.x, xi = a.y - c.y;   // 2 X[k]
+    const float yr = a.y + c.y, yi = c.x - a.x;   // 2 Y[k]
+    px[u] = 0.25f * (xr * xr + xi * xi);
+    py[u] = 0.25f * (yr * yr + yi * yi);
+  }
+  __syncwarp();
+  float* pw = reinterpret_cast<float*>(z);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    pw[u * 32 + lane] = px[u];
+    pw[256 + u * 32 + lane] = py[u];
+  }
+  __syncwarp();
+  if ((lane & 15) < kStoiBands) {
+    const int band = lane & 15, sig = lane >> 4;
+    const float* p = pw + sig * 256;
+    float acc = 0.f;
+    for (int k = c_stoi_lo[band]; k < c_stoi_hi[band]; ++k) acc += p[k];
+    b.tob[((int64_t)sig * b.totfr + g.offfr[pair] + m) * kStoiBands + band] = sqrtf(acc);
+  }
+}
+
+// ------------------------------------------------------ segment correlation
+constexpr int kCorrThreads = 128;
+
+__global__ void __launch_bounds__(kCorrThreads) estoi_corr_kernel(EstoiGeom g, EstoiBuffers b) {
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  const int nfr = b.nkept[pair] - 1;
+  __shared__ double red[32];
+  if (nfr < kStoiSeg) {  // pystoi: RuntimeWarning + sentinel
+    if (tid == 0) {
+      b.score[pair] = 1.0e-5;
+      b.status[pair] = 2;
+    }
+    return;
+  }
+  const int J = nfr - kStoiSeg + 1;
+  const float* __restrict__ X = b.tob + (g.offfr[pair]) * kStoiBands;
+  const float* __restrict__ Y = b.tob + (b.totfr + g.offfr[pair]) * kStoiBands;
+  double total = 0.0;
+  for (int m = tid; m < J; m += kCorrThreads) {
+    const float* xs = X + (int64_t)m * kStoiBands;
+    const float* ys = Y + (int64_t)m * kStoiBands;
+    float mux[kStoiBands], ivx[kStoiBands], muy[kStoiBands], ivy[kStoiBands];
+#pragma unroll
+    for (int k = 0; k < kStoiBands; ++k) {
+      float sx = 0.f, sy = 0.f;
+      for (int t = 0; t < kStoiSeg; ++t) {
+        sx += __ldg(xs + t * kStoiBands + k);
+        sy += __ldg(ys + t * kStoiBands + k);
+      }
+      sx *= (1.0f / kStoiSeg);
+      sy *= (1.0f / kStoiSeg);
+      float qx = 0.f, qy = 0.f;
+      for (int t = 0; t < kStoiSeg; ++t) {
+        const float dx = __ldg(xs + t * kStoiBands + k) - sx, dy = __ldg(ys + t * kStoiBands + k) - sy;
+        qx = fmaf(dx, dx, qx);
+        qy = fmaf(dy, dy, qy);
+      }
+      mux[k] = sx;
+      muy[k] = sy;
+      ivx[k] = 1.0f / sqrtf(qx);
+      ivy[k] = 1.0f / sqrtf(qy);
+    }
+    float acc = 0.f;
+    for (int t = 0; t < kStoiSeg; ++t) {
+      float vx[kStoiBands], vy[kStoiBands];
+      float cx = 0.f, cy = 0.f;
+#pragma unroll
+      for (int k = 0; k < kStoiBands; ++k) {
+        vx[k] = (__ldg(xs + t * kStoiBands + k) - mux[k]) * ivx[k];
+        vy[k] = (__ldg(ys + t * kStoiBands + k) - muy[k]) * ivy[k];
+        cx += vx[k];
+        cy += vy[k];
+      }
+      cx *= (1.0f / kStoiBands);
+      cy *= (1.0f / kStoiBands);
+      float nx = 0.f, ny = 0.f, xy = 0.f;
+#pragma unroll
+      for (int k = 0; k < kStoiBands; ++k) {
+        const float dx = vx[k] - cx, dy = vy[k] - cy;
+        nx = fmaf(dx, dx, nx);
+        ny = fmaf(dy, dy, ny);
+        xy = fmaf(dx, dy, xy);
+      }
+      acc += xy / sqrtf(nx * ny);
+    }
+    total += (double)acc * (1.0 / kStoiSeg);
+  }
+  total = block_sum(total, red);
+  if (tid == 0) {
+    b.score[pair] = total / (double)J;
+    b.status[pair] = 0;
+  }
+}
+
+// ------------------------------------------------------------- launchers
+void estoi_upload_tables(const float* win, const int* lo, const int* hi, const float* tw /*[256][2]*/, cudaStream_t s) {
+  cudaMemcpyToSymbolAsync(c_stoi_win, win, sizeof(float) * kStoiFrame, 0, cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(c_stoi_lo, lo, sizeof(int) * kStoiBands, 0, cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(c_stoi_hi, hi, sizeof(int) * kStoiBands, 0, cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(g_stoi_tw, tw, sizeof(float) * kStoiFft, 0, cudaMemcpyHostToDevice, s);
+  cudaStreamSynchronize(s);
+}
+
+int estoi_run(const EstoiGeom& g, const EstoiBuffers& b, int n, int max_n10, int max_nfa, KernelTimer* kt, cudaStream_t s) {
+  int launches = 0;
+  const int span = (int)(((int64_t)kRsTile * b.down) / b.up) + 2 * b.K + 4;
+  const size_t smem = (size_t)span * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(estoi_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kt_begin(kt, "estoi_resample", s);
+  estoi_resample_kernel<<<dim3((max_n10 + kRsTile - 1) / kRsTile, n, 2), kRsThreads, smem, s>>>(g, b, span);
+  kt_end(kt, s);
+  ++launches;
+  kt_begin(kt, "estoi_vad", s);
+  estoi_vad_kernel<<<n, kVadThreads, 0, s>>>(g, b);
+  kt_end(kt, s);
+  ++launches;
+  if (max_nfa > 1) {
+    kt_begin(kt, "estoi_tob", s);
+    estoi_tob_kernel<<<dim3((max_nfa - 1 + kTobWarps - 1) / kTobWarps, n), kTobWarps * 32, 0, s>>>(g, b);
+    kt_end(kt, s);
+    ++launches;
+  }
+  kt_begin(kt, "estoi_corr", s);
+  estoi_corr_kernel<<<n, kCorrThreads, 0, s>>>(g, b);
+  kt_end(kt, s);
+  ++launches;
+  return launches;
+}
+
+}  // namespace nele

@@ -550,30 +550,45 @@ void haspi_upload_tables(const float* cepm, const int* nhalf, const int* off, co
   cudaStreamSynchronize(s);
 }
 
-int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, bool f64, cudaStream_t s) {
+int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, bool f64, KernelTimer* kt, cudaStream_t s) {
   int launches = 0;
+  kt_begin(kt, "haspi_prep", s);
   haspi_prep_kernel<<<dim3(n, 2), kPrepThreads, 0, s>>>(g, b);
+  kt_end(kt, s);
   ++launches;
   const int items = 2 * n, ctas = (items + kEarWarps - 1) / kEarWarps;
+  kt_begin(kt, "haspi_control", s);
   if (f64) haspi_control_kernel<double><<<ctas, kEarWarps * 32, 0, s>>>(g, b, items);
   else haspi_control_kernel<float><<<ctas, kEarWarps * 32, 0, s>>>(g, b, items);
+  kt_end(kt, s);
   ++launches;
+  kt_begin(kt, "haspi_shift", s);
   haspi_shift_kernel<<<(n * 32 + 127) / 128, 128, 0, s>>>(b, n);
+  kt_end(kt, s);
   ++launches;
+  kt_begin(kt, "haspi_ear", s);
   if (f64) haspi_ear_kernel<double><<<ctas, kEarWarps * 32, 0, s>>>(g, b, items);
   else haspi_ear_kernel<float><<<ctas, kEarWarps * 32, 0, s>>>(g, b, items);
+  kt_end(kt, s);
   ++launches;
+  kt_begin(kt, "haspi_cep", s);
   haspi_cep_kernel<<<n, kCepThreads, 0, s>>>(g, b);
+  kt_end(kt, s);
   ++launches;
   cudaMemsetAsync(b.modsum, 0, sizeof(double) * (size_t)n * kNumCep * kNumMod * 5, s);
   const int tiles = (max_nsub + kModTile - 1) / kModTile;
+  kt_begin(kt, "haspi_modcorr", s);
   haspi_modcorr_kernel<<<dim3(n, kNumCep, tiles), kModThreads, modcorr_smem_bytes(), s>>>(g, b);
+  kt_end(kt, s);
   ++launches;
   return launches;
 }
 
-int haspi_finish(const HaspiBuffers& b, int n, double* intel, double* raw10, int32_t* status, cudaStream_t s) {
+int haspi_finish(const HaspiBuffers& b, int n, double* intel, double* raw10, int32_t* status, KernelTimer* kt,
+                 cudaStream_t s) {
+  kt_begin(kt, "haspi_score", s);
   haspi_score_kernel<<<(n + 127) / 128, 128, 0, s>>>(b, n, intel, raw10, status);
+  kt_end(kt, s);
   return 1;
 }
 

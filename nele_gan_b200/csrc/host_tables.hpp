@@ -233,6 +233,27 @@ inline void make_estoi_resampler(int fs_in, int fs_out, PolyFilter& pf) {
   for (auto& v : pf.h) v = v / s * p;
 }
 
+// Polyphase form of resample_poly's upfirdn: y[m] = sum_{k=-K..K} taps[r][k+K] x[n-k],
+// n = (m * down) / up, r = (m * down) % up, taps[r][k+K] = h[half + r + up k] (0 outside).
+struct PolyTaps {
+  int up = 1, down = 1, K = 0;
+  std::vector<double> taps;  // [up][2K+1]
+};
+inline void make_estoi_polytaps(int fs_in, int fs_out, PolyTaps& pt) {
+  PolyFilter pf;
+  make_estoi_resampler(fs_in, fs_out, pf);
+  pt.up = pf.up;
+  pt.down = pf.down;
+  pt.K = pf.half / pf.up + 1;
+  const int nt = 2 * pt.K + 1;
+  pt.taps.assign((size_t)pt.up * nt, 0.0);
+  for (int r = 0; r < pt.up; ++r)
+    for (int k = -pt.K; k <= pt.K; ++k) {
+      const int i = pf.half + r + pt.up * k;
+      if (i >= 0 && i <= 2 * pf.half) pt.taps[(size_t)r * nt + (k + pt.K)] = pf.h[i];
+    }
+}
+
 // one-third-octave band edges as rfft bin ranges [lo, hi) (pystoi.utils.thirdoct)
 inline void make_thirdoct_bins(int* lo, int* hi, int fs = 10000, int nfft = 512, int nb = 15, double fmin = 150.0) {
   const int nf = nfft / 2 + 1;

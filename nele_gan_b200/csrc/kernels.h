@@ -42,10 +42,101 @@ struct HaspiBuffers {
   int64_t pair_base;       // global index of the chunk's first pair (dither keying)
 };
 
+// Optional per-kernel CUDA-event timing on the launching stream (bench.py's
+// roofline figures).  Entries are filled in launch order; the engine sums them
+// by name after the stream has been synchronised.
+struct KernelTimer {
+  static constexpr int kMax = 512;
+  bool enabled = false;
+  int count = 0;
+  const char* names[kMax];
+  cudaEvent_t ev0[kMax], ev1[kMax];
+};
+inline void kt_begin(KernelTimer* kt, const char* name, cudaStream_t s) {
+  if (!kt || !kt->enabled || kt->count >= KernelTimer::kMax) return;
+  kt->names[kt->count] = name;
+  cudaEventRecord(kt->ev0[kt->count], s);
+}
+inline void kt_end(KernelTimer* kt, cudaStream_t s) {
+  if (!kt || !kt->enabled || kt->count >= KernelTimer::kMax) return;
+  cudaEventRecord(kt->ev1[kt->count], s);
+  ++kt->count;
+}
+
 void haspi_upload_constants(cudaStream_t s);
 // returns number of kernel launches issued
-int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, bool f64, cudaStream_t s);
+int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, bool f64, KernelTimer* kt, cudaStream_t s);
 // scores: raw Intel [n] and aveCM [n][10]; status byte per pair
-int haspi_finish(const HaspiBuffers& b, int n, double* intel, double* raw10, int32_t* status, cudaStream_t s);
+int haspi_finish(const HaspiBuffers& b, int n, double* intel, double* raw10, int32_t* status, KernelTimer* kt,
+                 cudaStream_t s);
+
+// ------------------------------------------------------------------ ESTOI
+struct EstoiGeom {
+  const int64_t* off16;
+  const int32_t* len16;
+  const int64_t* off10;  // start in the 10 kHz buffers (per signal plane)
+  const int32_t* n10;    // ceil(len * 10000 / fs)
+  const int64_t* offfr;  // start in the frame-indexed buffers
+  const int32_t* nfa;    // analysis frames: len(range(0, n10 - 256, 128))
+};
+struct EstoiBuffers {
+  const float* ref;
+  const float* deg;
+  float* x10;        // [2][tot10]
+  int64_t tot10;
+  double* energy;    // [totfr] frame energies of x (dB)
+  int32_t* kept;     // [totfr] indices of the frames that survive silent-frame removal
+  int32_t* nkept;    // [n]
+  float* tob;        // [2][totfr][15] one-third-octave magnitudes
+  int64_t totfr;
+  const double* taps;  // [up][2K+1]
+  int up, down, K;
+  double* score;     // [n]
+  int32_t* status;   // [n]
+};
+void estoi_upload_tables(const float* win, const int* lo, const int* hi, const float* tw, cudaStream_t s);
+int estoi_run(const EstoiGeom& g, const EstoiBuffers& b, int n, int max_n10, int max_nfa, KernelTimer* kt, cudaStream_t s);
+
+// ------------------------------------------------------------------- SIIB
+struct SiibGeom {
+  const int64_t* off16;
+  const int32_t* len16;
+  const int64_t* offW;   // start in wrapdb (frames of the untiled signal)
+  const int64_t* offF;   // start in the buffers indexed by frames of the tiled signal
+  const int64_t* F;      // frames of the tiled signal: ceil((M L - 400) / 200)
+};
+struct SiibBuffers {
+  const float* ref;
+  const float* deg;
+  double* wrapdb;        // [totW]
+  int32_t* M;            // [n] tiling factor of intel.py:71-75 (0: no active frame)
+  int32_t* wrap_active;  // [n]
+  double* mean;          // [n][2]
+  double* xdb;           // [totF]
+  int32_t* act;          // [totF] indices of the active frames
+  int32_t* Fa;           // [n]
+  float* logspec;        // [2][totF][32]
+  int64_t totF;
+  // per sub-chunk (indexed by pair - pair_lo)
+  int pair_lo;
+  double* base;          // [59][32][32] lag products
+  double* Sxx;           // [420][420]
+  float* Sxy;            // [420][420]
+  float* Syy;            // [420][420]
+  double* Lc;            // [420][420] Cholesky factor, Lc[m][i] = L[i][m]
+  float* G;              // [420][448] FP32 copy of the factor; Jacobi works in place
+  int32_t* perm;         // [420]
+  // per pair of the chunk
+  int32_t* rank;         // [n]
+  int32_t* sweeps;       // [n]
+  int32_t* sweep_rot;    // [n][16] rotations applied in each sweep (diagnostic)
+  float* lambda;         // [n][420]
+  float* rho;            // [n][420]
+  double* score;         // [n]
+  int32_t* status;       // [n]
+};
+void siib_upload_tables(const float* win, const float* decay, const float* g2t, const float* tw, cudaStream_t s);
+int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_tile, KernelTimer* kt, cudaStream_t s);
+int siib_run(const SiibGeom& g, const SiibBuffers& b, int n, int64_t max_F, KernelTimer* kt, cudaStream_t s);
 
 }  // namespace nele

@@ -1,0 +1,888 @@
+// SIIB^Gauss on sm_100a: batched restatement of intel.py:57-100 (wrapper VAD + tiling to
+// >= 25 s) and pysiib.SIIB(x, y, fs, gauss=True) (algorithm: oracle/pysiib_np.py).
+//
+//   siib_wrapvad_kernel  per pair CTA: the wrapper's VAD on the untiled clean signal
+//                        (intel.py:62-75) -> tiling factor M.  The tiled signal is never
+//                        materialised: frame f of it is x[(200 f + i) mod L].
+//   siib_vad_kernel      per pair CTA: means, frame powers of the tiled mean-removed x,
+//                        99.9th percentile by k-fold arg-max, ordered compaction of the
+//                        active frames (intel.py:37-50 semantics inside pysiib)
+//   siib_spec_kernel     per (pair, active frame) warp: Hann frame of x + i y, 400-point
+//                        FFT (fft400.cuh), power spectra, 28 gammatone band energies, log
+//                        -> logspec [t][32] (time-major, 28 bands + 4 zero lanes)
+//   siib_mask_kernel     per (pair, signal) warp, lane = band: forward temporal masking
+//                        (16 frames, sequential in time) and mean removal
+//   siib_cov_kernel      per (pair, lag block) warp: FP64 28x28 lag products
+//                        D_d = sum_t a_{t+max(0,-d)} b_{t+max(0,d)}^T for xx, yy (d = 0..14)
+//                        and xy (d = -14..14).  The 420 x 420 stacked covariances are
+//                        block-Toeplitz up to 14 edge terms per entry, so 59 blocks replace
+//                        three 420 x 420 x Nf products (8x fewer flops, exact).
+//   siib_expand_kernel   per pair CTA: walks every block diagonal with the one-term-out,
+//                        one-term-in recurrence -> centred scatter matrices Sxx (FP64),
+//                        Sxy, Syy (FP32)
+//   siib_chol_kernel     per pair CTA: diagonally pivoted left-looking Cholesky of Sxx in
+//                        FP64, stops at the numerical rank r -> L (FP32 copy, r columns)
+//   siib_jacobi_kernel   per pair CTA: one-sided (Hestenes) Jacobi on the r columns of L;
+//                        at convergence column j = sqrt(lambda_j) u_j, i.e. the KLT basis of
+//                        cov(X) without accumulating rotations.  Column blocks of 4 are held
+//                        in registers and paired by a round-robin tournament.
+//   siib_quad_kernel     per pair CTA: rho_j = u^T Sxy u / sqrt(lambda_j u^T Syy u), the
+//                        Gaussian channel capacity sum and the final score
+//
+// Rank-deficient inputs (a tiled signal whose length is a multiple of the 200-sample hop
+// repeats its frames exactly) stop the Cholesky early; the null space contributes zero
+// information, which is the exact-arithmetic value of the reference formula.
+#include "fft400.cuh"
+#include "kernels.h"
+
+namespace nele {
+
+constexpr int kSWin = 400, kSHop = 200, kSBins = 201, kSBands = 28, kSLanes = 32, kSStack = 15;
+constexpr int kSDim = kSBands * kSStack;  // 420
+constexpr int kSLd = 448;                 // padded column length of L (14 x 32)
+constexpr int kSBlocks = 59;              // xx d=0..14, yy d=0..14, xy d=-14..14
+constexpr int kSMaskT = 16;               // floor(0.2 s * 80 frames/s)
+constexpr double kEps = 2.220446049250313e-16;
+
+__constant__ float c_siib_win[kSWin];     // periodic Hann(400)
+__constant__ float c_siib_decay[kSMaskT];  // log(d + 1) / log(16)
+__device__ float g_siib_g2t[kSBins * kSLanes];  // squared gammatone responses, [bin][band]
+__device__ cpx g_siib_tw[kSWin];
+
+// ---------------------------------------------------------------- VAD helpers
+// power (dB) of Hann frame f of (x - mean); wrap = tiled signal, else zero padded
+__device__ __forceinline__ double frame_power_db(const float* __restrict__ x, int L, double mean, int64_t f,
+                                                 bool wrap, int lane) {
+  const int64_t s0 = f * kSHop;
+  int64_t base = wrap ? (s0 % L) : s0;
+  double ss = 0.0;
+  for (int i = lane; i < kSWin; i += 32) {
+    int64_t idx = base + i;
+    double v;
+    if (wrap) {
+      if (idx >= L) idx %= L;
+      v = (double)x[idx] - mean;
+    } else {
+      v = (idx < L) ? (double)x[idx] - mean : 0.0;
+    }
+    v *= (double)c_siib_win[i];
+    ss += v * v;
+  }
+  ss = warp_sum(ss);
+  return 10.0 * log10(ss / (double)kSWin + kEps);
+}
+
+// k-th largest (counting multiplicity) of v[0..n), k >= 1: k rounds of arg-max in the
+// total order (value descending, index ascending).  All threads get the result.
+__device__ double kth_largest(const double* __restrict__ v, int64_t n, int k, double* red, int64_t* redi) {
+  double pv = 1.0e300;
+  int64_t pi = -1;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = 0; r < k; ++r) {
+    double bv = -1.0e300;
+    int64_t bi = -1;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const double c = v[i];
+      const bool after = (c < pv) || (c == pv && i > pi);
+      if (after && (c > bv || (c == bv && i < bi) || bi < 0)) {
+        bv = c;
+        bi = i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    __syncthreads();
+    if (lane == 0) {
+      red[w] = bv;
+      redi[w] = bi;
+    }
+    __syncthreads();
+    bv = red[0];
+    bi = redi[0];
+    for (int j = 1; j < nw; ++j) {
+      const double ov = red[j];
+      const int64_t oi = redi[j];
+      if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    pv = bv;
+    pi = bi;
+  }
+  return pv;
+}
+
+__device__ __forceinline__ int percentile_rank(int64_t n) {  // k such that the k-th largest is sorted[ind]
+  int64_t ind = (int64_t)rint((double)n * 0.999) - 1;       // int(round(len * 0.999) - 1), round-half-even
+  if (ind < 0) ind += n;                                     // numpy negative index
+  if (ind < 0) ind = 0;
+  if (ind > n - 1) ind = n - 1;
+  return (int)(n - ind);
+}
+
+constexpr int kVadThreads = 256;
+
+__global__ void __launch_bounds__(kVadThreads) siib_wrapvad_kernel(SiibGeom g, SiibBuffers b, int no_tile) {
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  constexpr int NW = kVadThreads / 32;
+  const float* __restrict__ x = b.ref + g.off16[pair];
+  const int L = g.len16[pair];
+  const int Lp = max(L, kSWin + 1);
+  const int F1 = (Lp - kSWin + kSHop - 1) / kSHop;
+  double* __restrict__ db = b.wrapdb + g.offW[pair];
+  __shared__ double red[32];
+  __shared__ int64_t redi[32];
+  for (int f = wib; f < F1; f += NW) {
+    const double d = frame_power_db(x, L, 0.0, f, false, lane);
+    if (lane == 0) db[f] = d;
+  }
+  __syncthreads();
+  const double sel = kth_largest(db, F1, percentile_rank(F1), red, redi);
+  const double thr = sel - 40.0;
+  int cnt = 0;
+  for (int f = tid; f < F1; f += kVadThreads) cnt += (db[f] > thr) ? 1 : 0;
+  const int active = (int)block_sum((double)cnt, red);
+  if (tid == 0) {
+    int M = 1;
+    if (!no_tile && (double)active / 80.0 < 20.0) M = (active > 0) ? (int)floor(25.0 / ((double)active / 80.0)) : 0;
+    b.M[pair] = M;
+    b.wrap_active[pair] = active;
+  }
+}
+
+__global__ void __launch_bounds__(kVadThreads) siib_vad_kernel(SiibGeom g, SiibBuffers b) {
+  const int pair = b.pair_lo + blockIdx.x, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  constexpr int NW = kVadThreads / 32;
+  const float* __restrict__ x = b.ref + g.off16[pair];
+  const float* __restrict__ y = b.deg + g.off16[pair];
+  const int L = g.len16[pair];
+  const int64_t F = g.F[pair];
+  double* __restrict__ db = b.xdb + g.offF[pair];
+  int32_t* __restrict__ act = b.act + g.offF[pair];
+  __shared__ double red[32];
+  __shared__ int64_t redi[32];
+  __shared__ int s_cnt[NW];
+  __shared__ int s_base;
+  if (F <= 0) {
+    if (tid == 0) b.Fa[pair] = 0;
+    return;
+  }
+  double sx = 0.0, sy = 0.0;
+  for (int i = tid; i < L; i += kVadThreads) {
+    sx += (double)x[i];
+    sy += (double)y[i];
+  }
+  sx = block_sum(sx, red);
+  sy = block_sum(sy, red);
+  const double mx = sx / (double)L, my = sy / (double)L;
+  if (tid == 0) {
+    b.mean[2 * pair] = mx;
+    b.mean[2 * pair + 1] = my;
+  }
+  for (int64_t f = wib; f < F; f += NW) {
+    const double d = frame_power_db(x, L, mx, f, true, lane);
+    if (lane == 0) db[f] = d;
+  }
+  __syncthreads();
+  const double sel = kth_largest(db, F, percentile_rank(F), red, redi);
+  const double thr = sel - 40.0;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int64_t f0 = 0; f0 < F; f0 += kVadThreads) {
+    const int64_t f = f0 + tid;
+    const int keep = (f < F && db[f] > thr) ? 1 : 0;
+    int inc = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_cnt[wib] = inc;
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < NW; ++w) {
+      if (w < wib) woff += s_cnt[w];
+      tot += s_cnt[w];
+    }
+    const int base = s_base;
+    if (keep) act[base + woff + inc - 1] = (int32_t)f;
+    __syncthreads();
+    if (tid == 0) s_base = base + tot;
+    __syncthreads();
+  }
+  if (tid == 0) b.Fa[pair] = s_base;
+}
+
+// ------------------------------------------------------------- spectra
+constexpr int kSpecWarps = 8;
+struct SpecSmem {
+  cpx tw[kSWin];
+  float g2t[kSBins * kSLanes];
+  cpx z[kSpecWarps][kSWin];
+  cpx t[kSpecWarps][kSWin];
+};
+
+__global__ void __launch_bounds__(kSpecWarps * 32) siib_spec_kernel(SiibGeom g, SiibBuffers b) {
+  const int pair = b.pair_lo + blockIdx.y, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int Fa = b.Fa[pair];
+  if (blockIdx.x * kSpecWarps >= Fa) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SpecSmem& sm = *reinterpret_cast<SpecSmem*>(smem_raw);
+  for (int k = threadIdx.x; k < kSWin; k += kSpecWarps * 32) sm.tw[k] = g_siib_tw[k];
+  for (int k = threadIdx.x; k < kSBins * kSLanes; k += kSpecWarps * 32) sm.g2t[k] = g_siib_g2t[k];
+  __syncthreads();
+  const int t = blockIdx.x * kSpecWarps + wib;
+  if (t >= Fa) return;
+  const float* __restrict__ x = b.ref + g.off16[pair];
+  const float* __restrict__ y = b.deg + g.off16[pair];
+  const int L = g.len16[pair];
+  const float mx = (float)b.mean[2 * pair], my = (float)b.mean[2 * pair + 1];
+  const int64_t f = b.act[g.offF[pair] + t];
+  const int64_t base = (f * kSHop) % L;
+  cpx* z = sm.z[wib];
+  cpx* tt = sm.t[wib];
+  for (int i = lane; i < kSWin; i += 32) {
+    int64_t idx = base + i;
+    if (idx >= L) idx %= L;
+    const float w = c_siib_win[i];
+    z[i] = {w * (x[idx] - mx), w * (y[idx] - my)};
+  }
+  __syncwarp();
+  if (lane < 25) fft400_phase_a(lane, z, tt, sm.tw);
+  __syncwarp();
+  if (lane < 16) fft400_phase_b(lane, tt, z, sm.tw);
+  __syncwarp();
+  // power spectra of the two real signals, interleaved (px, py) into tt
+  float2* pw = reinterpret_cast<float2*>(tt);
+  for (int k = lane; k < kSBins; k += 32) {
+    const cpx a = z[k], c = z[(kSWin - k) % kSWin];
+    const float xr = a.x + c.x, xi = a.y - c.y, yr = a.y + c.y, yi = c.x - a.x;
+    pw[k] = make_float2(0.25f * (xr * xr + xi * xi), 0.25f * (yr * yr + yi * yi));
+  }
+  __syncwarp();
+  float ex = 0.f, ey = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < kSBins; ++k) {
+    const float2 p = pw[k];
+    const float gk = sm.g2t[k * kSLanes + lane];
+    ex = fmaf(gk, p.x, ex);
+    ey = fmaf(gk, p.y, ey);
+  }
+  const int64_t row = g.offF[pair] + t;
+  b.logspec[row * kSLanes + lane] = (lane < kSBands) ? logf(ex + (float)kEps) : 0.f;
+  b.logspec[(b.totF + row) * kSLanes + lane] = (lane < kSBands) ? logf(ey + (float)kEps) : 0.f;
+}
+
+// --------------------------------------------------- forward masking + de-mean
+__global__ void __launch_bounds__(128) siib_mask_kernel(SiibGeom g, SiibBuffers b, int n_items) {
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (item >= n_items) return;
+  const int pair = b.pair_lo + (item >> 1), q = item & 1;
+  const int Fa = b.Fa[pair];
+  float* __restrict__ X = b.logspec + ((int64_t)q * b.totF + g.offF[pair]) * kSLanes + lane;
+  float fl = 3.0e38f;
+  for (int t = 0; t < Fa; ++t) fl = fminf(fl, X[(int64_t)t * kSLanes]);
+  float hx[kSMaskT - 1], he[kSMaskT - 1];  // masked level and (level - floor) of the previous 15 frames
+#pragma unroll
+  for (int d = 0; d < kSMaskT - 1; ++d) {
+    hx[d] = -3.0e38f;
+    he[d] = 0.f;
+  }
+  double sum = 0.0;
+  for (int t = 0; t < Fa; ++t) {
+    float v = X[(int64_t)t * kSLanes];
+#pragma unroll
+    for (int d = 0; d < kSMaskT - 1; ++d) v = fmaxf(v, fmaf(-c_siib_decay[d + 1], he[d], hx[d]));
+#pragma unroll
+    for (int d = kSMaskT - 2; d > 0; --d) {
+      hx[d] = hx[d - 1];
+      he[d] = he[d - 1];
+    }
+    hx[0] = v;
+    he[0] = v - fl;
+    X[(int64_t)t * kSLanes] = v;
+    sum += (double)v;
+  }
+  const float mu = (Fa > 0) ? (float)(sum / (double)Fa) : 0.f;
+  for (int t = 0; t < Fa; ++t) X[(int64_t)t * kSLanes] = (lane < kSBands) ? X[(int64_t)t * kSLanes] - mu : 0.f;
+}
+
+// ---------------------------------------------------------- lag products
+// block id -> (type, lag): 0..14 xx d=id; 15..29 yy d=id-15; 30..58 xy d=id-44
+__device__ __forceinline__ void block_desc(int blk, int& ta, int& tb, int& d) {
+  if (blk < 15) { ta = 0; tb = 0; d = blk; }
+  else if (blk < 30) { ta = 1; tb = 1; d = blk - 15; }
+  else { ta = 0; tb = 1; d = blk - 44; }
+}
+
+constexpr int kCovWarps = 8;
+
+__global__ void __launch_bounds__(kCovWarps * 32) siib_cov_kernel(SiibGeom g, SiibBuffers b) {
+  const int lp = blockIdx.y, pair = b.pair_lo + lp, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int blk = blockIdx.x * kCovWarps + wib;
+  const int Fa = b.Fa[pair];
+  const int Nf = Fa - (kSStack - 1);
+  if (blk >= kSBlocks || Nf < 1) return;
+  int ta, tb, d;
+  block_desc(blk, ta, tb, d);
+  const int a0 = max(0, -d), b0 = max(0, d);
+  const int rg = lane >> 2, cg = lane & 3;
+  const float* __restrict__ A = b.logspec + ((int64_t)ta * b.totF + g.offF[pair] + a0) * kSLanes + 4 * rg;
+  const float* __restrict__ B = b.logspec + ((int64_t)tb * b.totF + g.offF[pair] + b0) * kSLanes + 8 * cg;
+  double acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+#pragma unroll 2
+  for (int t = 0; t < Nf; ++t) {
+    const float4 av = *reinterpret_cast<const float4*>(A + (int64_t)t * kSLanes);
+    const float4 b0v = *reinterpret_cast<const float4*>(B + (int64_t)t * kSLanes);
+    const float4 b1v = *reinterpret_cast<const float4*>(B + (int64_t)t * kSLanes + 4);
+    const double a[4] = {(double)av.x, (double)av.y, (double)av.z, (double)av.w};
+    const double c[8] = {(double)b0v.x, (double)b0v.y, (double)b0v.z, (double)b0v.w,
+                         (double)b1v.x, (double)b1v.y, (double)b1v.z, (double)b1v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], c[j], acc[i][j]);
+  }
+  double* __restrict__ out = b.base + ((int64_t)lp * kSBlocks + blk) * (kSLanes * kSLanes);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[(4 * rg + i) * kSLanes + 8 * cg + j] = acc[i][j];
+}
+
+// ------------------------------------------------------------------ expand
+constexpr int kExpThreads = 256;
+
+__global__ void __launch_bounds__(kExpThreads) siib_expand_kernel(SiibGeom g, SiibBuffers b) {
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  const int Fa = b.Fa[pair];
+  const int Nf = Fa - (kSStack - 1);
+  if (Nf < 2) return;
+  __shared__ double s_rs[2][kSDim];  // row sums of the stacked matrices
+  const float* __restrict__ X = b.logspec + (g.offF[pair]) * kSLanes;
+  const float* __restrict__ Y = b.logspec + (b.totF + g.offF[pair]) * kSLanes;
+  // sums over t < Nf of band j (k = 0), then slide
+  for (int item = wib; item < 2 * kSBands; item += kExpThreads / 32) {
+    const int q = item / kSBands, j = item % kSBands;
+    const float* S = (q ? Y : X) + j;
+    double s = 0.0;
+    for (int t = lane; t < Nf; t += 32) s += (double)S[(int64_t)t * kSLanes];
+    s = warp_sum(s);
+    if (lane == 0) {
+      s_rs[q][j] = s;
+      for (int k = 1; k < kSStack; ++k) {
+        s += (double)S[(int64_t)(Nf + k - 1) * kSLanes] - (double)S[(int64_t)(k - 1) * kSLanes];
+        s_rs[q][k * kSBands + j] = s;
+      }
+    }
+  }
+  __syncthreads();
+  const double inv_nf = 1.0 / (double)Nf;
+  double* __restrict__ Sxx = b.Sxx + (int64_t)lp * kSDim * kSDim;
+  float* __restrict__ Sxy = b.Sxy + (int64_t)lp * kSDim * kSDim;
+  float* __restrict__ Syy = b.Syy + (int64_t)lp * kSDim * kSDim;
+  const double* __restrict__ base = b.base + (int64_t)lp * kSBlocks * (kSLanes * kSLanes);
+  const int ndiag = kSBlocks * kSBands * kSBands;
+  for (int it = tid; it < ndiag; it += kExpThreads) {
+    const int blk = it / (kSBands * kSBands), rem = it % (kSBands * kSBands);
+    const int j1 = rem / kSBands, j2 = rem % kSBands;
+    int ta, tb, d;
+    block_desc(blk, ta, tb, d);
+    const float* A = (ta ? Y : X) + j1;
+    const float* B = (tb ? Y : X) + j2;
+    int k1 = max(0, -d), k2 = max(0, d);
+    double r = base[blk * (kSLanes * kSLanes) + j1 * kSLanes + j2];
+    const int steps = kSStack - (d < 0 ? -d : d);
+    for (int m = 0; m < steps; ++m) {
+      const int a = k1 * kSBands + j1, c = k2 * kSBands + j2;
+      const double v = r - s_rs[ta][a] * s_rs[tb][c] * inv_nf;
+      if (blk < 15) {
+        Sxx[(int64_t)a * kSDim + c] = v;
+        Sxx[(int64_t)c * kSDim + a] = v;
+      } else if (blk < 30) {
+        Syy[(int64_t)a * kSDim + c] = (float)v;
+        Syy[(int64_t)c * kSDim + a] = (float)v;
+      } else {
+        Sxy[(int64_t)a * kSDim + c] = (float)v;
+      }
+      if (m + 1 == steps) break;
+      // slide the summation window by one frame
+      r += (double)A[(int64_t)(Nf + k1) * kSLanes] * (double)B[(int64_t)(Nf + k2) * kSLanes] -
+           (double)A[(int64_t)k1 * kSLanes] * (double)B[(int64_t)k2 * kSLanes];
+      ++k1;
+      ++k2;
+    }
+  }
+}
+
+// --------------------------------------------------------------- Cholesky
+constexpr int kCholThreads = 448;
+
+// Thread i owns position i of the permuted index space: its permutation entry, its running
+// diagonal (Schur complement) and column i of Lc.  Two block barriers per elimination step.
+__global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, SiibBuffers b) {
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  constexpr int NW = kCholThreads / 32;
+  const int Nf = b.Fa[pair] - (kSStack - 1);
+  float* __restrict__ G = b.G + (int64_t)lp * kSDim * kSLd;
+  if (Nf < 2) {
+    if (tid == 0) b.rank[pair] = 0;
+    return;
+  }
+  const double* __restrict__ A = b.Sxx + (int64_t)lp * kSDim * kSDim;
+  double* __restrict__ Lc = b.Lc + (int64_t)lp * kSDim * kSDim;  // Lc[m][i] = L[i][m]
+  int32_t* __restrict__ gperm = b.perm + (int64_t)lp * kSDim;
+  __shared__ int s_perm[kSDim];
+  __shared__ double s_dg[kSDim];
+  __shared__ double s_row[kSDim];  // L[k][0..k)
+  __shared__ double s_rv[2][NW];
+  __shared__ int s_ri[2][NW];
+  const bool own = tid < kSDim;
+  int myperm = tid;
+  double mydg = own ? A[(int64_t)tid * kSDim + tid] : -1.0e300;
+  double tol = 0.0;
+  int rank = kSDim;
+  for (int k = 0; k < kSDim; ++k) {
+    // publish, then pick the largest remaining diagonal (every thread redundantly)
+    if (own) {
+      s_perm[tid] = myperm;
+      s_dg[tid] = mydg;
+    }
+    {
+      double v = (own && tid >= k) ? mydg : -1.0e300;
+      int vi = tid;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+        if (ov > v || (ov == v && oi < vi)) {
+          v = ov;
+          vi = oi;
+        }
+      }
+      if (lane == 0) {
+        s_rv[k & 1][wib] = v;
+        s_ri[k & 1][wib] = vi;
+      }
+    }
+    __syncthreads();
+    double piv = s_rv[k & 1][0];
+    int p = s_ri[k & 1][0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) {
+      const double ov = s_rv[k & 1][w];
+      const int oi = s_ri[k & 1][w];
+      if (ov > piv || (ov == piv && oi < p)) {
+        piv = ov;
+        p = oi;
+      }
+    }
+    if (k == 0) tol = piv * 1.0e-10;
+    if (!(piv > tol)) {
+      rank = k;
+      break;
+    }
+    // symmetric interchange k <-> p; s_row = row k of L after the interchange
+    if (tid < k) {
+      const double vp = Lc[(int64_t)tid * kSDim + p];
+      if (p != k) {
+        Lc[(int64_t)tid * kSDim + p] = Lc[(int64_t)tid * kSDim + k];
+        Lc[(int64_t)tid * kSDim + k] = vp;
+      }
+      s_row[tid] = vp;
+    }
+    const int pk = s_perm[p];  // permutation entry that moves to position k
+    if (p != k) {
+      if (tid == k) {
+        myperm = pk;
+        mydg = s_dg[p];
+      } else if (tid == p) {
+        myperm = s_perm[k];
+        mydg = s_dg[k];
+      }
+    }
+    __syncthreads();
+    const double lkk = sqrt(piv);
+    if (own) {
+      double l = 0.0;
+      if (tid > k) {
+        double s = A[(int64_t)pk * kSDim + myperm];
+        const double* col = Lc + tid;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int m = 0;
+        for (; m + 8 <= k; m += 8) {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = col[(int64_t)(m + u) * kSDim];
+          s0 = fma(v[0], s_row[m], s0);
+          s1 = fma(v[1], s_row[m + 1], s1);
+          s2 = fma(v[2], s_row[m + 2], s2);
+          s3 = fma(v[3], s_row[m + 3], s3);
+          s0 = fma(v[4], s_row[m + 4], s0);
+          s1 = fma(v[5], s_row[m + 5], s1);
+          s2 = fma(v[6], s_row[m + 6], s2);
+          s3 = fma(v[7], s_row[m + 7], s3);
+        }
+        for (; m < k; ++m) s0 = fma(col[(int64_t)m * kSDim], s_row[m], s0);
+        s -= (s0 + s1) + (s2 + s3);
+        l = s / lkk;
+        mydg -= l * l;
+      } else if (tid == k) {
+        l = lkk;
+      }
+      Lc[(int64_t)k * kSDim + tid] = l;
+    }
+    // the barrier at the top of the next step orders these writes before the next interchange
+  }
+  __syncthreads();
+  // FP32 copy of the factor for the Jacobi stage (after all interchanges), rows 420..447 zero
+  for (int m = 0; m < rank; ++m)
+    G[(int64_t)m * kSLd + tid] = own ? (float)Lc[(int64_t)m * kSDim + tid] : 0.f;
+  if (own) gperm[tid] = myperm;
+  if (tid == 0) b.rank[pair] = rank;
+}
+
+// ----------------------------------------------------------------- Jacobi
+constexpr int kJacWarps = 12;
+constexpr int kJacH = 4;                  // columns per block
+constexpr int kJacE = kSLd / 32;          // 14 elements per lane per column
+constexpr int kJacMaxSweeps = 14;
+constexpr float kJacTol = 1.5e-6f;
+
+struct ColBlock {
+  float v[kJacH][kJacE];
+  float nrm[kJacH];
+};
+
+__device__ __forceinline__ void load_block(ColBlock& c, const float* __restrict__ G, int first, int r, int lane) {
+#pragma unroll
+  for (int h = 0; h < kJacH; ++h) {
+    float s = 0.f;
+    if (first + h < r) {
+      const float* col = G + (int64_t)(first + h) * kSLd + lane;
+#pragma unroll
+      for (int e = 0; e < kJacE; ++e) {
+        c.v[h][e] = col[e * 32];
+        s = fmaf(c.v[h][e], c.v[h][e], s);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < kJacE; ++e) c.v[h][e] = 0.f;
+    }
+    c.nrm[h] = warp_sum(s);
+  }
+}
+__device__ __forceinline__ void store_block(const ColBlock& c, float* __restrict__ G, int first, int r, int lane) {
+#pragma unroll
+  for (int h = 0; h < kJacH; ++h)
+    if (first + h < r) {
+      float* col = G + (int64_t)(first + h) * kSLd + lane;
+#pragma unroll
+      for (int e = 0; e < kJacE; ++e) col[e * 32] = c.v[h][e];
+    }
+}
+// Hestenes rotation parameters for one column pair: a = |p|^2, b = |q|^2 (updated in place),
+// gmm = p.q.  Leaves (c, s) = (1, 0) when the pair is already orthogonal to working precision.
+__device__ __forceinline__ void rot_params(float gmm, float& a, float& b, float& c, float& s, int& nrot) {
+  c = 1.0f;
+  s = 0.0f;
+  if (a > 0.f && b > 0.f && fabsf(gmm) > kJacTol * sqrtf(a * b)) {
+    const float zeta = (b - a) / (2.0f * gmm);
+    const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
+    c = rsqrtf(1.0f + t * t);
+    s = c * t;
+    a -= t * gmm;
+    b += t * gmm;
+    ++nrot;
+  }
+}
+__device__ __forceinline__ float dot14(const float (&p)[kJacE], const float (&q)[kJacE]) {
+  float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+  for (int e = 0; e < kJacE; e += 2) {
+    g0 = fmaf(p[e], q[e], g0);
+    g1 = fmaf(p[e + 1], q[e + 1], g1);
+  }
+  return g0 + g1;
+}
+__device__ __forceinline__ void apply_rot(float (&p)[kJacE], float (&q)[kJacE], float c, float s) {
+  if (s != 0.f) {  // warp-uniform
+#pragma unroll
+    for (int e = 0; e < kJacE; ++e) {
+      const float a = p[e], bq = q[e];
+      p[e] = c * a - s * bq;
+      q[e] = fmaf(s, a, c * bq);
+    }
+  }
+}
+// four mutually independent rotations (p0,q0) .. (p3,q3), issued together so that the four
+// reduction / scalar chains overlap
+#define NELE_ROT4(P0, NP0, Q0, NQ0, P1, NP1, Q1, NQ1, P2, NP2, Q2, NQ2, P3, NP3, Q3, NQ3)   \
+  {                                                                                          \
+    float g0 = dot14(P0, Q0), g1 = dot14(P1, Q1), g2 = dot14(P2, Q2), g3 = dot14(P3, Q3);    \
+    _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) {                                     \
+      g0 += __shfl_xor_sync(0xffffffffu, g0, o);                                             \
+      g1 += __shfl_xor_sync(0xffffffffu, g1, o);                                             \
+      g2 += __shfl_xor_sync(0xffffffffu, g2, o);                                             \
+      g3 += __shfl_xor_sync(0xffffffffu, g3, o);                                             \
+    }                                                                                        \
+    float c0, s0, c1, s1, c2, s2, c3, s3;                                                    \
+    rot_params(g0, NP0, NQ0, c0, s0, nrot);                                                  \
+    rot_params(g1, NP1, NQ1, c1, s1, nrot);                                                  \
+    rot_params(g2, NP2, NQ2, c2, s2, nrot);                                                  \
+    rot_params(g3, NP3, NQ3, c3, s3, nrot);                                                  \
+    apply_rot(P0, Q0, c0, s0);                                                               \
+    apply_rot(P1, Q1, c1, s1);                                                               \
+    apply_rot(P2, Q2, c2, s2);                                                               \
+    apply_rot(P3, Q3, c3, s3);                                                               \
+  }
+
+__global__ void __launch_bounds__(kJacWarps * 32) siib_jacobi_kernel(SiibGeom g, SiibBuffers b) {
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int r = b.rank[pair];
+  if (r < 2) return;
+  float* __restrict__ G = b.G + (int64_t)lp * kSDim * kSLd;
+  int nb = (r + kJacH - 1) / kJacH;
+  if (nb & 1) ++nb;  // even number of blocks; the last one may be empty
+  __shared__ int s_rot;
+  int sweeps = 0;
+  for (; sweeps < kJacMaxSweeps; ++sweeps) {
+    if (threadIdx.x == 0) s_rot = 0;
+    __syncthreads();
+    int nrot = 0;
+    for (int round = 0; round < nb - 1; ++round) {
+      for (int k = wib; k < nb / 2; k += kJacWarps) {
+        // round-robin tournament (circle method), block nb-1 fixed
+        int bi, bj;
+        if (k == 0) {
+          bi = nb - 1;
+          bj = round;
+        } else {
+          bi = (round + k) % (nb - 1);
+          bj = (round - k + (nb - 1)) % (nb - 1);
+        }
+        if (bi > bj) {
+          const int t = bi;
+          bi = bj;
+          bj = t;
+        }
+        if (bj * kJacH >= r && round != 0) continue;  // partner is the empty pad block
+        ColBlock P, Q;
+        load_block(P, G, bi * kJacH, r, lane);
+        load_block(Q, G, bj * kJacH, r, lane);
+        if (round == 0) {  // pairs inside each block, once per sweep
+          NELE_ROT4(P.v[0], P.nrm[0], P.v[1], P.nrm[1], P.v[2], P.nrm[2], P.v[3], P.nrm[3],
+                    Q.v[0], Q.nrm[0], Q.v[1], Q.nrm[1], Q.v[2], Q.nrm[2], Q.v[3], Q.nrm[3]);
+          NELE_ROT4(P.v[0], P.nrm[0], P.v[2], P.nrm[2], P.v[1], P.nrm[1], P.v[3], P.nrm[3],
+                    Q.v[0], Q.nrm[0], Q.v[2], Q.nrm[2], Q.v[1], Q.nrm[1], Q.v[3], Q.nrm[3]);
+          NELE_ROT4(P.v[0], P.nrm[0], P.v[3], P.nrm[3], P.v[1], P.nrm[1], P.v[2], P.nrm[2],
+                    Q.v[0], Q.nrm[0], Q.v[3], Q.nrm[3], Q.v[1], Q.nrm[1], Q.v[2], Q.nrm[2]);
+        }
+        NELE_ROT4(P.v[0], P.nrm[0], Q.v[0], Q.nrm[0], P.v[1], P.nrm[1], Q.v[1], Q.nrm[1],
+                  P.v[2], P.nrm[2], Q.v[2], Q.nrm[2], P.v[3], P.nrm[3], Q.v[3], Q.nrm[3]);
+        NELE_ROT4(P.v[0], P.nrm[0], Q.v[1], Q.nrm[1], P.v[1], P.nrm[1], Q.v[2], Q.nrm[2],
+                  P.v[2], P.nrm[2], Q.v[3], Q.nrm[3], P.v[3], P.nrm[3], Q.v[0], Q.nrm[0]);
+        NELE_ROT4(P.v[0], P.nrm[0], Q.v[2], Q.nrm[2], P.v[1], P.nrm[1], Q.v[3], Q.nrm[3],
+                  P.v[2], P.nrm[2], Q.v[0], Q.nrm[0], P.v[3], P.nrm[3], Q.v[1], Q.nrm[1]);
+        NELE_ROT4(P.v[0], P.nrm[0], Q.v[3], Q.nrm[3], P.v[1], P.nrm[1], Q.v[0], Q.nrm[0],
+                  P.v[2], P.nrm[2], Q.v[1], Q.nrm[1], P.v[3], P.nrm[3], Q.v[2], Q.nrm[2]);
+        store_block(P, G, bi * kJacH, r, lane);
+        store_block(Q, G, bj * kJacH, r, lane);
+      }
+      __syncthreads();
+    }
+    if (lane == 0) {
+      if (nrot) atomicAdd(&s_rot, nrot);
+      if (sweeps < 16) atomicAdd(&b.sweep_rot[(int64_t)pair * 16 + sweeps], nrot);
+    }
+    __syncthreads();
+    const int tot = s_rot;
+    __syncthreads();
+    if (tot == 0) break;
+  }
+  if (threadIdx.x == 0) b.sweeps[pair] = sweeps;
+}
+
+// ------------------------------------------------------- quadratic forms + score
+constexpr int kQuadThreads = 448;
+constexpr int kQuadJ = 8;
+
+__global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, SiibBuffers b) {
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  constexpr int NW = kQuadThreads / 32;
+  const int Fa = b.Fa[pair];
+  const int Nf = Fa - (kSStack - 1);
+  const int M = b.M[pair];
+  if (M <= 0 || (double)Fa / 80.0 < 20.0 || Nf < 2) {  // pysiib: "at least 20 seconds of speech"
+    if (tid == 0) {
+      b.score[pair] = nan("");
+      b.status[pair] = 2;
+    }
+    return;
+  }
+  const int r = b.rank[pair];
+  const float* __restrict__ G = b.G + (int64_t)lp * kSDim * kSLd;
+  const float* __restrict__ Sxy = b.Sxy + (int64_t)lp * kSDim * kSDim;
+  const float* __restrict__ Syy = b.Syy + (int64_t)lp * kSDim * kSDim;
+  const int32_t* __restrict__ perm = b.perm + (int64_t)lp * kSDim;
+  __shared__ __align__(16) float s_u[kSDim][kQuadJ];  // unit eigenvectors in original coordinates
+  __shared__ float s_lam[kQuadJ];
+  __shared__ float s_part[NW][2 * kQuadJ];
+  __shared__ double s_info;
+  if (tid == 0) s_info = 0.0;
+  float* __restrict__ lam_out = b.lambda + (int64_t)pair * kSDim;
+  float* __restrict__ rho_out = b.rho + (int64_t)pair * kSDim;
+  for (int j0 = 0; j0 < r; j0 += kQuadJ) {
+    __syncthreads();
+    // norms of the columns j0..j0+7 (one warp per column), then scatter the unit vectors
+    if (wib < kQuadJ) {
+      float s = 0.f;
+      if (j0 + wib < r) {
+        const float* col = G + (int64_t)(j0 + wib) * kSLd;
+        for (int i = lane; i < kSDim; i += 32) s = fmaf(col[i], col[i], s);
+      }
+      s = warp_sum(s);
+      if (lane == 0) s_lam[wib] = s;
+    }
+    __syncthreads();
+    if (tid < kSDim) {
+      const int orig = perm[tid];
+#pragma unroll
+      for (int jj = 0; jj < kQuadJ; ++jj) {
+        const float lam = s_lam[jj];
+        s_u[orig][jj] = (j0 + jj < r && lam > 0.f) ? G[(int64_t)(j0 + jj) * kSLd + tid] * rsqrtf(lam) : 0.f;
+      }
+    }
+    __syncthreads();
+    float axy[kQuadJ], ayy[kQuadJ];
+#pragma unroll
+    for (int jj = 0; jj < kQuadJ; ++jj) axy[jj] = ayy[jj] = 0.f;
+    if (tid < kSDim) {
+#pragma unroll 2
+      for (int c = 0; c < kSDim; ++c) {
+        const float sxy = __ldg(Sxy + (int64_t)c * kSDim + tid), syy = __ldg(Syy + (int64_t)c * kSDim + tid);
+        const float4 u0 = *reinterpret_cast<const float4*>(&s_u[c][0]);
+        const float4 u1 = *reinterpret_cast<const float4*>(&s_u[c][4]);
+        const float uu[kQuadJ] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+        for (int jj = 0; jj < kQuadJ; ++jj) {
+          axy[jj] = fmaf(sxy, uu[jj], axy[jj]);
+          ayy[jj] = fmaf(syy, uu[jj], ayy[jj]);
+        }
+      }
+      // (u^T S)_i u_i
+#pragma unroll
+      for (int jj = 0; jj < kQuadJ; ++jj) {
+        axy[jj] *= s_u[tid][jj];
+        ayy[jj] *= s_u[tid][jj];
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < kQuadJ; ++jj) {
+      const float a = warp_sum(axy[jj]), c = warp_sum(ayy[jj]);
+      if (lane == 0) {
+        s_part[wib][jj] = a;
+        s_part[wib][kQuadJ + jj] = c;
+      }
+    }
+    __syncthreads();
+    if (tid < kQuadJ && j0 + tid < r) {
+      double a = 0.0, c = 0.0;
+      for (int w = 0; w < NW; ++w) {
+        a += (double)s_part[w][tid];
+        c += (double)s_part[w][kQuadJ + tid];
+      }
+      const double lam = (double)s_lam[tid];
+      double rho = 0.0;
+      if (lam > 0.0 && c > 0.0) rho = a / sqrt(lam * c);
+      if (rho > 1.0) rho = 1.0;
+      if (rho < -1.0) rho = -1.0;
+      const double pr = 0.75 * rho;
+      atomicAdd(&s_info, -0.5 * log2(1.0 - pr * pr));
+      lam_out[j0 + tid] = (float)lam;
+      rho_out[j0 + tid] = (float)rho;
+    }
+  }
+  __syncthreads();
+  for (int j = r + tid; j < kSDim; j += kQuadThreads) {
+    lam_out[j] = 0.f;
+    rho_out[j] = 0.f;
+  }
+  if (tid == 0) {
+    const double R = 1.0 / 200.0 * 16000.0;
+    const double v = R / (double)kSStack * s_info;
+    b.score[pair] = v > 0.0 ? v : 0.0;
+    b.status[pair] = 0;
+  }
+}
+
+// ------------------------------------------------------------- launchers
+void siib_upload_tables(const float* win, const float* decay, const float* g2t, const float* tw, cudaStream_t s) {
+  cudaMemcpyToSymbolAsync(c_siib_win, win, sizeof(float) * kSWin, 0, cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(c_siib_decay, decay, sizeof(float) * kSMaskT, 0, cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(g_siib_g2t, g2t, sizeof(float) * kSBins * kSLanes, 0, cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(g_siib_tw, tw, sizeof(float) * 2 * kSWin, 0, cudaMemcpyHostToDevice, s);
+  cudaFuncSetAttribute(siib_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpecSmem));
+  cudaStreamSynchronize(s);
+}
+
+int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_tile, KernelTimer* kt, cudaStream_t s) {
+  kt_begin(kt, "siib_wrapvad", s);
+  siib_wrapvad_kernel<<<n, kVadThreads, 0, s>>>(g, b, no_tile ? 1 : 0);
+  kt_end(kt, s);
+  return 1;
+}
+
+int siib_run(const SiibGeom& g, const SiibBuffers& b, int n, int64_t max_F, KernelTimer* kt, cudaStream_t s) {
+  int launches = 0;
+  kt_begin(kt, "siib_vad", s);
+  siib_vad_kernel<<<n, kVadThreads, 0, s>>>(g, b);
+  kt_end(kt, s);
+  ++launches;
+  if (max_F > 0) {
+    kt_begin(kt, "siib_spec", s);
+    siib_spec_kernel<<<dim3((unsigned)((max_F + kSpecWarps - 1) / kSpecWarps), n), kSpecWarps * 32, sizeof(SpecSmem), s>>>(g, b);
+    kt_end(kt, s);
+    ++launches;
+  }
+  kt_begin(kt, "siib_mask", s);
+  siib_mask_kernel<<<(2 * n + 3) / 4, 128, 0, s>>>(g, b, 2 * n);
+  kt_end(kt, s);
+  ++launches;
+  kt_begin(kt, "siib_cov", s);
+  siib_cov_kernel<<<dim3((kSBlocks + kCovWarps - 1) / kCovWarps, n), kCovWarps * 32, 0, s>>>(g, b);
+  kt_end(kt, s);
+  ++launches;
+  kt_begin(kt, "siib_expand", s);
+  siib_expand_kernel<<<n, kExpThreads, 0, s>>>(g, b);
+  kt_end(kt, s);
+  ++launches;
+  kt_begin(kt, "siib_chol", s);
+  siib_chol_kernel<<<n, kCholThreads, 0, s>>>(g, b);
+  kt_end(kt, s);
+  ++launches;
+  kt_begin(kt, "siib_jacobi", s);
+  siib_jacobi_kernel<<<n, kJacWarps * 32, 0, s>>>(g, b);
+  kt_end(kt, s);
+  ++launches;
+  kt_begin(kt, "siib_quad", s);
+  siib_quad_kernel<<<n, kQuadThreads, 0, s>>>(g, b);
+  kt_end(kt, s);
+  ++launches;
+  return launches;
+}
+
+}  // namespace nele

@@ -22,7 +22,7 @@ _METRIC_BITS = {"haspi": METRIC_HASPI, "siib": METRIC_SIIB, "estoi": METRIC_ESTO
 COL_SIIB, COL_HASPI, COL_ESTOI = 0, 1, 2
 
 SYMBOLS = ("nele_abi_version", "nele_create", "nele_destroy", "nele_last_error", "nele_score_batch",
-           "nele_get_stage", "nele_last_timing")
+           "nele_get_stage", "nele_last_timing", "nele_set_profiling", "nele_kernel_time")
 
 
 class NeleError(RuntimeError):
@@ -60,6 +60,11 @@ def load_library(path=None):
         lib.nele_get_stage.restype = C.c_int
         lib.nele_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         lib.nele_last_timing.restype = C.c_int
+        lib.nele_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        lib.nele_set_profiling.restype = C.c_int
+        lib.nele_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_int64)]
+        lib.nele_kernel_time.restype = C.c_int
         if path is None:
             _lib = lib
         return lib
@@ -193,12 +198,26 @@ class Engine:
         self._check(self._lib.nele_last_timing(self._h, C.byref(ms), C.byref(nl)), "nele_last_timing")
         return ms.value, nl.value
 
+    def set_profiling(self, on=True):
+        """Bracket every kernel launch of the following calls with CUDA events."""
+        self._check(self._lib.nele_set_profiling(self._h, 1 if on else 0), "nele_set_profiling")
+
+    def kernel_times(self):
+        """{kernel name: (summed ms, launches)} of the last call made with profiling on."""
+        out, i = {}, 0
+        name, ms, nl = C.c_char_p(), C.c_double(), C.c_int64()
+        while self._lib.nele_kernel_time(self._h, i, C.byref(name), C.byref(ms), C.byref(nl)) == 0:
+            out[name.value.decode()] = (ms.value, nl.value)
+            i += 1
+        return out
+
     _STAGE_DTYPES = {"haspi.mid": np.float64, "haspi.x24": np.float32, "haspi.bw": np.float64,
                      "haspi.shift": np.int32, "haspi.envlp": np.float32, "haspi.nsel": np.int32,
-                     "haspi.cep": np.float32, "haspi.cepmean": np.float64, "estoi.x10": np.float64,
-                     "estoi.tob": np.float64, "estoi.info": np.int32, "siib.tile": np.int32,
-                     "siib.logspec": np.float32, "siib.lambda": np.float32, "siib.rho": np.float32,
-                     "siib.cov": np.float32}
+                     "haspi.cep": np.float32, "haspi.cepmean": np.float64, "estoi.x10": np.float32,
+                     "estoi.tob": np.float32, "estoi.info": np.int32, "estoi.kept": np.int32,
+                     "siib.tile": np.int32, "siib.logspec": np.float32, "siib.lambda": np.float32,
+                     "siib.rho": np.float32, "siib.rank": np.int32, "siib.sxx": np.float64,
+                     "siib.sxy": np.float32, "siib.syy": np.float32}
 
     def stage(self, name, pair=0):
         """Flat array of stage ``name`` for ``pair`` of the last keep_stages call."""

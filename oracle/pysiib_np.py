@@ -129,7 +129,7 @@ def mi_ksg(x, y, k):
     return nats / np.log(2)
 
 
-def siib_features(x, y, window_length=400, window_shift=200, window='hanning', delta_dB=40.0):
+def siib_features(x, y, window_length=400, window_shift=200, window='hanning', delta_dB=40.0, stages=None):
     """Steps 1-5 up to (not including) the KLT: returns stacked X, Y and R."""
     R = 1 / window_shift * FS
     x = x - np.mean(x)
@@ -151,6 +151,8 @@ def siib_features(x, y, window_length=400, window_shift=200, window='hanning', d
     Y = forward_masking(Y, Tf)
     X = X - X.mean(axis=1, keepdims=True)
     Y = Y - Y.mean(axis=1, keepdims=True)
+    if stages is not None:
+        stages.update(vad=vad, X=X, Y=Y)
     return stack_frames(X, K_STACK), stack_frames(Y, K_STACK), R
 
 
@@ -167,7 +169,7 @@ def SIIB(x, y, fs_signal, gauss=False, use_MI_Kraskov=True, window_length=400,
         g = math.gcd(int(FS), int(fs_signal))
         x = resample_poly(x, FS // g, int(fs_signal) // g)
         y = resample_poly(y, FS // g, int(fs_signal) // g)
-    Xs, Ys, R = siib_features(x, y, window_length, window_shift, window, delta_dB)
+    Xs, Ys, R = siib_features(x, y, window_length, window_shift, window, delta_dB, stages=stages)
     lam, U = np.linalg.eigh(np.cov(Xs))
     Xk = U.T @ Xs
     Yk = U.T @ Ys
@@ -182,5 +184,5 @@ def SIIB(x, y, fs_signal, gauss=False, use_MI_Kraskov=True, window_length=400,
         cap = -0.5 * np.log2(1 - RHO_P ** 2)
         I_ch = np.array([min(mi_ksg(Xk[j], Yk[j], k), cap) for j in range(Xk.shape[0])])
     if stages is not None:
-        stages.update(nf=Xs.shape[1], lam=lam, I_ch=I_ch)
+        stages.update(nf=Xs.shape[1], lam=lam, I_ch=I_ch, rho=rho if gauss else None)
     return max(0.0, R / K_STACK * float(np.sum(I_ch)))
