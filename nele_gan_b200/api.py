@@ -1,0 +1,246 @@
+"""Host-side mirror of the reference's metric interface, on the CUDA engine.
+
+Same names, argument order, defaults and return types as the reference
+callables this path replaces:
+
+  pyHASPI/pyhaspi2.py:76     haspi_v2(x, fx, y, fy, HL=np.zeros(6)) -> (Intel, raw[10])
+  pysiib (intel.py:77,100)   SIIB(x, y, fs, gauss=True)            -> float
+  pystoi (intel.py:126,133)  stoi(x, y, fs, extended=True)         -> float
+  intel.py:57-140            {SIIB,HASPI,ESTOI}_Wrapper[_raw]_harvard(x, y, fs), mapping_*_harvard
+  audio_util.py:120-203      read_batch_{STOI,SIIB,HASPI}(clean_root, noise_root, enhanced_list, norm=True)
+  audio_util.py:267-321      read_batch_{STOI,SIIB,HASPI}_DRC(clean_root, noise_root, enhanced_list)
+
+Every call goes through ``libnele_score.so`` (include/nele_score.h); there is
+no numpy implementation of any metric here, and nothing under ``oracle/`` is
+imported.  The per-pair functions are thin (one pair per engine call); the
+``read_batch_*`` functions and :func:`score_batch` score a whole list in one
+call, which is what the engine is built for.
+"""
+import os
+import warnings
+
+import numpy as np
+
+from . import engine as _eng
+
+__all__ = ["haspi_v2", "haspi", "SIIB", "stoi", "score_batch",
+           "SIIB_Wrapper_harvard", "SIIB_Wrapper_raw_harvard", "mapping_SIIB_harvard",
+           "HASPI_Wrapper_harvard", "HASPI_Wrapper_raw_harvard", "mapping_HASPI_harvard",
+           "ESTOI_Wrapper_harvard", "ESTOI_Wrapper_raw_harvard", "mapping_ESTOI_harvard",
+           "read_batch_STOI", "read_batch_SIIB", "read_batch_HASPI",
+           "read_batch_STOI_DRC", "read_batch_SIIB_DRC", "read_batch_HASPI_DRC"]
+
+fs = 16000  # audio_util.py:10
+
+
+def _engine():
+    return _eng.default_engine()
+
+
+def _f32(x):
+    return np.ascontiguousarray(np.asarray(x), dtype=np.float32)
+
+
+# ------------------------------------------------------------------ HASPI
+def haspi_v2(x, fx, y, fy, HL=np.zeros(6), seed=None):
+    """pyhaspi2.py:76-107.  Returns ``(Intel, raw)`` with ``raw`` the ten
+    modulation-band correlations.  The reference draws its 0.1 dB cepstral
+    dither from the global numpy stream (pyhaspi2.py:362-365); here it comes
+    from a counter-based generator keyed by ``seed`` (default: drawn from
+    ``np.random`` so that ``np.random.seed`` makes calls reproducible, as it
+    does for the reference)."""
+    if fx != fy:
+        raise ValueError("haspi_v2: the engine needs fx == fy (got %r, %r)" % (fx, fy))
+    if fx > 24000:
+        raise NotImplementedError  # pyhaspi2.py:819-820
+    x, y = _f32(x), _f32(y)
+    L = min(len(x), len(y))
+    if seed is None:
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+    hl = np.asarray(HL, dtype=np.float64)
+    r = _engine().score_batch([x[:L]], [y[:L]], fs=int(fx), metrics=("haspi",), mapped=False, seed=seed,
+                              hl=None if not hl.any() else hl)
+    if r.metric_status("haspi")[0] == _eng.ST_BELOW_THR:
+        raise Exception('Function ebm_CepCoef: Signal below threshold')  # pyhaspi2.py:357-358
+    return np.float64(r.haspi[0]), r.haspi_raw[0].copy()
+
+
+def haspi(x, fx, y, fy, HL=np.zeros(6), alpha=-1.0):
+    """pyhaspi2.py:109-157 (HASPI version 1).  Not on the NELE-GAN labelling path
+    (intel.py uses haspi_v2 only); its fine-structure back-end is the next row
+    of the scope table and is not built yet."""
+    raise NotImplementedError("haspi (v1) is not built yet; NELE-GAN's labelling path calls haspi_v2")
+
+
+# ------------------------------------------------------------------- SIIB
+def SIIB(x, y, fs_signal, gauss=False, use_MI_Kraskov=True, window_length=400, window_shift=200,
+         window='hanning', delta_dB=40.0):
+    """pysiib.SIIB.  NELE-GAN always passes ``gauss=True`` (intel.py:77,100):
+    SIIB^Gauss, which is what the engine computes.  No tiling here -- that is
+    the wrapper's job (intel.py:71-75) -- so fewer than 20 s of active speech
+    raises like pysiib does."""
+    if not gauss:
+        raise NotImplementedError("SIIB with the k-NN estimator (gauss=False) is not built; "
+                                  "NELE-GAN's labelling path uses gauss=True")
+    if (window_length, window_shift, window, delta_dB) != (400, 200, 'hanning', 40.0):
+        raise NotImplementedError("only pysiib's default analysis parameters are supported")
+    x, y = _f32(x), _f32(y)
+    if x.shape != y.shape:
+        raise ValueError('x and y should have the same length')
+    r = _engine().score_batch([x], [y], fs=int(fs_signal), metrics=("siib",), mapped=False, siib_no_tile=True)
+    st = r.metric_status("siib")[0]
+    if st == _eng.ST_TOO_SHORT:
+        raise ValueError('stimuli must have at least 20 seconds of speech')
+    if st == _eng.ST_BAD_RATE:
+        raise NotImplementedError("SIIB: only 16 kHz input is supported (audio_util.py:131 asserts it)")
+    return float(r.siib[0])
+
+
+# ------------------------------------------------------------------ ESTOI
+def stoi(x, y, fs_sig, extended=False):
+    """pystoi.stoi.  NELE-GAN always passes ``extended=True`` (intel.py:126,133)."""
+    if not extended:
+        raise NotImplementedError("classic STOI is not built; NELE-GAN's labelling path uses extended=True")
+    x, y = np.asarray(x), np.asarray(y)
+    if x.shape != y.shape:
+        raise Exception('x and y should have the same length,' + 'found {} and {}'.format(x.shape, y.shape))
+    r = _engine().score_batch([_f32(x)], [_f32(y)], fs=int(fs_sig), metrics=("estoi",), mapped=False)
+    if r.metric_status("estoi")[0] == _eng.ST_TOO_SHORT:
+        warnings.warn('Not enough STFT frames to compute intermediate intelligibility measure after removing '
+                      'silent frames. Returning 1e-5. Please check you wav files', RuntimeWarning)
+    return float(r.estoi[0])
+
+
+# --------------------------------------------------- intel.py wrappers
+def mapping_SIIB_harvard(x):      # intel.py:102-106
+    return 1 / (1 + np.exp(-0.06 * (x - 32)))
+
+
+def mapping_HASPI_harvard(x):     # intel.py:116-120
+    return 1 / (1 + np.exp(-0.95 * (x - 2.8)))
+
+
+def mapping_ESTOI_harvard(x):     # intel.py:136-140
+    return 1 / (1 + np.exp(-8.0 * (x - 0.25)))
+
+
+def _one(metric, x, y, fs_, mapped):
+    r = _engine().score_batch([_f32(x)], [_f32(y)], fs=int(fs_), metrics=(metric,), mapped=mapped,
+                              seed=int(np.random.randint(0, 2 ** 31 - 1)))
+    return r
+
+
+def SIIB_Wrapper_raw_harvard(x, y, fs):      # intel.py:57-77 (VAD, tile to >= 25 s, SIIB^Gauss)
+    return float(_one("siib", x, y, fs, False).siib[0])
+
+
+def SIIB_Wrapper_harvard(x, y, fs):          # intel.py:79-100
+    return float(_one("siib", x, y, fs, True).siib[0])
+
+
+def HASPI_Wrapper_raw_harvard(x, y, fs):     # intel.py:112-114
+    return float(_one("haspi", x, y, fs, False).haspi[0])
+
+
+def HASPI_Wrapper_harvard(x, y, fs):         # intel.py:108-110
+    return float(_one("haspi", x, y, fs, True).haspi[0])
+
+
+def ESTOI_Wrapper_raw_harvard(x, y, fs):     # intel.py:122-127
+    return float(_one("estoi", x, y, fs, False).estoi[0])
+
+
+def ESTOI_Wrapper_harvard(x, y, fs):         # intel.py:129-134
+    return float(_one("estoi", x, y, fs, True).estoi[0])
+
+
+# ------------------------------------------------------- batched forms
+def score_batch(refs, degs, fs=16000, metrics=("siib", "haspi", "estoi"), norm=True, seed=0, **kw):
+    """All labels of a list of (clean, degraded) pairs in one engine call.
+    Returns ``float64[n, 3]`` in the column order {SIIB, HASPI, ESTOI} that
+    train_nele.py:320-322 computes and audio_util.py:367-389 serialises."""
+    return _engine().score_batch(refs, degs, fs=fs, metrics=metrics, mapped=norm, seed=seed, **kw).scores
+
+
+def _load16k(path):
+    """``librosa.load(path, sr=16000)`` for the 16 kHz PCM WAV files the
+    reference writes (train_nele.py:313) and asserts on (audio_util.py:131)."""
+    from scipy.io import wavfile
+    sr, x = wavfile.read(path)
+    assert sr == 16000
+    if x.dtype == np.int16:
+        return x.astype(np.float32) / 32768.0
+    if x.dtype == np.int32:
+        return (x.astype(np.float64) / 2147483648.0).astype(np.float32)
+    return x.astype(np.float32)
+
+
+def _wave_name(enhanced_file, drc):
+    f = enhanced_file.split('/')[-1]
+    if drc:
+        return f                                     # audio_util.py:268-269
+    return (f.split('@')[0] if '@' in f else f[:-4]) + '.wav'   # audio_util.py:121-126
+
+
+def _read_pairs(clean_root, noise_root, enhanced_list, drc):
+    refs, degs = [], []
+    for en in enhanced_list:
+        name = _wave_name(en, drc)
+        clean, noise, enh = _load16k(clean_root + name), _load16k(noise_root + name), _load16k(en)
+        m = min(len(clean), len(enh))                # audio_util.py:134-137
+        refs.append(clean[:m])
+        degs.append(enh[:m] + noise[:m])
+    return refs, degs
+
+
+def _read_batch(metric, col, clean_root, noise_root, enhanced_list, norm, drc):
+    if not len(enhanced_list):
+        return []
+    refs, degs = _read_pairs(clean_root, noise_root, list(enhanced_list), drc)
+    r = _engine().score_batch(refs, degs, fs=fs, metrics=(metric,), mapped=bool(norm),
+                              seed=int(np.random.randint(0, 2 ** 31 - 1)))
+    return [float(v) for v in r.scores[:, col]]
+
+
+def read_batch_STOI(clean_root, noise_root, enhanced_list, norm=True):      # audio_util.py:145-147
+    return _read_batch("estoi", _eng.COL_ESTOI, clean_root, noise_root, enhanced_list, norm, False)
+
+
+def read_batch_SIIB(clean_root, noise_root, enhanced_list, norm=True):      # audio_util.py:173-175
+    return _read_batch("siib", _eng.COL_SIIB, clean_root, noise_root, enhanced_list, norm, False)
+
+
+def read_batch_HASPI(clean_root, noise_root, enhanced_list, norm=True):     # audio_util.py:201-203
+    return _read_batch("haspi", _eng.COL_HASPI, clean_root, noise_root, enhanced_list, norm, False)
+
+
+def read_batch_STOI_DRC(clean_root, noise_root, enhanced_list):             # audio_util.py:281-283
+    return _read_batch("estoi", _eng.COL_ESTOI, clean_root, noise_root, enhanced_list, True, True)
+
+
+def read_batch_SIIB_DRC(clean_root, noise_root, enhanced_list):             # audio_util.py:300-302
+    return _read_batch("siib", _eng.COL_SIIB, clean_root, noise_root, enhanced_list, True, True)
+
+
+def read_batch_HASPI_DRC(clean_root, noise_root, enhanced_list):            # audio_util.py:319-321
+    return _read_batch("haspi", _eng.COL_HASPI, clean_root, noise_root, enhanced_list, True, True)
+
+
+def read_batch_all(clean_root, noise_root, enhanced_list, norm=True, drc=False, seed=None):
+    """The three read_batch_* calls of one sampling round (train_nele.py:320-322
+    or :333-335) fused: the WAV files are read once and scored in one engine
+    call.  Returns ``(siib, haspi, estoi)`` lists."""
+    if not len(enhanced_list):
+        return [], [], []
+    refs, degs = _read_pairs(clean_root, noise_root, list(enhanced_list), drc)
+    if seed is None:
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+    s = _engine().score_batch(refs, degs, fs=fs, mapped=bool(norm), seed=seed).scores
+    return [float(v) for v in s[:, 0]], [float(v) for v in s[:, 1]], [float(v) for v in s[:, 2]]
+
+
+def dropin_path():
+    """Directory to put in front of ``sys.path`` so that the reference's own
+    ``intel.py`` / ``audio_util.py`` import the engine-backed ``pyHASPI.pyhaspi2``,
+    ``pysiib`` and ``pystoi.stoi``."""
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")

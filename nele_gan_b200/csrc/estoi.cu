@@ -19,7 +19,7 @@ namespace nele {
 
 constexpr int kStoiFrame = 256, kStoiHop = 128, kStoiFft = 512, kStoiBands = 15, kStoiSeg = 30;
 
-__constant__ float c_stoi_win[kStoiFrame];     // MATLAB hanning(256)
+__device__ float g_stoi_win[kStoiFrame];       // MATLAB hanning(256); staged in shared memory by its users
 __constant__ int c_stoi_lo[kStoiBands], c_stoi_hi[kStoiBands];
 __device__ float2 g_stoi_tw[kStoiFft / 2];     // exp(-2 pi i k / 512)
 
@@ -72,10 +72,13 @@ __global__ void __launch_bounds__(kVadThreads) estoi_vad_kernel(EstoiGeom g, Est
   __shared__ double red[32];
   __shared__ int s_cnt[NW];
   __shared__ int s_base;
+  __shared__ float s_win[kStoiFrame];
   if (nfa <= 0) {
     if (tid == 0) b.nkept[pair] = 0;
     return;
   }
+  s_win[tid] = g_stoi_win[tid];
+  __syncthreads();
   double mx = -1.0e300;
   for (int f = wib; f < nfa; f += NW) {
     const float* fr = x + (int64_t)f * kStoiHop;
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(kVadThreads) estoi_vad_kernel(EstoiGeom g, Est
 #pragma unroll
     for (int k = 0; k < kStoiFrame / 32; ++k) {
       const int i = k * 32 + lane;
-      const double v = (double)c_stoi_win[i] * (double)fr[i];
+      const double v = (double)s_win[i] * (double)fr[i];
       ss += v * v;
     }
     ss = warp_sum(ss);
@@ -133,7 +136,11 @@ __global__ void __launch_bounds__(kTobWarps * 32) estoi_tob_kernel(EstoiGeom g, 
   const int nfr = nk - 1;  // STFT frames of the silence-removed signal
   __shared__ float2 s_z[kTobWarps][kStoiFft];
   __shared__ float2 s_tw[kStoiFft / 2];
-  for (int k = threadIdx.x; k < kStoiFft / 2; k += kTobWarps * 32) s_tw[k] = g_stoi_tw[k];
+  __shared__ float s_win[kStoiFrame];
+  for (int k = threadIdx.x; k < kStoiFft / 2; k += kTobWarps * 32) {
+    s_tw[k] = g_stoi_tw[k];
+    s_win[k] = g_stoi_win[k];
+  }
   __syncthreads();
   const int m = blockIdx.x * kTobWarps + wib;
   if (m >= nfr) return;
@@ -148,16 +155,16 @@ __global__ void __launch_bounds__(kTobWarps * 32) estoi_tob_kernel(EstoiGeom g, 
 #pragma unroll
   for (int k = 0; k < kStoiFrame / 32; ++k) {
     const int i = k * 32 + lane;
-    const float w = c_stoi_win[i];
+    const float w = s_win[i];
     float vx = w * x[sc + i], vy = w * y[sc + i];
     if (i < kStoiHop) {
       if (sp >= 0) {
-        const float w2 = c_stoi_win[i + kStoiHop];
+        const float w2 = s_win[i + kStoiHop];
         vx = fmaf(w2, x[sp + i + kStoiHop], vx);
         vy = fmaf(w2, y[sp + i + kStoiHop], vy);
       }
     } else {
-      const float w2 = c_stoi_win[i - kStoiHop];
+      const float w2 = s_win[i - kStoiHop];
       vx = fmaf(w2, x[sn + i - kStoiHop], vx);
       vy = fmaf(w2, y[sn + i - kStoiHop], vy);
     }
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__(kCorrThreads) estoi_corr_kernel(EstoiGeom g, E
 
 // ------------------------------------------------------------- launchers
 void estoi_upload_tables(const float* win, const int* lo, const int* hi, const float* tw /*[256][2]*/, cudaStream_t s) {
-  cudaMemcpyToSymbolAsync(c_stoi_win, win, sizeof(float) * kStoiFrame, 0, cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(g_stoi_win, win, sizeof(float) * kStoiFrame, 0, cudaMemcpyHostToDevice, s);
   cudaMemcpyToSymbolAsync(c_stoi_lo, lo, sizeof(int) * kStoiBands, 0, cudaMemcpyHostToDevice, s);
   cudaMemcpyToSymbolAsync(c_stoi_hi, hi, sizeof(int) * kStoiBands, 0, cudaMemcpyHostToDevice, s);
   cudaMemcpyToSymbolAsync(g_stoi_tw, tw, sizeof(float) * kStoiFft, 0, cudaMemcpyHostToDevice, s);

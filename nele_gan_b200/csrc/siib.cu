@@ -32,8 +32,12 @@
 // Rank-deficient inputs (a tiled signal whose length is a multiple of the 200-sample hop
 // repeats its frames exactly) stop the Cholesky early; the null space contributes zero
 // information, which is the exact-arithmetic value of the reference formula.
+#include <cooperative_groups.h>
+
 #include "fft400.cuh"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace nele {
 
@@ -44,7 +48,8 @@ constexpr int kSBlocks = 59;              // xx d=0..14, yy d=0..14, xy d=-14..1
 constexpr int kSMaskT = 16;               // floor(0.2 s * 80 frames/s)
 constexpr double kEps = 2.220446049250313e-16;
 
-__constant__ float c_siib_win[kSWin];     // periodic Hann(400)
+__device__ float g_siib_win[kSWin];       // periodic Hann(400); staged in shared memory by its users
+                                          // (lane-indexed reads of __constant__ data serialise)
 __constant__ float c_siib_decay[kSMaskT];  // log(d + 1) / log(16)
 __device__ float g_siib_g2t[kSBins * kSLanes];  // squared gammatone responses, [bin][band]
 __device__ cpx g_siib_tw[kSWin];
@@ -52,7 +57,7 @@ __device__ cpx g_siib_tw[kSWin];
 // ---------------------------------------------------------------- VAD helpers
 // power (dB) of Hann frame f of (x - mean); wrap = tiled signal, else zero padded
 __device__ __forceinline__ double frame_power_db(const float* __restrict__ x, int L, double mean, int64_t f,
-                                                 bool wrap, int lane) {
+                                                 bool wrap, int lane, const float* __restrict__ win) {
   const int64_t s0 = f * kSHop;
   int64_t base = wrap ? (s0 % L) : s0;
   double ss = 0.0;
@@ -65,7 +70,7 @@ __device__ __forceinline__ double frame_power_db(const float* __restrict__ x, in
     } else {
       v = (idx < L) ? (double)x[idx] - mean : 0.0;
     }
-    v *= (double)c_siib_win[i];
+    v *= (double)win[i];
     ss += v * v;
   }
   ss = warp_sum(ss);
@@ -140,8 +145,11 @@ __global__ void __launch_bounds__(kVadThreads) siib_wrapvad_kernel(SiibGeom g, S
   double* __restrict__ db = b.wrapdb + g.offW[pair];
   __shared__ double red[32];
   __shared__ int64_t redi[32];
+  __shared__ float s_win[kSWin];
+  for (int i = tid; i < kSWin; i += kVadThreads) s_win[i] = g_siib_win[i];
+  __syncthreads();
   for (int f = wib; f < F1; f += NW) {
-    const double d = frame_power_db(x, L, 0.0, f, false, lane);
+    const double d = frame_power_db(x, L, 0.0, f, false, lane, s_win);
     if (lane == 0) db[f] = d;
   }
   __syncthreads();
@@ -171,10 +179,12 @@ __global__ void __launch_bounds__(kVadThreads) siib_vad_kernel(SiibGeom g, SiibB
   __shared__ int64_t redi[32];
   __shared__ int s_cnt[NW];
   __shared__ int s_base;
+  __shared__ float s_win[kSWin];
   if (F <= 0) {
     if (tid == 0) b.Fa[pair] = 0;
     return;
   }
+  for (int i = tid; i < kSWin; i += kVadThreads) s_win[i] = g_siib_win[i];
   double sx = 0.0, sy = 0.0;
   for (int i = tid; i < L; i += kVadThreads) {
     sx += (double)x[i];
@@ -188,7 +198,7 @@ __global__ void __launch_bounds__(kVadThreads) siib_vad_kernel(SiibGeom g, SiibB
     b.mean[2 * pair + 1] = my;
   }
   for (int64_t f = wib; f < F; f += NW) {
-    const double d = frame_power_db(x, L, mx, f, true, lane);
+    const double d = frame_power_db(x, L, mx, f, true, lane, s_win);
     if (lane == 0) db[f] = d;
   }
   __syncthreads();
@@ -225,6 +235,7 @@ __global__ void __launch_bounds__(kVadThreads) siib_vad_kernel(SiibGeom g, SiibB
 constexpr int kSpecWarps = 8;
 struct SpecSmem {
   cpx tw[kSWin];
+  float win[kSWin];
   float g2t[kSBins * kSLanes];
   cpx z[kSpecWarps][kSWin];
   cpx t[kSpecWarps][kSWin];
@@ -236,7 +247,10 @@ __global__ void __launch_bounds__(kSpecWarps * 32) siib_spec_kernel(SiibGeom g, 
   if (blockIdx.x * kSpecWarps >= Fa) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SpecSmem& sm = *reinterpret_cast<SpecSmem*>(smem_raw);
-  for (int k = threadIdx.x; k < kSWin; k += kSpecWarps * 32) sm.tw[k] = g_siib_tw[k];
+  for (int k = threadIdx.x; k < kSWin; k += kSpecWarps * 32) {
+    sm.tw[k] = g_siib_tw[k];
+    sm.win[k] = g_siib_win[k];
+  }
   for (int k = threadIdx.x; k < kSBins * kSLanes; k += kSpecWarps * 32) sm.g2t[k] = g_siib_g2t[k];
   __syncthreads();
   const int t = blockIdx.x * kSpecWarps + wib;
@@ -252,7 +266,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32) siib_spec_kernel(SiibGeom g, 
   for (int i = lane; i < kSWin; i += 32) {
     int64_t idx = base + i;
     if (idx >= L) idx %= L;
-    const float w = c_siib_win[i];
+    const float w = sm.win[i];
     z[i] = {w * (x[idx] - mx), w * (y[idx] - my)};
   }
   __syncwarp();
@@ -429,10 +443,16 @@ __global__ void __launch_bounds__(kExpThreads) siib_expand_kernel(SiibGeom g, Si
 }
 
 // --------------------------------------------------------------- Cholesky
+// Diagonally pivoted Cholesky in FP64, blocked right-looking (LAPACK dpstrf's scheme): the
+// current panel of 32 columns of L lives in shared memory, each elimination step costs one
+// block barrier, one coalesced row of the trailing matrix and a <= 31-term dot product from
+// shared memory, and the trailing matrix is updated once per panel (420^2 * 8 B read + write
+// per panel instead of re-reading every earlier column of L at every step).  Rows are never
+// permuted: thread a owns original row a; only the order in which pivots are taken defines the
+// columns of L, and the one-sided Jacobi that follows does not care about the row order.
 constexpr int kCholThreads = 448;
+constexpr int kCholW = 32;
 
-// Thread i owns position i of the permuted index space: its permutation entry, its running
-// diagonal (Schur complement) and column i of Lc.  Two block barriers per elimination step.
 __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, SiibBuffers b) {
   const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   constexpr int NW = kCholThreads / 32;
@@ -442,27 +462,26 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
     if (tid == 0) b.rank[pair] = 0;
     return;
   }
-  const double* __restrict__ A = b.Sxx + (int64_t)lp * kSDim * kSDim;
-  double* __restrict__ Lc = b.Lc + (int64_t)lp * kSDim * kSDim;  // Lc[m][i] = L[i][m]
-  int32_t* __restrict__ gperm = b.perm + (int64_t)lp * kSDim;
-  __shared__ int s_perm[kSDim];
-  __shared__ double s_dg[kSDim];
-  __shared__ double s_row[kSDim];  // L[k][0..k)
+  const double* __restrict__ A0 = b.Sxx + (int64_t)lp * kSDim * kSDim;
+  double* __restrict__ W = b.Lc + (int64_t)lp * kSDim * kSDim;  // trailing matrix after the first panel
+  extern __shared__ __align__(16) double s_panel[];              // Lp[m][a], m < 32, a < 420
   __shared__ double s_rv[2][NW];
   __shared__ int s_ri[2][NW];
+  __shared__ unsigned char s_done[kSDim];
   const bool own = tid < kSDim;
-  int myperm = tid;
-  double mydg = own ? A[(int64_t)tid * kSDim + tid] : -1.0e300;
+  bool done = false;
+  double mydg = own ? A0[(int64_t)tid * kSDim + tid] : -1.0e300;
+  if (own) s_done[tid] = 0;
   double tol = 0.0;
   int rank = kSDim;
-  for (int k = 0; k < kSDim; ++k) {
-    // publish, then pick the largest remaining diagonal (every thread redundantly)
-    if (own) {
-      s_perm[tid] = myperm;
-      s_dg[tid] = mydg;
-    }
-    {
-      double v = (own && tid >= k) ? mydg : -1.0e300;
+  bool stop = false;
+  for (int k0 = 0; k0 < kSDim && !stop; k0 += kCholW) {
+    const double* __restrict__ As = (k0 == 0) ? A0 : W;
+    const int kb = min(kCholW, kSDim - k0);
+    int j = 0;
+    for (; j < kb; ++j) {
+      const int k = k0 + j;
+      double v = (own && !done) ? mydg : -1.0e300;
       int vi = tid;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -477,81 +496,74 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
         s_rv[k & 1][wib] = v;
         s_ri[k & 1][wib] = vi;
       }
-    }
-    __syncthreads();
-    double piv = s_rv[k & 1][0];
-    int p = s_ri[k & 1][0];
+      __syncthreads();  // also orders the previous step's panel writes before this step's reads
+      double piv = s_rv[k & 1][0];
+      int astar = s_ri[k & 1][0];
 #pragma unroll
-    for (int w = 1; w < NW; ++w) {
-      const double ov = s_rv[k & 1][w];
-      const int oi = s_ri[k & 1][w];
-      if (ov > piv || (ov == piv && oi < p)) {
-        piv = ov;
-        p = oi;
-      }
-    }
-    if (k == 0) tol = piv * 1.0e-10;
-    if (!(piv > tol)) {
-      rank = k;
-      break;
-    }
-    // symmetric interchange k <-> p; s_row = row k of L after the interchange
-    if (tid < k) {
-      const double vp = Lc[(int64_t)tid * kSDim + p];
-      if (p != k) {
-        Lc[(int64_t)tid * kSDim + p] = Lc[(int64_t)tid * kSDim + k];
-        Lc[(int64_t)tid * kSDim + k] = vp;
-      }
-      s_row[tid] = vp;
-    }
-    const int pk = s_perm[p];  // permutation entry that moves to position k
-    if (p != k) {
-      if (tid == k) {
-        myperm = pk;
-        mydg = s_dg[p];
-      } else if (tid == p) {
-        myperm = s_perm[k];
-        mydg = s_dg[k];
-      }
-    }
-    __syncthreads();
-    const double lkk = sqrt(piv);
-    if (own) {
-      double l = 0.0;
-      if (tid > k) {
-        double s = A[(int64_t)pk * kSDim + myperm];
-        const double* col = Lc + tid;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int m = 0;
-        for (; m + 8 <= k; m += 8) {
-          double v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = col[(int64_t)(m + u) * kSDim];
-          s0 = fma(v[0], s_row[m], s0);
-          s1 = fma(v[1], s_row[m + 1], s1);
-          s2 = fma(v[2], s_row[m + 2], s2);
-          s3 = fma(v[3], s_row[m + 3], s3);
-          s0 = fma(v[4], s_row[m + 4], s0);
-          s1 = fma(v[5], s_row[m + 5], s1);
-          s2 = fma(v[6], s_row[m + 6], s2);
-          s3 = fma(v[7], s_row[m + 7], s3);
+      for (int w = 1; w < NW; ++w) {
+        const double ov = s_rv[k & 1][w];
+        const int oi = s_ri[k & 1][w];
+        if (ov > piv || (ov == piv && oi < astar)) {
+          piv = ov;
+          astar = oi;
         }
-        for (; m < k; ++m) s0 = fma(col[(int64_t)m * kSDim], s_row[m], s0);
-        s -= (s0 + s1) + (s2 + s3);
-        l = s / lkk;
-        mydg -= l * l;
-      } else if (tid == k) {
-        l = lkk;
       }
-      Lc[(int64_t)k * kSDim + tid] = l;
+      if (k == 0) tol = piv * 1.0e-10;
+      if (!(piv > tol)) {
+        rank = k;
+        stop = true;
+        break;
+      }
+      const double lkk = sqrt(piv);
+      double l = 0.0;
+      if (own && !done) {
+        if (tid == astar) {
+          l = lkk;
+          done = true;
+          s_done[tid] = 1;
+        } else {
+          double s0 = As[(int64_t)astar * kSDim + tid], s1 = 0.0;
+          int m = 0;
+          for (; m + 2 <= j; m += 2) {
+            s0 = fma(-s_panel[m * kSDim + tid], s_panel[m * kSDim + astar], s0);
+            s1 = fma(-s_panel[(m + 1) * kSDim + tid], s_panel[(m + 1) * kSDim + astar], s1);
+          }
+          if (m < j) s0 = fma(-s_panel[m * kSDim + tid], s_panel[m * kSDim + astar], s0);
+          l = (s0 + s1) / lkk;
+          mydg -= l * l;
+        }
+      }
+      if (own) s_panel[j * kSDim + tid] = l;
+      G[(int64_t)k * kSLd + tid] = (float)l;  // rows 420..447 (and eliminated rows) are zero
     }
-    // the barrier at the top of the next step orders these writes before the next interchange
+    __syncthreads();
+    if (stop || k0 + kb >= kSDim) break;
+    // trailing update with the finished panel: W[a][c] = As[a][c] - sum_m Lp[m][a] Lp[m][c]
+    for (int a0 = 4 * wib; a0 < kSDim; a0 += 4 * NW) {
+      bool live[4];
+      bool any = false;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        live[i] = !s_done[a0 + i];
+        any |= live[i];
+      }
+      if (!any) continue;
+      for (int c = lane; c < kSDim; c += 32) {
+        if (s_done[c]) continue;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+        for (int m = 0; m < kCholW; ++m) {
+          const double lc = s_panel[m * kSDim + c];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fma(s_panel[m * kSDim + a0 + i], lc, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (live[i]) W[(int64_t)(a0 + i) * kSDim + c] = As[(int64_t)(a0 + i) * kSDim + c] - acc[i];
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // FP32 copy of the factor for the Jacobi stage (after all interchanges), rows 420..447 zero
-  for (int m = 0; m < rank; ++m)
-    G[(int64_t)m * kSLd + tid] = own ? (float)Lc[(int64_t)m * kSDim + tid] : 0.f;
-  if (own) gperm[tid] = myperm;
   if (tid == 0) b.rank[pair] = rank;
 }
 
@@ -559,7 +571,7 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
 constexpr int kJacWarps = 12;
 constexpr int kJacH = 4;                  // columns per block
 constexpr int kJacE = kSLd / 32;          // 14 elements per lane per column
-constexpr int kJacMaxSweeps = 14;
+constexpr int kJacMaxSweeps = 15;
 constexpr float kJacTol = 1.5e-6f;
 
 struct ColBlock {
@@ -650,70 +662,200 @@ __device__ __forceinline__ void apply_rot(float (&p)[kJacE], float (&q)[kJacE], 
     apply_rot(P3, Q3, c3, s3);                                                               \
   }
 
-__global__ void __launch_bounds__(kJacWarps * 32) siib_jacobi_kernel(SiibGeom g, SiibBuffers b) {
-  const int lp = blockIdx.x, pair = b.pair_lo + lp, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+// Shared-memory / cluster version of the tournament.  The r columns are cut into S = 2 CL
+// super-blocks; every CTA of a CL-wide thread-block cluster keeps two super-blocks in shared
+// memory (2 x 56 columns x 1792 B = 196 KB) and rotates every column pair inside and between
+// them with the columns held in registers (4 + 4 per warp, four independent rotations in
+// flight).  Between the S - 1 super-rounds of a sweep the CTAs swap super-blocks through
+// global memory (L2) and meet at a cluster barrier; CL = 1 (r <= 112) never leaves the SM.
+constexpr int kJ2Warps = 14;
+constexpr int kJ2MaxSb = 56;  // columns per super-block (14 blocks of 4)
+
+__device__ __forceinline__ void load_block_s(ColBlock& c, const float* slot, int first, int lane) {
+#pragma unroll
+  for (int h = 0; h < kJacH; ++h) {
+    const float* col = slot + (first + h) * kSLd + lane;
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < kJacE; ++e) {
+      c.v[h][e] = col[e * 32];
+      s = fmaf(c.v[h][e], c.v[h][e], s);
+    }
+    c.nrm[h] = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int h = 0; h < kJacH; ++h) c.nrm[h] += __shfl_xor_sync(0xffffffffu, c.nrm[h], o);
+  }
+}
+__device__ __forceinline__ void store_block_s(const ColBlock& c, float* slot, int first, int lane) {
+#pragma unroll
+  for (int h = 0; h < kJacH; ++h) {
+    float* col = slot + (first + h) * kSLd + lane;
+#pragma unroll
+    for (int e = 0; e < kJacE; ++e) col[e * 32] = c.v[h][e];
+  }
+}
+__device__ __forceinline__ void rotate_within(ColBlock& P, ColBlock& Q, int& nrot) {
+  NELE_ROT4(P.v[0], P.nrm[0], P.v[1], P.nrm[1], P.v[2], P.nrm[2], P.v[3], P.nrm[3],
+            Q.v[0], Q.nrm[0], Q.v[1], Q.nrm[1], Q.v[2], Q.nrm[2], Q.v[3], Q.nrm[3]);
+  NELE_ROT4(P.v[0], P.nrm[0], P.v[2], P.nrm[2], P.v[1], P.nrm[1], P.v[3], P.nrm[3],
+            Q.v[0], Q.nrm[0], Q.v[2], Q.nrm[2], Q.v[1], Q.nrm[1], Q.v[3], Q.nrm[3]);
+  NELE_ROT4(P.v[0], P.nrm[0], P.v[3], P.nrm[3], P.v[1], P.nrm[1], P.v[2], P.nrm[2],
+            Q.v[0], Q.nrm[0], Q.v[3], Q.nrm[3], Q.v[1], Q.nrm[1], Q.v[2], Q.nrm[2]);
+}
+__device__ __forceinline__ void rotate_cross(ColBlock& P, ColBlock& Q, int& nrot) {
+  NELE_ROT4(P.v[0], P.nrm[0], Q.v[0], Q.nrm[0], P.v[1], P.nrm[1], Q.v[1], Q.nrm[1],
+            P.v[2], P.nrm[2], Q.v[2], Q.nrm[2], P.v[3], P.nrm[3], Q.v[3], Q.nrm[3]);
+  NELE_ROT4(P.v[0], P.nrm[0], Q.v[1], Q.nrm[1], P.v[1], P.nrm[1], Q.v[2], Q.nrm[2],
+            P.v[2], P.nrm[2], Q.v[3], Q.nrm[3], P.v[3], P.nrm[3], Q.v[0], Q.nrm[0]);
+  NELE_ROT4(P.v[0], P.nrm[0], Q.v[2], Q.nrm[2], P.v[1], P.nrm[1], Q.v[3], Q.nrm[3],
+            P.v[2], P.nrm[2], Q.v[0], Q.nrm[0], P.v[3], P.nrm[3], Q.v[1], Q.nrm[1]);
+  NELE_ROT4(P.v[0], P.nrm[0], Q.v[3], Q.nrm[3], P.v[1], P.nrm[1], Q.v[0], Q.nrm[0],
+            P.v[2], P.nrm[2], Q.v[1], Q.nrm[1], P.v[3], P.nrm[3], Q.v[2], Q.nrm[2]);
+}
+// circle-method pairing of `np` players (np even), round `round`, table k -> (i, j)
+__device__ __forceinline__ void circle_pair(int np, int round, int k, int& i, int& j) {
+  if (k == 0) {
+    i = np - 1;
+    j = round;
+  } else {
+    i = (round + k) % (np - 1);
+    j = (round - k + (np - 1)) % (np - 1);
+  }
+}
+
+template <int CL>
+__global__ void __launch_bounds__(kJ2Warps * 32) siib_jacobi2_kernel(SiibGeom g, SiibBuffers b, int rank_lo, int rank_hi) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (CL == 1) ? 0 : (int)cluster.block_rank();
+  const int lp = blockIdx.x / CL, pair = b.pair_lo + lp, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int r = b.rank[pair];
-  if (r < 2) return;
+  if (r < rank_lo || r > rank_hi) return;  // same decision in every CTA of the cluster
   float* __restrict__ G = b.G + (int64_t)lp * kSDim * kSLd;
-  int nb = (r + kJacH - 1) / kJacH;
-  if (nb & 1) ++nb;  // even number of blocks; the last one may be empty
+  constexpr int S = 2 * CL;
+  const int sbp = 4 * ((((r + S - 1) / S) + 3) / 4);  // columns per super-block, multiple of 4, <= 56
+  const int nblk = sbp / kJacH;                        // 4-column blocks per super-block
+  const int nbe = (nblk + 1) & ~1;                     // padded to even for the inner tournament
+  extern __shared__ __align__(16) float s_slot[];      // [2][sbp][448]
+  float* slotA = s_slot;
+  float* slotB = s_slot + sbp * kSLd;
   __shared__ int s_rot;
+  int32_t* __restrict__ grot = b.sweep_rot + (int64_t)pair * 16;
+
+  auto load_super = [&](float* slot, int u) {
+    // columns [u sbp, (u + 1) sbp) of G, zero beyond r; 128-bit copies
+    const int c0 = u * sbp;
+    for (int idx = threadIdx.x; idx < sbp * (kSLd / 4); idx += kJ2Warps * 32) {
+      const int c = idx / (kSLd / 4), q4 = idx % (kSLd / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 + c < r) v = *reinterpret_cast<const float4*>(G + (int64_t)(c0 + c) * kSLd + 4 * q4);
+      *reinterpret_cast<float4*>(slot + c * kSLd + 4 * q4) = v;
+    }
+  };
+  auto store_super = [&](const float* slot, int u) {
+    const int c0 = u * sbp;
+    for (int idx = threadIdx.x; idx < sbp * (kSLd / 4); idx += kJ2Warps * 32) {
+      const int c = idx / (kSLd / 4), q4 = idx % (kSLd / 4);
+      if (c0 + c < r)
+        *reinterpret_cast<float4*>(G + (int64_t)(c0 + c) * kSLd + 4 * q4) = *reinterpret_cast<const float4*>(slot + c * kSLd + 4 * q4);
+    }
+  };
+
+  int ua = 0, ub = 1;
+  if (CL == 1) {
+    load_super(slotA, 0);
+    load_super(slotB, 1);
+    __syncthreads();
+  }
   int sweeps = 0;
   for (; sweeps < kJacMaxSweeps; ++sweeps) {
+    int nrot = 0;
+    for (int rho = 0; rho < S - 1; ++rho) {
+      if (CL > 1) {
+        circle_pair(S, rho, crank, ua, ub);
+        load_super(slotA, ua);
+        load_super(slotB, ub);
+        __syncthreads();
+      }
+      if (rho == 0) {
+        // every pair inside super-block A and inside super-block B (once per sweep: in round 0 the
+        // S super-blocks are spread over the CL CTAs, two each)
+        for (int lr = 0; lr < nbe - 1; ++lr) {
+          for (int item = wib; item < nbe; item += kJ2Warps) {
+            float* slot = (item < nbe / 2) ? slotA : slotB;
+            int bi, bj;
+            circle_pair(nbe, lr, item % (nbe / 2), bi, bj);
+            if (bi > bj) {
+              const int t = bi;
+              bi = bj;
+              bj = t;
+            }
+            const bool pad = bj >= nblk;  // partner is the padding block
+            if (pad && lr != 0) continue;
+            ColBlock P, Q;
+            load_block_s(P, slot, bi * kJacH, lane);
+            if (!pad) load_block_s(Q, slot, bj * kJacH, lane);
+            else {
+#pragma unroll
+              for (int h = 0; h < kJacH; ++h) {
+                Q.nrm[h] = 0.f;
+#pragma unroll
+                for (int e = 0; e < kJacE; ++e) Q.v[h][e] = 0.f;
+              }
+            }
+            if (lr == 0) rotate_within(P, Q, nrot);
+            if (!pad) rotate_cross(P, Q, nrot);
+            store_block_s(P, slot, bi * kJacH, lane);
+            if (!pad) store_block_s(Q, slot, bj * kJacH, lane);
+          }
+          __syncthreads();
+        }
+      }
+      // every pair between super-block A and super-block B
+      for (int sh = 0; sh < nblk; ++sh) {
+        for (int a = wib; a < nblk; a += kJ2Warps) {
+          const int bq = (a + sh) % nblk;
+          ColBlock P, Q;
+          load_block_s(P, slotA, a * kJacH, lane);
+          load_block_s(Q, slotB, bq * kJacH, lane);
+          rotate_cross(P, Q, nrot);
+          store_block_s(P, slotA, a * kJacH, lane);
+          store_block_s(Q, slotB, bq * kJacH, lane);
+        }
+        __syncthreads();
+      }
+      if (CL > 1) {
+        store_super(slotA, ua);
+        store_super(slotB, ub);
+        __threadfence();
+        cluster.sync();
+      }
+    }
+    // rotations of this sweep over the whole cluster
     if (threadIdx.x == 0) s_rot = 0;
     __syncthreads();
-    int nrot = 0;
-    for (int round = 0; round < nb - 1; ++round) {
-      for (int k = wib; k < nb / 2; k += kJacWarps) {
-        // round-robin tournament (circle method), block nb-1 fixed
-        int bi, bj;
-        if (k == 0) {
-          bi = nb - 1;
-          bj = round;
-        } else {
-          bi = (round + k) % (nb - 1);
-          bj = (round - k + (nb - 1)) % (nb - 1);
-        }
-        if (bi > bj) {
-          const int t = bi;
-          bi = bj;
-          bj = t;
-        }
-        if (bj * kJacH >= r && round != 0) continue;  // partner is the empty pad block
-        ColBlock P, Q;
-        load_block(P, G, bi * kJacH, r, lane);
-        load_block(Q, G, bj * kJacH, r, lane);
-        if (round == 0) {  // pairs inside each block, once per sweep
-          NELE_ROT4(P.v[0], P.nrm[0], P.v[1], P.nrm[1], P.v[2], P.nrm[2], P.v[3], P.nrm[3],
-                    Q.v[0], Q.nrm[0], Q.v[1], Q.nrm[1], Q.v[2], Q.nrm[2], Q.v[3], Q.nrm[3]);
-          NELE_ROT4(P.v[0], P.nrm[0], P.v[2], P.nrm[2], P.v[1], P.nrm[1], P.v[3], P.nrm[3],
-                    Q.v[0], Q.nrm[0], Q.v[2], Q.nrm[2], Q.v[1], Q.nrm[1], Q.v[3], Q.nrm[3]);
-          NELE_ROT4(P.v[0], P.nrm[0], P.v[3], P.nrm[3], P.v[1], P.nrm[1], P.v[2], P.nrm[2],
-                    Q.v[0], Q.nrm[0], Q.v[3], Q.nrm[3], Q.v[1], Q.nrm[1], Q.v[2], Q.nrm[2]);
-        }
-        NELE_ROT4(P.v[0], P.nrm[0], Q.v[0], Q.nrm[0], P.v[1], P.nrm[1], Q.v[1], Q.nrm[1],
-                  P.v[2], P.nrm[2], Q.v[2], Q.nrm[2], P.v[3], P.nrm[3], Q.v[3], Q.nrm[3]);
-        NELE_ROT4(P.v[0], P.nrm[0], Q.v[1], Q.nrm[1], P.v[1], P.nrm[1], Q.v[2], Q.nrm[2],
-                  P.v[2], P.nrm[2], Q.v[3], Q.nrm[3], P.v[3], P.nrm[3], Q.v[0], Q.nrm[0]);
-        NELE_ROT4(P.v[0], P.nrm[0], Q.v[2], Q.nrm[2], P.v[1], P.nrm[1], Q.v[3], Q.nrm[3],
-                  P.v[2], P.nrm[2], Q.v[0], Q.nrm[0], P.v[3], P.nrm[3], Q.v[1], Q.nrm[1]);
-        NELE_ROT4(P.v[0], P.nrm[0], Q.v[3], Q.nrm[3], P.v[1], P.nrm[1], Q.v[0], Q.nrm[0],
-                  P.v[2], P.nrm[2], Q.v[1], Q.nrm[1], P.v[3], P.nrm[3], Q.v[2], Q.nrm[2]);
-        store_block(P, G, bi * kJacH, r, lane);
-        store_block(Q, G, bj * kJacH, r, lane);
-      }
+    if (lane == 0 && nrot) atomicAdd(&s_rot, nrot);
+    __syncthreads();
+    int tot = s_rot;
+    if (CL > 1) {
+      if (threadIdx.x == 0 && tot) atomicAdd(&grot[sweeps], tot);
+      __threadfence();
+      cluster.sync();
+      tot = *reinterpret_cast<volatile int32_t*>(&grot[sweeps]);
+      cluster.sync();
+    } else {
+      if (threadIdx.x == 0) grot[sweeps] = tot;
       __syncthreads();
     }
-    if (lane == 0) {
-      if (nrot) atomicAdd(&s_rot, nrot);
-      if (sweeps < 16) atomicAdd(&b.sweep_rot[(int64_t)pair * 16 + sweeps], nrot);
-    }
-    __syncthreads();
-    const int tot = s_rot;
-    __syncthreads();
     if (tot == 0) break;
   }
-  if (threadIdx.x == 0) b.sweeps[pair] = sweeps;
+  if (CL == 1) {
+    store_super(slotA, 0);
+    store_super(slotB, 1);
+  }
+  if (threadIdx.x == 0 && crank == 0) b.sweeps[pair] = sweeps;
 }
 
 // ------------------------------------------------------- quadratic forms + score
@@ -737,7 +879,6 @@ __global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, Sii
   const float* __restrict__ G = b.G + (int64_t)lp * kSDim * kSLd;
   const float* __restrict__ Sxy = b.Sxy + (int64_t)lp * kSDim * kSDim;
   const float* __restrict__ Syy = b.Syy + (int64_t)lp * kSDim * kSDim;
-  const int32_t* __restrict__ perm = b.perm + (int64_t)lp * kSDim;
   __shared__ __align__(16) float s_u[kSDim][kQuadJ];  // unit eigenvectors in original coordinates
   __shared__ float s_lam[kQuadJ];
   __shared__ float s_part[NW][2 * kQuadJ];
@@ -759,7 +900,7 @@ __global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, Sii
     }
     __syncthreads();
     if (tid < kSDim) {
-      const int orig = perm[tid];
+      const int orig = tid;  // the factor keeps the original row order
 #pragma unroll
       for (int jj = 0; jj < kQuadJ; ++jj) {
         const float lam = s_lam[jj];
@@ -831,11 +972,14 @@ __global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, Sii
 
 // ------------------------------------------------------------- launchers
 void siib_upload_tables(const float* win, const float* decay, const float* g2t, const float* tw, cudaStream_t s) {
-  cudaMemcpyToSymbolAsync(c_siib_win, win, sizeof(float) * kSWin, 0, cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(g_siib_win, win, sizeof(float) * kSWin, 0, cudaMemcpyHostToDevice, s);
   cudaMemcpyToSymbolAsync(c_siib_decay, decay, sizeof(float) * kSMaskT, 0, cudaMemcpyHostToDevice, s);
   cudaMemcpyToSymbolAsync(g_siib_g2t, g2t, sizeof(float) * kSBins * kSLanes, 0, cudaMemcpyHostToDevice, s);
   cudaMemcpyToSymbolAsync(g_siib_tw, tw, sizeof(float) * 2 * kSWin, 0, cudaMemcpyHostToDevice, s);
   cudaFuncSetAttribute(siib_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpecSmem));
+  cudaFuncSetAttribute(siib_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholW * kSDim * (int)sizeof(double));
+  cudaFuncSetAttribute(siib_jacobi2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kJ2MaxSb * kSLd * (int)sizeof(float));
+  cudaFuncSetAttribute(siib_jacobi2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kJ2MaxSb * kSLd * (int)sizeof(float));
   cudaStreamSynchronize(s);
 }
 
@@ -871,13 +1015,33 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, int n, int64_t max_F, Kern
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "siib_chol", s);
-  siib_chol_kernel<<<n, kCholThreads, 0, s>>>(g, b);
+  siib_chol_kernel<<<n, kCholThreads, kCholW * kSDim * sizeof(double), s>>>(g, b);
   kt_end(kt, s);
   ++launches;
-  kt_begin(kt, "siib_jacobi", s);
-  siib_jacobi_kernel<<<n, kJacWarps * 32, 0, s>>>(g, b);
-  kt_end(kt, s);
-  ++launches;
+  {
+    // r <= 112: one CTA per pair, everything in shared memory; larger ranks: 4-CTA clusters
+    const size_t smem = (size_t)2 * kJ2MaxSb * kSLd * sizeof(float);
+    kt_begin(kt, "siib_jacobi", s);
+    siib_jacobi2_kernel<1><<<n, kJ2Warps * 32, smem, s>>>(g, b, 2, 2 * kJ2MaxSb);
+    kt_end(kt, s);
+    ++launches;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * n);
+    cfg.blockDim = dim3(kJ2Warps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    kt_begin(kt, "siib_jacobi_cluster", s);
+    cudaLaunchKernelEx(&cfg, siib_jacobi2_kernel<4>, g, b, 2 * kJ2MaxSb + 1, kSDim);
+    kt_end(kt, s);
+    ++launches;
+  }
   kt_begin(kt, "siib_quad", s);
   siib_quad_kernel<<<n, kQuadThreads, 0, s>>>(g, b);
   kt_end(kt, s);

@@ -141,8 +141,8 @@ def test_siib_mapped_no_tile_and_too_short(eng):
     r = eng.score_batch([x], [y], metrics=("siib",), mapped=False, siib_no_tile=True)
     assert np.isnan(r.siib[0]) and r.metric_status("siib")[0] == 2
     # >= 20 s of active speech: the wrapper does not tile (M = 1)
-    xl = np.concatenate([make_pair(10 + k, 48000)[0] for k in range(14)])
-    yl = np.concatenate([make_pair(10 + k, 48000)[1] for k in range(14)])
+    xl = np.concatenate([make_pair(10 + k, 48000)[0] for k in range(24)])
+    yl = np.concatenate([make_pair(10 + k, 48000)[1] for k in range(24)])
     want, M, _ = _oracle_siib(xl, yl)
     rr = eng.score_batch([xl], [yl], metrics=("siib",), mapped=False, keep_stages=True)
     assert eng.stage("siib.tile")[0] == M
