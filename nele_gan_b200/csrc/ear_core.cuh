@@ -180,20 +180,21 @@ NELE_HD double bw_from_control(double sumsq, double gain, int n, double bwmin, d
 // IHC adaptation, then the 52-tap Hann FIR of ebm_EnvFilt evaluated only at
 // the kept (every 9th) positions.  The lane runs on its own time axis delayed
 // by `shift` samples so that group-delay compensation (pyhaspi2.py:1124-1129)
-// costs nothing: at loop index i it consumes input sample i - shift.
+// costs nothing: at loop index i it consumes input sample i - shift.  The
+// carrier is owned by the caller (the clean and the processed signal of a pair
+// share it: same band, same shift).
 template <typename T>
 struct EarLane {
-  Carrier<T> car;
   GtCoef<T> kc, ks;
   Gt4<T> fc, fs;
   T zlp, v1, v2;
   T m11, m12, m21, m22, g1, g2;
-  float r1inv, thr_low, crfac, attn_ohc, lvl_ihc;
+  float r1inv, thr_low, crfac, attn_ohc;
+  float ctl_db;   // 65 + 20 log10(control gain): level of the control envelope = ctl_db + 10 log10(|u|^2)
+  float sig_db;   // 65 - attnIHC + 20 log10(signal gain)
   float acc[6];
-  int shift;
 
-  NELE_HD void init(const BandConst& b, int q, double bw_sig, int shift_, const IhcConst& ih) {
-    car.init(b.cf);
+  NELE_HD void init(const BandConst& b, int q, double bw_sig, const IhcConst& ih) {
     kc = make_gt<T>(b.bw1, b.erb);
     ks = make_gt<T>(bw_sig, b.erb);
     fc.reset();
@@ -205,29 +206,29 @@ struct EarLane {
     thr_low = (float)b.lowknee[q];
     crfac = (float)(1.0 - 1.0 / b.cr[q]);
     attn_ohc = (float)b.attn_ohc[q];
-    lvl_ihc = (float)(65.0 - b.attn_ihc[q]);
-    shift = shift_;
+    ctl_db = (float)(65.0 + 20.0 * log10((double)kc.gain));
+    sig_db = (float)(65.0 - b.attn_ihc[q] + 20.0 * log10((double)ks.gain));
     for (int d = 0; d < 6; ++d) acc[d] = 0.f;
   }
 
-  // one input sample -> IHC-adapted envelope in dB SL (pyhaspi2.py:1207-1229)
-  NELE_HD float sample(T x) {
-    car.advance();
-    const T xr = x * car.c, xi = x * car.s;
+  // one input sample, already demodulated by the carrier (xr, xi) -> IHC-adapted
+  // envelope in dB SL (pyhaspi2.py:1207-1229).  Levels are taken from the squared
+  // magnitudes (10 log10 |u|^2 = 20 log10 |u|), which saves the two square roots;
+  // the reference's 1e-30 floors only matter for exact silence, where both forms
+  // clamp to the same value (thrLow for the control level, 0 dB SL for the envelope).
+  NELE_HD float sample(T xr, T xi) {
     const float pc = (float)fc.step(kc, xr, xi);
     const float ps = (float)fs.step(ks, xr, xi);
-    const float ctrl = kc.gain * sqrtf(pc);
-    const float env = ks.gain * sqrtf(ps);
     // eb_EnvCompressBM (:982-999)
-    float le = 65.0f + db20(fmaxf(ctrl, 1.0e-30f));
+    float le = ctl_db + 0.5f * db20(pc);
     le = fminf(fmaxf(le, thr_low), 100.0f);
     const float g = undb20(-attn_ohc - (le - thr_low) * crfac);
     const T b0 = (T)0.095107983402496;
     const T glp = b0 * (T)g + zlp;
     zlp = b0 * (T)g + (T)0.809784033195007 * glp;
-    const float envc = (float)glp * env;
-    // eb_EnvSL2 (:1080-1083)
-    const float v0 = fmaxf(lvl_ihc + db20(envc + 1.0e-30f), 0.0f);
+    // eb_EnvSL2 (:1080-1083) on env = glp * gain * sqrt(ps)
+    const float gl = (float)glp;
+    const float v0 = fmaxf(sig_db + 0.5f * db20(gl * gl * ps), 0.0f);
     // eb_IHCadapt (:1065-1073)
     const T V0 = (T)v0;
     const T n1 = m11 * v1 + m12 * v2 + g1 * V0;

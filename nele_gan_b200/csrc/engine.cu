@@ -42,6 +42,9 @@ struct KernelStat {
 struct nele_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t s_estoi = nullptr, s_siib = nullptr;  // the three metric pipelines run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_estoi = nullptr, ev_siib = nullptr;
+  bool serial = true;                                  // one stream unless NELE_CONCURRENT=1
   std::string err;
   bool f64 = false;  // recurrence precision of the ear model (NELE_HASPI_F64=1)
 
@@ -173,6 +176,12 @@ extern "C" int nele_create(int device, nele_engine** out) {
   e->device = device;
   const char* p = getenv("NELE_HASPI_F64");
   e->f64 = (p && p[0] == '1');
+  // One stream by default: every kernel of the three pipelines fills the SMs on its own (register-
+  // or shared-memory-limited occupancy), so running the metrics on concurrent streams measured
+  // 381.7 vs 385.6 ms per 4096-pair step and blurs the per-kernel timings.  NELE_CONCURRENT=1
+  // turns the fork/join on (useful for small batches).
+  p = getenv("NELE_CONCURRENT");
+  e->serial = !(p && p[0] == '1');
   e->all_bufs = {&e->bands, &e->rs_taps, &e->st_taps, &e->in_ref, &e->in_deg, &e->geom, &e->sgeom, &e->dither,
                  &e->x24, &e->mid, &e->bw, &e->shift, &e->envlp, &e->rowsel, &e->nsel, &e->cep, &e->cepmean, &e->modsum,
                  &e->x10, &e->st_energy, &e->st_kept, &e->st_nkept, &e->st_tob,
@@ -194,6 +203,11 @@ extern "C" int nele_create(int device, nele_engine** out) {
   CUC(cudaEventCreate(&e->ev0));
   CUC(cudaEventCreate(&e->ev1));
   CUC(cudaEventCreateWithFlags(&e->ev_M, cudaEventDisableTiming));
+  CUC(cudaStreamCreateWithFlags(&e->s_estoi, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&e->s_siib, cudaStreamNonBlocking));
+  CUC(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  CUC(cudaEventCreateWithFlags(&e->ev_estoi, cudaEventDisableTiming));
+  CUC(cudaEventCreateWithFlags(&e->ev_siib, cudaEventDisableTiming));
   haspi_upload_constants(e->stream);
   upload_metric_tables(e->stream);
   CUC(cudaGetLastError());
@@ -216,6 +230,11 @@ extern "C" void nele_destroy(nele_engine* e) {
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->ev_M) cudaEventDestroy(e->ev_M);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_estoi) cudaEventDestroy(e->ev_estoi);
+  if (e->ev_siib) cudaEventDestroy(e->ev_siib);
+  if (e->s_estoi) cudaStreamDestroy(e->s_estoi);
+  if (e->s_siib) cudaStreamDestroy(e->s_siib);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -479,6 +498,14 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
     RESERVE(e, e->out_sst, (size_t)cn * sizeof(int32_t));
 
     CU(e, cudaEventRecord(e->ev0, s));
+    // fork: HASPI stays on the launching stream, ESTOI and SIIB get their own so that the
+    // latency-bound kernels of one metric fill the SMs the others leave idle
+    cudaStream_t se = e->serial ? s : e->s_estoi, ss = e->serial ? s : e->s_siib;
+    if (!e->serial) {
+      CU(e, cudaEventRecord(e->ev_fork, s));
+      CU(e, cudaStreamWaitEvent(se, e->ev_fork, 0));
+      CU(e, cudaStreamWaitEvent(ss, e->ev_fork, 0));
+    }
     // ---- SIIB stage 0: wrapper VAD -> tiling factors (the host needs them to size the rest)
     SiibBuffers sb;
     memset(&sb, 0, sizeof(sb));
@@ -497,9 +524,9 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       sb.wrapdb = (double*)e->sb_wrapdb.p;
       sb.M = (int32_t*)e->sb_M.p;
       sb.wrap_active = (int32_t*)e->sb_wact.p;
-      e->last_launches += siib_run_wrapvad(sg, sb, cn, flags & NELE_FLAG_SIIB_NO_TILE, kt, s);
-      CU(e, cudaMemcpyAsync(e->h_M, sb.M, (size_t)cn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-      CU(e, cudaEventRecord(e->ev_M, s));
+      e->last_launches += siib_run_wrapvad(sg, sb, cn, flags & NELE_FLAG_SIIB_NO_TILE, kt, ss);
+      CU(e, cudaMemcpyAsync(e->h_M, sb.M, (size_t)cn * sizeof(int32_t), cudaMemcpyDeviceToHost, ss));
+      CU(e, cudaEventRecord(e->ev_M, ss));
     }
     // ---- HASPI
     HaspiBuffers hb;
@@ -565,7 +592,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       eb.K = e->st_K;
       eb.score = (double*)e->out_estoi.p;
       eb.status = (int32_t*)e->out_est.p;
-      e->last_launches += estoi_run(eg, eb, cn, max_n10, max_nfa, kt, s);
+      e->last_launches += estoi_run(eg, eb, cn, max_n10, max_nfa, kt, se);
     }
     // ---- SIIB main pipeline
     e->g_M.assign(cn, 0);
@@ -593,7 +620,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       const size_t o_offF = sp.add(e->g_offF.data(), cn * sizeof(int64_t));
       const size_t o_F = sp.add(e->g_F.data(), cn * sizeof(int64_t));
       RESERVE(e, e->sgeom, sp.blob.size());
-      CU(e, cudaMemcpyAsync(e->sgeom.p, sp.blob.data(), sp.blob.size(), cudaMemcpyHostToDevice, s));
+      CU(e, cudaMemcpyAsync(e->sgeom.p, sp.blob.data(), sp.blob.size(), cudaMemcpyHostToDevice, ss));
       sg.offF = (const int64_t*)((const char*)e->sgeom.p + o_offF);
       sg.F = (const int64_t*)((const char*)e->sgeom.p + o_F);
       const int64_t tFa = std::max<int64_t>(tF, 1);
@@ -614,7 +641,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       RESERVE(e, e->sb_sweeps, (size_t)cn * 17 * sizeof(int32_t));
       RESERVE(e, e->sb_lambda, (size_t)cn * 420 * sizeof(float));
       RESERVE(e, e->sb_rho, (size_t)cn * 420 * sizeof(float));
-      CU(e, cudaStreamSynchronize(s));  // sp.blob is a stack temporary
+      CU(e, cudaStreamSynchronize(ss));  // sp.blob is a stack temporary (HASPI / ESTOI keep running on their streams)
       sb.mean = (double*)e->sb_mean.p;
       sb.xdb = (double*)e->sb_xdb.p;
       sb.act = (int32_t*)e->sb_act.p;
@@ -635,16 +662,22 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       sb.rho = (float*)e->sb_rho.p;
       sb.score = (double*)e->out_siib.p;
       sb.status = (int32_t*)e->out_sst.p;
-      CU(e, cudaMemsetAsync(e->sb_sweeps.p, 0, (size_t)cn * 17 * sizeof(int32_t), s));
+      CU(e, cudaMemsetAsync(e->sb_sweeps.p, 0, (size_t)cn * 17 * sizeof(int32_t), ss));
       for (int lo_p = 0; lo_p < cn; lo_p += sub) {
         const int sn = std::min(sub, cn - lo_p);
         int64_t maxF = 0;
         for (int i = 0; i < sn; ++i) maxF = std::max(maxF, e->g_F[lo_p + i]);
         sb.pair_lo = lo_p;
-        e->last_launches += siib_run(sg, sb, sn, maxF, kt, s);
+        e->last_launches += siib_run(sg, sb, sn, maxF, kt, ss);
         e->sub_lo = lo_p;
         e->sub_n = sn;
       }
+    }
+    if (!e->serial) {  // join
+      CU(e, cudaEventRecord(e->ev_estoi, se));
+      CU(e, cudaEventRecord(e->ev_siib, ss));
+      CU(e, cudaStreamWaitEvent(s, e->ev_estoi, 0));
+      CU(e, cudaStreamWaitEvent(s, e->ev_siib, 0));
     }
     CU(e, cudaEventRecord(e->ev1, s));
     CU(e, cudaGetLastError());

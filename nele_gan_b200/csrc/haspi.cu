@@ -58,6 +58,8 @@ __device__ __forceinline__ double mid_step(MidState& s, double x) {
 }
 
 constexpr int kPrepThreads = 256;
+constexpr int kPrepGroups = 85;                       // 3 threads x 4 outputs each = 12 outputs per group
+constexpr int kPrepSpan = kPrepGroups * 8 + 128 + 16;  // staged inputs per tile
 
 __global__ void __launch_bounds__(kPrepThreads) haspi_prep_kernel(PairGeom g, HaspiBuffers b) {
   const int pair = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
@@ -77,7 +79,9 @@ __global__ void __launch_bounds__(kPrepThreads) haspi_prep_kernel(PairGeom g, Ha
     ss += v * v;
   }
   ss = block_sum(ss, red);
-  const double inv_rms = 1.0 / sqrt(ss / (double)L);
+  // all-zero (or non-finite) input: the reference divides by zero and ends in "Signal below
+  // threshold"; scale by 0 instead so that every later stage stays finite and nsel comes out 0
+  const double inv_rms = (ss > 0.0 && ss < 1.0e300) ? 1.0 / sqrt(ss / (double)L) : 0.0;
 
   // 2. resample to 24 kHz (resampy kaiser_best, phase-tabulated) or copy
   double ss24 = 0.0;
@@ -86,6 +90,68 @@ __global__ void __launch_bounds__(kPrepThreads) haspi_prep_kernel(PairGeom g, Ha
       const float v = (float)((double)src[t] * inv_rms);
       x24[t] = v;
       ss24 += (double)v * (double)v;
+    }
+  } else if (b.rs_up == 3 && b.rs_down == 2) {
+    // 16 -> 24 kHz fast path.  y[t] = sum_{m=-63..64} T[r][m] x[n + m], n = floor(2t/3), r = 2t mod 3.
+    // A thread owns four outputs of one phase, t = 12 v + phi + 3 j (n advances by 2 per j), so each
+    // tap is fetched once for four FP64 FMAs and the inputs slide through an 8-register window.
+    // Inputs are staged in shared memory as FP64 with a (a + a/8) skew: lanes 8 samples apart hit
+    // distinct banks.
+    __shared__ double s_tap[3][130];
+    extern __shared__ double s_xin[];  // skewed tile of inputs
+    for (int k = tid; k < 3 * 128; k += kPrepThreads) {
+      const int r = k / 128, m = k % 128;  // m = 0..127 <-> offset m - 63
+      // taps[r][0..63] weigh x[n - i]; taps[r][64..127] weigh x[n + 1 + k]
+      s_tap[r][m] = (m <= 63) ? b.rs_taps[r * 128 + (63 - m)] : b.rs_taps[r * 128 + 64 + (m - 64)];
+    }
+    const int n_out = (int)(((int64_t)L * 3) / 2);  // int(L * ratio); the tail up to N is zero (fix_length)
+    const int v_loc = tid / 3, phi = tid % 3;
+    const bool worker = tid < kPrepGroups * 3;
+    for (int tile0 = 0; tile0 < N; tile0 += kPrepGroups * 12) {
+      // inputs needed: n in [8 V0 - 63, 8 (V0 + groups) + 1 + 64 + 6], V0 = tile0 / 12
+      const int in0 = (tile0 / 12) * 8 - 63;
+      __syncthreads();
+      for (int u = tid; u < kPrepSpan; u += kPrepThreads) {
+        const int jx = in0 + u;
+        s_xin[u + (u >> 3)] = (jx >= 0 && jx < L) ? (double)src[jx] : 0.0;
+      }
+      __syncthreads();
+      if (worker) {
+        const int t0 = tile0 + 12 * v_loc + phi;       // first of the four outputs
+        const int n = (2 * t0) / 3, r = (2 * t0) % 3;  // t0 = 12 v + phi -> n = 8 v + {0, 0, 1}
+        const int base = n - 63 - in0;                 // staged index of x[n - 63]
+        const double* __restrict__ tp = s_tap[r];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        double w[8];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          const int u = base + k;
+          w[k] = s_xin[u + (u >> 3)];
+        }
+#pragma unroll 1
+        for (int m0 = 0; m0 < 128; m0 += 8) {
+#pragma unroll
+          for (int sft = 0; sft < 8; ++sft) {
+            const int u = base + m0 + sft + 7;
+            w[(sft + 7) & 7] = s_xin[u + (u >> 3)];
+            const double tm = tp[m0 + sft];
+            a0 = fma(tm, w[sft & 7], a0);
+            a1 = fma(tm, w[(sft + 2) & 7], a1);
+            a2 = fma(tm, w[(sft + 4) & 7], a2);
+            a3 = fma(tm, w[(sft + 6) & 7], a3);
+          }
+        }
+        const double acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int t = t0 + 3 * j;
+          if (t < N) {
+            const float v = (t < n_out) ? (float)(acc[j] * inv_rms) : 0.f;
+            x24[t] = v;
+            ss24 += (double)v * (double)v;
+          }
+        }
+      }
     }
   } else {
     const int n_out = (int)(((int64_t)L * b.rs_up) / b.rs_down);  // int(L * ratio)
@@ -110,7 +176,7 @@ __global__ void __launch_bounds__(kPrepThreads) haspi_prep_kernel(PairGeom g, Ha
   }
   ss24 = block_sum(ss24, red);
   // (xRMS / yRMS) * y with xRMS = 1 after the normalisation above (pyhaspi2.py:816-818)
-  const double scale = (b.rs_up == 1 && b.rs_down == 1) ? 1.0 : 1.0 / sqrt(ss24 / (double)N);
+  const double scale = (b.rs_up == 1 && b.rs_down == 1 || !(ss24 > 0.0)) ? 1.0 : 1.0 / sqrt(ss24 / (double)N);
   __syncthreads();
 
   // 3. middle ear as a blocked linear recurrence: each thread filters one
@@ -160,6 +226,7 @@ __global__ void __launch_bounds__(kPrepThreads) haspi_prep_kernel(PairGeom g, Ha
 
 // --------------------------------------------------------------- control
 constexpr int kEarWarps = 4;          // warps per CTA in the lane = band kernels
+constexpr int kEarChunkMax = 576;     // delay-line capacity of the main pass (kEarChunk)
 constexpr int kCtlChunk = 256;
 
 template <typename T>
@@ -201,70 +268,94 @@ __global__ void haspi_shift_kernel(HaspiBuffers b, int n) {
   if (pair >= n) return;
   const double gd = gt_group_delay(b.bw[((int64_t)pair * 2 + 0) * kBands + lane], b.bands[lane].erb);
   const double gmax = warp_max(gd);
-  b.shift[(int64_t)pair * kBands + lane] = (int)(gmax - gd);
+  const double sh = gmax - gd;  // 0 .. ~435 samples for BW in [1, 4]
+  b.shift[(int64_t)pair * kBands + lane] = (sh >= 0.0 && sh < (double)kEarChunkMax) ? (int)sh : 0;
 }
 
 // ------------------------------------------------------------------ main
-constexpr int kEarChunk = 576;  // 64 blocks of 9 samples; ring of two chunks per warp
+constexpr int kEarChunk = 576;  // 64 blocks of 9 samples; ring of two chunks per warp and signal
 
+// One warp per pair, lane = band; each lane runs the clean and the processed signal
+// side by side (two independent recurrence chains per thread: the sample loop is
+// latency bound, and the carrier, the delay-line index and the loop bookkeeping are
+// shared because both signals use the shifts of BWx, pyhaspi2.py:1239-1240).
 template <typename T>
-__global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_kernel(PairGeom g, HaspiBuffers b, int n_items) {
+__global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_kernel(PairGeom g, HaspiBuffers b, int n_pairs) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int item = blockIdx.x * kEarWarps + wib;
-  if (item >= n_items) return;
-  const int pair = item >> 1, q = item & 1;
-  const double* __restrict__ mid = b.mid + (int64_t)q * b.tot24 + g.off24[pair];
+  const int pair = blockIdx.x * kEarWarps + wib;
+  if (pair >= n_pairs) return;
+  const double* __restrict__ midx = b.mid + g.off24[pair];
+  const double* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
   const int N = g.n24[pair], nsub = g.nsub[pair];
-  float* __restrict__ out = b.envlp + ((int64_t)q * b.totsub + g.offsub[pair]) * kBands;
-  __shared__ T s_ring[kEarWarps][2 * kEarChunk];
-  T* ring = s_ring[wib];
+  float* __restrict__ outx = b.envlp + (g.offsub[pair]) * kBands;
+  float* __restrict__ outy = b.envlp + (b.totsub + g.offsub[pair]) * kBands;
+  extern __shared__ __align__(16) unsigned char s_ring_raw[];  // [kEarWarps][2][2 * kEarChunk] of T
+  T* ringx = reinterpret_cast<T*>(s_ring_raw) + (size_t)wib * 4 * kEarChunk;
+  T* ringy = ringx + 2 * kEarChunk;
 
-  EarLane<T> L;
+  EarLane<T> Lx, Ly;
+  Carrier<T> car;
+  int shift;
   {
     const BandConst bc = b.bands[lane];
-    L.init(bc, q, b.bw[((int64_t)pair * 2 + q) * kBands + lane], b.shift[(int64_t)pair * kBands + lane], c_ihc);
+    shift = b.shift[(int64_t)pair * kBands + lane];
+    car.init(bc.cf);
+    Lx.init(bc, 0, b.bw[((int64_t)pair * 2 + 0) * kBands + lane], c_ihc);
+    Ly.init(bc, 1, b.bw[((int64_t)pair * 2 + 1) * kBands + lane], c_ihc);
   }
-  int rp = (L.shift == 0) ? 0 : 2 * kEarChunk - L.shift;  // ring slot of sample i - shift
-  const int nblk = nsub + 2;                               // output j completes after block j + 2
+  int rp = (shift == 0) ? 0 : 2 * kEarChunk - shift;  // ring slot of sample i - shift
+  const int nblk = nsub + 2;                           // output j completes after block j + 2
   const int nchunks = (nblk * 9 + kEarChunk - 1) / kEarChunk;
   for (int c = 0; c < nchunks; ++c) {
     const int i0 = c * kEarChunk;
-    T* half = ring + (c & 1) * kEarChunk;
+    T* hx = ringx + (c & 1) * kEarChunk;
+    T* hy = ringy + (c & 1) * kEarChunk;
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < kEarChunk / 32; ++k) {
       const int t = i0 + k * 32 + lane;
-      half[k * 32 + lane] = (t < N) ? (T)mid[t] : (T)0;
+      hx[k * 32 + lane] = (t < N) ? (T)midx[t] : (T)0;
+      hy[k * 32 + lane] = (t < N) ? (T)midy[t] : (T)0;
     }
     __syncwarp();
     {  // re-seed the carrier from the exact phase (lane-local time axis)
-      const int t = i0 - L.shift;
-      if (t >= 0) L.car.seed_before(t);
-      else if (t + kEarChunk > 0) L.car.seed_before(0);
+      const int t = i0 - shift;
+      if (t >= 0) car.seed_before(t);
+      else if (t + kEarChunk > 0) car.seed_before(0);
     }
     const int blk_end = min((c + 1) * (kEarChunk / 9), nblk);
     for (int blk = c * (kEarChunk / 9); blk < blk_end; ++blk) {
       const int ib = blk * 9;
-      float v[9];
+      float vx[9], vy[9];
 #pragma unroll
       for (int p = 0; p < 9; ++p) {
         const int i = ib + p;
-        const T x = ring[rp];
+        const T xs = ringx[rp], ys = ringy[rp];
         rp = (rp + 1 == 2 * kEarChunk) ? 0 : rp + 1;
-        v[p] = (i >= L.shift && i < N) ? L.sample(x) : 0.f;
+        if (i >= shift && i < N) {
+          car.advance();
+          vx[p] = Lx.sample(xs * car.c, xs * car.s);
+          vy[p] = Ly.sample(ys * car.c, ys * car.s);
+        } else {
+          vx[p] = 0.f;
+          vy[p] = 0.f;
+        }
       }
-      L.template accumulate<0>(v[0], c_envfir);
-      L.template accumulate<1>(v[1], c_envfir);
-      L.template accumulate<2>(v[2], c_envfir);
-      L.template accumulate<3>(v[3], c_envfir);
-      L.template accumulate<4>(v[4], c_envfir);
-      L.template accumulate<5>(v[5], c_envfir);
-      L.template accumulate<6>(v[6], c_envfir);
-      L.template accumulate<7>(v[7], c_envfir);
-      L.template accumulate<8>(v[8], c_envfir);
-      const float o = L.emit();
+      Lx.template accumulate<0>(vx[0], c_envfir); Ly.template accumulate<0>(vy[0], c_envfir);
+      Lx.template accumulate<1>(vx[1], c_envfir); Ly.template accumulate<1>(vy[1], c_envfir);
+      Lx.template accumulate<2>(vx[2], c_envfir); Ly.template accumulate<2>(vy[2], c_envfir);
+      Lx.template accumulate<3>(vx[3], c_envfir); Ly.template accumulate<3>(vy[3], c_envfir);
+      Lx.template accumulate<4>(vx[4], c_envfir); Ly.template accumulate<4>(vy[4], c_envfir);
+      Lx.template accumulate<5>(vx[5], c_envfir); Ly.template accumulate<5>(vy[5], c_envfir);
+      Lx.template accumulate<6>(vx[6], c_envfir); Ly.template accumulate<6>(vy[6], c_envfir);
+      Lx.template accumulate<7>(vx[7], c_envfir); Ly.template accumulate<7>(vy[7], c_envfir);
+      Lx.template accumulate<8>(vx[8], c_envfir); Ly.template accumulate<8>(vy[8], c_envfir);
+      const float ox = Lx.emit(), oy = Ly.emit();
       const int j = blk - 2;
-      if (j >= 0) out[(int64_t)j * kBands + lane] = o;
+      if (j >= 0) {
+        outx[(int64_t)j * kBands + lane] = ox;
+        outy[(int64_t)j * kBands + lane] = oy;
+      }
     }
   }
 }
@@ -547,13 +638,15 @@ void haspi_upload_tables(const float* cepm, const int* nhalf, const int* off, co
   cudaMemcpyToSymbolAsync(c_mod_off, off, sizeof(int) * (kNumMod + 1), 0, cudaMemcpyHostToDevice, s);
   cudaMemcpyToSymbolAsync(g_modtaps, taps, sizeof(float) * ntaps, 0, cudaMemcpyHostToDevice, s);
   cudaFuncSetAttribute(haspi_modcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)modcorr_smem_bytes());
+  cudaFuncSetAttribute(haspi_ear_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(kEarWarps * 4 * kEarChunk * sizeof(double)));
   cudaStreamSynchronize(s);
 }
 
 int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, bool f64, KernelTimer* kt, cudaStream_t s) {
   int launches = 0;
   kt_begin(kt, "haspi_prep", s);
-  haspi_prep_kernel<<<dim3(n, 2), kPrepThreads, 0, s>>>(g, b);
+  haspi_prep_kernel<<<dim3(n, 2), kPrepThreads, (kPrepSpan + kPrepSpan / 8 + 8) * sizeof(double), s>>>(g, b);
   kt_end(kt, s);
   ++launches;
   const int items = 2 * n, ctas = (items + kEarWarps - 1) / kEarWarps;
@@ -567,8 +660,9 @@ int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, boo
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "haspi_ear", s);
-  if (f64) haspi_ear_kernel<double><<<ctas, kEarWarps * 32, 0, s>>>(g, b, items);
-  else haspi_ear_kernel<float><<<ctas, kEarWarps * 32, 0, s>>>(g, b, items);
+  const int ear_ctas = (n + kEarWarps - 1) / kEarWarps;
+  if (f64) haspi_ear_kernel<double><<<ear_ctas, kEarWarps * 32, kEarWarps * 4 * kEarChunk * sizeof(double), s>>>(g, b, n);
+  else haspi_ear_kernel<float><<<ear_ctas, kEarWarps * 32, kEarWarps * 4 * kEarChunk * sizeof(float), s>>>(g, b, n);
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "haspi_cep", s);

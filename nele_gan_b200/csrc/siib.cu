@@ -339,37 +339,67 @@ __device__ __forceinline__ void block_desc(int blk, int& ta, int& tb, int& d) {
 }
 
 constexpr int kCovWarps = 8;
+constexpr int kCovTile = 64;                        // frames per staged tile
+constexpr int kCovRows = kCovTile + kSStack - 1;    // + 14 frames of lag reach
 
+// The eight warps of a CTA own eight lag blocks of the same pair and walk the time axis
+// together: each tile of frames is converted to FP64 once into shared memory (the F2F
+// conversions, not the DFMAs, bound a version that converted per use) and every warp
+// accumulates its 32 x 32 block (28 x 28 used) from broadcast shared-memory reads.
 __global__ void __launch_bounds__(kCovWarps * 32) siib_cov_kernel(SiibGeom g, SiibBuffers b) {
   const int lp = blockIdx.y, pair = b.pair_lo + lp, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int blk = blockIdx.x * kCovWarps + wib;
   const int Fa = b.Fa[pair];
   const int Nf = Fa - (kSStack - 1);
-  if (blk >= kSBlocks || Nf < 1) return;
-  int ta, tb, d;
-  block_desc(blk, ta, tb, d);
+  if (Nf < 1) return;
+  __shared__ __align__(16) double s_x[2][kCovRows][kSLanes];
+  const bool active = blk < kSBlocks;
+  int ta = 0, tb = 0, d = 0;
+  if (active) block_desc(blk, ta, tb, d);
   const int a0 = max(0, -d), b0 = max(0, d);
   const int rg = lane >> 2, cg = lane & 3;
-  const float* __restrict__ A = b.logspec + ((int64_t)ta * b.totF + g.offF[pair] + a0) * kSLanes + 4 * rg;
-  const float* __restrict__ B = b.logspec + ((int64_t)tb * b.totF + g.offF[pair] + b0) * kSLanes + 8 * cg;
+  const float* __restrict__ X = b.logspec + (g.offF[pair]) * kSLanes;
+  const float* __restrict__ Y = b.logspec + (b.totF + g.offF[pair]) * kSLanes;
   double acc[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  for (int t0 = 0; t0 < Nf; t0 += kCovTile) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * kCovRows * (kSLanes / 4); idx += kCovWarps * 32) {
+      const int q = idx / (kCovRows * (kSLanes / 4)), rem = idx % (kCovRows * (kSLanes / 4));
+      const int row = rem / (kSLanes / 4), c4 = rem % (kSLanes / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t0 + row < Fa) v = *reinterpret_cast<const float4*>((q ? Y : X) + (int64_t)(t0 + row) * kSLanes + 4 * c4);
+      double* dst = &s_x[q][row][4 * c4];
+      dst[0] = (double)v.x;
+      dst[1] = (double)v.y;
+      dst[2] = (double)v.z;
+      dst[3] = (double)v.w;
+    }
+    __syncthreads();
+    if (!active) continue;
+    const int nt = min(kCovTile, Nf - t0);
+    const double* A = &s_x[ta][a0][4 * rg];
+    const double* B = &s_x[tb][b0][8 * cg];
 #pragma unroll 2
-  for (int t = 0; t < Nf; ++t) {
-    const float4 av = *reinterpret_cast<const float4*>(A + (int64_t)t * kSLanes);
-    const float4 b0v = *reinterpret_cast<const float4*>(B + (int64_t)t * kSLanes);
-    const float4 b1v = *reinterpret_cast<const float4*>(B + (int64_t)t * kSLanes + 4);
-    const double a[4] = {(double)av.x, (double)av.y, (double)av.z, (double)av.w};
-    const double c[8] = {(double)b0v.x, (double)b0v.y, (double)b0v.z, (double)b0v.w,
-                         (double)b1v.x, (double)b1v.y, (double)b1v.z, (double)b1v.w};
+    for (int t = 0; t < nt; ++t) {
+      const double2 a01 = *reinterpret_cast<const double2*>(A + t * kSLanes);
+      const double2 a23 = *reinterpret_cast<const double2*>(A + t * kSLanes + 2);
+      const double2 c01 = *reinterpret_cast<const double2*>(B + t * kSLanes);
+      const double2 c23 = *reinterpret_cast<const double2*>(B + t * kSLanes + 2);
+      const double2 c45 = *reinterpret_cast<const double2*>(B + t * kSLanes + 4);
+      const double2 c67 = *reinterpret_cast<const double2*>(B + t * kSLanes + 6);
+      const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+      const double c[8] = {c01.x, c01.y, c23.x, c23.y, c45.x, c45.y, c67.x, c67.y};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], c[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], c[j], acc[i][j]);
+    }
   }
+  if (!active) return;
   double* __restrict__ out = b.base + ((int64_t)lp * kSBlocks + blk) * (kSLanes * kSLanes);
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -668,7 +698,8 @@ __device__ __forceinline__ void apply_rot(float (&p)[kJacE], float (&q)[kJacE], 
 // them with the columns held in registers (4 + 4 per warp, four independent rotations in
 // flight).  Between the S - 1 super-rounds of a sweep the CTAs swap super-blocks through
 // global memory (L2) and meet at a cluster barrier; CL = 1 (r <= 112) never leaves the SM.
-constexpr int kJ2Warps = 14;
+constexpr int kJ2Warps = 14;       // cluster kernel: one warp per 4-column block of a 56-column super-block
+constexpr int kJ2WarpsSmall = 12;  // single-CTA kernel: 168 registers per thread, no spills
 constexpr int kJ2MaxSb = 56;  // columns per super-block (14 blocks of 4)
 
 __device__ __forceinline__ void load_block_s(ColBlock& c, const float* slot, int first, int lane) {
@@ -726,8 +757,8 @@ __device__ __forceinline__ void circle_pair(int np, int round, int k, int& i, in
   }
 }
 
-template <int CL>
-__global__ void __launch_bounds__(kJ2Warps * 32) siib_jacobi2_kernel(SiibGeom g, SiibBuffers b, int rank_lo, int rank_hi) {
+template <int CL, int NWARP>
+__global__ void __launch_bounds__(NWARP * 32) siib_jacobi2_kernel(SiibGeom g, SiibBuffers b, int rank_lo, int rank_hi) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (CL == 1) ? 0 : (int)cluster.block_rank();
   const int lp = blockIdx.x / CL, pair = b.pair_lo + lp, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -747,7 +778,7 @@ __global__ void __launch_bounds__(kJ2Warps * 32) siib_jacobi2_kernel(SiibGeom g,
   auto load_super = [&](float* slot, int u) {
     // columns [u sbp, (u + 1) sbp) of G, zero beyond r; 128-bit copies
     const int c0 = u * sbp;
-    for (int idx = threadIdx.x; idx < sbp * (kSLd / 4); idx += kJ2Warps * 32) {
+    for (int idx = threadIdx.x; idx < sbp * (kSLd / 4); idx += NWARP * 32) {
       const int c = idx / (kSLd / 4), q4 = idx % (kSLd / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c0 + c < r) v = *reinterpret_cast<const float4*>(G + (int64_t)(c0 + c) * kSLd + 4 * q4);
@@ -756,7 +787,7 @@ __global__ void __launch_bounds__(kJ2Warps * 32) siib_jacobi2_kernel(SiibGeom g,
   };
   auto store_super = [&](const float* slot, int u) {
     const int c0 = u * sbp;
-    for (int idx = threadIdx.x; idx < sbp * (kSLd / 4); idx += kJ2Warps * 32) {
+    for (int idx = threadIdx.x; idx < sbp * (kSLd / 4); idx += NWARP * 32) {
       const int c = idx / (kSLd / 4), q4 = idx % (kSLd / 4);
       if (c0 + c < r)
         *reinterpret_cast<float4*>(G + (int64_t)(c0 + c) * kSLd + 4 * q4) = *reinterpret_cast<const float4*>(slot + c * kSLd + 4 * q4);
@@ -783,7 +814,7 @@ __global__ void __launch_bounds__(kJ2Warps * 32) siib_jacobi2_kernel(SiibGeom g,
         // every pair inside super-block A and inside super-block B (once per sweep: in round 0 the
         // S super-blocks are spread over the CL CTAs, two each)
         for (int lr = 0; lr < nbe - 1; ++lr) {
-          for (int item = wib; item < nbe; item += kJ2Warps) {
+          for (int item = wib; item < nbe; item += NWARP) {
             float* slot = (item < nbe / 2) ? slotA : slotB;
             int bi, bj;
             circle_pair(nbe, lr, item % (nbe / 2), bi, bj);
@@ -815,7 +846,7 @@ __global__ void __launch_bounds__(kJ2Warps * 32) siib_jacobi2_kernel(SiibGeom g,
       }
       // every pair between super-block A and super-block B
       for (int sh = 0; sh < nblk; ++sh) {
-        for (int a = wib; a < nblk; a += kJ2Warps) {
+        for (int a = wib; a < nblk; a += NWARP) {
           const int bq = (a + sh) % nblk;
           ColBlock P, Q;
           load_block_s(P, slotA, a * kJacH, lane);
@@ -978,8 +1009,8 @@ void siib_upload_tables(const float* win, const float* decay, const float* g2t, 
   cudaMemcpyToSymbolAsync(g_siib_tw, tw, sizeof(float) * 2 * kSWin, 0, cudaMemcpyHostToDevice, s);
   cudaFuncSetAttribute(siib_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpecSmem));
   cudaFuncSetAttribute(siib_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholW * kSDim * (int)sizeof(double));
-  cudaFuncSetAttribute(siib_jacobi2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kJ2MaxSb * kSLd * (int)sizeof(float));
-  cudaFuncSetAttribute(siib_jacobi2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kJ2MaxSb * kSLd * (int)sizeof(float));
+  cudaFuncSetAttribute(siib_jacobi2_kernel<1, kJ2WarpsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kJ2MaxSb * kSLd * (int)sizeof(float));
+  cudaFuncSetAttribute(siib_jacobi2_kernel<4, kJ2Warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kJ2MaxSb * kSLd * (int)sizeof(float));
   cudaStreamSynchronize(s);
 }
 
@@ -1022,7 +1053,7 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, int n, int64_t max_F, Kern
     // r <= 112: one CTA per pair, everything in shared memory; larger ranks: 4-CTA clusters
     const size_t smem = (size_t)2 * kJ2MaxSb * kSLd * sizeof(float);
     kt_begin(kt, "siib_jacobi", s);
-    siib_jacobi2_kernel<1><<<n, kJ2Warps * 32, smem, s>>>(g, b, 2, 2 * kJ2MaxSb);
+    siib_jacobi2_kernel<1, kJ2WarpsSmall><<<n, kJ2WarpsSmall * 32, smem, s>>>(g, b, 2, 2 * kJ2MaxSb);
     kt_end(kt, s);
     ++launches;
     cudaLaunchConfig_t cfg = {};
@@ -1038,7 +1069,7 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, int n, int64_t max_F, Kern
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     kt_begin(kt, "siib_jacobi_cluster", s);
-    cudaLaunchKernelEx(&cfg, siib_jacobi2_kernel<4>, g, b, 2 * kJ2MaxSb + 1, kSDim);
+    cudaLaunchKernelEx(&cfg, siib_jacobi2_kernel<4, kJ2Warps>, g, b, 2 * kJ2MaxSb + 1, kSDim);
     kt_end(kt, s);
     ++launches;
   }

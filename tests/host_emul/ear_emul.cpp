@@ -48,13 +48,21 @@ static void run(const std::vector<double> mid[2], int N, FILE* fo) {
   for (int q = 0; q < 2; ++q)
     for (int b = 0; b < kBands; ++b) {
       EarLane<T> L;
-      L.init(bc[b], q, bw[q][b], shift[b], ih);
+      Carrier<T> car;
+      car.init(bc[b].cf);
+      L.init(bc[b], q, bw[q][b], ih);
       for (int blk = 0; blk < nsub + 2; ++blk) {
         float v[9];
         for (int p = 0; p < 9; ++p) {
-          const int i = blk * 9 + p, t = i - L.shift;
-          if (t >= 0 && (t % 576 == 0)) L.car.seed_before(t);
-          v[p] = (t >= 0 && i < N) ? L.sample((T)mid[q][t]) : 0.f;
+          const int i = blk * 9 + p, t = i - shift[b];
+          if (t >= 0 && (t % 576 == 0)) car.seed_before(t);
+          if (t >= 0 && i < N) {
+            car.advance();
+            const T xs = (T)mid[q][t];
+            v[p] = L.sample(xs * car.c, xs * car.s);
+          } else {
+            v[p] = 0.f;
+          }
         }
         L.template accumulate<0>(v[0], fir); L.template accumulate<1>(v[1], fir);
         L.template accumulate<2>(v[2], fir); L.template accumulate<3>(v[3], fir);
