@@ -23,7 +23,7 @@ import numpy as np
 
 from . import engine as _eng
 
-__all__ = ["haspi_v2", "haspi", "SIIB", "stoi", "score_batch",
+__all__ = ["haspi_v2", "haspi", "SIIB", "stoi", "score_batch", "score_tensors", "read_batch_all",
            "SIIB_Wrapper_harvard", "SIIB_Wrapper_raw_harvard", "mapping_SIIB_harvard",
            "HASPI_Wrapper_harvard", "HASPI_Wrapper_raw_harvard", "mapping_HASPI_harvard",
            "ESTOI_Wrapper_harvard", "ESTOI_Wrapper_raw_harvard", "mapping_ESTOI_harvard",
@@ -237,6 +237,44 @@ def read_batch_all(clean_root, noise_root, enhanced_list, norm=True, drc=False, 
         seed = int(np.random.randint(0, 2 ** 31 - 1))
     s = _engine().score_batch(refs, degs, fs=fs, mapped=bool(norm), seed=seed).scores
     return [float(v) for v in s[:, 0]], [float(v) for v in s[:, 1]], [float(v) for v in s[:, 2]]
+
+
+def score_tensors(ref, deg, lengths=None, fs=16000, metrics=("siib", "haspi", "estoi"), norm=True, seed=0,
+                  pcm16=False, **kw):
+    """In-loop tensor boundary (train_nele.py:303-322 without the WAV round trip):
+    ``ref`` / ``deg`` are CUDA float32 torch tensors ``[n, Lmax]`` (clean, and
+    enhanced + noise as audio_util.py:139 forms it), ``lengths`` the valid
+    samples per row (default: all of ``Lmax``).  The waveforms stay on the
+    device -- the engine reads them through ``data_ptr()`` -- and only the
+    per-pair records come back.  ``pcm16=True`` reproduces what the reference's
+    ``sf.write(..., 'PCM_16')`` + ``librosa.load`` round trip (train_nele.py:313,
+    audio_util.py:186-189) does to the degraded signal's *enhanced* component;
+    here it is applied to ``deg`` as a whole.  Returns a float64 torch tensor
+    ``[n, 3]`` = {SIIB, HASPI, ESTOI} on the CPU."""
+    import torch
+    if not (ref.is_cuda and deg.is_cuda):
+        raise ValueError("score_tensors needs CUDA tensors (the engine has no CPU path)")
+    if ref.shape != deg.shape or ref.dim() != 2:
+        raise ValueError("ref and deg must both be [n, Lmax]")
+    ref = ref.detach().to(torch.float32).contiguous()
+    deg = deg.detach().to(torch.float32).contiguous()
+    if pcm16:
+        deg = torch.clamp(torch.round(deg * 32768.0), -32768.0, 32767.0) / 32768.0
+    n, lmax = ref.shape
+    if lmax % 4:  # rows must start 16-byte aligned
+        pad = 4 - lmax % 4
+        ref = torch.nn.functional.pad(ref, (0, pad))
+        deg = torch.nn.functional.pad(deg, (0, pad))
+    stride = ref.shape[1]
+    lens = np.full(n, lmax, dtype=np.int32) if lengths is None else np.asarray(lengths, dtype=np.int32)
+    if lens.shape != (n,) or lens.min() <= 0 or lens.max() > lmax:
+        raise ValueError("lengths must be n values in (0, Lmax]")
+    offs = np.arange(n, dtype=np.int64) * stride
+    eng = _eng.default_engine(ref.device.index)
+    torch.cuda.current_stream(ref.device).synchronize()   # the engine runs on its own stream
+    r = eng.score_packed(ref.data_ptr(), deg.data_ptr(), offs, lens, fs=fs, metrics=metrics, mapped=bool(norm),
+                         seed=seed, device_input=True, **kw)
+    return torch.from_numpy(r.scores)
 
 
 def dropin_path():

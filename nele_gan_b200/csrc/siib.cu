@@ -58,20 +58,25 @@ __device__ cpx g_siib_tw[kSWin];
 // power (dB) of Hann frame f of (x - mean); wrap = tiled signal, else zero padded
 __device__ __forceinline__ double frame_power_db(const float* __restrict__ x, int L, double mean, int64_t f,
                                                  bool wrap, int lane, const float* __restrict__ win) {
-  const int64_t s0 = f * kSHop;
-  int64_t base = wrap ? (s0 % L) : s0;
+  // f * 200 < 2^31 for every frame count the engine admits (F <= 400 000)
+  const int s0 = (int)f * kSHop;
+  const int base = wrap ? (s0 % L) : s0;
   double ss = 0.0;
-  for (int i = lane; i < kSWin; i += 32) {
-    int64_t idx = base + i;
-    double v;
-    if (wrap) {
-      if (idx >= L) idx %= L;
-      v = (double)x[idx] - mean;
-    } else {
-      v = (idx < L) ? (double)x[idx] - mean : 0.0;
+#pragma unroll
+  for (int k = 0; k < (kSWin + 31) / 32; ++k) {
+    const int i = k * 32 + lane;
+    if (i < kSWin) {
+      int idx = base + i;
+      double v;
+      if (wrap) {
+        if (idx >= L) idx = (L >= kSWin) ? idx - L : idx % L;
+        v = (double)x[idx] - mean;
+      } else {
+        v = (idx < L) ? (double)x[idx] - mean : 0.0;
+      }
+      v *= (double)win[i];
+      ss = fma(v, v, ss);
     }
-    v *= (double)win[i];
-    ss += v * v;
   }
   ss = warp_sum(ss);
   return 10.0 * log10(ss / (double)kSWin + kEps);
@@ -134,6 +139,9 @@ __device__ __forceinline__ int percentile_rank(int64_t n) {  // k such that the 
 }
 
 constexpr int kVadThreads = 256;
+// the tiled-signal VAD re-reads its waveform M times: 1024-thread CTAs keep the number of
+// resident waveforms (2 per SM x 192 KB) inside the L2
+constexpr int kVad2Threads = 1024;
 
 __global__ void __launch_bounds__(kVadThreads) siib_wrapvad_kernel(SiibGeom g, SiibBuffers b, int no_tile) {
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -166,9 +174,9 @@ __global__ void __launch_bounds__(kVadThreads) siib_wrapvad_kernel(SiibGeom g, S
   }
 }
 
-__global__ void __launch_bounds__(kVadThreads) siib_vad_kernel(SiibGeom g, SiibBuffers b) {
+__global__ void __launch_bounds__(kVad2Threads) siib_vad_kernel(SiibGeom g, SiibBuffers b) {
   const int pair = b.pair_lo + blockIdx.x, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-  constexpr int NW = kVadThreads / 32;
+  constexpr int NW = kVad2Threads / 32;
   const float* __restrict__ x = b.ref + g.off16[pair];
   const float* __restrict__ y = b.deg + g.off16[pair];
   const int L = g.len16[pair];
@@ -184,9 +192,9 @@ __global__ void __launch_bounds__(kVadThreads) siib_vad_kernel(SiibGeom g, SiibB
     if (tid == 0) b.Fa[pair] = 0;
     return;
   }
-  for (int i = tid; i < kSWin; i += kVadThreads) s_win[i] = g_siib_win[i];
+  for (int i = tid; i < kSWin; i += kVad2Threads) s_win[i] = g_siib_win[i];
   double sx = 0.0, sy = 0.0;
-  for (int i = tid; i < L; i += kVadThreads) {
+  for (int i = tid; i < L; i += kVad2Threads) {
     sx += (double)x[i];
     sy += (double)y[i];
   }
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(kVadThreads) siib_vad_kernel(SiibGeom g, SiibB
   const double thr = sel - 40.0;
   if (tid == 0) s_base = 0;
   __syncthreads();
-  for (int64_t f0 = 0; f0 < F; f0 += kVadThreads) {
+  for (int64_t f0 = 0; f0 < F; f0 += kVad2Threads) {
     const int64_t f = f0 + tid;
     const int keep = (f < F && db[f] > thr) ? 1 : 0;
     int inc = keep;
@@ -340,31 +348,53 @@ __device__ __forceinline__ void block_desc(int blk, int& ta, int& tb, int& d) {
 
 constexpr int kCovWarps = 8;
 constexpr int kCovTile = 64;                        // frames per staged tile
-constexpr int kCovRows = kCovTile + kSStack - 1;    // + 14 frames of lag reach
+constexpr int kCovRows = kCovTile + kSStack;        // + 15 frames of lag reach (two lags per warp)
+constexpr int kCovTasks = 31;                       // warp tasks per pair: two consecutive lags each
 
-// The eight warps of a CTA own eight lag blocks of the same pair and walk the time axis
-// together: each tile of frames is converted to FP64 once into shared memory (the F2F
-// conversions, not the DFMAs, bound a version that converted per use) and every warp
-// accumulates its 32 x 32 block (28 x 28 used) from broadcast shared-memory reads.
+// task -> (type of A rows, type of B rows, first lag e >= 0, number of lags 1 or 2, transposed store)
+//   0..7   xx lags (0,1) (2,3) ... (12,13) (14)        8..15  yy likewise
+//   16..23 xy lags >= 0 likewise                        24..30 yx lags (1,2) ... (13,14): stored
+//   transposed as the xy blocks of negative lag (D_xy,-e[jx][jy] = D_yx,e[jy][jx])
+__device__ __forceinline__ void cov_task(int task, int& ta, int& tb, int& e, int& nl, bool& tr) {
+  tr = false;
+  if (task < 24) {
+    const int grp = task >> 3, k = task & 7;
+    ta = (grp == 1) ? 1 : 0;
+    tb = (grp == 0) ? 0 : 1;
+    e = 2 * k;
+    nl = (k == 7) ? 1 : 2;
+  } else {
+    ta = 1;
+    tb = 0;
+    e = 1 + 2 * (task - 24);
+    nl = 2;
+    tr = true;
+  }
+}
+
+// The eight warps of a CTA walk the time axis together: each tile of frames is converted to
+// FP64 once into shared memory and every warp accumulates two 32 x 32 lag blocks (28 x 28 used)
+// that share their A rows; the B rows of lag e + 1 at frame t are the B rows of lag e at frame
+// t + 1, so one new B row per frame feeds 64 FP64 FMAs per lane (6 LDS.128 per 64 DFMA).
 __global__ void __launch_bounds__(kCovWarps * 32) siib_cov_kernel(SiibGeom g, SiibBuffers b) {
   const int lp = blockIdx.y, pair = b.pair_lo + lp, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int blk = blockIdx.x * kCovWarps + wib;
+  const int task = blockIdx.x * kCovWarps + wib;
   const int Fa = b.Fa[pair];
   const int Nf = Fa - (kSStack - 1);
   if (Nf < 1) return;
   __shared__ __align__(16) double s_x[2][kCovRows][kSLanes];
-  const bool active = blk < kSBlocks;
-  int ta = 0, tb = 0, d = 0;
-  if (active) block_desc(blk, ta, tb, d);
-  const int a0 = max(0, -d), b0 = max(0, d);
-  const int rg = lane >> 2, cg = lane & 3;
+  const bool active = task < kCovTasks;
+  int ta = 0, tb = 0, e = 0, nl = 1;
+  bool tr = false;
+  if (active) cov_task(task, ta, tb, e, nl, tr);
+  const int rg = lane >> 3, cg = lane & 7;  // rows 8 rg .. 8 rg + 7 of A, columns 4 cg .. 4 cg + 3 of B
   const float* __restrict__ X = b.logspec + (g.offF[pair]) * kSLanes;
   const float* __restrict__ Y = b.logspec + (b.totF + g.offF[pair]) * kSLanes;
-  double acc[4][8];
+  double acc0[8][4], acc1[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = 0.0;
   for (int t0 = 0; t0 < Nf; t0 += kCovTile) {
     __syncthreads();
     for (int idx = threadIdx.x; idx < 2 * kCovRows * (kSLanes / 4); idx += kCovWarps * 32) {
@@ -381,30 +411,49 @@ __global__ void __launch_bounds__(kCovWarps * 32) siib_cov_kernel(SiibGeom g, Si
     __syncthreads();
     if (!active) continue;
     const int nt = min(kCovTile, Nf - t0);
-    const double* A = &s_x[ta][a0][4 * rg];
-    const double* B = &s_x[tb][b0][8 * cg];
+    const double* A = &s_x[ta][0][8 * rg];
+    const double* B = &s_x[tb][e][4 * cg];
+    double2 c01 = *reinterpret_cast<const double2*>(B), c23 = *reinterpret_cast<const double2*>(B + 2);
 #pragma unroll 2
     for (int t = 0; t < nt; ++t) {
       const double2 a01 = *reinterpret_cast<const double2*>(A + t * kSLanes);
       const double2 a23 = *reinterpret_cast<const double2*>(A + t * kSLanes + 2);
-      const double2 c01 = *reinterpret_cast<const double2*>(B + t * kSLanes);
-      const double2 c23 = *reinterpret_cast<const double2*>(B + t * kSLanes + 2);
-      const double2 c45 = *reinterpret_cast<const double2*>(B + t * kSLanes + 4);
-      const double2 c67 = *reinterpret_cast<const double2*>(B + t * kSLanes + 6);
-      const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-      const double c[8] = {c01.x, c01.y, c23.x, c23.y, c45.x, c45.y, c67.x, c67.y};
+      const double2 a45 = *reinterpret_cast<const double2*>(A + t * kSLanes + 4);
+      const double2 a67 = *reinterpret_cast<const double2*>(A + t * kSLanes + 6);
+      const double2 n01 = *reinterpret_cast<const double2*>(B + (t + 1) * kSLanes);      // lag e + 1 now,
+      const double2 n23 = *reinterpret_cast<const double2*>(B + (t + 1) * kSLanes + 2);  // lag e next frame
+      const double a[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
+      const double c[4] = {c01.x, c01.y, c23.x, c23.y};
+      const double n[4] = {n01.x, n01.y, n23.x, n23.y};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], c[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) {
+          acc0[i][j] = fma(a[i], c[j], acc0[i][j]);
+          acc1[i][j] = fma(a[i], n[j], acc1[i][j]);
+        }
+      c01 = n01;
+      c23 = n23;
     }
   }
   if (!active) return;
-  double* __restrict__ out = b.base + ((int64_t)lp * kSBlocks + blk) * (kSLanes * kSLanes);
+  // block ids of siib_expand_kernel: xx lag d -> d, yy -> 15 + d, xy lag d (-14..14) -> 44 + d
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int l = 0; l < 2; ++l) {
+    if (l >= nl) break;
+    const int lag = e + l;
+    const int blk = tr ? (44 - lag) : (ta == 0 && tb == 0) ? lag : (ta == 1 && tb == 1) ? 15 + lag : 44 + lag;
+    double* __restrict__ out = b.base + ((int64_t)lp * kSBlocks + blk) * (kSLanes * kSLanes);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out[(4 * rg + i) * kSLanes + 8 * cg + j] = acc[i][j];
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double v = l ? acc1[i][j] : acc0[i][j];
+        const int ra = 8 * rg + i, cb = 4 * cg + j;
+        if (tr) out[cb * kSLanes + ra] = v;
+        else out[ra * kSLanes + cb] = v;
+      }
+  }
 }
 
 // ------------------------------------------------------------------ expand
@@ -891,7 +940,7 @@ __global__ void __launch_bounds__(NWARP * 32) siib_jacobi2_kernel(SiibGeom g, Si
 
 // ------------------------------------------------------- quadratic forms + score
 constexpr int kQuadThreads = 448;
-constexpr int kQuadJ = 8;
+constexpr int kQuadJ = 16;  // eigenvectors per pass over Sxy / Syy (each pass re-reads 1.4 MB)
 
 __global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, SiibBuffers b) {
   const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -920,14 +969,14 @@ __global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, Sii
   for (int j0 = 0; j0 < r; j0 += kQuadJ) {
     __syncthreads();
     // norms of the columns j0..j0+7 (one warp per column), then scatter the unit vectors
-    if (wib < kQuadJ) {
+    for (int jj = wib; jj < kQuadJ; jj += NW) {
       float s = 0.f;
-      if (j0 + wib < r) {
-        const float* col = G + (int64_t)(j0 + wib) * kSLd;
+      if (j0 + jj < r) {
+        const float* col = G + (int64_t)(j0 + jj) * kSLd;
         for (int i = lane; i < kSDim; i += 32) s = fmaf(col[i], col[i], s);
       }
       s = warp_sum(s);
-      if (lane == 0) s_lam[wib] = s;
+      if (lane == 0) s_lam[jj] = s;
     }
     __syncthreads();
     if (tid < kSDim) {
@@ -943,12 +992,15 @@ __global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, Sii
 #pragma unroll
     for (int jj = 0; jj < kQuadJ; ++jj) axy[jj] = ayy[jj] = 0.f;
     if (tid < kSDim) {
-#pragma unroll 2
+#pragma unroll 4
       for (int c = 0; c < kSDim; ++c) {
         const float sxy = __ldg(Sxy + (int64_t)c * kSDim + tid), syy = __ldg(Syy + (int64_t)c * kSDim + tid);
         const float4 u0 = *reinterpret_cast<const float4*>(&s_u[c][0]);
         const float4 u1 = *reinterpret_cast<const float4*>(&s_u[c][4]);
-        const float uu[kQuadJ] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        const float4 u2 = *reinterpret_cast<const float4*>(&s_u[c][8]);
+        const float4 u3 = *reinterpret_cast<const float4*>(&s_u[c][12]);
+        const float uu[kQuadJ] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w,
+                                  u2.x, u2.y, u2.z, u2.w, u3.x, u3.y, u3.z, u3.w};
 #pragma unroll
         for (int jj = 0; jj < kQuadJ; ++jj) {
           axy[jj] = fmaf(sxy, uu[jj], axy[jj]);
@@ -1024,7 +1076,7 @@ int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_til
 int siib_run(const SiibGeom& g, const SiibBuffers& b, int n, int64_t max_F, KernelTimer* kt, cudaStream_t s) {
   int launches = 0;
   kt_begin(kt, "siib_vad", s);
-  siib_vad_kernel<<<n, kVadThreads, 0, s>>>(g, b);
+  siib_vad_kernel<<<n, kVad2Threads, 0, s>>>(g, b);
   kt_end(kt, s);
   ++launches;
   if (max_F > 0) {
@@ -1038,7 +1090,7 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, int n, int64_t max_F, Kern
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "siib_cov", s);
-  siib_cov_kernel<<<dim3((kSBlocks + kCovWarps - 1) / kCovWarps, n), kCovWarps * 32, 0, s>>>(g, b);
+  siib_cov_kernel<<<dim3((kCovTasks + kCovWarps - 1) / kCovWarps, n), kCovWarps * 32, 0, s>>>(g, b);
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "siib_expand", s);

@@ -128,3 +128,25 @@ def test_read_batch_functions_match_oracle_per_file(api, tmp_path):
     assert np.allclose(s3, siib, atol=1e-9) and np.allclose(e3, estoi, atol=1e-9)
     assert np.abs(np.array(h3) - want[:, 1]).max() < 3e-3
     assert api.read_batch_SIIB(cr, nr, []) == []
+
+
+def test_score_tensors_matches_host_path(api):
+    """In-loop tensor boundary: CUDA tensors in, records out, waveforms never leave the device."""
+    import torch
+    from nele_gan_b200.synth import make_pair
+    lens = [33536, 40111, 29999]
+    pairs = [make_pair(60 + i, L)[:2] for i, L in enumerate(lens)]
+    lmax = max(lens)
+    ref = torch.zeros((3, lmax), dtype=torch.float32)
+    deg = torch.zeros((3, lmax), dtype=torch.float32)
+    for i, (x, y) in enumerate(pairs):
+        ref[i, :lens[i]] = torch.from_numpy(x)
+        deg[i, :lens[i]] = torch.from_numpy(y)
+    got = api.score_tensors(ref.cuda(), deg.cuda(), lens, norm=True, seed=3)
+    want = api.score_batch([p[0] for p in pairs], [p[1] for p in pairs], norm=True, seed=3)
+    assert got.shape == (3, 3) and got.dtype == torch.float64
+    assert np.allclose(got.numpy(), want, rtol=1e-9, atol=1e-12)
+    q = api.score_tensors(ref.cuda(), deg.cuda(), lens, norm=True, seed=3, pcm16=True)
+    assert np.abs(q.numpy() - want).max() < 5e-3            # 16-bit rounding of the degraded signal barely moves the labels
+    with pytest.raises(ValueError):
+        api.score_tensors(ref, deg, lens)                   # CPU tensors: no CPU path
