@@ -133,21 +133,32 @@ struct Carrier {
 
 #define NELE_LOG2_10 3.3219280948873623f
 #define NELE_20_OVER_LOG2_10 6.0205999132796239f /* 20 log10(2) */
+#define NELE_10_OVER_LOG2_10 3.0102999566398120f /* 10 log10(2) */
 
-NELE_HD float db20(float v) {  // 20 log10(v)
+// single-instruction log2 / exp2 (MUFU.LG2 / MUFU.EX2, denormals flushed): __log2f / exp2f wrap
+// the same instructions in a denormal rescue (compare, scale, fix-up: 4 and 3 extra instructions
+// per call) that the ear model does not need -- inputs below 1.2e-38 are exact silence and clamp
+// to the same floor as log2(0) = -inf.
+NELE_HD float fast_lg2(float v) {
 #if defined(__CUDA_ARCH__)
-  return NELE_20_OVER_LOG2_10 * __log2f(v);
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 #else
-  return NELE_20_OVER_LOG2_10 * log2f(v);
+  return log2f(v);
 #endif
 }
-NELE_HD float undb20(float d) {  // 10^(d/20)
+NELE_HD float fast_ex2(float v) {
 #if defined(__CUDA_ARCH__)
-  return exp2f(d * (NELE_LOG2_10 / 20.0f));
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 #else
-  return exp2f(d * (NELE_LOG2_10 / 20.0f));
+  return exp2f(v);
 #endif
 }
+NELE_HD float db20(float v) { return NELE_20_OVER_LOG2_10 * fast_lg2(v); }          // 20 log10(v)
+NELE_HD float undb20(float d) { return fast_ex2(d * (NELE_LOG2_10 / 20.0f)); }      // 10^(d/20)
 
 // Control-path lane: envelope power accumulation for eb_BWadjust
 // (pyhaspi2.py:1202-1205, 917-980).
@@ -189,9 +200,11 @@ struct EarLane {
   Gt4<T> fc, fs;
   T zlp, v1, v2;
   T m11, m12, m21, m22, g1, g2;
-  float r1inv, thr_low, crfac, attn_ohc;
-  float ctl_db;   // 65 + 20 log10(control gain): level of the control envelope = ctl_db + 10 log10(|u|^2)
-  float sig_db;   // 65 - attnIHC + 20 log10(signal gain)
+  float r1inv, thr_low;
+  float crfac_l2;  // (1 - 1/CR) log2(10)/20: compression slope in log2 units per dB
+  float ohc_l2;    // -attnOHC log2(10)/20
+  float ctl_db;    // 65 + 20 log10(control gain): level of the control envelope = ctl_db + 10 log10(|u|^2)
+  float sig_db;    // 65 - attnIHC + 20 log10(signal gain)
   float acc[6];
 
   NELE_HD void init(const BandConst& b, int q, double bw_sig, const IhcConst& ih) {
@@ -204,8 +217,8 @@ struct EarLane {
     g1 = (T)ih.g1; g2 = (T)ih.g2;
     r1inv = (float)ih.r1inv;
     thr_low = (float)b.lowknee[q];
-    crfac = (float)(1.0 - 1.0 / b.cr[q]);
-    attn_ohc = (float)b.attn_ohc[q];
+    crfac_l2 = (float)((1.0 - 1.0 / b.cr[q]) * 3.3219280948873623 / 20.0);
+    ohc_l2 = (float)(-b.attn_ohc[q] * 3.3219280948873623 / 20.0);
     ctl_db = (float)(65.0 + 20.0 * log10((double)kc.gain));
     sig_db = (float)(65.0 - b.attn_ihc[q] + 20.0 * log10((double)ks.gain));
     for (int d = 0; d < 6; ++d) acc[d] = 0.f;
@@ -220,15 +233,15 @@ struct EarLane {
     const float pc = (float)fc.step(kc, xr, xi);
     const float ps = (float)fs.step(ks, xr, xi);
     // eb_EnvCompressBM (:982-999)
-    float le = ctl_db + 0.5f * db20(pc);
+    float le = fmaf(NELE_10_OVER_LOG2_10, fast_lg2(pc), ctl_db);
     le = fminf(fmaxf(le, thr_low), 100.0f);
-    const float g = undb20(-attn_ohc - (le - thr_low) * crfac);
+    const float g = fast_ex2(fmaf(thr_low - le, crfac_l2, ohc_l2));  // 10^((-attnOHC - (le - thrLow)(1 - 1/CR)) / 20)
     const T b0 = (T)0.095107983402496;
     const T glp = b0 * (T)g + zlp;
     zlp = b0 * (T)g + (T)0.809784033195007 * glp;
     // eb_EnvSL2 (:1080-1083) on env = glp * gain * sqrt(ps)
     const float gl = (float)glp;
-    const float v0 = fmaxf(sig_db + 0.5f * db20(gl * gl * ps), 0.0f);
+    const float v0 = fmaxf(fmaf(NELE_10_OVER_LOG2_10, fast_lg2(gl * gl * ps), sig_db), 0.0f);
     // eb_IHCadapt (:1065-1073)
     const T V0 = (T)v0;
     const T n1 = m11 * v1 + m12 * v2 + g1 * V0;

@@ -303,6 +303,9 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_kernel(PairGeom g, H
     Lx.init(bc, 0, b.bw[((int64_t)pair * 2 + 0) * kBands + lane], c_ihc);
     Ly.init(bc, 1, b.bw[((int64_t)pair * 2 + 1) * kBands + lane], c_ihc);
   }
+  int wshift = shift;  // largest delay of the warp (band 31, up to ~435 samples)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wshift = max(wshift, __shfl_xor_sync(0xffffffffu, wshift, o));
   int rp = (shift == 0) ? 0 : 2 * kEarChunk - shift;  // ring slot of sample i - shift
   const int nblk = nsub + 2;                           // output j completes after block j + 2
   const int nchunks = (nblk * 9 + kEarChunk - 1) / kEarChunk;
@@ -327,18 +330,31 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_kernel(PairGeom g, H
     for (int blk = c * (kEarChunk / 9); blk < blk_end; ++blk) {
       const int ib = blk * 9;
       float vx[9], vy[9];
+      if (ib >= wshift && ib + 9 <= N) {
+        // steady state (all but the first ~50 and the last block): every lane is past its own
+        // delay and inside the signal, so the nine samples need no per-sample predicates
 #pragma unroll
-      for (int p = 0; p < 9; ++p) {
-        const int i = ib + p;
-        const T xs = ringx[rp], ys = ringy[rp];
-        rp = (rp + 1 == 2 * kEarChunk) ? 0 : rp + 1;
-        if (i >= shift && i < N) {
+        for (int p = 0; p < 9; ++p) {
+          const T xs = ringx[rp], ys = ringy[rp];
+          rp = (rp + 1 == 2 * kEarChunk) ? 0 : rp + 1;
           car.advance();
           vx[p] = Lx.sample(xs * car.c, xs * car.s);
           vy[p] = Ly.sample(ys * car.c, ys * car.s);
-        } else {
-          vx[p] = 0.f;
-          vy[p] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+          const int i = ib + p;
+          const T xs = ringx[rp], ys = ringy[rp];
+          rp = (rp + 1 == 2 * kEarChunk) ? 0 : rp + 1;
+          if (i >= shift && i < N) {
+            car.advance();
+            vx[p] = Lx.sample(xs * car.c, xs * car.s);
+            vy[p] = Ly.sample(ys * car.c, ys * car.s);
+          } else {
+            vx[p] = 0.f;
+            vy[p] = 0.f;
+          }
         }
       }
       Lx.template accumulate<0>(vx[0], c_envfir); Ly.template accumulate<0>(vy[0], c_envfir);

@@ -686,19 +686,39 @@ __device__ __forceinline__ void store_block(const ColBlock& c, float* __restrict
     }
 }
 // Hestenes rotation parameters for one column pair: a = |p|^2, b = |q|^2 (updated in place),
-// gmm = p.q.  Leaves (c, s) = (1, 0) when the pair is already orthogonal to working precision.
+// gmm = p.q.  Branch-free (every lane holds the same values; a branch here costs a convergence
+// barrier per rotation): a pair that is already orthogonal to working precision gets t = 0,
+// i.e. (c, s) = (1, 0).  Hardware approximations (rcp / sqrt / rsqrt, 1-2 ulp) are enough: the
+// rotation only has to be orthogonal to rounding (c^2 + s^2 = c^2 (1 + t^2) = 1), its angle is
+// re-estimated from exact dot products the next time the pair meets, and the column norms are
+// recomputed every time a block is loaded.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void rot_params(float gmm, float& a, float& b, float& c, float& s, int& nrot) {
-  c = 1.0f;
-  s = 0.0f;
-  if (a > 0.f && b > 0.f && fabsf(gmm) > kJacTol * sqrtf(a * b)) {
-    const float zeta = (b - a) / (2.0f * gmm);
-    const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
-    c = rsqrtf(1.0f + t * t);
-    s = c * t;
-    a -= t * gmm;
-    b += t * gmm;
-    ++nrot;
-  }
+  const bool rot = (gmm * gmm > (kJacTol * kJacTol) * (a * b)) && (a > 0.f) && (b > 0.f);
+  const float zeta = (b - a) * fast_rcp(2.0f * gmm);           // +-inf / NaN when gmm == 0: masked below
+  const float az = fabsf(zeta);
+  float t = fast_rcp(az + fast_sqrt(fmaf(zeta, zeta, 1.0f)));  // 1 / (|z| + sqrt(1 + z^2)); 0 for huge |z|
+  t = rot ? copysignf(t, zeta) : 0.0f;
+  c = fast_rsqrt(fmaf(t, t, 1.0f));
+  s = c * t;
+  const float tg = rot ? t * gmm : 0.0f;
+  a -= tg;
+  b += tg;
+  nrot += rot ? 1 : 0;
 }
 __device__ __forceinline__ float dot14(const float (&p)[kJacE], const float (&q)[kJacE]) {
   float g0 = 0.f, g1 = 0.f;
@@ -710,13 +730,11 @@ __device__ __forceinline__ float dot14(const float (&p)[kJacE], const float (&q)
   return g0 + g1;
 }
 __device__ __forceinline__ void apply_rot(float (&p)[kJacE], float (&q)[kJacE], float c, float s) {
-  if (s != 0.f) {  // warp-uniform
 #pragma unroll
-    for (int e = 0; e < kJacE; ++e) {
-      const float a = p[e], bq = q[e];
-      p[e] = c * a - s * bq;
-      q[e] = fmaf(s, a, c * bq);
-    }
+  for (int e = 0; e < kJacE; ++e) {
+    const float a = p[e], bq = q[e];
+    p[e] = fmaf(-s, bq, c * a);
+    q[e] = fmaf(s, a, c * bq);
   }
 }
 // four mutually independent rotations (p0,q0) .. (p3,q3), issued together so that the four
@@ -735,10 +753,12 @@ __device__ __forceinline__ void apply_rot(float (&p)[kJacE], float (&q)[kJacE], 
     rot_params(g1, NP1, NQ1, c1, s1, nrot);                                                  \
     rot_params(g2, NP2, NQ2, c2, s2, nrot);                                                  \
     rot_params(g3, NP3, NQ3, c3, s3, nrot);                                                  \
-    apply_rot(P0, Q0, c0, s0);                                                               \
-    apply_rot(P1, Q1, c1, s1);                                                               \
-    apply_rot(P2, Q2, c2, s2);                                                               \
-    apply_rot(P3, Q3, c3, s3);                                                               \
+    if (s0 != 0.f || s1 != 0.f || s2 != 0.f || s3 != 0.f) { /* one warp-uniform branch */    \
+      apply_rot(P0, Q0, c0, s0);                                                             \
+      apply_rot(P1, Q1, c1, s1);                                                             \
+      apply_rot(P2, Q2, c2, s2);                                                             \
+      apply_rot(P3, Q3, c3, s3);                                                             \
+    }                                                                                        \
   }
 
 // Shared-memory / cluster version of the tournament.  The r columns are cut into S = 2 CL
@@ -747,7 +767,7 @@ __device__ __forceinline__ void apply_rot(float (&p)[kJacE], float (&q)[kJacE], 
 // them with the columns held in registers (4 + 4 per warp, four independent rotations in
 // flight).  Between the S - 1 super-rounds of a sweep the CTAs swap super-blocks through
 // global memory (L2) and meet at a cluster barrier; CL = 1 (r <= 112) never leaves the SM.
-constexpr int kJ2Warps = 14;       // cluster kernel: one warp per 4-column block of a 56-column super-block
+constexpr int kJ2Warps = 12;       // cluster kernel (168 registers per thread, no spills)
 constexpr int kJ2WarpsSmall = 12;  // single-CTA kernel: 168 registers per thread, no spills
 constexpr int kJ2MaxSb = 56;  // columns per super-block (14 blocks of 4)
 
@@ -893,18 +913,26 @@ __global__ void __launch_bounds__(NWARP * 32) siib_jacobi2_kernel(SiibGeom g, Si
           __syncthreads();
         }
       }
-      // every pair between super-block A and super-block B
-      for (int sh = 0; sh < nblk; ++sh) {
-        for (int a = wib; a < nblk; a += NWARP) {
-          const int bq = (a + sh) % nblk;
-          ColBlock P, Q;
-          load_block_s(P, slotA, a * kJacH, lane);
-          load_block_s(Q, slotB, bq * kJacH, lane);
-          rotate_cross(P, Q, nrot);
-          store_block_s(P, slotA, a * kJacH, lane);
-          store_block_s(Q, slotB, bq * kJacH, lane);
+      // every pair between super-block A and super-block B.  Pair k = sh * nblk + a joins block a
+      // of A with block (a + sh) mod nblk of B; any window of fewer than nblk consecutive k is
+      // conflict free (it spans at most two shifts), so NWARP warps take NWARP pairs per barrier
+      // even when nblk is not a multiple of NWARP.
+      {
+        const int npairs = nblk * nblk;
+        const int per = (nblk <= NWARP) ? nblk : NWARP;
+        for (int k0 = 0; k0 < npairs; k0 += per) {
+          const int k = k0 + wib;
+          if (wib < per && k < npairs) {
+            const int a = k % nblk, bq = (a + k / nblk) % nblk;
+            ColBlock P, Q;
+            load_block_s(P, slotA, a * kJacH, lane);
+            load_block_s(Q, slotB, bq * kJacH, lane);
+            rotate_cross(P, Q, nrot);
+            store_block_s(P, slotA, a * kJacH, lane);
+            store_block_s(Q, slotB, bq * kJacH, lane);
+          }
+          __syncthreads();
         }
-        __syncthreads();
       }
       if (CL > 1) {
         store_super(slotA, ua);
