@@ -445,7 +445,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
   // was measured and lost: 348.8 vs 340.9 ms end to end -- the kernels want the larger batch.)
   const int64_t kMaxChunkSamples = 256LL * 1000 * 1000;  // input-rate samples per signal
   const int kMaxChunkPairs = 4096, kHostChunkPairs = 4096;
-  const int kSiibSub = 1024;                              // pairs per SIIB matrix sub-chunk
+  const int kSiibSub = 4096;                              // pairs per SIIB matrix sub-chunk (6.2 MB of matrices per pair)
   std::vector<ChunkPlan> plans;
   plan_chunks(offs, lens, n, dev_in, dev_in ? kMaxChunkPairs : kHostChunkPairs,
               kMaxChunkSamples, plans);

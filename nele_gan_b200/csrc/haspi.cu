@@ -25,6 +25,9 @@
 // overhead of a time-parallel scan of the 4th-order complex gammatone.
 #include <stdio.h>
 
+#include <stdlib.h>
+
+#include "host_tables.hpp"
 #include "kernels.h"
 
 namespace nele {
@@ -603,6 +606,75 @@ __global__ void __launch_bounds__(kModThreads) haspi_modcorr_kernel(PairGeom g, 
   }
 }
 
+// ------------------------------------- modulation filter + corr, recursive form
+// One thread per (cepstral coefficient, modulation band) of a pair, both signals: the three
+// sliding complex sums of host::make_mod_recursions per signal, the band output, and the five
+// correlation sums, all in FP64 registers; no atomics, no shared memory.  Replaces the direct-form
+// kernel above (kept behind NELE_MODCORR_FIR=1 for A/B checks).
+__device__ host::ModRecBand g_modrec[kNumMod];  // read once per thread into registers (lane-indexed
+                                                // __constant__ reads would serialise on every step)
+
+constexpr int kMod2Threads = 64;  // 50 used: 5 coefficients x 10 bands
+
+__global__ void __launch_bounds__(kMod2Threads) haspi_modcorr2_kernel(PairGeom g, HaspiBuffers b) {
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  const int n = b.nsel[pair];
+  if (tid >= kNumCep * kNumMod || n <= 1) return;
+  const int j = tid / kNumMod, m = tid % kNumMod;
+  const int64_t rbase = g.offsub[pair];
+  const float* __restrict__ cx = b.cep + (int64_t)(0 * kNumCep + j) * b.totsub + rbase;
+  const float* __restrict__ cy = b.cep + (int64_t)(1 * kNumCep + j) * b.totsub + rbase;
+  const double mx = b.cepmean[(int64_t)pair * 2 * kNumCep + j];
+  const double my = b.cepmean[(int64_t)pair * 2 * kNumCep + kNumCep + j];
+  double rr[3], ri[3], ar[3], ai[3], br[3], bi[3], wg[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    rr[k] = g_modrec[m].rot[k][0];
+    ri[k] = g_modrec[m].rot[k][1];
+    ar[k] = g_modrec[m].cin[k][0];
+    ai[k] = g_modrec[m].cin[k][1];
+    br[k] = -g_modrec[m].cout[k][0];
+    bi[k] = -g_modrec[m].cout[k][1];
+    wg[k] = g_modrec[m].wgt[k];
+  }
+  const int nh = g_modrec[m].nh;
+  double xr[3] = {0, 0, 0}, xi[3] = {0, 0, 0}, yr[3] = {0, 0, 0}, yi[3] = {0, 0, 0};
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+#pragma unroll 2
+  for (int i = -(nh + 1); i < n - 1; ++i) {  // advance the window centre from i to i + 1
+    const int a = i + 1 + nh, o = i - nh;
+    const double xin = (a < n) ? (double)__ldg(cx + a) - mx : 0.0, yin = (a < n) ? (double)__ldg(cy + a) - my : 0.0;
+    const double xout = (o >= 0) ? (double)__ldg(cx + o) - mx : 0.0, yout = (o >= 0) ? (double)__ldg(cy + o) - my : 0.0;
+    double vx = 0.0, vy = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double dxr = fma(ar[k], xin, br[k] * xout), dxi = fma(ai[k], xin, bi[k] * xout);
+      const double dyr = fma(ar[k], yin, br[k] * yout), dyi = fma(ai[k], yin, bi[k] * yout);
+      const double nxr = fma(rr[k], xr[k], fma(-ri[k], xi[k], dxr)), nxi = fma(rr[k], xi[k], fma(ri[k], xr[k], dxi));
+      const double nyr = fma(rr[k], yr[k], fma(-ri[k], yi[k], dyr)), nyi = fma(rr[k], yi[k], fma(ri[k], yr[k], dyi));
+      xr[k] = nxr;
+      xi[k] = nxi;
+      yr[k] = nyr;
+      yi[k] = nyi;
+      vx = fma(wg[k], nxr, vx);
+      vy = fma(wg[k], nyr, vy);
+    }
+    if (i + 1 >= 0) {
+      s0 += vx;
+      s1 += vy;
+      s2 = fma(vx, vx, s2);
+      s3 = fma(vy, vy, s3);
+      s4 = fma(vx, vy, s4);
+    }
+  }
+  double* dst = b.modsum + ((((int64_t)pair * kNumCep + j) * kNumMod) + m) * 5;
+  dst[0] = s0;
+  dst[1] = s1;
+  dst[2] = s2;
+  dst[3] = s3;
+  dst[4] = s4;
+}
+
 // ---------------------------------------------------------------- score
 __global__ void haspi_score_kernel(HaspiBuffers b, int n, double* intel, double* raw10, int32_t* status) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
@@ -654,6 +726,12 @@ void haspi_upload_tables(const float* cepm, const int* nhalf, const int* off, co
   cudaMemcpyToSymbolAsync(c_mod_off, off, sizeof(int) * (kNumMod + 1), 0, cudaMemcpyHostToDevice, s);
   cudaMemcpyToSymbolAsync(g_modtaps, taps, sizeof(float) * ntaps, 0, cudaMemcpyHostToDevice, s);
   cudaFuncSetAttribute(haspi_modcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)modcorr_smem_bytes());
+  {
+    host::ModRecBand mr[kNumMod];
+    host::make_mod_recursions(mr);
+    cudaMemcpyToSymbolAsync(g_modrec, mr, sizeof(mr), 0, cudaMemcpyHostToDevice, s);
+    cudaStreamSynchronize(s);  // mr is a stack temporary
+  }
   cudaFuncSetAttribute(haspi_ear_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kEarWarps * 4 * kEarChunk * sizeof(double)));
   cudaStreamSynchronize(s);
@@ -685,10 +763,18 @@ int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, boo
   haspi_cep_kernel<<<n, kCepThreads, 0, s>>>(g, b);
   kt_end(kt, s);
   ++launches;
-  cudaMemsetAsync(b.modsum, 0, sizeof(double) * (size_t)n * kNumCep * kNumMod * 5, s);
-  const int tiles = (max_nsub + kModTile - 1) / kModTile;
+  static const bool fir = [] {
+    const char* p = getenv("NELE_MODCORR_FIR");
+    return p && p[0] == '1';
+  }();
   kt_begin(kt, "haspi_modcorr", s);
-  haspi_modcorr_kernel<<<dim3(n, kNumCep, tiles), kModThreads, modcorr_smem_bytes(), s>>>(g, b);
+  if (fir) {
+    cudaMemsetAsync(b.modsum, 0, sizeof(double) * (size_t)n * kNumCep * kNumMod * 5, s);
+    const int tiles = (max_nsub + kModTile - 1) / kModTile;
+    haspi_modcorr_kernel<<<dim3(n, kNumCep, tiles), kModThreads, modcorr_smem_bytes(), s>>>(g, b);
+  } else {
+    haspi_modcorr2_kernel<<<n, kMod2Threads, 0, s>>>(g, b);
+  }
   kt_end(kt, s);
   ++launches;
   return launches;
