@@ -37,7 +37,7 @@ extern "C" {
 #define NELE_ABI_VERSION 1
 
 /* metric mask */
-#define NELE_METRIC_HASPI 0x1u /* HASPI v2  (pyhaspi2.py:76-107)   */
+#define NELE_METRIC_HASPI 0x1u /* HASPI v2  (pyhaspi2.py:76-107); version 1 (:109-157) with NELE_FLAG_HASPI_V1 */
 #define NELE_METRIC_SIIB  0x2u /* SIIB^Gauss (pysiib.SIIB(..., gauss=True)) with the wrapper's >=25 s tiling (intel.py:57-100) */
 #define NELE_METRIC_ESTOI 0x4u /* ESTOI     (pystoi.stoi extended=True) */
 #define NELE_METRIC_ALL   0x7u
@@ -48,6 +48,10 @@ extern "C" {
 #define NELE_FLAG_NO_DITHER     0x04u /* HASPI: zero cepstral dither (parity / deterministic mode) */
 #define NELE_FLAG_SIIB_NO_TILE  0x08u /* SIIB: plain pysiib.SIIB semantics, no wrapper tiling */
 #define NELE_FLAG_KEEP_STAGES   0x10u /* keep per-stage tensors of this call for nele_get_stage() */
+#define NELE_FLAG_HASPI_V1      0x20u /* NELE_METRIC_HASPI computes HASPI version 1, haspi() of pyhaspi2.py:109-157:
+                                         scores[.][1] = Intel (alpha = -1, never mapped), haspi_raw[.][0..3] =
+                                         {CepCorr, cov3 low, mid, high}, [4..9] = NaN.  NELE_FLAG_NO_DITHER also
+                                         zeroes the basilar-membrane threshold noise (pyhaspi2.py:1091-1095). */
 
 /* error codes (function return values) */
 #define NELE_OK              0
@@ -124,6 +128,11 @@ int nele_score_batch(nele_engine* e, const float* ref, const float* deg, const i
  *   "haspi.envlp"  f32 [2][nsub][32]   ebm_EnvFilt output            (pyhaspi2.py:412-413)
  *   "haspi.nsel"   i32 [1]             frames above threshold        (pyhaspi2.py:355-356)
  *   "haspi.cep"    f32 [2][5][nsel]    de-meaned cepstra 2..6        (pyhaspi2.py:366-374)
+ *   "haspi1.segsum" f32 [4][nblk][32]  (NELE_FLAG_HASPI_V1) Hann-weighted sums of the envelopes over the
+ *                                      192-sample blocks: {x rising half, x falling half, y rising, y falling};
+ *                                      eb_EnvSmooth segment s = (rise[s] + fall[s+1]) / sum(window) (pyhaspi2.py:692-700)
+ *   "haspi1.cov"   f32 [nseg][32]      eb_BMcovary sigcov, transposed   (pyhaspi2.py:643-657)
+ *   "haspi1.msx"   f32 [nseg][32]      eb_BMcovary sigMSx, transposed
  *   "estoi.x10"    f32 [2][n10]        10 kHz signals (pystoi resample_oct)
  *   "estoi.info"   i32 [3]             {n10, analysis frames, frames kept by the 40 dB mask}
  *   "estoi.kept"   i32 [kept]          indices of the kept frames

@@ -65,11 +65,30 @@ def haspi_v2(x, fx, y, fy, HL=np.zeros(6), seed=None):
     return np.float64(r.haspi[0]), r.haspi_raw[0].copy()
 
 
-def haspi(x, fx, y, fy, HL=np.zeros(6), alpha=-1.0):
-    """pyhaspi2.py:109-157 (HASPI version 1).  Not on the NELE-GAN labelling path
-    (intel.py uses haspi_v2 only); its fine-structure back-end is the next row
-    of the scope table and is not built yet."""
-    raise NotImplementedError("haspi (v1) is not built yet; NELE-GAN's labelling path calls haspi_v2")
+def haspi(x, fx, y, fy, HL=np.zeros(6), alpha=-1.0, seed=None):
+    """pyhaspi2.py:109-157 (HASPI version 1).  Returns ``(Intel, raw)`` with
+    ``raw = [CepCorr, cov3_low, cov3_mid, cov3_high]``.  Not on the NELE-GAN
+    labelling path (intel.py calls haspi_v2 only) but part of the module's
+    interface.  The basilar-membrane threshold noise the reference draws from
+    the global numpy stream (pyhaspi2.py:1091-1095) comes from the engine's
+    counter-based generator keyed by ``seed`` (default: drawn from
+    ``np.random``, so ``np.random.seed`` makes calls reproducible)."""
+    if fx != fy:
+        raise ValueError("haspi: the engine needs fx == fy (got %r, %r)" % (fx, fy))
+    if fx > 24000:
+        raise NotImplementedError  # pyhaspi2.py:819-820
+    x, y = _f32(x), _f32(y)
+    L = min(len(x), len(y))
+    if seed is None:
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+    hl = np.asarray(HL, dtype=np.float64)
+    r = _engine().score_batch([x[:L]], [y[:L]], fs=int(fx), metrics=("haspi",), mapped=False, seed=seed,
+                              hl=None if not hl.any() else hl, haspi_v1=True)
+    if r.metric_status("haspi")[0] == _eng.ST_BELOW_THR:
+        raise Exception('Function eb_melcor: Signal below threshold, outputs set to 0.')  # pyhaspi2.py:722-723
+    raw = r.haspi_raw[0, :4].copy()
+    arg = -9.047 + 14.816 * raw[0] + 4.616 * raw[3]                       # pyhaspi2.py:146-149
+    return np.float64(1.0 / (1.0 + np.exp(alpha * arg))), raw            # :152
 
 
 # ------------------------------------------------------------------- SIIB

@@ -104,6 +104,24 @@ struct Gt4 {
     i4 = ni;
     return ur * ur + ui * ui;
   }
+  // same, also handing back the complex output (the basilar-membrane path needs its phase)
+  NELE_HD T step_ri(const GtCoef<T>& k, T xr, T xi, T& ur, T& ui) {
+    r1 = k.a * r1 + xr;
+    i1 = k.a * i1 + xi;
+    r2 = k.a * r2 + r1;
+    i2 = k.a * i2 + i1;
+    r3 = k.a * r3 + r2;
+    i3 = k.a * i3 + i2;
+    const T nr = k.a * r4 + r3;
+    const T ni = k.a * i4 + i3;
+    ur = nr + k.c1 * r4 + k.c2 * rp;
+    ui = ni + k.c1 * i4 + k.c2 * ip;
+    rp = r4;
+    ip = i4;
+    r4 = nr;
+    i4 = ni;
+    return ur * ur + ui * ui;
+  }
 };
 
 // carrier cos(w t), -sin(w t) (pyhaspi2.py:843-861 rotates by -w); advanced by
@@ -249,6 +267,37 @@ struct EarLane {
     v1 = n1;
     v2 = n2;
     return fmaxf((float)(V0 - n1) * r1inv, 0.0f);
+  }
+
+  // HASPI version 1 needs the basilar-membrane motion as well (pyhaspi2.py:899, 996-998,
+  // 1086-1087, 1075-1077): bm = gain (ur cos + ui sin) scaled by the three gains the envelope
+  // went through.  The dB-SL and adaptation gains telescope, (y + e)/(env + e) * (out + e)/(y + e)
+  // = (out + e)/(env + e) with e = 1e-30, so bm = glp gain (ur c + ui s) (out + e) / (env + e),
+  // env = glp gain |u| the compressed envelope.  (cs, sn) is the carrier the caller demodulated
+  // with, i.e. the reference's (coscf, sincf).
+  NELE_HD float sample_bm(T xr, T xi, T cs, T sn, float& bm) {
+    const float pc = (float)fc.step(kc, xr, xi);
+    T ur, ui;
+    const float ps = (float)fs.step_ri(ks, xr, xi, ur, ui);
+    float le = fmaf(NELE_10_OVER_LOG2_10, fast_lg2(pc), ctl_db);
+    le = fminf(fmaxf(le, thr_low), 100.0f);
+    const float g = fast_ex2(fmaf(thr_low - le, crfac_l2, ohc_l2));
+    const T b0 = (T)0.095107983402496;
+    const T glp = b0 * (T)g + zlp;
+    zlp = b0 * (T)g + (T)0.809784033195007 * glp;
+    const float gl = (float)glp;
+    const float v0 = fmaxf(fmaf(NELE_10_OVER_LOG2_10, fast_lg2(gl * gl * ps), sig_db), 0.0f);
+    const T V0 = (T)v0;
+    const T n1 = m11 * v1 + m12 * v2 + g1 * V0;
+    const T n2 = m21 * v1 + m22 * v2 + g2 * V0;
+    v1 = n1;
+    v2 = n2;
+    const float out = fmaxf((float)(V0 - n1) * r1inv, 0.0f);
+    const float sg = gl * ks.gain;
+    const float env = sg * sqrtf(ps);
+    const float fine = (float)(ur * cs + ui * sn);
+    bm = (sg * fine) * ((out + 1.0e-30f) / (env + 1.0e-30f));
+    return out;
   }
 
   // FIR bookkeeping.  Sample at loop index i = 9 b + P contributes

@@ -59,6 +59,7 @@ struct nele_engine {
   // workspace (grow-only)
   DevBuf in_ref[2], in_deg[2], geom, sgeom, dither;  // inputs double-buffered: chunk k + 1 uploads while chunk k computes
   DevBuf x24, mid, bw, shift, envlp, rowsel, nsel, cep, cepmean, modsum;            // HASPI
+  DevBuf v1_bm, v1_segsum, v1_cov, v1_msx, v1_xsum, v1_cepcorr, v1_cov3, v1_status;  // HASPI version 1
   DevBuf x10, st_energy, st_kept, st_nkept, st_tob;                                 // ESTOI
   DevBuf sb_wrapdb, sb_M, sb_wact, sb_mean, sb_xdb, sb_act, sb_Fa, sb_logspec;      // SIIB, per chunk
   DevBuf sb_base, sb_Sxx, sb_Sxy, sb_Syy, sb_Lc, sb_G, sb_perm;                     // SIIB, per sub-chunk
@@ -72,9 +73,10 @@ struct nele_engine {
   // geometry of the last chunk (for nele_get_stage)
   bool stages_valid = false;
   uint32_t stage_metrics = 0;
-  std::vector<int64_t> g_off16, g_off24, g_offsub, g_off10, g_offfr, g_offW, g_offF, g_F;
+  std::vector<int64_t> g_off16, g_off24, g_offsub, g_off10, g_offfr, g_offW, g_offF, g_F, g_offblk;
   std::vector<int32_t> g_len16, g_n24, g_nsub, g_n10, g_nfa, g_M;
-  int64_t tot24 = 0, totsub = 0, tot10 = 0, totfr = 0, totF = 0;
+  int64_t tot24 = 0, totsub = 0, tot10 = 0, totfr = 0, totF = 0, totblk = 0;
+  bool stage_v1 = false;
   int chunk_n = 0, sub_lo = 0, sub_n = 0;
 
   bool profiling = false;
@@ -135,6 +137,7 @@ static void upload_metric_tables(cudaStream_t s) {
     host::ModFilters mf;
     host::make_mod_filters(mf);
     haspi_upload_tables(cepm, mf.nhalf, mf.offset, mf.taps.data(), (int)mf.taps.size(), s);
+    haspi_v1_upload_tables(cepm, s);
   }
   {
     float win[256], tw[512];
@@ -186,6 +189,7 @@ extern "C" int nele_create(int device, nele_engine** out) {
   e->serial = !(p && p[0] == '1');
   e->all_bufs = {&e->bands, &e->rs_taps, &e->st_taps, &e->in_ref[0], &e->in_ref[1], &e->in_deg[0], &e->in_deg[1], &e->geom, &e->sgeom, &e->dither,
                  &e->x24, &e->mid, &e->bw, &e->shift, &e->envlp, &e->rowsel, &e->nsel, &e->cep, &e->cepmean, &e->modsum,
+                 &e->v1_bm, &e->v1_segsum, &e->v1_cov, &e->v1_msx, &e->v1_xsum, &e->v1_cepcorr, &e->v1_cov3, &e->v1_status,
                  &e->x10, &e->st_energy, &e->st_kept, &e->st_nkept, &e->st_tob,
                  &e->sb_wrapdb, &e->sb_M, &e->sb_wact, &e->sb_mean, &e->sb_xdb, &e->sb_act, &e->sb_Fa, &e->sb_logspec,
                  &e->sb_base, &e->sb_Sxx, &e->sb_Sxy, &e->sb_Syy, &e->sb_Lc, &e->sb_G, &e->sb_perm,
@@ -426,6 +430,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
   const bool siib_rate_ok = fs == 16000;  // audio_util.py:131,159,187 assert it; the wrapper's R = fs / 200 presumes it
   const bool dev_in = flags & NELE_FLAG_DEVICE_INPUT;
   const bool mapped = flags & NELE_FLAG_MAPPED;
+  const bool haspi_v1 = do_haspi && (flags & NELE_FLAG_HASPI_V1);
   int rc = ensure_tables(e, fs, haspi_rate_ok, hl, s);
   if (rc != NELE_OK) return rc;
 
@@ -444,11 +449,14 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
   // chunk k.  (Cutting a 4096-pair call into two 2048-pair chunks to hide half of its own upload
   // was measured and lost: 348.8 vs 340.9 ms end to end -- the kernels want the larger batch.)
   const int64_t kMaxChunkSamples = 256LL * 1000 * 1000;  // input-rate samples per signal
-  const int kMaxChunkPairs = 4096, kHostChunkPairs = 4096;
+  // HASPI version 1 stages the basilar-membrane motion of both signals in HBM (384 bytes per input
+  // sample at 16 kHz): smaller chunks
+  const int64_t kMaxChunkSamplesV1 = 64LL * 1000 * 1000;
+  const int kMaxChunkPairs = haspi_v1 ? 2048 : 4096, kHostChunkPairs = kMaxChunkPairs;
   const int kSiibSub = 4096;                              // pairs per SIIB matrix sub-chunk (6.2 MB of matrices per pair)
   std::vector<ChunkPlan> plans;
   plan_chunks(offs, lens, n, dev_in, dev_in ? kMaxChunkPairs : kHostChunkPairs,
-              kMaxChunkSamples, plans);
+              haspi_v1 ? kMaxChunkSamplesV1 : kMaxChunkSamples, plans);
   if (!dev_in) {
     rc = upload_chunk(e, plans[0], 0, ref, deg, offs, lens);
     if (rc != NELE_OK) return rc;
@@ -465,9 +473,9 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
     // ---- geometry
     e->g_off16.resize(cn); e->g_len16.resize(cn); e->g_off24.resize(cn); e->g_n24.resize(cn);
     e->g_offsub.resize(cn); e->g_nsub.resize(cn); e->g_off10.resize(cn); e->g_n10.resize(cn);
-    e->g_offfr.resize(cn); e->g_nfa.resize(cn); e->g_offW.resize(cn);
-    int64_t t24 = 0, tsub = 0, t10 = 0, tfr = 0, tW = 0;
-    int max_nsub = 0, max_n10 = 0, max_nfa = 0;
+    e->g_offfr.resize(cn); e->g_nfa.resize(cn); e->g_offW.resize(cn); e->g_offblk.resize(cn);
+    int64_t t24 = 0, tsub = 0, t10 = 0, tfr = 0, tW = 0, tblk = 0;
+    int max_nsub = 0, max_n10 = 0, max_nfa = 0, max_n24 = 0;
     for (int i = 0; i < cn; ++i) {
       const int L = lens[first + i];
       e->g_len16[i] = L;
@@ -478,9 +486,12 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       e->g_nsub[i] = nsub;
       e->g_off24[i] = t24;
       e->g_offsub[i] = tsub;
+      e->g_offblk[i] = tblk;
       t24 += (n24 + 31) & ~31;
       tsub += nsub;
+      tblk += (n24 + 191) / 192;
       max_nsub = std::max(max_nsub, nsub);
+      max_n24 = std::max(max_n24, n24);
       const int n10 = (int)(((int64_t)L * e->st_up + e->st_down - 1) / e->st_down);
       const int nfa = n10 > 256 ? (n10 - 256 + 127) / 128 : 0;
       e->g_n10[i] = n10;
@@ -499,6 +510,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
     e->totsub = tsub;
     e->tot10 = t10;
     e->totfr = tfr;
+    e->totblk = tblk;
     e->chunk_n = cn;
 
     // ---- inputs
@@ -516,6 +528,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
     const size_t o_off10 = gp.add(e->g_off10.data(), cn * sizeof(int64_t));
     const size_t o_offfr = gp.add(e->g_offfr.data(), cn * sizeof(int64_t));
     const size_t o_offW = gp.add(e->g_offW.data(), cn * sizeof(int64_t));
+    const size_t o_offblk = gp.add(e->g_offblk.data(), cn * sizeof(int64_t));
     const size_t o_len16 = gp.add(e->g_len16.data(), cn * sizeof(int32_t));
     const size_t o_n24 = gp.add(e->g_n24.data(), cn * sizeof(int32_t));
     const size_t o_nsub = gp.add(e->g_nsub.data(), cn * sizeof(int32_t));
@@ -532,6 +545,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
     g.len16 = (const int32_t*)(gb + o_len16);
     g.n24 = (const int32_t*)(gb + o_n24);
     g.nsub = (const int32_t*)(gb + o_nsub);
+    g.offblk = (const int64_t*)(gb + o_offblk);
     EstoiGeom eg;
     eg.off16 = g.off16;
     eg.len16 = g.len16;
@@ -594,12 +608,23 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       RESERVE(e, e->mid, (size_t)2 * t24 * sizeof(double));
       RESERVE(e, e->bw, (size_t)cn * 2 * kBands * sizeof(double));
       RESERVE(e, e->shift, (size_t)cn * kBands * sizeof(int32_t));
-      RESERVE(e, e->envlp, (size_t)2 * tsub * kBands * sizeof(float));
-      RESERVE(e, e->rowsel, (size_t)tsub * sizeof(int32_t));
-      RESERVE(e, e->nsel, (size_t)cn * sizeof(int32_t));
-      RESERVE(e, e->cep, (size_t)2 * kNumCep * tsub * sizeof(float));
-      RESERVE(e, e->cepmean, (size_t)cn * 2 * kNumCep * sizeof(double));
-      RESERVE(e, e->modsum, (size_t)cn * kNumCep * kNumMod * 5 * sizeof(double));
+      if (!haspi_v1) {
+        RESERVE(e, e->envlp, (size_t)2 * tsub * kBands * sizeof(float));
+        RESERVE(e, e->rowsel, (size_t)tsub * sizeof(int32_t));
+        RESERVE(e, e->nsel, (size_t)cn * sizeof(int32_t));
+        RESERVE(e, e->cep, (size_t)2 * kNumCep * tsub * sizeof(float));
+        RESERVE(e, e->cepmean, (size_t)cn * 2 * kNumCep * sizeof(double));
+        RESERVE(e, e->modsum, (size_t)cn * kNumCep * kNumMod * 5 * sizeof(double));
+      } else {
+        RESERVE(e, e->v1_bm, (size_t)2 * t24 * kBands * sizeof(float));
+        RESERVE(e, e->v1_segsum, (size_t)4 * tblk * kBands * sizeof(float));
+        RESERVE(e, e->v1_cov, (size_t)tblk * kBands * sizeof(float));
+        RESERVE(e, e->v1_msx, (size_t)tblk * kBands * sizeof(float));
+        RESERVE(e, e->v1_xsum, (size_t)tblk * sizeof(double));
+        RESERVE(e, e->v1_cepcorr, (size_t)cn * sizeof(double));
+        RESERVE(e, e->v1_cov3, (size_t)cn * 3 * sizeof(double));
+        RESERVE(e, e->v1_status, (size_t)cn * sizeof(int32_t));
+      }
       hb.ref = d_ref;
       hb.deg = d_deg;
       hb.x24 = (float*)e->x24.p;
@@ -623,8 +648,23 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       hb.seed = seed;
       hb.no_dither = (flags & NELE_FLAG_NO_DITHER) ? 1 : 0;
       hb.pair_base = first;
-      e->last_launches += haspi_run(g, hb, cn, max_nsub, e->f64, kt, s);
-      e->last_launches += haspi_finish(hb, cn, (double*)e->out_haspi.p, (double*)e->out_raw.p, (int32_t*)e->out_hst.p, kt, s);
+      if (!haspi_v1) {
+        e->last_launches += haspi_run(g, hb, cn, max_nsub, e->f64, kt, s);
+        e->last_launches += haspi_finish(hb, cn, (double*)e->out_haspi.p, (double*)e->out_raw.p, (int32_t*)e->out_hst.p, kt, s);
+      } else {
+        HaspiV1Buffers vb;
+        vb.bm = (float*)e->v1_bm.p;
+        vb.segsum = (float*)e->v1_segsum.p;
+        vb.totblk = tblk;
+        vb.cov = (float*)e->v1_cov.p;
+        vb.msx = (float*)e->v1_msx.p;
+        vb.xsum = (double*)e->v1_xsum.p;
+        vb.cepcorr = (double*)e->v1_cepcorr.p;
+        vb.cov3 = (double*)e->v1_cov3.p;
+        vb.status = (int32_t*)e->v1_status.p;
+        e->last_launches += haspi_v1_run(g, hb, vb, cn, max_n24, e->f64, kt, s);
+        e->last_launches += haspi_v1_finish(g, vb, cn, (double*)e->out_haspi.p, (double*)e->out_raw.p, (int32_t*)e->out_hst.p, kt, s);
+      }
     }
     // ---- ESTOI
     if (run_estoi) {
@@ -770,7 +810,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
         if (haspi_rate_ok) {
           hs = h_hst[i];
           v = h_haspi[i];
-          if (mapped && hs == NELE_ST_OK) v = 1.0 / (1.0 + exp(-0.95 * (v - 2.8)));  // intel.py:116-120
+          if (mapped && hs == NELE_ST_OK && !haspi_v1) v = 1.0 / (1.0 + exp(-0.95 * (v - 2.8)));  // intel.py:116-120
           if (haspi_raw) memcpy(haspi_raw + (size_t)gi * kNumMod, h_raw.data() + (size_t)i * kNumMod, kNumMod * sizeof(double));
         } else if (haspi_raw) {
           for (int m = 0; m < kNumMod; ++m) haspi_raw[(size_t)gi * kNumMod + m] = kNaN;
@@ -799,6 +839,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       if (status) status[gi] = st;
     }
     e->stages_valid = (flags & NELE_FLAG_KEEP_STAGES) && plans.size() == 1;
+    e->stage_v1 = haspi_v1;
     e->stage_metrics = (run_haspi ? NELE_METRIC_HASPI : 0) | (run_siib ? NELE_METRIC_SIIB : 0) | (run_estoi ? NELE_METRIC_ESTOI : 0);
   }
   return NELE_OK;
@@ -830,11 +871,13 @@ extern "C" int nele_get_stage(nele_engine* e, const char* name, int pair, void* 
   const int64_t o24 = e->g_off24[pair], osub = e->g_offsub[pair];
   const int n24 = e->g_n24[pair], nsub = e->g_nsub[pair];
   std::string nm(name);
-  const uint32_t need = nm.rfind("haspi.", 0) == 0 ? NELE_METRIC_HASPI : nm.rfind("estoi.", 0) == 0 ? NELE_METRIC_ESTOI : NELE_METRIC_SIIB;
+  const uint32_t need = (nm.rfind("haspi.", 0) == 0 || nm.rfind("haspi1.", 0) == 0) ? NELE_METRIC_HASPI : nm.rfind("estoi.", 0) == 0 ? NELE_METRIC_ESTOI : NELE_METRIC_SIIB;
   if (!(e->stage_metrics & need)) return fail(e, NELE_E_ARG, "nele_get_stage: '%s' belongs to a metric the last call did not run", name);
   auto dev_i32 = [&](const DevBuf& b, size_t idx, int32_t* out) -> cudaError_t {
     return cudaMemcpy(out, (const int32_t*)b.p + idx, sizeof(int32_t), cudaMemcpyDeviceToHost);
   };
+  if (e->stage_v1 && (nm == "haspi.envlp" || nm == "haspi.nsel" || nm == "haspi.cep" || nm == "haspi.cepmean"))
+    return fail(e, NELE_E_ARG, "nele_get_stage: '%s' is a HASPI version 2 stage; the last call ran version 1", name);
   if (nm == "haspi.mid") {
     for (int q = 0; q < 2; ++q) pieces.push_back({(double*)e->mid.p + q * e->tot24 + o24, n24 * sizeof(double)});
   } else if (nm == "haspi.x24") {
@@ -855,6 +898,16 @@ extern "C" int nele_get_stage(nele_engine* e, const char* name, int pair, void* 
         pieces.push_back({(float*)e->cep.p + (size_t)(q * kNumCep + j) * e->totsub + osub, (size_t)nsel * sizeof(float)});
   } else if (nm == "haspi.cepmean") {
     pieces.push_back({(double*)e->cepmean.p + (size_t)pair * 2 * kNumCep, 2 * kNumCep * sizeof(double)});
+  } else if (nm == "haspi1.segsum" || nm == "haspi1.cov" || nm == "haspi1.msx") {
+    if (!e->stage_v1) return fail(e, NELE_E_ARG, "nele_get_stage: '%s' needs a NELE_FLAG_HASPI_V1 call", name);
+    const int64_t ob = e->g_offblk[pair];
+    const int nblk = (n24 + 191) / 192;
+    const int nseg = n24 < 192 ? 0 : 1 + n24 / 384 + (n24 - 192) / 384;
+    if (nm == "haspi1.segsum") {
+      for (int q = 0; q < 4; ++q) pieces.push_back({(float*)e->v1_segsum.p + (q * e->totblk + ob) * kBands, (size_t)nblk * kBands * sizeof(float)});
+    } else {
+      pieces.push_back({(float*)(nm == "haspi1.cov" ? e->v1_cov.p : e->v1_msx.p) + ob * kBands, (size_t)nseg * kBands * sizeof(float)});
+    }
   } else if (nm == "estoi.x10") {
     for (int q = 0; q < 2; ++q) pieces.push_back({(float*)e->x10.p + q * e->tot10 + e->g_off10[pair], (size_t)e->g_n10[pair] * sizeof(float)});
   } else if (nm == "estoi.info") {

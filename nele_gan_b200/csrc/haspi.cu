@@ -29,6 +29,7 @@
 
 #include "host_tables.hpp"
 #include "kernels.h"
+#include "philox.cuh"
 
 namespace nele {
 
@@ -380,35 +381,6 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_kernel(PairGeom g, H
 }
 
 // ------------------------------------------------------------- cepstra
-__device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
-  const uint64_t p = (uint64_t)a * b;
-  *hi = (uint32_t)(p >> 32);
-  return (uint32_t)p;
-}
-// Philox4x32-10 counter-based generator (Salmon et al. 2011)
-__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t h0, h1;
-    const uint32_t l0 = mulhilo(0xD2511F53u, c[0], &h0), l1 = mulhilo(0xCD9E8D57u, c[2], &h1);
-    const uint32_t n0 = h1 ^ c[1] ^ k0, n2 = h0 ^ c[3] ^ k1;
-    c[0] = n0; c[1] = l1; c[2] = n2; c[3] = l0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-}
-// unit normal for (seed, stream = pair*2+q, row, band)
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t stream, uint32_t row, uint32_t band) {
-  uint32_t c[4] = {row, band >> 1, (uint32_t)stream, (uint32_t)(stream >> 32)};
-  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-  const float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float r = sqrtf(-2.0f * __logf(u1));
-  float sn, cs;
-  __sincosf(6.283185307179586f * u2, &sn, &cs);
-  return (band & 1) ? r * sn : r * cs;
-}
-
 constexpr int kCepThreads = 256;
 
 __global__ void __launch_bounds__(kCepThreads) haspi_cep_kernel(PairGeom g, HaspiBuffers b) {
@@ -737,7 +709,7 @@ void haspi_upload_tables(const float* cepm, const int* nhalf, const int* off, co
   cudaStreamSynchronize(s);
 }
 
-int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, bool f64, KernelTimer* kt, cudaStream_t s) {
+int haspi_run_front(const PairGeom& g, const HaspiBuffers& b, int n, bool f64, KernelTimer* kt, cudaStream_t s) {
   int launches = 0;
   kt_begin(kt, "haspi_prep", s);
   haspi_prep_kernel<<<dim3(n, 2), kPrepThreads, (kPrepSpan + kPrepSpan / 8 + 8) * sizeof(double), s>>>(g, b);
@@ -753,6 +725,11 @@ int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, boo
   haspi_shift_kernel<<<(n * 32 + 127) / 128, 128, 0, s>>>(b, n);
   kt_end(kt, s);
   ++launches;
+  return launches;
+}
+
+int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, bool f64, KernelTimer* kt, cudaStream_t s) {
+  int launches = haspi_run_front(g, b, n, f64, kt, s);
   kt_begin(kt, "haspi_ear", s);
   const int ear_ctas = (n + kEarWarps - 1) / kEarWarps;
   if (f64) haspi_ear_kernel<double><<<ear_ctas, kEarWarps * 32, kEarWarps * 4 * kEarChunk * sizeof(double), s>>>(g, b, n);

@@ -15,6 +15,7 @@ struct PairGeom {
   const int32_t* n24;    // ceil(len * 24000 / fs)
   const int64_t* offsub; // start (in rows of 32) in the decimated-envelope buffers
   const int32_t* nsub;   // ceil(n24 / 9)
+  const int64_t* offblk; // start (in rows of 32) in the HASPI v1 buffers indexed by 192-sample blocks
 };
 
 struct HaspiBuffers {
@@ -69,6 +70,29 @@ int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, boo
 // scores: raw Intel [n] and aveCM [n][10]; status byte per pair
 int haspi_finish(const HaspiBuffers& b, int n, double* intel, double* raw10, int32_t* status, KernelTimer* kt,
                  cudaStream_t s);
+
+// --------------------------------------------------------------- HASPI v1
+// Back-end of haspi() (pyhaspi2.py:109-157) on the same ear model: the envelopes are smoothed
+// to 16 ms segments inside the ear kernel, the basilar-membrane motion goes through HBM once.
+struct HaspiV1Buffers {
+  float* bm;         // [2][tot24][32] delay-compensated BM motion (+ threshold noise) of x and y
+  float* segsum;     // [2 signals][2 (rising, falling half window)][totblk][32] windowed block sums
+  int64_t totblk;
+  float* cov;        // [totblk][32] segment cross-covariance (eb_BMcovary sigcov)
+  float* msx;        // [totblk][32] 2 * MSx (eb_BMcovary sigMSx)
+  double* xsum;      // [totblk] segment loudness of eb_3LevelCovary (-1e300 = below threshold)
+  double* cepcorr;   // [n]
+  double* cov3;      // [n][3]
+  int32_t* status;   // [n] 0 ok, 1 below threshold
+};
+void haspi_v1_upload_tables(const float* cepm, cudaStream_t s);
+// prep / control / shift kernels of haspi_run, then the v1 ear kernel and back-end
+int haspi_v1_run(const PairGeom& g, const HaspiBuffers& b, const HaspiV1Buffers& v, int n, int max_n24, bool f64,
+                 KernelTimer* kt, cudaStream_t s);
+int haspi_v1_finish(const PairGeom& g, const HaspiV1Buffers& v, int n, double* intel, double* raw10, int32_t* status,
+                    KernelTimer* kt, cudaStream_t s);
+// front half of haspi_run (prep, control, shift), shared by both versions
+int haspi_run_front(const PairGeom& g, const HaspiBuffers& b, int n, bool f64, KernelTimer* kt, cudaStream_t s);
 
 // ------------------------------------------------------------------ ESTOI
 struct EstoiGeom {
