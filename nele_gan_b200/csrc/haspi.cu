@@ -383,6 +383,11 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_kernel(PairGeom g, H
 // ------------------------------------------------------------- cepstra
 constexpr int kCepThreads = 256;
 
+// One thread per envelope row (the 32 band values of a row are one 128-byte line): the loudness
+// test costs 32 EX2 + adds per row instead of a warp reduction, and the projection keeps its
+// 2 x 2 x 5 accumulators in registers with the basis as immediate constant operands.  A thread
+// projects two consecutive kept rows, so that one Philox block (four normals) dithers one band
+// of both rows and both signals.
 __global__ void __launch_bounds__(kCepThreads) haspi_cep_kernel(PairGeom g, HaspiBuffers b) {
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   constexpr int NW = kCepThreads / 32;
@@ -390,22 +395,26 @@ __global__ void __launch_bounds__(kCepThreads) haspi_cep_kernel(PairGeom g, Hasp
   const int64_t rbase = g.offsub[pair];
   const float* __restrict__ ex = b.envlp + rbase * kBands;
   const float* __restrict__ ey = b.envlp + (b.totsub + rbase) * kBands;
-  int32_t* __restrict__ rowsel = b.rowsel + rbase;
+  int32_t* __restrict__ keep = b.rowsel + rbase;  // compacted list of the kept rows
   __shared__ int s_cnt[NW];
   __shared__ int s_base;
   __shared__ double s_sum[NW][2 * kNumCep];
-
-  // 1. loudness of every reference frame (pyhaspi2.py:352-355)
-  for (int r = wib; r < nsub; r += NW) {
-    const float lin = warp_sum(undb20(ex[(int64_t)r * kBands + lane]));
-    if (lane == 0) rowsel[r] = (db20(lin * (1.0f / kBands)) > 2.5f) ? 1 : 0;
-  }
   if (tid == 0) s_base = 0;
   __syncthreads();
-  // 2. exclusive scan of the keep flags -> compacted row index
+  // 1. loudness of every reference frame (pyhaspi2.py:352-355) + ordered compaction
   for (int r0 = 0; r0 < nsub; r0 += kCepThreads) {
     const int r = r0 + tid;
-    const int f = (r < nsub) ? rowsel[r] : 0;
+    int f = 0;
+    if (r < nsub) {
+      const float4* row = reinterpret_cast<const float4*>(ex + (int64_t)r * kBands);
+      float lin = 0.f;
+#pragma unroll
+      for (int q4 = 0; q4 < kBands / 4; ++q4) {
+        const float4 v = row[q4];
+        lin += undb20(v.x) + undb20(v.y) + undb20(v.z) + undb20(v.w);
+      }
+      f = (db20(lin * (1.0f / kBands)) > 2.5f) ? 1 : 0;
+    }
     int inc = f;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -414,12 +423,13 @@ __global__ void __launch_bounds__(kCepThreads) haspi_cep_kernel(PairGeom g, Hasp
     }
     if (lane == 31) s_cnt[wib] = inc;
     __syncthreads();
-    int woff = 0;
-    for (int w = 0; w < wib; ++w) woff += s_cnt[w];
-    int tot = 0;
-    for (int w = 0; w < NW; ++w) tot += s_cnt[w];
+    int woff = 0, tot = 0;
+    for (int w = 0; w < NW; ++w) {
+      if (w < wib) woff += s_cnt[w];
+      tot += s_cnt[w];
+    }
     const int base = s_base;
-    if (r < nsub) rowsel[r] = f ? (base + woff + inc - 1) : -1;
+    if (f) keep[base + woff + inc - 1] = r;
     __syncthreads();
     if (tid == 0) s_base = base + tot;
     __syncthreads();
@@ -427,42 +437,79 @@ __global__ void __launch_bounds__(kCepThreads) haspi_cep_kernel(PairGeom g, Hasp
   const int nsel = s_base;
   if (tid == 0) b.nsel[pair] = nsel;
 
-  // 3. dither + projection of the kept frames (pyhaspi2.py:359-367), column sums
-  float cm[kNumCep];
+  // 2. dither + projection of the kept frames (pyhaspi2.py:359-367), column sums
+  float sum[2 * kNumCep];
 #pragma unroll
-  for (int j = 0; j < kNumCep; ++j) cm[j] = c_cepm[lane * kNumCep + j];
-  double sum[2 * kNumCep];
-#pragma unroll
-  for (int j = 0; j < 2 * kNumCep; ++j) sum[j] = 0.0;
+  for (int j = 0; j < 2 * kNumCep; ++j) sum[j] = 0.f;
   const uint64_t gp = (uint64_t)(b.pair_base + pair);
-  for (int r = wib; r < nsub; r += NW) {
-    const int ci = rowsel[r];
-    if (ci < 0) continue;
-    float vx = ex[(int64_t)r * kBands + lane], vy = ey[(int64_t)r * kBands + lane];
-    if (!b.no_dither) {
-      if (b.dither) {
-        if (ci < b.dither_rows) {
-          vx += 0.1f * b.dither[(int64_t)ci * kBands + lane];
-          vy += 0.1f * b.dither[(b.dither_rows + ci) * kBands + lane];
+  const int mode = b.no_dither ? 0 : (b.dither ? 1 : 2);
+  for (int k = tid; 2 * k < nsel; k += kCepThreads) {
+    const int ca = 2 * k, cb = 2 * k + 1;
+    const bool hb = cb < nsel;
+    const int ra = keep[ca], rb = hb ? keep[cb] : ra;
+    const float4* xa = reinterpret_cast<const float4*>(ex + (int64_t)ra * kBands);
+    const float4* ya = reinterpret_cast<const float4*>(ey + (int64_t)ra * kBands);
+    const float4* xb = reinterpret_cast<const float4*>(ex + (int64_t)rb * kBands);
+    const float4* yb = reinterpret_cast<const float4*>(ey + (int64_t)rb * kBands);
+    float pxa[kNumCep], pya[kNumCep], pxb[kNumCep], pyb[kNumCep];
+#pragma unroll
+    for (int j = 0; j < kNumCep; ++j) pxa[j] = pya[j] = pxb[j] = pyb[j] = 0.f;
+#pragma unroll
+    for (int q4 = 0; q4 < kBands / 4; ++q4) {
+      const float4 vxa = xa[q4], vya = ya[q4], vxb = xb[q4], vyb = yb[q4];
+      float exa[4] = {vxa.x, vxa.y, vxa.z, vxa.w}, eya[4] = {vya.x, vya.y, vya.z, vya.w};
+      float exb[4] = {vxb.x, vxb.y, vxb.z, vxb.w}, eyb[4] = {vyb.x, vyb.y, vyb.z, vyb.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int band = 4 * q4 + u;
+        if (mode == 1) {
+          if (ca < b.dither_rows) {
+            exa[u] += 0.1f * b.dither[(int64_t)ca * kBands + band];
+            eya[u] += 0.1f * b.dither[(b.dither_rows + ca) * kBands + band];
+          }
+          if (cb < b.dither_rows) {
+            exb[u] += 0.1f * b.dither[(int64_t)cb * kBands + band];
+            eyb[u] += 0.1f * b.dither[(b.dither_rows + cb) * kBands + band];
+          }
+        } else if (mode == 2) {
+          float z[4];
+          philox_normal4(b.seed, gp, (uint32_t)k, (uint32_t)band, z);
+          exa[u] = fmaf(0.1f, z[0], exa[u]);
+          eya[u] = fmaf(0.1f, z[1], eya[u]);
+          exb[u] = fmaf(0.1f, z[2], exb[u]);
+          eyb[u] = fmaf(0.1f, z[3], eyb[u]);
         }
-      } else {
-        vx += 0.1f * philox_normal(b.seed, gp * 2 + 0, (uint32_t)ci, (uint32_t)lane);
-        vy += 0.1f * philox_normal(b.seed, gp * 2 + 1, (uint32_t)ci, (uint32_t)lane);
+#pragma unroll
+        for (int j = 0; j < kNumCep; ++j) {
+          const float cm = c_cepm[band * kNumCep + j];
+          pxa[j] = fmaf(exa[u], cm, pxa[j]);
+          pya[j] = fmaf(eya[u], cm, pya[j]);
+          pxb[j] = fmaf(exb[u], cm, pxb[j]);
+          pyb[j] = fmaf(eyb[u], cm, pyb[j]);
+        }
       }
     }
 #pragma unroll
     for (int j = 0; j < kNumCep; ++j) {
-      const float px = warp_sum(vx * cm[j]), py = warp_sum(vy * cm[j]);
-      if (lane == 0) {
-        b.cep[(int64_t)(0 * kNumCep + j) * b.totsub + rbase + ci] = px;
-        b.cep[(int64_t)(1 * kNumCep + j) * b.totsub + rbase + ci] = py;
-        sum[j] += (double)px;
-        sum[kNumCep + j] += (double)py;
+      float* cx = b.cep + (int64_t)(0 * kNumCep + j) * b.totsub + rbase;
+      float* cy = b.cep + (int64_t)(1 * kNumCep + j) * b.totsub + rbase;
+      cx[ca] = pxa[j];
+      cy[ca] = pya[j];
+      sum[j] += pxa[j];
+      sum[kNumCep + j] += pya[j];
+      if (hb) {
+        cx[cb] = pxb[j];
+        cy[cb] = pyb[j];
+        sum[j] += pxb[j];
+        sum[kNumCep + j] += pyb[j];
       }
     }
   }
-  if (lane == 0)
-    for (int j = 0; j < 2 * kNumCep; ++j) s_sum[wib][j] = sum[j];
+#pragma unroll
+  for (int j = 0; j < 2 * kNumCep; ++j) {
+    const double t = warp_sum((double)sum[j]);
+    if (lane == 0) s_sum[wib][j] = t;
+  }
   __syncthreads();
   if (tid < 2 * kNumCep) {
     double t = 0.0;

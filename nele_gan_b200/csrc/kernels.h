@@ -28,7 +28,7 @@ struct HaspiBuffers {
   int32_t* shift;        // [n][32]
   float* envlp;          // [2][totsub][32]
   int64_t totsub;
-  int32_t* rowsel;       // [totsub] compacted index of each envelope row, -1 = dropped
+  int32_t* rowsel;       // [totsub] per pair: ordered list of the envelope rows above the loudness threshold
   int32_t* nsel;         // [n]
   float* cep;            // [2][5][totsub]  (pair p, signal q, coef j at ((q*5+j)*totsub + offsub[p]))
   double* cepmean;       // [n][2][5]
@@ -138,8 +138,11 @@ struct SiibBuffers {
   double* mean;          // [n][2]
   double* xdb;           // [totF]
   int32_t* act;          // [totF] indices of the active frames
+  int32_t* aidx;         // [totF] frame (first period only) -> index in act
+  int32_t* src;          // [totF] active frame -> row of lograw holding its spectrum (first occurrence)
   int32_t* Fa;           // [n]
-  float* logspec;        // [2][totF][32]
+  float* lograw;         // [2][totF][32] log band energies of the distinct active frames
+  float* logspec;        // [2][totF][32] after forward masking and mean removal
   int64_t totF;
   // per sub-chunk (indexed by pair - pair_lo)
   int pair_lo;

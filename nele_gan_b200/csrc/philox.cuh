@@ -51,4 +51,22 @@ __device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t stream, u
   n1 = sqrtf(-2.0f * __logf(u3)) * __cosf(6.283185307179586f * u4);
 }
 
+// four independent unit normals (two Box-Muller pairs, sine and cosine branch of each)
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, uint32_t row, uint32_t band, float (&z)[4]) {
+  uint32_t c[4] = {row, band, (uint32_t)stream, (uint32_t)(stream >> 32) ^ 0x2545f491u};
+  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u3 = ((float)(c[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u4 = ((float)(c[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float r0 = sqrtf(-2.0f * __logf(u1)), r1 = sqrtf(-2.0f * __logf(u3));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u2, &s0, &c0);
+  __sincosf(6.283185307179586f * u4, &s1, &c1);
+  z[0] = r0 * c0;
+  z[1] = r0 * s0;
+  z[2] = r1 * c1;
+  z[3] = r1 * s1;
+}
+
 }  // namespace nele

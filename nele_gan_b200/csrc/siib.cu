@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(kVad2Threads) siib_vad_kernel(SiibGeom g, Siib
   const int64_t F = g.F[pair];
   double* __restrict__ db = b.xdb + g.offF[pair];
   int32_t* __restrict__ act = b.act + g.offF[pair];
+  int32_t* __restrict__ aidx = b.aidx + g.offF[pair];
+  int32_t* __restrict__ src = b.src + g.offF[pair];
   __shared__ double red[32];
   __shared__ int64_t redi[32];
   __shared__ int s_cnt[NW];
@@ -205,10 +207,24 @@ __global__ void __launch_bounds__(kVad2Threads) siib_vad_kernel(SiibGeom g, Siib
     b.mean[2 * pair] = mx;
     b.mean[2 * pair + 1] = my;
   }
-  for (int64_t f = wib; f < F; f += NW) {
+  // Frame f of the tiled signal starts at sample (200 f) mod L: frames one period apart
+  // (per = L / gcd(L, 200) frames) are identical, so only the first period is analysed -- here and
+  // in the spectrum kernel -- and the rest copied (a 3.0 s utterance tiled 8 times has 240
+  // distinct frames out of 1920).
+  int gcd = L, r200 = kSHop;
+  while (r200) {
+    const int t = gcd % r200;
+    gcd = r200;
+    r200 = t;
+  }
+  const int64_t per = L / gcd;
+  const int64_t Fu = (per < F) ? per : F;
+  for (int64_t f = wib; f < Fu; f += NW) {
     const double d = frame_power_db(x, L, mx, f, true, lane, s_win);
     if (lane == 0) db[f] = d;
   }
+  __syncthreads();
+  for (int64_t f = Fu + tid; f < F; f += kVad2Threads) db[f] = db[f % per];
   __syncthreads();
   const double sel = kth_largest(db, F, percentile_rank(F), red, redi);
   const double thr = sel - 40.0;
@@ -231,12 +247,21 @@ __global__ void __launch_bounds__(kVad2Threads) siib_vad_kernel(SiibGeom g, Siib
       tot += s_cnt[w];
     }
     const int base = s_base;
-    if (keep) act[base + woff + inc - 1] = (int32_t)f;
+    if (keep) {
+      act[base + woff + inc - 1] = (int32_t)f;
+      if (f < Fu) aidx[f] = base + woff + inc - 1;
+    }
     __syncthreads();
     if (tid == 0) s_base = base + tot;
     __syncthreads();
   }
-  if (tid == 0) b.Fa[pair] = s_base;
+  const int Fa = s_base;
+  if (tid == 0) b.Fa[pair] = Fa;
+  // row of the raw spectra that active frame t reads: its own, or that of its first occurrence
+  for (int t = tid; t < Fa; t += kVad2Threads) {
+    const int64_t f = act[t];
+    src[t] = (f < Fu) ? t : aidx[f % per];
+  }
 }
 
 // ------------------------------------------------------------- spectra
@@ -263,6 +288,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32) siib_spec_kernel(SiibGeom g, 
   __syncthreads();
   const int t = blockIdx.x * kSpecWarps + wib;
   if (t >= Fa) return;
+  if (b.src[g.offF[pair] + t] != t) return;  // a copy of an earlier frame (siib_vad_kernel)
   const float* __restrict__ x = b.ref + g.off16[pair];
   const float* __restrict__ y = b.deg + g.off16[pair];
   const int L = g.len16[pair];
@@ -299,8 +325,8 @@ __global__ void __launch_bounds__(kSpecWarps * 32) siib_spec_kernel(SiibGeom g, 
     ey = fmaf(gk, p.y, ey);
   }
   const int64_t row = g.offF[pair] + t;
-  b.logspec[row * kSLanes + lane] = (lane < kSBands) ? logf(ex + (float)kEps) : 0.f;
-  b.logspec[(b.totF + row) * kSLanes + lane] = (lane < kSBands) ? logf(ey + (float)kEps) : 0.f;
+  b.lograw[row * kSLanes + lane] = (lane < kSBands) ? logf(ex + (float)kEps) : 0.f;
+  b.lograw[(b.totF + row) * kSLanes + lane] = (lane < kSBands) ? logf(ey + (float)kEps) : 0.f;
 }
 
 // --------------------------------------------------- forward masking + de-mean
@@ -311,8 +337,10 @@ __global__ void __launch_bounds__(128) siib_mask_kernel(SiibGeom g, SiibBuffers 
   const int pair = b.pair_lo + (item >> 1), q = item & 1;
   const int Fa = b.Fa[pair];
   float* __restrict__ X = b.logspec + ((int64_t)q * b.totF + g.offF[pair]) * kSLanes + lane;
+  const float* __restrict__ R = b.lograw + ((int64_t)q * b.totF + g.offF[pair]) * kSLanes + lane;
+  const int32_t* __restrict__ src = b.src + g.offF[pair];
   float fl = 3.0e38f;
-  for (int t = 0; t < Fa; ++t) fl = fminf(fl, X[(int64_t)t * kSLanes]);
+  for (int t = 0; t < Fa; ++t) fl = fminf(fl, R[(int64_t)src[t] * kSLanes]);
   float hx[kSMaskT - 1], he[kSMaskT - 1];  // masked level and (level - floor) of the previous 15 frames
 #pragma unroll
   for (int d = 0; d < kSMaskT - 1; ++d) {
@@ -321,7 +349,7 @@ __global__ void __launch_bounds__(128) siib_mask_kernel(SiibGeom g, SiibBuffers 
   }
   double sum = 0.0;
   for (int t = 0; t < Fa; ++t) {
-    float v = X[(int64_t)t * kSLanes];
+    float v = R[(int64_t)src[t] * kSLanes];
 #pragma unroll
     for (int d = 0; d < kSMaskT - 1; ++d) v = fmaxf(v, fmaf(-c_siib_decay[d + 1], he[d], hx[d]));
 #pragma unroll
@@ -350,6 +378,9 @@ constexpr int kCovWarps = 8;
 constexpr int kCovTile = 64;                        // frames per staged tile
 constexpr int kCovRows = kCovTile + kSStack;        // + 15 frames of lag reach (two lags per warp)
 constexpr int kCovTasks = 31;                       // warp tasks per pair: two consecutive lags each
+constexpr int kCovTasks64 = 8;                      // the xx tasks: FP64 (the rank decision of the Cholesky needs
+                                                    // exact duplicates to stay exact); yy / xy / yx run in FP32
+constexpr int kCov32Warps = 12;                     // 23 FP32 tasks = two CTAs of 12 warps per pair
 
 // task -> (type of A rows, type of B rows, first lag e >= 0, number of lags 1 or 2, transposed store)
 //   0..7   xx lags (0,1) (2,3) ... (12,13) (14)        8..15  yy likewise
@@ -382,8 +413,8 @@ __global__ void __launch_bounds__(kCovWarps * 32) siib_cov_kernel(SiibGeom g, Si
   const int Fa = b.Fa[pair];
   const int Nf = Fa - (kSStack - 1);
   if (Nf < 1) return;
-  __shared__ __align__(16) double s_x[2][kCovRows][kSLanes];
-  const bool active = task < kCovTasks;
+  __shared__ __align__(16) double s_x[1][kCovRows][kSLanes];
+  const bool active = task < kCovTasks64;
   int ta = 0, tb = 0, e = 0, nl = 1;
   bool tr = false;
   if (active) cov_task(task, ta, tb, e, nl, tr);
@@ -397,7 +428,7 @@ __global__ void __launch_bounds__(kCovWarps * 32) siib_cov_kernel(SiibGeom g, Si
     for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = 0.0;
   for (int t0 = 0; t0 < Nf; t0 += kCovTile) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 2 * kCovRows * (kSLanes / 4); idx += kCovWarps * 32) {
+    for (int idx = threadIdx.x; idx < kCovRows * (kSLanes / 4); idx += kCovWarps * 32) {  // xx only: X rows
       const int q = idx / (kCovRows * (kSLanes / 4)), rem = idx % (kCovRows * (kSLanes / 4));
       const int row = rem / (kSLanes / 4), c4 = rem % (kSLanes / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -449,6 +480,93 @@ __global__ void __launch_bounds__(kCovWarps * 32) siib_cov_kernel(SiibGeom g, Si
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const double v = l ? acc1[i][j] : acc0[i][j];
+        const int ra = 8 * rg + i, cb = 4 * cg + j;
+        if (tr) out[cb * kSLanes + ra] = v;
+        else out[ra * kSLanes + cb] = v;
+      }
+  }
+}
+
+// FP32 twin of the kernel above for the yy, xy and yx tasks (8..30).  Syy and Sxy are stored
+// in FP32 anyway; the sums run in FP32 per 64-frame tile and the tile sums are added to a second
+// FP32 accumulator (two-level summation: ~4e-7 relative error over 1900 frames, an order below
+// what moves the score by 1e-4).
+__global__ void __launch_bounds__(kCov32Warps * 32) siib_cov32_kernel(SiibGeom g, SiibBuffers b) {
+  const int lp = blockIdx.y, pair = b.pair_lo + lp, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int task = kCovTasks64 + blockIdx.x * kCov32Warps + wib;
+  const int Fa = b.Fa[pair];
+  const int Nf = Fa - (kSStack - 1);
+  if (Nf < 1) return;
+  __shared__ __align__(16) float s_x[2][kCovRows][kSLanes];
+  const bool active = task < kCovTasks;
+  int ta = 0, tb = 0, e = 0, nl = 1;
+  bool tr = false;
+  if (active) cov_task(task, ta, tb, e, nl, tr);
+  const int rg = lane >> 3, cg = lane & 7;
+  const float* __restrict__ X = b.logspec + (g.offF[pair]) * kSLanes;
+  const float* __restrict__ Y = b.logspec + (b.totF + g.offF[pair]) * kSLanes;
+  float tot0[8][4], tot1[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tot0[i][j] = tot1[i][j] = 0.f;
+  for (int t0 = 0; t0 < Nf; t0 += kCovTile) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * kCovRows * (kSLanes / 4); idx += kCov32Warps * 32) {
+      const int q = idx / (kCovRows * (kSLanes / 4)), rem = idx % (kCovRows * (kSLanes / 4));
+      const int row = rem / (kSLanes / 4), c4 = rem % (kSLanes / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t0 + row < Fa) v = *reinterpret_cast<const float4*>((q ? Y : X) + (int64_t)(t0 + row) * kSLanes + 4 * c4);
+      *reinterpret_cast<float4*>(&s_x[q][row][4 * c4]) = v;
+    }
+    __syncthreads();
+    if (!active) continue;
+    const int nt = min(kCovTile, Nf - t0);
+    const float* A = &s_x[ta][0][8 * rg];
+    const float* B = &s_x[tb][e][4 * cg];
+    float acc0[8][4], acc1[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = 0.f;
+    float4 cc = *reinterpret_cast<const float4*>(B);
+#pragma unroll 2
+    for (int t = 0; t < nt; ++t) {
+      const float4 a0 = *reinterpret_cast<const float4*>(A + t * kSLanes);
+      const float4 a1 = *reinterpret_cast<const float4*>(A + t * kSLanes + 4);
+      const float4 nn = *reinterpret_cast<const float4*>(B + (t + 1) * kSLanes);  // lag e + 1 now, lag e next frame
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float c[4] = {cc.x, cc.y, cc.z, cc.w};
+      const float n[4] = {nn.x, nn.y, nn.z, nn.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc0[i][j] = fmaf(a[i], c[j], acc0[i][j]);
+          acc1[i][j] = fmaf(a[i], n[j], acc1[i][j]);
+        }
+      cc = nn;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        tot0[i][j] += acc0[i][j];
+        tot1[i][j] += acc1[i][j];
+      }
+  }
+  if (!active) return;
+#pragma unroll
+  for (int l = 0; l < 2; ++l) {
+    if (l >= nl) break;
+    const int lag = e + l;
+    const int blk = tr ? (44 - lag) : (ta == 1 && tb == 1) ? 15 + lag : 44 + lag;
+    double* __restrict__ out = b.base + ((int64_t)lp * kSBlocks + blk) * (kSLanes * kSLanes);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double v = (double)(l ? tot1[i][j] : tot0[i][j]);
         const int ra = 8 * rg + i, cb = 4 * cg + j;
         if (tr) out[cb * kSLanes + ra] = v;
         else out[ra * kSLanes + cb] = v;
@@ -1118,7 +1236,11 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, int n, int64_t max_F, Kern
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "siib_cov", s);
-  siib_cov_kernel<<<dim3((kCovTasks + kCovWarps - 1) / kCovWarps, n), kCovWarps * 32, 0, s>>>(g, b);
+  siib_cov_kernel<<<dim3((kCovTasks64 + kCovWarps - 1) / kCovWarps, n), kCovWarps * 32, 0, s>>>(g, b);
+  kt_end(kt, s);
+  ++launches;
+  kt_begin(kt, "siib_cov32", s);
+  siib_cov32_kernel<<<dim3((kCovTasks - kCovTasks64 + kCov32Warps - 1) / kCov32Warps, n), kCov32Warps * 32, 0, s>>>(g, b);
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "siib_expand", s);
