@@ -53,6 +53,8 @@ extern "C" {
                                          {CepCorr, cov3 low, mid, high}, [4..9] = NaN.  NELE_FLAG_NO_DITHER also
                                          zeroes the basilar-membrane threshold noise (pyhaspi2.py:1091-1095). */
 
+#define NELE_FLAG_STOI_CLASSIC  0x40u /* NELE_METRIC_ESTOI computes classic STOI, pystoi.stoi(..., extended=False) */
+
 /* error codes (function return values) */
 #define NELE_OK              0
 #define NELE_E_ARG          -1 /* bad argument (null pointer, n < 0, unsupported fs ...) */

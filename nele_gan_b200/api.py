@@ -117,13 +117,14 @@ def SIIB(x, y, fs_signal, gauss=False, use_MI_Kraskov=True, window_length=400, w
 
 # ------------------------------------------------------------------ ESTOI
 def stoi(x, y, fs_sig, extended=False):
-    """pystoi.stoi.  NELE-GAN always passes ``extended=True`` (intel.py:126,133)."""
-    if not extended:
-        raise NotImplementedError("classic STOI is not built; NELE-GAN's labelling path uses extended=True")
+    """pystoi.stoi.  NELE-GAN always passes ``extended=True`` (intel.py:126,133);
+    classic STOI (``extended=False``, pystoi's default) runs on the same pipeline
+    with the clipped-correlation back-end."""
     x, y = np.asarray(x), np.asarray(y)
     if x.shape != y.shape:
         raise Exception('x and y should have the same length,' + 'found {} and {}'.format(x.shape, y.shape))
-    r = _engine().score_batch([_f32(x)], [_f32(y)], fs=int(fs_sig), metrics=("estoi",), mapped=False)
+    r = _engine().score_batch([_f32(x)], [_f32(y)], fs=int(fs_sig), metrics=("estoi",), mapped=False,
+                              stoi_classic=not extended)
     if r.metric_status("estoi")[0] == _eng.ST_TOO_SHORT:
         warnings.warn('Not enough STFT frames to compute intermediate intelligibility measure after removing '
                       'silent frames. Returning 1e-5. Please check you wav files', RuntimeWarning)

@@ -690,7 +690,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       eb.K = e->st_K;
       eb.score = (double*)e->out_estoi.p;
       eb.status = (int32_t*)e->out_est.p;
-      e->last_launches += estoi_run(eg, eb, cn, max_n10, max_nfa, kt, se);
+      e->last_launches += estoi_run(eg, eb, cn, max_n10, max_nfa, flags & NELE_FLAG_STOI_CLASSIC, kt, se);
     }
     // ---- SIIB main pipeline
     e->g_M.assign(cn, 0);

@@ -220,7 +220,46 @@ __global__ void __launch_bounds__(kTobWarps * 32) estoi_tob_kernel(EstoiGeom g, 
 // ------------------------------------------------------ segment correlation
 constexpr int kCorrThreads = 128;
 
-__global__ void __launch_bounds__(kCorrThreads) estoi_corr_kernel(EstoiGeom g, EstoiBuffers b) {
+// classic STOI (pystoi.stoi(..., extended=False)): per segment and band, y is scaled to the
+// energy of x, clipped at x (1 + 10^(15/20)) and correlated with x over the 30 frames
+__device__ __forceinline__ float stoi_classic_segment(const float* __restrict__ xs, const float* __restrict__ ys) {
+  const float kEpsF = 2.220446049250313e-16f, kClip = 1.0f + 5.623413251903491f;  // BETA = -15 dB
+  float acc = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < kStoiBands; ++k) {
+    float xv[kStoiSeg], yv[kStoiSeg];
+    float ex = 0.f, ey = 0.f;
+#pragma unroll
+    for (int t = 0; t < kStoiSeg; ++t) {
+      xv[t] = __ldg(xs + t * kStoiBands + k);
+      yv[t] = __ldg(ys + t * kStoiBands + k);
+      ex = fmaf(xv[t], xv[t], ex);
+      ey = fmaf(yv[t], yv[t], ey);
+    }
+    const float nrm = sqrtf(ex / (ey + kEpsF));
+    float mx = 0.f, my = 0.f;
+#pragma unroll
+    for (int t = 0; t < kStoiSeg; ++t) {
+      yv[t] = fminf(yv[t] * nrm, xv[t] * kClip);
+      mx += xv[t];
+      my += yv[t];
+    }
+    mx *= (1.0f / kStoiSeg);
+    my *= (1.0f / kStoiSeg);
+    float qx = 0.f, qy = 0.f, xy = 0.f;
+#pragma unroll
+    for (int t = 0; t < kStoiSeg; ++t) {
+      const float dx = xv[t] - mx, dy = yv[t] - my;
+      qx = fmaf(dx, dx, qx);
+      qy = fmaf(dy, dy, qy);
+      xy = fmaf(dx, dy, xy);
+    }
+    acc += xy / ((sqrtf(qx) + kEpsF) * (sqrtf(qy) + kEpsF));
+  }
+  return acc * (1.0f / kStoiBands);
+}
+
+__global__ void __launch_bounds__(kCorrThreads) estoi_corr_kernel(EstoiGeom g, EstoiBuffers b, int classic) {
   const int pair = blockIdx.x, tid = threadIdx.x;
   const int nfr = b.nkept[pair] - 1;
   __shared__ double red[32];
@@ -238,6 +277,10 @@ __global__ void __launch_bounds__(kCorrThreads) estoi_corr_kernel(EstoiGeom g, E
   for (int m = tid; m < J; m += kCorrThreads) {
     const float* xs = X + (int64_t)m * kStoiBands;
     const float* ys = Y + (int64_t)m * kStoiBands;
+    if (classic) {
+      total += (double)stoi_classic_segment(xs, ys);
+      continue;
+    }
     float mux[kStoiBands], ivx[kStoiBands], muy[kStoiBands], ivy[kStoiBands];
 #pragma unroll
     for (int k = 0; k < kStoiBands; ++k) {
@@ -300,7 +343,8 @@ void estoi_upload_tables(const float* win, const int* lo, const int* hi, const f
   cudaStreamSynchronize(s);
 }
 
-int estoi_run(const EstoiGeom& g, const EstoiBuffers& b, int n, int max_n10, int max_nfa, KernelTimer* kt, cudaStream_t s) {
+int estoi_run(const EstoiGeom& g, const EstoiBuffers& b, int n, int max_n10, int max_nfa, bool classic, KernelTimer* kt,
+              cudaStream_t s) {
   int launches = 0;
   const int span = (int)(((int64_t)kRsTile * b.down) / b.up) + 2 * b.K + 4;
   const size_t smem = (size_t)span * sizeof(float);
@@ -321,7 +365,7 @@ int estoi_run(const EstoiGeom& g, const EstoiBuffers& b, int n, int max_n10, int
     ++launches;
   }
   kt_begin(kt, "estoi_corr", s);
-  estoi_corr_kernel<<<n, kCorrThreads, 0, s>>>(g, b);
+  estoi_corr_kernel<<<n, kCorrThreads, 0, s>>>(g, b, classic ? 1 : 0);
   kt_end(kt, s);
   ++launches;
   return launches;

@@ -765,51 +765,24 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
 }
 
 // ----------------------------------------------------------------- Jacobi
-constexpr int kJacWarps = 12;
 constexpr int kJacH = 4;                  // columns per block
 constexpr int kJacE = kSLd / 32;          // 14 elements per lane per column
 constexpr int kJacMaxSweeps = 15;
 constexpr float kJacTol = 1.5e-6f;
 
+// A block of four columns in registers.  Columns are held *scaled*: true column = scl * v.  A
+// Hestenes rotation (p, q) <- (c (p - t q), c (q + t p)) then costs two FMAs per element pair
+// instead of four operations -- the common factor c goes into the scales -- and the squared
+// norms are carried along by the update formulas |p|^2 -= t p.q, |q|^2 += t p.q.  Scales and
+// norms live next to the columns in shared memory (s_meta) for the length of a round; they are
+// folded back / recomputed exactly once per round (<= 111 rotations per column: no underflow,
+// norm drift ~1e-5).
 struct ColBlock {
   float v[kJacH][kJacE];
   float nrm[kJacH];
+  float scl[kJacH];
 };
 
-__device__ __forceinline__ void load_block(ColBlock& c, const float* __restrict__ G, int first, int r, int lane) {
-#pragma unroll
-  for (int h = 0; h < kJacH; ++h) {
-    float s = 0.f;
-    if (first + h < r) {
-      const float* col = G + (int64_t)(first + h) * kSLd + lane;
-#pragma unroll
-      for (int e = 0; e < kJacE; ++e) {
-        c.v[h][e] = col[e * 32];
-        s = fmaf(c.v[h][e], c.v[h][e], s);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < kJacE; ++e) c.v[h][e] = 0.f;
-    }
-    c.nrm[h] = warp_sum(s);
-  }
-}
-__device__ __forceinline__ void store_block(const ColBlock& c, float* __restrict__ G, int first, int r, int lane) {
-#pragma unroll
-  for (int h = 0; h < kJacH; ++h)
-    if (first + h < r) {
-      float* col = G + (int64_t)(first + h) * kSLd + lane;
-#pragma unroll
-      for (int e = 0; e < kJacE; ++e) col[e * 32] = c.v[h][e];
-    }
-}
-// Hestenes rotation parameters for one column pair: a = |p|^2, b = |q|^2 (updated in place),
-// gmm = p.q.  Branch-free (every lane holds the same values; a branch here costs a convergence
-// barrier per rotation): a pair that is already orthogonal to working precision gets t = 0,
-// i.e. (c, s) = (1, 0).  Hardware approximations (rcp / sqrt / rsqrt, 1-2 ulp) are enough: the
-// rotation only has to be orthogonal to rounding (c^2 + s^2 = c^2 (1 + t^2) = 1), its angle is
-// re-estimated from exact dot products the next time the pair meets, and the column norms are
-// recomputed every time a block is loaded.
 __device__ __forceinline__ float fast_rcp(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -825,17 +798,29 @@ __device__ __forceinline__ float fast_rsqrt(float x) {
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ void rot_params(float gmm, float& a, float& b, float& c, float& s, int& nrot) {
-  const bool rot = (gmm * gmm > (kJacTol * kJacTol) * (a * b)) && (a > 0.f) && (b > 0.f);
-  const float zeta = (b - a) * fast_rcp(2.0f * gmm);           // +-inf / NaN when gmm == 0: masked below
+// Rotation parameters for one column pair.  gs = dot product of the scaled columns; a = |p|^2,
+// b = |q|^2 (true, updated in place); dp, dq the scales (updated in place); tp, tq the factors of
+// the scaled update p~ -= tp q~, q~ += tq p~.  Branch-free (every lane holds the same values; a
+// branch here costs a convergence barrier per rotation): a pair that is already orthogonal to
+// working precision gets t = 0.  Hardware approximations (rcp / sqrt / rsqrt, 1-2 ulp) are enough:
+// the angle is re-estimated from exact dot products the next time the pair meets.
+__device__ __forceinline__ void rot_params(float gs, float& a, float& b, float& dp, float& dq, float& tp, float& tq,
+                                           int& nrot) {
+  const float g = gs * (dp * dq);
+  const bool rot = (g * g > (kJacTol * kJacTol) * (a * b)) && (a > 0.f) && (b > 0.f);
+  const float zeta = (b - a) * fast_rcp(2.0f * g);             // +-inf / NaN when g == 0: masked below
   const float az = fabsf(zeta);
   float t = fast_rcp(az + fast_sqrt(fmaf(zeta, zeta, 1.0f)));  // 1 / (|z| + sqrt(1 + z^2)); 0 for huge |z|
   t = rot ? copysignf(t, zeta) : 0.0f;
-  c = fast_rsqrt(fmaf(t, t, 1.0f));
-  s = c * t;
-  const float tg = rot ? t * gmm : 0.0f;
+  const float c = fast_rsqrt(fmaf(t, t, 1.0f));
+  const float tg = rot ? t * g : 0.0f;
   a -= tg;
   b += tg;
+  const float rpq = dq * fast_rcp(dp);
+  tp = t * rpq;
+  tq = t * fast_rcp(rpq);
+  dp *= c;
+  dq *= c;
   nrot += rot ? 1 : 0;
 }
 __device__ __forceinline__ float dot14(const float (&p)[kJacE], const float (&q)[kJacE]) {
@@ -847,37 +832,55 @@ __device__ __forceinline__ float dot14(const float (&p)[kJacE], const float (&q)
   }
   return g0 + g1;
 }
-__device__ __forceinline__ void apply_rot(float (&p)[kJacE], float (&q)[kJacE], float c, float s) {
+__device__ __forceinline__ void apply_rot(float (&p)[kJacE], float (&q)[kJacE], float tp, float tq) {
 #pragma unroll
   for (int e = 0; e < kJacE; ++e) {
     const float a = p[e], bq = q[e];
-    p[e] = fmaf(-s, bq, c * a);
-    q[e] = fmaf(s, a, c * bq);
+    p[e] = fmaf(-tp, bq, a);
+    q[e] = fmaf(tq, a, bq);
   }
 }
+// Warp sums of four values, every lane gets all four: two halving exchanges leave each lane with
+// one partial, three butterfly steps finish it, four broadcasts hand the results out
+// (10 SHFL + 6 FADD instead of 20 + 20).  The summation order is the same on every lane.
+__device__ __forceinline__ void warp_sum4(float& g0, float& g1, float& g2, float& g3, int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8;
+  const float s0 = h16 ? g0 : g2, s1 = h16 ? g1 : g3;
+  float k0 = h16 ? g2 : g0, k1 = h16 ? g3 : g1;
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  const float s = h8 ? k0 : k1;
+  float k = h8 ? k1 : k0;
+  k += __shfl_xor_sync(0xffffffffu, s, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  g0 = __shfl_sync(0xffffffffu, k, 0);
+  g1 = __shfl_sync(0xffffffffu, k, 8);
+  g2 = __shfl_sync(0xffffffffu, k, 16);
+  g3 = __shfl_sync(0xffffffffu, k, 24);
+}
 // four mutually independent rotations (p0,q0) .. (p3,q3), issued together so that the four
-// reduction / scalar chains overlap
-#define NELE_ROT4(P0, NP0, Q0, NQ0, P1, NP1, Q1, NQ1, P2, NP2, Q2, NQ2, P3, NP3, Q3, NQ3)   \
-  {                                                                                          \
-    float g0 = dot14(P0, Q0), g1 = dot14(P1, Q1), g2 = dot14(P2, Q2), g3 = dot14(P3, Q3);    \
-    _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) {                                     \
-      g0 += __shfl_xor_sync(0xffffffffu, g0, o);                                             \
-      g1 += __shfl_xor_sync(0xffffffffu, g1, o);                                             \
-      g2 += __shfl_xor_sync(0xffffffffu, g2, o);                                             \
-      g3 += __shfl_xor_sync(0xffffffffu, g3, o);                                             \
-    }                                                                                        \
-    float c0, s0, c1, s1, c2, s2, c3, s3;                                                    \
-    rot_params(g0, NP0, NQ0, c0, s0, nrot);                                                  \
-    rot_params(g1, NP1, NQ1, c1, s1, nrot);                                                  \
-    rot_params(g2, NP2, NQ2, c2, s2, nrot);                                                  \
-    rot_params(g3, NP3, NQ3, c3, s3, nrot);                                                  \
-    if (s0 != 0.f || s1 != 0.f || s2 != 0.f || s3 != 0.f) { /* one warp-uniform branch */    \
-      apply_rot(P0, Q0, c0, s0);                                                             \
-      apply_rot(P1, Q1, c1, s1);                                                             \
-      apply_rot(P2, Q2, c2, s2);                                                             \
-      apply_rot(P3, Q3, c3, s3);                                                             \
-    }                                                                                        \
+// scalar chains overlap.  Arguments per column: values, squared norm, scale.
+#define NELE_ROT4_(P0, NP0, DP0, Q0, NQ0, DQ0, P1, NP1, DP1, Q1, NQ1, DQ1, P2, NP2, DP2, Q2, NQ2, DQ2, P3, NP3, DP3, \
+                  Q3, NQ3, DQ3)                                                                                      \
+  {                                                                                                                  \
+    float g0 = dot14(P0, Q0), g1 = dot14(P1, Q1), g2 = dot14(P2, Q2), g3 = dot14(P3, Q3);                            \
+    warp_sum4(g0, g1, g2, g3, lane);                                                                                 \
+    float tp0, tq0, tp1, tq1, tp2, tq2, tp3, tq3;                                                                    \
+    rot_params(g0, NP0, NQ0, DP0, DQ0, tp0, tq0, nrot);                                                              \
+    rot_params(g1, NP1, NQ1, DP1, DQ1, tp1, tq1, nrot);                                                              \
+    rot_params(g2, NP2, NQ2, DP2, DQ2, tp2, tq2, nrot);                                                              \
+    rot_params(g3, NP3, NQ3, DP3, DQ3, tp3, tq3, nrot);                                                              \
+    if (tp0 != 0.f || tp1 != 0.f || tp2 != 0.f || tp3 != 0.f) { /* one warp-uniform branch */                        \
+      apply_rot(P0, Q0, tp0, tq0);                                                                                   \
+      apply_rot(P1, Q1, tp1, tq1);                                                                                   \
+      apply_rot(P2, Q2, tp2, tq2);                                                                                   \
+      apply_rot(P3, Q3, tp3, tq3);                                                                                   \
+    }                                                                                                                \
   }
+#define NELE_COL(B, h) B.v[h], B.nrm[h], B.scl[h]
+#define NELE_ROT4(...) NELE_ROT4_(__VA_ARGS__)
 
 // Shared-memory / cluster version of the tournament.  The r columns are cut into S = 2 CL
 // super-blocks; every CTA of a CL-wide thread-block cluster keeps two super-blocks in shared
@@ -885,53 +888,47 @@ __device__ __forceinline__ void apply_rot(float (&p)[kJacE], float (&q)[kJacE], 
 // them with the columns held in registers (4 + 4 per warp, four independent rotations in
 // flight).  Between the S - 1 super-rounds of a sweep the CTAs swap super-blocks through
 // global memory (L2) and meet at a cluster barrier; CL = 1 (r <= 112) never leaves the SM.
-constexpr int kJ2Warps = 12;       // cluster kernel (168 registers per thread, no spills)
-constexpr int kJ2WarpsSmall = 12;  // single-CTA kernel: 168 registers per thread, no spills
-constexpr int kJ2MaxSb = 56;  // columns per super-block (14 blocks of 4)
+constexpr int kJ2Warps = 12;       // cluster kernel
+constexpr int kJ2WarpsSmall = 12;  // single-CTA kernel
+constexpr int kJ2MaxSb = 56;       // columns per super-block (14 blocks of 4)
 
-__device__ __forceinline__ void load_block_s(ColBlock& c, const float* slot, int first, int lane) {
+__device__ __forceinline__ void load_block_s(ColBlock& c, const float* slot, const float2* meta, int first, int lane) {
 #pragma unroll
   for (int h = 0; h < kJacH; ++h) {
     const float* col = slot + (first + h) * kSLd + lane;
-    float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < kJacE; ++e) {
-      c.v[h][e] = col[e * 32];
-      s = fmaf(c.v[h][e], c.v[h][e], s);
-    }
-    c.nrm[h] = s;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int h = 0; h < kJacH; ++h) c.nrm[h] += __shfl_xor_sync(0xffffffffu, c.nrm[h], o);
+    for (int e = 0; e < kJacE; ++e) c.v[h][e] = col[e * 32];
+    const float2 m = meta[first + h];
+    c.nrm[h] = m.x;
+    c.scl[h] = m.y;
   }
 }
-__device__ __forceinline__ void store_block_s(const ColBlock& c, float* slot, int first, int lane) {
+__device__ __forceinline__ void store_block_s(const ColBlock& c, float* slot, float2* meta, int first, int lane) {
 #pragma unroll
   for (int h = 0; h < kJacH; ++h) {
     float* col = slot + (first + h) * kSLd + lane;
 #pragma unroll
     for (int e = 0; e < kJacE; ++e) col[e * 32] = c.v[h][e];
+    if (lane == 0) meta[first + h] = make_float2(c.nrm[h], c.scl[h]);
   }
 }
-__device__ __forceinline__ void rotate_within(ColBlock& P, ColBlock& Q, int& nrot) {
-  NELE_ROT4(P.v[0], P.nrm[0], P.v[1], P.nrm[1], P.v[2], P.nrm[2], P.v[3], P.nrm[3],
-            Q.v[0], Q.nrm[0], Q.v[1], Q.nrm[1], Q.v[2], Q.nrm[2], Q.v[3], Q.nrm[3]);
-  NELE_ROT4(P.v[0], P.nrm[0], P.v[2], P.nrm[2], P.v[1], P.nrm[1], P.v[3], P.nrm[3],
-            Q.v[0], Q.nrm[0], Q.v[2], Q.nrm[2], Q.v[1], Q.nrm[1], Q.v[3], Q.nrm[3]);
-  NELE_ROT4(P.v[0], P.nrm[0], P.v[3], P.nrm[3], P.v[1], P.nrm[1], P.v[2], P.nrm[2],
-            Q.v[0], Q.nrm[0], Q.v[3], Q.nrm[3], Q.v[1], Q.nrm[1], Q.v[2], Q.nrm[2]);
+__device__ __forceinline__ void rotate_within(ColBlock& P, ColBlock& Q, int& nrot, int lane) {
+  NELE_ROT4(NELE_COL(P, 0), NELE_COL(P, 1), NELE_COL(P, 2), NELE_COL(P, 3),
+            NELE_COL(Q, 0), NELE_COL(Q, 1), NELE_COL(Q, 2), NELE_COL(Q, 3));
+  NELE_ROT4(NELE_COL(P, 0), NELE_COL(P, 2), NELE_COL(P, 1), NELE_COL(P, 3),
+            NELE_COL(Q, 0), NELE_COL(Q, 2), NELE_COL(Q, 1), NELE_COL(Q, 3));
+  NELE_ROT4(NELE_COL(P, 0), NELE_COL(P, 3), NELE_COL(P, 1), NELE_COL(P, 2),
+            NELE_COL(Q, 0), NELE_COL(Q, 3), NELE_COL(Q, 1), NELE_COL(Q, 2));
 }
-__device__ __forceinline__ void rotate_cross(ColBlock& P, ColBlock& Q, int& nrot) {
-  NELE_ROT4(P.v[0], P.nrm[0], Q.v[0], Q.nrm[0], P.v[1], P.nrm[1], Q.v[1], Q.nrm[1],
-            P.v[2], P.nrm[2], Q.v[2], Q.nrm[2], P.v[3], P.nrm[3], Q.v[3], Q.nrm[3]);
-  NELE_ROT4(P.v[0], P.nrm[0], Q.v[1], Q.nrm[1], P.v[1], P.nrm[1], Q.v[2], Q.nrm[2],
-            P.v[2], P.nrm[2], Q.v[3], Q.nrm[3], P.v[3], P.nrm[3], Q.v[0], Q.nrm[0]);
-  NELE_ROT4(P.v[0], P.nrm[0], Q.v[2], Q.nrm[2], P.v[1], P.nrm[1], Q.v[3], Q.nrm[3],
-            P.v[2], P.nrm[2], Q.v[0], Q.nrm[0], P.v[3], P.nrm[3], Q.v[1], Q.nrm[1]);
-  NELE_ROT4(P.v[0], P.nrm[0], Q.v[3], Q.nrm[3], P.v[1], P.nrm[1], Q.v[0], Q.nrm[0],
-            P.v[2], P.nrm[2], Q.v[1], Q.nrm[1], P.v[3], P.nrm[3], Q.v[2], Q.nrm[2]);
+__device__ __forceinline__ void rotate_cross(ColBlock& P, ColBlock& Q, int& nrot, int lane) {
+  NELE_ROT4(NELE_COL(P, 0), NELE_COL(Q, 0), NELE_COL(P, 1), NELE_COL(Q, 1),
+            NELE_COL(P, 2), NELE_COL(Q, 2), NELE_COL(P, 3), NELE_COL(Q, 3));
+  NELE_ROT4(NELE_COL(P, 0), NELE_COL(Q, 1), NELE_COL(P, 1), NELE_COL(Q, 2),
+            NELE_COL(P, 2), NELE_COL(Q, 3), NELE_COL(P, 3), NELE_COL(Q, 0));
+  NELE_ROT4(NELE_COL(P, 0), NELE_COL(Q, 2), NELE_COL(P, 1), NELE_COL(Q, 3),
+            NELE_COL(P, 2), NELE_COL(Q, 0), NELE_COL(P, 3), NELE_COL(Q, 1));
+  NELE_ROT4(NELE_COL(P, 0), NELE_COL(Q, 3), NELE_COL(P, 1), NELE_COL(Q, 0),
+            NELE_COL(P, 2), NELE_COL(Q, 1), NELE_COL(P, 3), NELE_COL(Q, 2));
 }
 // circle-method pairing of `np` players (np even), round `round`, table k -> (i, j)
 __device__ __forceinline__ void circle_pair(int np, int round, int k, int& i, int& j) {
@@ -959,6 +956,7 @@ __global__ void __launch_bounds__(NWARP * 32) siib_jacobi2_kernel(SiibGeom g, Si
   extern __shared__ __align__(16) float s_slot[];      // [2][sbp][448]
   float* slotA = s_slot;
   float* slotB = s_slot + sbp * kSLd;
+  __shared__ float2 s_meta[2][kJ2MaxSb];               // (squared norm, scale) of every resident column
   __shared__ int s_rot;
   int32_t* __restrict__ grot = b.sweep_rot + (int64_t)pair * 16;
 
@@ -980,6 +978,23 @@ __global__ void __launch_bounds__(NWARP * 32) siib_jacobi2_kernel(SiibGeom g, Si
         *reinterpret_cast<float4*>(G + (int64_t)(c0 + c) * kSLd + 4 * q4) = *reinterpret_cast<const float4*>(slot + c * kSLd + 4 * q4);
     }
   };
+  // fold the scales into the columns (fresh = false) and recompute the norms exactly
+  auto refresh_meta = [&](bool fresh) {
+    for (int c = wib; c < 2 * sbp; c += NWARP) {
+      const int sl = c >= sbp, cc = sl ? c - sbp : c;
+      float* col = (sl ? slotB : slotA) + cc * kSLd + lane;
+      const float d = fresh ? 1.0f : s_meta[sl][cc].y;
+      float ss = 0.f;
+#pragma unroll
+      for (int e = 0; e < kJacE; ++e) {
+        const float v = col[e * 32] * d;
+        col[e * 32] = v;
+        ss = fmaf(v, v, ss);
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) s_meta[sl][cc] = make_float2(ss, 1.0f);
+    }
+  };
 
   int ua = 0, ub = 1;
   if (CL == 1) {
@@ -997,12 +1012,16 @@ __global__ void __launch_bounds__(NWARP * 32) siib_jacobi2_kernel(SiibGeom g, Si
         load_super(slotB, ub);
         __syncthreads();
       }
+      refresh_meta(CL > 1 || sweeps == 0);
+      __syncthreads();
       if (rho == 0) {
         // every pair inside super-block A and inside super-block B (once per sweep: in round 0 the
         // S super-blocks are spread over the CL CTAs, two each)
         for (int lr = 0; lr < nbe - 1; ++lr) {
           for (int item = wib; item < nbe; item += NWARP) {
-            float* slot = (item < nbe / 2) ? slotA : slotB;
+            const int sl = (item < nbe / 2) ? 0 : 1;
+            float* slot = sl ? slotB : slotA;
+            float2* meta = s_meta[sl];
             int bi, bj;
             circle_pair(nbe, lr, item % (nbe / 2), bi, bj);
             if (bi > bj) {
@@ -1013,20 +1032,21 @@ __global__ void __launch_bounds__(NWARP * 32) siib_jacobi2_kernel(SiibGeom g, Si
             const bool pad = bj >= nblk;  // partner is the padding block
             if (pad && lr != 0) continue;
             ColBlock P, Q;
-            load_block_s(P, slot, bi * kJacH, lane);
-            if (!pad) load_block_s(Q, slot, bj * kJacH, lane);
+            load_block_s(P, slot, meta, bi * kJacH, lane);
+            if (!pad) load_block_s(Q, slot, meta, bj * kJacH, lane);
             else {
 #pragma unroll
               for (int h = 0; h < kJacH; ++h) {
                 Q.nrm[h] = 0.f;
+                Q.scl[h] = 1.f;
 #pragma unroll
                 for (int e = 0; e < kJacE; ++e) Q.v[h][e] = 0.f;
               }
             }
-            if (lr == 0) rotate_within(P, Q, nrot);
-            if (!pad) rotate_cross(P, Q, nrot);
-            store_block_s(P, slot, bi * kJacH, lane);
-            if (!pad) store_block_s(Q, slot, bj * kJacH, lane);
+            if (lr == 0) rotate_within(P, Q, nrot, lane);
+            if (!pad) rotate_cross(P, Q, nrot, lane);
+            store_block_s(P, slot, meta, bi * kJacH, lane);
+            if (!pad) store_block_s(Q, slot, meta, bj * kJacH, lane);
           }
           __syncthreads();
         }
@@ -1043,16 +1063,18 @@ __global__ void __launch_bounds__(NWARP * 32) siib_jacobi2_kernel(SiibGeom g, Si
           if (wib < per && k < npairs) {
             const int a = k % nblk, bq = (a + k / nblk) % nblk;
             ColBlock P, Q;
-            load_block_s(P, slotA, a * kJacH, lane);
-            load_block_s(Q, slotB, bq * kJacH, lane);
-            rotate_cross(P, Q, nrot);
-            store_block_s(P, slotA, a * kJacH, lane);
-            store_block_s(Q, slotB, bq * kJacH, lane);
+            load_block_s(P, slotA, s_meta[0], a * kJacH, lane);
+            load_block_s(Q, slotB, s_meta[1], bq * kJacH, lane);
+            rotate_cross(P, Q, nrot, lane);
+            store_block_s(P, slotA, s_meta[0], a * kJacH, lane);
+            store_block_s(Q, slotB, s_meta[1], bq * kJacH, lane);
           }
           __syncthreads();
         }
       }
       if (CL > 1) {
+        refresh_meta(false);  // the global copy holds true (unscaled) columns
+        __syncthreads();
         store_super(slotA, ua);
         store_super(slotB, ub);
         __threadfence();
@@ -1075,9 +1097,17 @@ __global__ void __launch_bounds__(NWARP * 32) siib_jacobi2_kernel(SiibGeom g, Si
       if (threadIdx.x == 0) grot[sweeps] = tot;
       __syncthreads();
     }
-    if (tot == 0) break;
+    // Quadratic convergence: a sweep that still found only a handful of pairs above the
+    // threshold (out of r (r - 1) / 2) leaves nothing for the next one; skip the empty
+    // verification sweep.
+    if (tot <= r / 8) {
+      ++sweeps;
+      break;
+    }
   }
   if (CL == 1) {
+    refresh_meta(false);
+    __syncthreads();
     store_super(slotA, 0);
     store_super(slotB, 1);
   }

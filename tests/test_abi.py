@@ -50,6 +50,8 @@ def test_constants_match_header():
     assert vals["NELE_FLAG_NO_DITHER"] == engine.FLAG_NO_DITHER
     assert vals["NELE_FLAG_SIIB_NO_TILE"] == engine.FLAG_SIIB_NO_TILE
     assert vals["NELE_FLAG_KEEP_STAGES"] == engine.FLAG_KEEP_STAGES
+    assert vals["NELE_FLAG_HASPI_V1"] == engine.FLAG_HASPI_V1
+    assert vals["NELE_FLAG_STOI_CLASSIC"] == engine.FLAG_STOI_CLASSIC
     assert vals["NELE_ST_TOO_SHORT"] == engine.ST_TOO_SHORT
 
 

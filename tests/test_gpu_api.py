@@ -79,6 +79,17 @@ def test_stoi_signature_and_sentinel(api, golden):
         api.stoi(g["x"], g["y"][:-1], 16000, extended=True)
 
 
+def test_classic_stoi(api, golden):
+    """pystoi's default, extended=False: same pipeline, clipped-correlation back-end."""
+    from oracle import pystoi_np
+    for name in ("toy_train_clean", "toy_test_clean", "synth_2_48000"):
+        g = golden[name]
+        want = pystoi_np.stoi(g["x"].astype(np.float64), g["y"].astype(np.float64), 16000, extended=False)
+        assert abs(api.stoi(g["x"], g["y"], 16000) - want) < 1e-4
+    g = golden["synth_0_24000"]
+    assert abs(api.stoi(g["x"], g["x"], 16000, extended=False) - 1.0) < 1e-5
+
+
 def _write_corpus(tmp, n=5):
     from scipy.io import wavfile
     from nele_gan_b200.synth import make_pair
