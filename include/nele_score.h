@@ -54,6 +54,8 @@ extern "C" {
                                          zeroes the basilar-membrane threshold noise (pyhaspi2.py:1091-1095). */
 
 #define NELE_FLAG_STOI_CLASSIC  0x40u /* NELE_METRIC_ESTOI computes classic STOI, pystoi.stoi(..., extended=False) */
+#define NELE_FLAG_SIIB_KNN      0x80u /* NELE_METRIC_SIIB uses pysiib's k-nearest-neighbour (Kraskov) estimator,
+                                         SIIB(x, y, fs, gauss=False), instead of SIIB^Gauss */
 
 /* error codes (function return values) */
 #define NELE_OK              0
@@ -69,6 +71,7 @@ extern "C" {
 #define NELE_ST_TOO_SHORT    2 /* ESTOI < 30 frames: score = 1e-5 (pystoi sentinel);
                                   SIIB < 20 s of active speech after tiling: score = NaN */
 #define NELE_ST_BAD_RATE     3 /* sampling rate not supported for this metric: score = NaN */
+#define NELE_ST_UNSUPPORTED  4 /* SIIB k-NN estimator: more than 16384 KLT frames (score = NaN) */
 #define NELE_ST_SKIPPED      0xff /* metric not requested */
 
 typedef struct nele_engine nele_engine;

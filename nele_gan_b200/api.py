@@ -94,24 +94,27 @@ def haspi(x, fx, y, fy, HL=np.zeros(6), alpha=-1.0, seed=None):
 # ------------------------------------------------------------------- SIIB
 def SIIB(x, y, fs_signal, gauss=False, use_MI_Kraskov=True, window_length=400, window_shift=200,
          window='hanning', delta_dB=40.0):
-    """pysiib.SIIB.  NELE-GAN always passes ``gauss=True`` (intel.py:77,100):
-    SIIB^Gauss, which is what the engine computes.  No tiling here -- that is
-    the wrapper's job (intel.py:71-75) -- so fewer than 20 s of active speech
-    raises like pysiib does."""
-    if not gauss:
-        raise NotImplementedError("SIIB with the k-NN estimator (gauss=False) is not built; "
-                                  "NELE-GAN's labelling path uses gauss=True")
+    """pysiib.SIIB.  NELE-GAN always passes ``gauss=True`` (intel.py:77,100),
+    SIIB^Gauss; ``gauss=False`` (pysiib's default) runs the k-nearest-neighbour
+    (Kraskov) estimator on the same KLT.  No tiling here -- that is the
+    wrapper's job (intel.py:71-75) -- so fewer than 20 s of active speech raises
+    like pysiib does."""
+    if not gauss and not use_MI_Kraskov:
+        raise NotImplementedError("only the Kraskov k-NN estimator is built for gauss=False")
     if (window_length, window_shift, window, delta_dB) != (400, 200, 'hanning', 40.0):
         raise NotImplementedError("only pysiib's default analysis parameters are supported")
     x, y = _f32(x), _f32(y)
     if x.shape != y.shape:
         raise ValueError('x and y should have the same length')
-    r = _engine().score_batch([x], [y], fs=int(fs_signal), metrics=("siib",), mapped=False, siib_no_tile=True)
+    r = _engine().score_batch([x], [y], fs=int(fs_signal), metrics=("siib",), mapped=False, siib_no_tile=True,
+                              siib_knn=not gauss)
     st = r.metric_status("siib")[0]
     if st == _eng.ST_TOO_SHORT:
         raise ValueError('stimuli must have at least 20 seconds of speech')
     if st == _eng.ST_BAD_RATE:
         raise NotImplementedError("SIIB: only 16 kHz input is supported (audio_util.py:131 asserts it)")
+    if st == _eng.ST_UNSUPPORTED:
+        raise NotImplementedError("SIIB k-NN estimator: more than 16384 frames after stacking")
     return float(r.siib[0])
 
 

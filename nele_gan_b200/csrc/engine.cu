@@ -64,6 +64,7 @@ struct nele_engine {
   DevBuf sb_wrapdb, sb_M, sb_wact, sb_mean, sb_xdb, sb_act, sb_aidx, sb_src, sb_Fa, sb_lograw, sb_logspec;      // SIIB, per chunk
   DevBuf sb_base, sb_Sxx, sb_Sxy, sb_Syy, sb_Lc, sb_G, sb_perm;                     // SIIB, per sub-chunk
   DevBuf sb_rank, sb_sweeps, sb_lambda, sb_rho;
+  DevBuf kn_xk, kn_info, kn_digamma;  // SIIB k-NN estimator
   DevBuf out_haspi, out_raw, out_hst, out_estoi, out_est, out_siib, out_sst;
   std::vector<DevBuf*> all_bufs;
   int32_t* h_M = nullptr;  // pinned
@@ -193,7 +194,7 @@ extern "C" int nele_create(int device, nele_engine** out) {
                  &e->x10, &e->st_energy, &e->st_kept, &e->st_nkept, &e->st_tob,
                  &e->sb_wrapdb, &e->sb_M, &e->sb_wact, &e->sb_mean, &e->sb_xdb, &e->sb_act, &e->sb_aidx, &e->sb_src, &e->sb_Fa, &e->sb_lograw, &e->sb_logspec,
                  &e->sb_base, &e->sb_Sxx, &e->sb_Sxy, &e->sb_Syy, &e->sb_Lc, &e->sb_G, &e->sb_perm,
-                 &e->sb_rank, &e->sb_sweeps, &e->sb_lambda, &e->sb_rho,
+                 &e->sb_rank, &e->sb_sweeps, &e->sb_lambda, &e->sb_rho, &e->kn_xk, &e->kn_info, &e->kn_digamma,
                  &e->out_haspi, &e->out_raw, &e->out_hst, &e->out_estoi, &e->out_est, &e->out_siib, &e->out_sst};
 #define CUC(call)                                                                             \
   do {                                                                                        \
@@ -722,7 +723,8 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       sg.offF = (const int64_t*)((const char*)e->sgeom.p + o_offF);
       sg.F = (const int64_t*)((const char*)e->sgeom.p + o_F);
       const int64_t tFa = std::max<int64_t>(tF, 1);
-      const int sub = std::min(cn, kSiibSub);
+      const bool siib_knn = flags & NELE_FLAG_SIIB_KNN;
+      const int sub = std::min(cn, siib_knn ? 512 : kSiibSub);
       RESERVE(e, e->sb_mean, (size_t)cn * 2 * sizeof(double));
       RESERVE(e, e->sb_xdb, (size_t)tFa * sizeof(double));
       RESERVE(e, e->sb_act, (size_t)tFa * sizeof(int32_t));
@@ -767,12 +769,34 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       sb.score = (double*)e->out_siib.p;
       sb.status = (int32_t*)e->out_sst.p;
       CU(e, cudaMemsetAsync(e->sb_sweeps.p, 0, (size_t)cn * 17 * sizeof(int32_t), ss));
+      SiibKnnBuffers kb;
+      memset(&kb, 0, sizeof(kb));
+      if (siib_knn) {
+        int64_t maxF_all = 0;
+        for (int i = 0; i < cn; ++i) maxF_all = std::max(maxF_all, e->g_F[i]);
+        kb.ld = (std::max<int64_t>(maxF_all, 32) + 31) & ~(int64_t)31;
+        constexpr int kNDig = 16384 + 2;
+        if (!e->kn_digamma.p) {
+          std::vector<double> dg(kNDig, 0.0);
+          dg[1] = -0.57721566490153286;
+          for (int m = 1; m + 1 < kNDig; ++m) dg[m + 1] = dg[m] + 1.0 / (double)m;
+          RESERVE(e, e->kn_digamma, kNDig * sizeof(double));
+          CU(e, cudaMemcpyAsync(e->kn_digamma.p, dg.data(), kNDig * sizeof(double), cudaMemcpyHostToDevice, ss));
+          CU(e, cudaStreamSynchronize(ss));
+        }
+        RESERVE(e, e->kn_xk, (size_t)sub * 2 * 420 * kb.ld * sizeof(float));
+        RESERVE(e, e->kn_info, (size_t)cn * 420 * sizeof(double));
+        kb.xk = (float*)e->kn_xk.p;
+        kb.info = (double*)e->kn_info.p;
+        kb.digamma = (const double*)e->kn_digamma.p;
+        kb.ndigamma = kNDig;
+      }
       for (int lo_p = 0; lo_p < cn; lo_p += sub) {
         const int sn = std::min(sub, cn - lo_p);
         int64_t maxF = 0;
         for (int i = 0; i < sn; ++i) maxF = std::max(maxF, e->g_F[lo_p + i]);
         sb.pair_lo = lo_p;
-        e->last_launches += siib_run(sg, sb, sn, maxF, kt, ss);
+        e->last_launches += siib_run(sg, sb, siib_knn ? &kb : nullptr, sn, maxF, kt, ss);
         e->sub_lo = lo_p;
         e->sub_n = sn;
       }

@@ -163,8 +163,20 @@ struct SiibBuffers {
   double* score;         // [n]
   int32_t* status;       // [n]
 };
+// k-NN (Kraskov) estimator of pysiib.SIIB(..., gauss=False): siib_knn.cu
+struct SiibKnnBuffers {
+  float* xk;             // [sub][2][420][ld] KLT-domain series of x and y (per sub-chunk)
+  int64_t ld;            // row stride (frames, padded)
+  double* info;          // [n][420] per-component information, bits
+  const double* digamma; // [ndigamma] digamma(m), m = 0 unused
+  int ndigamma;
+};
+void siib_knn_setup();
+int siib_run_knn(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers& kb, int n, int64_t max_F, KernelTimer* kt,
+                 cudaStream_t s);
 void siib_upload_tables(const float* win, const float* decay, const float* g2t, const float* tw, cudaStream_t s);
 int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_tile, KernelTimer* kt, cudaStream_t s);
-int siib_run(const SiibGeom& g, const SiibBuffers& b, int n, int64_t max_F, KernelTimer* kt, cudaStream_t s);
+// kb != nullptr: k-NN estimator instead of the Gaussian quadratic forms
+int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, int n, int64_t max_F, KernelTimer* kt, cudaStream_t s);
 
 }  // namespace nele

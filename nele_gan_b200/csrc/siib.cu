@@ -1239,6 +1239,7 @@ void siib_upload_tables(const float* win, const float* decay, const float* g2t, 
   cudaFuncSetAttribute(siib_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholW * kSDim * (int)sizeof(double));
   cudaFuncSetAttribute(siib_jacobi2_kernel<1, kJ2WarpsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kJ2MaxSb * kSLd * (int)sizeof(float));
   cudaFuncSetAttribute(siib_jacobi2_kernel<4, kJ2Warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kJ2MaxSb * kSLd * (int)sizeof(float));
+  siib_knn_setup();
   cudaStreamSynchronize(s);
 }
 
@@ -1249,7 +1250,7 @@ int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_til
   return 1;
 }
 
-int siib_run(const SiibGeom& g, const SiibBuffers& b, int n, int64_t max_F, KernelTimer* kt, cudaStream_t s) {
+int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, int n, int64_t max_F, KernelTimer* kt, cudaStream_t s) {
   int launches = 0;
   kt_begin(kt, "siib_vad", s);
   siib_vad_kernel<<<n, kVad2Threads, 0, s>>>(g, b);
@@ -1305,6 +1306,7 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, int n, int64_t max_F, Kern
     kt_end(kt, s);
     ++launches;
   }
+  if (kb) return launches + siib_run_knn(g, b, *kb, n, max_F, kt, s);
   kt_begin(kt, "siib_quad", s);
   siib_quad_kernel<<<n, kQuadThreads, 0, s>>>(g, b);
   kt_end(kt, s);

@@ -62,8 +62,23 @@ def test_siib_plain_equals_wrapper_on_explicitly_tiled_signal(api):
     assert abs(api.SIIB_Wrapper_harvard(x, y, 16000) - api.mapping_SIIB_harvard(wrapped)) < 1e-6
     with pytest.raises(ValueError, match="at least 20 seconds"):
         api.SIIB(x, y, 16000, gauss=True)
-    with pytest.raises(NotImplementedError):
-        api.SIIB(x, y, 16000)                        # gauss=False (k-NN) is not on the NELE-GAN path
+    with pytest.raises(ValueError, match="at least 20 seconds"):
+        api.SIIB(x, y, 16000)                        # gauss=False: same precondition
+
+
+def test_siib_knn_estimator_matches_oracle(api):
+    """pysiib's default estimator (gauss=False): Kraskov k-NN mutual information per KLT
+    component.  Tolerance: BASELINE.json's 0.5 % relative bound on SIIB."""
+    from nele_gan_b200.synth import make_pair
+    from oracle import intel_np, pysiib_np
+    for i, L in ((3, 52345), (5, 47003)):
+        x, y, _ = make_pair(i, L)
+        M, _ = intel_np.siib_tiling_factor(x, 16000)
+        xt, yt = np.hstack([x] * M), np.hstack([y] * M)
+        want = pysiib_np.SIIB(xt.astype(np.float64), yt.astype(np.float64), 16000, gauss=False)
+        got = api.SIIB(xt, yt, 16000)
+        assert abs(got - want) <= 5e-3 * want, (got, want)
+        assert got != api.SIIB(xt, yt, 16000, gauss=True)
 
 
 def test_stoi_signature_and_sentinel(api, golden):
