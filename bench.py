@@ -116,7 +116,9 @@ def kernel_bytes_per_pair(name, L16, Nf=1950, rank=420):
         "siib_vad": 2 * 4 * L16,
         "siib_spec": 2 * 4 * L16 + 2 * 128 * F,
         "siib_mask": 2 * 2 * 128 * F,
-        "siib_cov": 2 * 128 * F + 59 * 8192,
+        "siib_jacobi_cluster": 2 * rank * 448 * 4,
+        "siib_cov": 128 * F + 15 * 8192,            # xx lag blocks, FP64
+        "siib_cov32": 2 * 128 * F + 44 * 8192,      # yy, xy, yx lag blocks, FP32 sums
         "siib_expand": 59 * 8192 + 420 * 420 * (8 + 4 + 4),
         "siib_chol": 420 * 420 * 8 + rank * 448 * 4,
         "siib_jacobi": 2 * rank * 448 * 4,

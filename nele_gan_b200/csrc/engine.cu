@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <map>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -793,10 +794,14 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       }
       for (int lo_p = 0; lo_p < cn; lo_p += sub) {
         const int sn = std::min(sub, cn - lo_p);
-        int64_t maxF = 0;
-        for (int i = 0; i < sn; ++i) maxF = std::max(maxF, e->g_F[lo_p + i]);
+        int64_t maxF = 0, maxU = 0;
+        for (int i = 0; i < sn; ++i) {
+          const int64_t Fi = e->g_F[lo_p + i], Li = lens[first + lo_p + i];
+          maxF = std::max(maxF, Fi);
+          maxU = std::max(maxU, std::min(Fi, Li / std::gcd<int64_t>(Li, 200)));  // distinct frames of the tiled signal
+        }
         sb.pair_lo = lo_p;
-        e->last_launches += siib_run(sg, sb, siib_knn ? &kb : nullptr, sn, maxF, kt, ss);
+        e->last_launches += siib_run(sg, sb, siib_knn ? &kb : nullptr, sn, maxF, maxU, kt, ss);
         e->sub_lo = lo_p;
         e->sub_n = sn;
       }

@@ -13,6 +13,8 @@
 //                          band magnitudes [nfr][15] for both signals
 //   estoi_corr_kernel      per pair CTA, one thread per 30-frame segment: row then column
 //                          normalisation and the correlation sum
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace nele {
@@ -24,38 +26,59 @@ __constant__ int c_stoi_lo[kStoiBands], c_stoi_hi[kStoiBands];
 __device__ float2 g_stoi_tw[kStoiFft / 2];     // exp(-2 pi i k / 512)
 
 // ------------------------------------------------------------- resample
-constexpr int kRsTile = 1024, kRsThreads = 256;
+constexpr int kRsThreads = 256, kRsJ = 4;
 
-__global__ void __launch_bounds__(kRsThreads) estoi_resample_kernel(EstoiGeom g, EstoiBuffers b, int span) {
+// A thread owns kRsJ outputs of one polyphase branch, m, m + up, ... (same taps, inputs `down`
+// apart): every tap is fetched once for kRsJ independent FP64 FMA chains.  A CTA covers
+// tile = kRsJ * up * groups consecutive outputs with groups * up threads.
+__global__ void __launch_bounds__(kRsThreads) estoi_resample_kernel(EstoiGeom g, EstoiBuffers b, int span, int groups,
+                                                                    int taps_in_smem) {
   const int pair = blockIdx.y, q = blockIdx.z, tid = threadIdx.x;
   const int n_out = g.n10[pair];
-  const int m0 = blockIdx.x * kRsTile;
+  const int tile = kRsJ * b.up * groups;
+  const int m0 = blockIdx.x * tile;
   if (m0 >= n_out) return;
   const float* __restrict__ src = (q == 0 ? b.ref : b.deg) + g.off16[pair];
   const int L = g.len16[pair];
   float* __restrict__ dst = b.x10 + (int64_t)q * b.tot10 + g.off10[pair];
-  extern __shared__ float s_in[];
+  extern __shared__ __align__(16) unsigned char s_rs_raw[];
   if (b.up == 1 && b.down == 1) {
-    for (int m = m0 + tid; m < min(m0 + kRsTile, n_out); m += kRsThreads) dst[m] = src[m];
+    for (int m = m0 + tid; m < min(m0 + tile, n_out); m += kRsThreads) dst[m] = src[m];
     return;
   }
+  const int nt = 2 * b.K + 1;
+  double* s_tap = reinterpret_cast<double*>(s_rs_raw);
+  float* s_in = reinterpret_cast<float*>(s_rs_raw + (taps_in_smem ? (size_t)b.up * nt * sizeof(double) : 0));
   // staged index u <-> input sample base + u, base = n(m0) - K
   const int base = (int)(((int64_t)m0 * b.down) / b.up) - b.K;
   for (int u = tid; u < span; u += kRsThreads) {
     const int j = base + u;
     s_in[u] = (j >= 0 && j < L) ? src[j] : 0.f;
   }
+  if (taps_in_smem)
+    for (int u = tid; u < b.up * nt; u += kRsThreads) s_tap[u] = b.taps[u];
   __syncthreads();
-  const int nt = 2 * b.K + 1;
-  for (int m = m0 + tid; m < min(m0 + kRsTile, n_out); m += kRsThreads) {
-    const int64_t pos = (int64_t)m * b.down;
-    const int n = (int)(pos / b.up), r = (int)(pos % b.up);
-    const double* __restrict__ tp = b.taps + (size_t)r * nt;
-    const float* xs = s_in + (n - base) + b.K;  // xs[-k'] with k' = k + K -> x[n - k]
-    double acc = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < nt; ++k) acc = fma(__ldg(tp + k), (double)xs[-k], acc);
-    dst[m] = (float)acc;
+  const int nthr = groups * b.up;  // outputs m, m + nthr, m + 2 nthr, ...: same branch (nthr is a multiple of up),
+  if (tid >= nthr) return;         // and consecutive lanes read consecutive-ish inputs (no bank conflicts)
+  const int m = m0 + tid;
+  const int64_t pos = (int64_t)m * b.down;
+  const int n = (int)(pos / b.up), r = (int)(pos % b.up);
+  const double* __restrict__ tp = (taps_in_smem ? s_tap : b.taps) + (size_t)r * nt;
+  const int sj = b.down * groups;  // input distance between the outputs of one thread
+  const float* xs = s_in + (n - base) + b.K;  // xs[j sj - k'] with k' = k + K -> x[n + j sj - k]
+  double acc[kRsJ];
+#pragma unroll
+  for (int j = 0; j < kRsJ; ++j) acc[j] = 0.0;
+#pragma unroll 2
+  for (int k = 0; k < nt; ++k) {
+    const double t = tp[k];
+#pragma unroll
+    for (int j = 0; j < kRsJ; ++j) acc[j] = fma(t, (double)xs[j * sj - k], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kRsJ; ++j) {
+    const int mj = m + j * nthr;
+    if (mj < n_out) dst[mj] = (float)acc[j];
   }
 }
 
@@ -346,12 +369,16 @@ void estoi_upload_tables(const float* win, const int* lo, const int* hi, const f
 int estoi_run(const EstoiGeom& g, const EstoiBuffers& b, int n, int max_n10, int max_nfa, bool classic, KernelTimer* kt,
               cudaStream_t s) {
   int launches = 0;
-  const int span = (int)(((int64_t)kRsTile * b.down) / b.up) + 2 * b.K + 4;
-  const size_t smem = (size_t)span * sizeof(float);
+  const int groups = std::max(1, kRsThreads / b.up);       // (an `up` above 256 never occurs for audio rates)
+  const int tile = kRsJ * b.up * groups;
+  const int span = (int)(((int64_t)tile * b.down) / b.up) + 2 * b.K + 4;
+  const size_t tap_bytes = (size_t)b.up * (2 * b.K + 1) * sizeof(double);
+  const int taps_in_smem = tap_bytes <= 64 * 1024;
+  const size_t smem = (size_t)span * sizeof(float) + (taps_in_smem ? tap_bytes : 0);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(estoi_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kt_begin(kt, "estoi_resample", s);
-  estoi_resample_kernel<<<dim3((max_n10 + kRsTile - 1) / kRsTile, n, 2), kRsThreads, smem, s>>>(g, b, span);
+  estoi_resample_kernel<<<dim3((max_n10 + tile - 1) / tile, n, 2), kRsThreads, smem, s>>>(g, b, span, groups, taps_in_smem);
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "estoi_vad", s);

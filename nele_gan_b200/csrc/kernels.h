@@ -177,6 +177,8 @@ int siib_run_knn(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers& 
 void siib_upload_tables(const float* win, const float* decay, const float* g2t, const float* tw, cudaStream_t s);
 int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_tile, KernelTimer* kt, cudaStream_t s);
 // kb != nullptr: k-NN estimator instead of the Gaussian quadratic forms
-int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, int n, int64_t max_F, KernelTimer* kt, cudaStream_t s);
+// max_unique: upper bound over the pairs of the number of distinct frames, min(F, L / gcd(L, 200))
+int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, int n, int64_t max_F, int64_t max_unique,
+             KernelTimer* kt, cudaStream_t s);
 
 }  // namespace nele

@@ -34,6 +34,8 @@
 // information, which is the exact-arithmetic value of the reference formula.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include "fft400.cuh"
 #include "kernels.h"
 
@@ -278,6 +280,13 @@ __global__ void __launch_bounds__(kSpecWarps * 32) siib_spec_kernel(SiibGeom g, 
   const int pair = b.pair_lo + blockIdx.y, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int Fa = b.Fa[pair];
   if (blockIdx.x * kSpecWarps >= Fa) return;
+  {
+    // nothing to do when every frame of this CTA is a copy of an earlier one (siib_vad_kernel):
+    // leave before the 29 KB of tables are staged
+    const int tw = blockIdx.x * kSpecWarps + wib;
+    const int need = (tw < Fa) && (b.src[g.offF[pair] + tw] == tw);
+    if (!__syncthreads_or(need)) return;
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SpecSmem& sm = *reinterpret_cast<SpecSmem*>(smem_raw);
   for (int k = threadIdx.x; k < kSWin; k += kSpecWarps * 32) {
@@ -663,6 +672,7 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
   double* __restrict__ W = b.Lc + (int64_t)lp * kSDim * kSDim;  // trailing matrix after the first panel
   extern __shared__ __align__(16) double s_panel[];              // Lp[m][a], m < 32, a < 420
   __shared__ double s_rv[2][NW];
+  __shared__ double s_mx[NW];
   __shared__ int s_ri[2][NW];
   __shared__ unsigned char s_done[kSDim];
   const bool own = tid < kSDim;
@@ -735,6 +745,22 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
     }
     __syncthreads();
     if (stop || k0 + kb >= kSDim) break;
+    {
+      // The diagonal is maintained step by step: if no admissible pivot is left the factorisation
+      // is complete (numerical rank = k0 + kb) and the trailing update would be wasted work.
+      double v = (own && !done) ? mydg : -1.0e300;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+      if (lane == 0) s_mx[wib] = v;
+      __syncthreads();
+      double vm = s_mx[0];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) vm = fmax(vm, s_mx[w]);
+      if (!(vm > tol)) {
+        rank = k0 + kb;
+        break;
+      }
+    }
     // trailing update with the finished panel: W[a][c] = As[a][c] - sum_m Lp[m][a] Lp[m][c]
     for (int a0 = 4 * wib; a0 < kSDim; a0 += 4 * NW) {
       bool live[4];
@@ -1250,7 +1276,8 @@ int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_til
   return 1;
 }
 
-int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, int n, int64_t max_F, KernelTimer* kt, cudaStream_t s) {
+int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, int n, int64_t max_F, int64_t max_unique,
+             KernelTimer* kt, cudaStream_t s) {
   int launches = 0;
   kt_begin(kt, "siib_vad", s);
   siib_vad_kernel<<<n, kVad2Threads, 0, s>>>(g, b);
@@ -1258,7 +1285,8 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, 
   ++launches;
   if (max_F > 0) {
     kt_begin(kt, "siib_spec", s);
-    siib_spec_kernel<<<dim3((unsigned)((max_F + kSpecWarps - 1) / kSpecWarps), n), kSpecWarps * 32, sizeof(SpecSmem), s>>>(g, b);
+    // active index t <= frame f, and frames beyond the first period are copies: t < max_unique is enough
+    siib_spec_kernel<<<dim3((unsigned)((std::min(max_F, max_unique) + kSpecWarps - 1) / kSpecWarps), n), kSpecWarps * 32, sizeof(SpecSmem), s>>>(g, b);
     kt_end(kt, s);
     ++launches;
   }

@@ -176,3 +176,30 @@ def test_score_tensors_matches_host_path(api):
     assert np.abs(q.numpy() - want).max() < 5e-3            # 16-bit rounding of the degraded signal barely moves the labels
     with pytest.raises(ValueError):
         api.score_tensors(ref, deg, lens)                   # CPU tensors: no CPU path
+
+
+def test_inloop_sampling_round_matches_the_file_based_reference_flow(api):
+    """train_nele.py:286-322 without files: band gains -> Resyn -> PCM-16 -> + noise -> labels,
+    against the numpy restatement of the same steps scored by the oracle."""
+    import torch
+    from nele_gan_b200 import inloop
+    from nele_gan_b200.synth import make_pair
+    from oracle import intel_np, resyn_np
+    n, L = 2, 33536                                            # the toy corpus' utterance length
+    pairs = [make_pair(70 + i, L) for i in range(n)]
+    clean = np.stack([p[0] for p in pairs])
+    noise = np.stack([p[1] - p[0] for p in pairs])
+    T = 1 + L // 256
+    alpha2 = np.random.default_rng(5).uniform(0.5, 2.5, size=(n, T, 64)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    got = inloop.label_sampling_round(torch.from_numpy(alpha2).to(dev), torch.from_numpy(clean).to(dev),
+                                      torch.from_numpy(noise).to(dev), norm=False, no_dither=True).numpy()
+    for i in range(n):
+        enh = resyn_np.resyn(resyn_np.stft(clean[i]), alpha2[i].astype(np.float64))
+        enh = np.clip(np.round(enh * 32768.0), -32768, 32767) / 32768.0
+        m = min(L, len(enh))
+        deg = (enh[:m] + noise[i][:m]).astype(np.float32)
+        want = intel_np.score_pair(clean[i][:m], deg, 16000, norm=False, noise=None)
+        assert abs(got[i, 0] - want[0]) <= 5e-3 * abs(want[0])
+        assert abs(got[i, 1] - want[1]) <= 1e-3
+        assert abs(got[i, 2] - want[2]) <= 1e-3
