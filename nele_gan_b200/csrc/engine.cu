@@ -62,7 +62,7 @@ struct nele_engine {
   DevBuf x24, mid, bw, shift, envlp, rowsel, nsel, cep, cepmean, modsum;            // HASPI
   DevBuf v1_bm, v1_segsum, v1_cov, v1_msx, v1_xsum, v1_cepcorr, v1_cov3, v1_status;  // HASPI version 1
   DevBuf x10, st_energy, st_kept, st_nkept, st_tob;                                 // ESTOI
-  DevBuf sb_wrapdb, sb_M, sb_wact, sb_mean, sb_xdb, sb_act, sb_aidx, sb_src, sb_Fa, sb_lograw, sb_logspec;      // SIIB, per chunk
+  DevBuf sb_wrapdb, sb_M, sb_wact, sb_mean, sb_xdb, sb_act, sb_aidx, sb_src, sb_Fa, sb_Pact, sb_perflag, sb_lograw, sb_logspec;      // SIIB, per chunk
   DevBuf sb_base, sb_Sxx, sb_Sxy, sb_Syy, sb_Lc, sb_G, sb_perm;                     // SIIB, per sub-chunk
   DevBuf sb_rank, sb_sweeps, sb_lambda, sb_rho;
   DevBuf kn_xk, kn_info, kn_digamma;  // SIIB k-NN estimator
@@ -193,7 +193,7 @@ extern "C" int nele_create(int device, nele_engine** out) {
                  &e->x24, &e->mid, &e->bw, &e->shift, &e->envlp, &e->rowsel, &e->nsel, &e->cep, &e->cepmean, &e->modsum,
                  &e->v1_bm, &e->v1_segsum, &e->v1_cov, &e->v1_msx, &e->v1_xsum, &e->v1_cepcorr, &e->v1_cov3, &e->v1_status,
                  &e->x10, &e->st_energy, &e->st_kept, &e->st_nkept, &e->st_tob,
-                 &e->sb_wrapdb, &e->sb_M, &e->sb_wact, &e->sb_mean, &e->sb_xdb, &e->sb_act, &e->sb_aidx, &e->sb_src, &e->sb_Fa, &e->sb_lograw, &e->sb_logspec,
+                 &e->sb_wrapdb, &e->sb_M, &e->sb_wact, &e->sb_mean, &e->sb_xdb, &e->sb_act, &e->sb_aidx, &e->sb_src, &e->sb_Fa, &e->sb_Pact, &e->sb_perflag, &e->sb_lograw, &e->sb_logspec,
                  &e->sb_base, &e->sb_Sxx, &e->sb_Sxy, &e->sb_Syy, &e->sb_Lc, &e->sb_G, &e->sb_perm,
                  &e->sb_rank, &e->sb_sweeps, &e->sb_lambda, &e->sb_rho, &e->kn_xk, &e->kn_info, &e->kn_digamma,
                  &e->out_haspi, &e->out_raw, &e->out_hst, &e->out_estoi, &e->out_est, &e->out_siib, &e->out_sst};
@@ -732,6 +732,8 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       RESERVE(e, e->sb_aidx, (size_t)tFa * sizeof(int32_t));
       RESERVE(e, e->sb_src, (size_t)tFa * sizeof(int32_t));
       RESERVE(e, e->sb_Fa, (size_t)cn * sizeof(int32_t));
+      RESERVE(e, e->sb_Pact, (size_t)cn * sizeof(int32_t));
+      RESERVE(e, e->sb_perflag, (size_t)cn * 2 * sizeof(int32_t));
       RESERVE(e, e->sb_lograw, (size_t)2 * (tFa + 1) * 32 * sizeof(float));
       RESERVE(e, e->sb_logspec, (size_t)2 * (tFa + 1) * 32 * sizeof(float));
       RESERVE(e, e->sb_base, (size_t)sub * 59 * 1024 * sizeof(double));
@@ -752,6 +754,8 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       sb.aidx = (int32_t*)e->sb_aidx.p;
       sb.src = (int32_t*)e->sb_src.p;
       sb.Fa = (int32_t*)e->sb_Fa.p;
+      sb.Pact = (int32_t*)e->sb_Pact.p;
+      sb.perflag = (int32_t*)e->sb_perflag.p;
       sb.lograw = (float*)e->sb_lograw.p;
       sb.logspec = (float*)e->sb_logspec.p;
       sb.totF = tFa + 1;

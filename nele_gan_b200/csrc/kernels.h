@@ -142,6 +142,8 @@ struct SiibBuffers {
   int32_t* aidx;         // [totF] frame (first period only) -> index in act
   int32_t* src;          // [totF] active frame -> row of lograw holding its spectrum (first occurrence)
   int32_t* Fa;           // [n]
+  int32_t* Pact;         // [n] active frames per period of the tiled signal (0 = no repetition)
+  int32_t* perflag;      // [n][2] masked features of x / y verified periodic from the second period on
   float* lograw;         // [2][totF][32] log band energies of the distinct active frames
   float* logspec;        // [2][totF][32] after forward masking and mean removal
   int64_t totF;

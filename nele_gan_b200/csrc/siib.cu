@@ -264,6 +264,19 @@ __global__ void __launch_bounds__(kVad2Threads) siib_vad_kernel(SiibGeom g, Siib
     const int64_t f = act[t];
     src[t] = (f < Fu) ? t : aidx[f % per];
   }
+  if (tid == 0) {  // active frames per period of the tiled signal (0: the signal does not repeat within F frames)
+    int P = 0;
+    if (per < F) {
+      int lo = 0, hi = Fa;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (act[mid] < per) lo = mid + 1;
+        else hi = mid;
+      }
+      P = lo;
+    }
+    b.Pact[pair] = P;
+  }
 }
 
 // ------------------------------------------------------------- spectra
@@ -373,6 +386,15 @@ __global__ void __launch_bounds__(128) siib_mask_kernel(SiibGeom g, SiibBuffers 
   }
   const float mu = (Fa > 0) ? (float)(sum / (double)Fa) : 0.f;
   for (int t = 0; t < Fa; ++t) X[(int64_t)t * kSLanes] = (lane < kSBands) ? X[(int64_t)t * kSLanes] - mu : 0.f;
+  // The raw frames of a tiled signal repeat with period P; the masked ones do so only once the
+  // start-up transient of the recurrence has died out.  Verify (bit-exact) that everything from
+  // the second period on repeats: the lag-product kernels then sum two periods instead of all.
+  const int P = b.Pact[pair];
+  int ok = (P > 0 && 2 * P + kSStack <= Fa) ? 1 : 0;
+  if (ok)
+    for (int t = P; t + P < Fa; ++t) ok &= (X[(int64_t)t * kSLanes] == X[(int64_t)(t + P) * kSLanes]) ? 1 : 0;
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0) b.perflag[2 * pair + q] = ok;
 }
 
 // ---------------------------------------------------------- lag products
@@ -381,6 +403,31 @@ __device__ __forceinline__ void block_desc(int blk, int& ta, int& tb, int& d) {
   if (blk < 15) { ta = 0; tb = 0; d = blk; }
   else if (blk < 30) { ta = 1; tb = 1; d = blk - 15; }
   else { ta = 0; tb = 1; d = blk - 44; }
+}
+
+// Summation plan of the lag products.  Plain: t = 0 .. Nf - 1, weight 1.  Periodic (frames
+// repeat with period P from t = P on, verified by siib_mask_kernel): with Nf - P = q P + rem the
+// sum over t >= P is q + 1 times the first rem frames of the period plus q times the rest, so
+// only t < 2 P is visited, the A row of frame t weighted by w(t).
+struct CovSpan {
+  int ne, P, rem, q;
+  __device__ __forceinline__ double w(int t) const { return (t < P) ? 1.0 : (t < P + rem) ? (double)(q + 1) : (double)q; }
+};
+__device__ __forceinline__ CovSpan cov_span(const SiibBuffers& b, int pair, int Nf, bool need_y) {
+  CovSpan s;
+  s.ne = Nf;
+  s.P = Nf;  // plain: every frame below P, weight 1
+  s.rem = 0;
+  s.q = 0;
+  const int P = b.Pact[pair];
+  const bool periodic = b.perflag[2 * pair] && (!need_y || b.perflag[2 * pair + 1]);
+  if (periodic && P > 0 && Nf >= 2 * P) {
+    s.P = P;
+    s.q = (Nf - P) / P;
+    s.rem = (Nf - P) % P;
+    s.ne = 2 * P;
+  }
+  return s;
 }
 
 constexpr int kCovWarps = 8;
@@ -422,7 +469,8 @@ __global__ void __launch_bounds__(kCovWarps * 32) siib_cov_kernel(SiibGeom g, Si
   const int Fa = b.Fa[pair];
   const int Nf = Fa - (kSStack - 1);
   if (Nf < 1) return;
-  __shared__ __align__(16) double s_x[1][kCovRows][kSLanes];
+  __shared__ __align__(16) double s_x[2][kCovRows][kSLanes];  // [0] rows weighted (A side), [1] plain (B side)
+  const CovSpan span = cov_span(b, pair, Nf, false);
   const bool active = task < kCovTasks64;
   int ta = 0, tb = 0, e = 0, nl = 1;
   bool tr = false;
@@ -435,24 +483,29 @@ __global__ void __launch_bounds__(kCovWarps * 32) siib_cov_kernel(SiibGeom g, Si
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = 0.0;
-  for (int t0 = 0; t0 < Nf; t0 += kCovTile) {
+  for (int t0 = 0; t0 < span.ne; t0 += kCovTile) {
     __syncthreads();
     for (int idx = threadIdx.x; idx < kCovRows * (kSLanes / 4); idx += kCovWarps * 32) {  // xx only: X rows
-      const int q = idx / (kCovRows * (kSLanes / 4)), rem = idx % (kCovRows * (kSLanes / 4));
-      const int row = rem / (kSLanes / 4), c4 = rem % (kSLanes / 4);
+      const int row = idx / (kSLanes / 4), c4 = idx % (kSLanes / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t0 + row < Fa) v = *reinterpret_cast<const float4*>((q ? Y : X) + (int64_t)(t0 + row) * kSLanes + 4 * c4);
-      double* dst = &s_x[q][row][4 * c4];
-      dst[0] = (double)v.x;
-      dst[1] = (double)v.y;
-      dst[2] = (double)v.z;
-      dst[3] = (double)v.w;
+      if (t0 + row < Fa) v = *reinterpret_cast<const float4*>(X + (int64_t)(t0 + row) * kSLanes + 4 * c4);
+      const double w = span.w(t0 + row);  // integer weights: exact in FP64
+      double* dw = &s_x[0][row][4 * c4];
+      double* dp = &s_x[1][row][4 * c4];
+      dp[0] = (double)v.x;
+      dp[1] = (double)v.y;
+      dp[2] = (double)v.z;
+      dp[3] = (double)v.w;
+      dw[0] = w * (double)v.x;
+      dw[1] = w * (double)v.y;
+      dw[2] = w * (double)v.z;
+      dw[3] = w * (double)v.w;
     }
     __syncthreads();
     if (!active) continue;
-    const int nt = min(kCovTile, Nf - t0);
-    const double* A = &s_x[ta][0][8 * rg];
-    const double* B = &s_x[tb][e][4 * cg];
+    const int nt = min(kCovTile, span.ne - t0);
+    const double* A = &s_x[0][0][8 * rg];
+    const double* B = &s_x[1][e][4 * cg];
     double2 c01 = *reinterpret_cast<const double2*>(B), c23 = *reinterpret_cast<const double2*>(B + 2);
 #pragma unroll 2
     for (int t = 0; t < nt; ++t) {
@@ -506,7 +559,8 @@ __global__ void __launch_bounds__(kCov32Warps * 32) siib_cov32_kernel(SiibGeom g
   const int Fa = b.Fa[pair];
   const int Nf = Fa - (kSStack - 1);
   if (Nf < 1) return;
-  __shared__ __align__(16) float s_x[2][kCovRows][kSLanes];
+  __shared__ __align__(16) float s_x[4][kCovRows][kSLanes];  // [0], [1]: x, y rows weighted (A side); [2], [3]: plain
+  const CovSpan span = cov_span(b, pair, Nf, true);
   const bool active = task < kCovTasks;
   int ta = 0, tb = 0, e = 0, nl = 1;
   bool tr = false;
@@ -519,20 +573,26 @@ __global__ void __launch_bounds__(kCov32Warps * 32) siib_cov32_kernel(SiibGeom g
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) tot0[i][j] = tot1[i][j] = 0.f;
-  for (int t0 = 0; t0 < Nf; t0 += kCovTile) {
+  for (int t0 = 0; t0 < span.ne; t0 += kCovTile) {
     __syncthreads();
     for (int idx = threadIdx.x; idx < 2 * kCovRows * (kSLanes / 4); idx += kCov32Warps * 32) {
       const int q = idx / (kCovRows * (kSLanes / 4)), rem = idx % (kCovRows * (kSLanes / 4));
       const int row = rem / (kSLanes / 4), c4 = rem % (kSLanes / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (t0 + row < Fa) v = *reinterpret_cast<const float4*>((q ? Y : X) + (int64_t)(t0 + row) * kSLanes + 4 * c4);
+      *reinterpret_cast<float4*>(&s_x[2 + q][row][4 * c4]) = v;
+      const float w = (float)span.w(t0 + row);
+      v.x *= w;
+      v.y *= w;
+      v.z *= w;
+      v.w *= w;
       *reinterpret_cast<float4*>(&s_x[q][row][4 * c4]) = v;
     }
     __syncthreads();
     if (!active) continue;
-    const int nt = min(kCovTile, Nf - t0);
+    const int nt = min(kCovTile, span.ne - t0);
     const float* A = &s_x[ta][0][8 * rg];
-    const float* B = &s_x[tb][e][4 * cg];
+    const float* B = &s_x[2 + tb][e][4 * cg];
     float acc0[8][4], acc1[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
