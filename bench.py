@@ -14,7 +14,8 @@ Metric: audio-seconds scored per second, whole job.
   e2e    the same batch through the public API with HOST (pinned) buffers: the
          host->device copy of the waveforms and the device->host copy of the
          per-pair records are inside the timed region (for N > 1 also the NCCL
-         gather of the records)
+         gather of the records); the upload of step k + 1 is started with
+         nele_prefetch before the blocking call of step k
   roofline       dominant kernel: algorithmic bytes per launch / its CUDA-event
                  duration, against MEASURED_PEAKS.json
   cpu_baseline   the CPU oracle (a port of the reference algorithms, oracle/) on
@@ -267,8 +268,14 @@ def main():
     for _ in range(max(1, a.warmup // 2)):
         step_host()
     barrier()
+    # every step uploads its own 1.57 GB of waveforms; the upload of step k + 1 is started
+    # (nele_prefetch, copy stream, second staging slot) before the blocking call of step k, so it
+    # overlaps that step's kernels.  The first upload of the timed region is not hidden.
     t0 = time.perf_counter()
-    for _ in range(a.steps):
+    eng.prefetch(h_ref.data_ptr(), h_deg.data_ptr(), offs, lens)
+    for k in range(a.steps):
+        if k + 1 < a.steps:
+            eng.prefetch(h_ref.data_ptr(), h_deg.data_ptr(), offs, lens)
         r = step_host()
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
@@ -305,7 +312,8 @@ def main():
             "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic", "config": config,
             "e2e": {"value": audio_s * world / (ms_e2e / a.steps * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h_ref.numel() * 4 * 2), "d2h_bytes_per_step": int(n * (14 * 8 + 4)),
-                    "ms_per_step": ms_e2e / a.steps},
+                    "ms_per_step": ms_e2e / a.steps,
+                    "pipelining": "upload of step k+1 (nele_prefetch) overlaps the kernels of step k; every step's H2D and D2H copies are inside the timed region"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",

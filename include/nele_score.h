@@ -123,6 +123,19 @@ int nele_score_batch(nele_engine* e, const float* ref, const float* deg, const i
                      double* scores, double* haspi_raw, int32_t* status, void* stream);
 
 /*
+ * Optional pipelining across calls for host inputs: start the host -> device upload of an upcoming
+ * nele_score_batch(e, ref, deg, offs, lens, n, ..., flags, ...) call now, on the engine's copy
+ * stream, into the staging slot the current call does not use.  Returns at once; the matching
+ * nele_score_batch call (same ref, deg, n) finds its waveforms already on the device, so the
+ * upload of call k + 1 hides behind the kernels of call k.  The host buffers must stay unchanged
+ * until that call returns.  The reference has no counterpart (its pool re-reads WAV files per
+ * task, audio_util.py:128-139); a no-op for device inputs and for calls that need more than one
+ * chunk (those pipeline their own uploads).
+ */
+int nele_prefetch(nele_engine* e, const float* ref, const float* deg, const int64_t* offs, const int32_t* lens, int n,
+                  uint32_t flags);
+
+/*
  * Parity-test access to the per-stage tensors of the last nele_score_batch
  * call made with NELE_FLAG_KEEP_STAGES.  Copies stage `name` of pair `pair`
  * into dst (capacity cap bytes) and reports its size; dst may be NULL to query

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <numeric>
 #include <string>
@@ -46,6 +47,16 @@ struct nele_engine {
   cudaStream_t s_estoi = nullptr, s_siib = nullptr;  // the three metric pipelines run concurrently
   cudaStream_t s_copy = nullptr;                       // host -> device input uploads
   cudaEvent_t ev_in[2] = {nullptr, nullptr};
+  // nele_prefetch: chunk 0 of an upcoming call already uploaded (or uploading) into a staging slot
+  struct Prefetched {
+    bool valid = false;
+    const float *ref = nullptr, *deg = nullptr;
+    int n = 0;
+    int64_t tot = 0;
+    uint64_t seq = 0;
+  } pf[2];
+  uint64_t pf_seq = 0;
+  int next_slot = 0;  // staging slot the next call (or prefetch) starts with
   cudaEvent_t ev_fork = nullptr, ev_estoi = nullptr, ev_siib = nullptr;
   bool serial = true;                                  // one stream unless NELE_CONCURRENT=1
   std::string err;
@@ -68,6 +79,8 @@ struct nele_engine {
   DevBuf kn_xk, kn_info, kn_digamma;  // SIIB k-NN estimator
   DevBuf out_haspi, out_raw, out_hst, out_estoi, out_est, out_siib, out_sst;
   std::vector<DevBuf*> all_bufs;
+  char *h_geom = nullptr, *h_sgeom = nullptr;  // pinned staging of the geometry blobs (read by blob_copy_kernel)
+  size_t h_geom_cap = 0, h_sgeom_cap = 0;
   int32_t* h_M = nullptr;  // pinned
   size_t h_M_cap = 0;
   cudaEvent_t ev_M = nullptr;
@@ -232,6 +245,8 @@ extern "C" void nele_destroy(nele_engine* e) {
   cudaSetDevice(e->device);
   for (DevBuf* b : e->all_bufs)
     if (b->p) cudaFree(b->p);
+  if (e->h_geom) cudaFreeHost(e->h_geom);
+  if (e->h_sgeom) cudaFreeHost(e->h_sgeom);
   if (e->h_M) cudaFreeHost(e->h_M);
   if (e->kt_events)
     for (int i = 0; i < KernelTimer::kMax; ++i) {
@@ -326,6 +341,31 @@ struct GeomPacker {
     return off;
   }
 };
+
+// The per-chunk geometry arrays reach the device through a copy *kernel* that reads pinned host
+// memory: a cudaMemcpyAsync would queue on the host-to-device copy engine behind whatever
+// waveform upload (next chunk, nele_prefetch) is in flight there and stall the kernels for tens
+// of milliseconds.
+__global__ void blob_copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+static int push_blob(nele_engine* e, const std::vector<char>& blob, char** pinned, size_t* cap, DevBuf& dev, cudaStream_t s) {
+  const size_t bytes = (blob.size() + 15) & ~(size_t)15;
+  if (*cap < bytes) {
+    if (*pinned) cudaFreeHost(*pinned);
+    *pinned = nullptr;
+    *cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    CU(e, cudaMallocHost((void**)pinned, want));
+    *cap = want;
+  }
+  memcpy(*pinned, blob.data(), blob.size());
+  RESERVE(e, dev, bytes);
+  const size_t n16 = bytes / 16;
+  blob_copy_kernel<<<(unsigned)std::min<size_t>((n16 + 255) / 256, 64), 256, 0, s>>>((const uint4*)*pinned, (uint4*)dev.p, n16);
+  CU(e, cudaGetLastError());
+  return NELE_OK;
+}
 
 static void collect_kernel_times(nele_engine* e) {
   // called after the stream has been synchronised
@@ -454,23 +494,44 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
   // HASPI version 1 stages the basilar-membrane motion of both signals in HBM (384 bytes per input
   // sample at 16 kHz): smaller chunks
   const int64_t kMaxChunkSamplesV1 = 64LL * 1000 * 1000;
-  const int kMaxChunkPairs = haspi_v1 ? 2048 : 4096, kHostChunkPairs = kMaxChunkPairs;
+  const int kMaxChunkPairs = haspi_v1 ? 2048 : 4096;
+  int kHostChunkPairs = kMaxChunkPairs;
+  if (const char* hc = getenv("NELE_HOST_CHUNK")) {  // tuning knob: pairs per chunk when the inputs come from the host
+    const int v = atoi(hc);
+    if (v > 0) kHostChunkPairs = std::min(v, kMaxChunkPairs);
+  }
   const int kSiibSub = 4096;                              // pairs per SIIB matrix sub-chunk (6.2 MB of matrices per pair)
+  static const bool trace = [] { const char* p = getenv("NELE_TRACE"); return p && p[0] == '1'; }();
+  const auto t_call = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
   std::vector<ChunkPlan> plans;
   plan_chunks(offs, lens, n, dev_in, dev_in ? kMaxChunkPairs : kHostChunkPairs,
               haspi_v1 ? kMaxChunkSamplesV1 : kMaxChunkSamples, plans);
+  int slot0 = e->next_slot;
   if (!dev_in) {
-    rc = upload_chunk(e, plans[0], 0, ref, deg, offs, lens);
-    if (rc != NELE_OK) return rc;
+    // chunk 0 may already be on its way (nele_prefetch): take the oldest matching slot
+    int hit = -1;
+    for (int k = 0; k < 2; ++k)
+      if (e->pf[k].valid && e->pf[k].ref == ref && e->pf[k].deg == deg && e->pf[k].n == n && e->pf[k].tot == plans[0].tot &&
+          (hit < 0 || e->pf[k].seq < e->pf[hit].seq))
+        hit = k;
+    if (hit >= 0) {
+      slot0 = hit;
+      e->pf[hit].valid = false;
+      if (plans.size() > 1) e->pf[hit ^ 1].valid = false;  // the second chunk will overwrite the other slot
+    } else {
+      if (e->pf[slot0].valid) slot0 ^= 1;                   // do not clobber a pending prefetch
+      if (e->pf[slot0].valid || plans.size() > 1) e->pf[0].valid = e->pf[1].valid = false;
+      rc = upload_chunk(e, plans[0], slot0, ref, deg, offs, lens);
+      if (rc != NELE_OK) return rc;
+    }
+    if (trace) fprintf(stderr, "[nele] first upload %s at %.2f ms\n", hit >= 0 ? "was prefetched" : "queued", since());
+    e->next_slot = (slot0 + (int)plans.size()) & 1;
   }
   for (size_t ci = 0; ci < plans.size(); ++ci) {
     const ChunkPlan& cp = plans[ci];
     const int first = cp.first, last = cp.last;
-    const int slot = (int)(ci & 1);
-    if (!dev_in && ci + 1 < plans.size()) {  // the other slot was released when chunk ci - 1 finished
-      rc = upload_chunk(e, plans[ci + 1], slot ^ 1, ref, deg, offs, lens);
-      if (rc != NELE_OK) return rc;
-    }
+    const int slot = (slot0 + (int)ci) & 1;
     const int cn = last - first;
     // ---- geometry
     e->g_off16.resize(cn); e->g_len16.resize(cn); e->g_off24.resize(cn); e->g_n24.resize(cn);
@@ -536,9 +597,13 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
     const size_t o_nsub = gp.add(e->g_nsub.data(), cn * sizeof(int32_t));
     const size_t o_n10 = gp.add(e->g_n10.data(), cn * sizeof(int32_t));
     const size_t o_nfa = gp.add(e->g_nfa.data(), cn * sizeof(int32_t));
-    RESERVE(e, e->geom, gp.blob.size());
-    CU(e, cudaMemcpyAsync(e->geom.p, gp.blob.data(), gp.blob.size(), cudaMemcpyHostToDevice, s));
-    CU(e, cudaStreamSynchronize(s));  // the blob is a stack temporary; also keeps H2D out of the kernel timing
+    rc = push_blob(e, gp.blob, &e->h_geom, &e->h_geom_cap, e->geom, s);
+    if (rc != NELE_OK) return rc;
+    if (!dev_in && ci + 1 < plans.size()) {  // the other slot was released when chunk ci - 1 finished
+      rc = upload_chunk(e, plans[ci + 1], slot ^ 1, ref, deg, offs, lens);
+      if (rc != NELE_OK) return rc;
+      if (trace) fprintf(stderr, "[nele] chunk %zu: next upload queued at %.2f ms\n", ci, since());
+    }
     const char* gb = (const char*)e->geom.p;
     PairGeom g;
     g.off16 = (const int64_t*)(gb + o_off16);
@@ -571,6 +636,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
     RESERVE(e, e->out_siib, cn * sizeof(double));
     RESERVE(e, e->out_sst, (size_t)cn * sizeof(int32_t));
 
+    if (trace) fprintf(stderr, "[nele] chunk %zu: geometry on device at %.2f ms\n", ci, since());
     CU(e, cudaEventRecord(e->ev0, s));
     // fork: HASPI stays on the launching stream, ESTOI and SIIB get their own so that the
     // latency-bound kernels of one metric fill the SMs the others leave idle
@@ -719,8 +785,8 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       GeomPacker sp;
       const size_t o_offF = sp.add(e->g_offF.data(), cn * sizeof(int64_t));
       const size_t o_F = sp.add(e->g_F.data(), cn * sizeof(int64_t));
-      RESERVE(e, e->sgeom, sp.blob.size());
-      CU(e, cudaMemcpyAsync(e->sgeom.p, sp.blob.data(), sp.blob.size(), cudaMemcpyHostToDevice, ss));
+      rc = push_blob(e, sp.blob, &e->h_sgeom, &e->h_sgeom_cap, e->sgeom, ss);
+      if (rc != NELE_OK) return rc;
       sg.offF = (const int64_t*)((const char*)e->sgeom.p + o_offF);
       sg.F = (const int64_t*)((const char*)e->sgeom.p + o_F);
       const int64_t tFa = std::max<int64_t>(tF, 1);
@@ -747,7 +813,6 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       RESERVE(e, e->sb_sweeps, (size_t)cn * 17 * sizeof(int32_t));
       RESERVE(e, e->sb_lambda, (size_t)cn * 420 * sizeof(float));
       RESERVE(e, e->sb_rho, (size_t)cn * 420 * sizeof(float));
-      CU(e, cudaStreamSynchronize(ss));  // sp.blob is a stack temporary (HASPI / ESTOI keep running on their streams)
       sb.mean = (double*)e->sb_mean.p;
       sb.xdb = (double*)e->sb_xdb.p;
       sb.act = (int32_t*)e->sb_act.p;
@@ -818,6 +883,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
     }
     CU(e, cudaEventRecord(e->ev1, s));
     CU(e, cudaGetLastError());
+    if (trace) fprintf(stderr, "[nele] chunk %zu: all kernels queued at %.2f ms\n", ci, since());
 
     // ---- results
     std::vector<double> h_haspi(cn), h_raw((size_t)cn * kNumMod), h_estoi(cn), h_siib(cn);
@@ -836,6 +902,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       CU(e, cudaMemcpyAsync(h_sst.data(), e->out_sst.p, cn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
     CU(e, cudaStreamSynchronize(s));
+    if (trace) fprintf(stderr, "[nele] chunk %zu: results on host at %.2f ms\n", ci, since());
     float ms = 0.f;
     CU(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     e->last_kernel_ms += ms;
@@ -881,6 +948,37 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
     e->stage_v1 = haspi_v1;
     e->stage_metrics = (run_haspi ? NELE_METRIC_HASPI : 0) | (run_siib ? NELE_METRIC_SIIB : 0) | (run_estoi ? NELE_METRIC_ESTOI : 0);
   }
+  return NELE_OK;
+}
+
+extern "C" int nele_prefetch(nele_engine* e, const float* ref, const float* deg, const int64_t* offs, const int32_t* lens,
+                             int n, uint32_t flags) {
+  if (!e) return NELE_E_ARG;
+  if (n <= 0 || !ref || !deg || !offs || !lens) return fail(e, NELE_E_ARG, "nele_prefetch: null pointer or n <= 0");
+  if (flags & NELE_FLAG_DEVICE_INPUT) return NELE_OK;  // nothing to upload
+  for (int i = 0; i < n; ++i)
+    if (lens[i] <= 0 || offs[i] < 0) return fail(e, NELE_E_ARG, "nele_prefetch: pair %d has length %d / offset %lld", i, lens[i], (long long)offs[i]);
+  CU(e, cudaSetDevice(e->device));
+  const bool haspi_v1 = flags & NELE_FLAG_HASPI_V1;
+  int max_pairs = haspi_v1 ? 2048 : 4096;
+  if (const char* hc = getenv("NELE_HOST_CHUNK")) {
+    const int v = atoi(hc);
+    if (v > 0) max_pairs = std::min(v, max_pairs);
+  }
+  std::vector<ChunkPlan> plans;
+  plan_chunks(offs, lens, n, false, max_pairs, haspi_v1 ? 64LL * 1000 * 1000 : 256LL * 1000 * 1000, plans);
+  if (plans.size() != 1) return NELE_OK;  // multi-chunk calls pipeline their own uploads
+  int slot = e->next_slot;
+  if (e->pf[slot].valid) slot ^= 1;
+  if (e->pf[slot].valid) return NELE_OK;  // both staging slots hold pending prefetches
+  int rc = upload_chunk(e, plans[0], slot, ref, deg, offs, lens);
+  if (rc != NELE_OK) return rc;
+  e->pf[slot].valid = true;
+  e->pf[slot].ref = ref;
+  e->pf[slot].deg = deg;
+  e->pf[slot].n = n;
+  e->pf[slot].tot = plans[0].tot;
+  e->pf[slot].seq = ++e->pf_seq;
   return NELE_OK;
 }
 

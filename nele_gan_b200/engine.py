@@ -21,7 +21,7 @@ ST_OK, ST_BELOW_THR, ST_TOO_SHORT, ST_BAD_RATE, ST_UNSUPPORTED, ST_SKIPPED = 0, 
 _METRIC_BITS = {"haspi": METRIC_HASPI, "siib": METRIC_SIIB, "estoi": METRIC_ESTOI, "stoi": METRIC_ESTOI}
 COL_SIIB, COL_HASPI, COL_ESTOI = 0, 1, 2
 
-SYMBOLS = ("nele_abi_version", "nele_create", "nele_destroy", "nele_last_error", "nele_score_batch",
+SYMBOLS = ("nele_abi_version", "nele_create", "nele_destroy", "nele_last_error", "nele_score_batch", "nele_prefetch",
            "nele_get_stage", "nele_last_timing", "nele_set_profiling", "nele_kernel_time")
 
 
@@ -55,6 +55,8 @@ def load_library(path=None):
                                          C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int64, C.c_uint64,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.nele_score_batch.restype = C.c_int
+        lib.nele_prefetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
+        lib.nele_prefetch.restype = C.c_int
         lib.nele_get_stage.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t,
                                        C.POINTER(C.c_size_t)]
         lib.nele_get_stage.restype = C.c_int
@@ -173,6 +175,19 @@ class Engine:
                                         None if stream is None else int(stream))
         self._check(rc, "nele_score_batch")
         return BatchResult(scores, raw, status)
+
+    def prefetch(self, ref, deg, offs, lens, haspi_v1=False):
+        """Start uploading the host waveforms of an upcoming ``score_packed`` call (same ``ref`` /
+        ``deg`` pointers and pair count) while the current one computes; see ``nele_prefetch``."""
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        if isinstance(ref, np.ndarray):
+            pref, pdeg = ref.ctypes.data, deg.ctypes.data
+        else:
+            pref, pdeg = int(ref), int(deg)
+        rc = self._lib.nele_prefetch(self._h, pref, pdeg, offs.ctypes.data, lens.ctypes.data, int(lens.shape[0]),
+                                     FLAG_HASPI_V1 if haspi_v1 else 0)
+        self._check(rc, "nele_prefetch")
 
     # ----------------------------------------------------------------- high level
     def score_batch(self, refs, degs, fs=16000, metrics=("siib", "haspi", "estoi"), mapped=True, **kw):

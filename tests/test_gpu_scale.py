@@ -70,3 +70,27 @@ def test_argument_errors(eng):
         eng.score_packed(x, x, np.array([0]), np.array([1000]), fs=0)
     r = eng.score_batch([], [])
     assert r.scores.shape == (0, 3)
+
+
+def test_prefetch_gives_identical_results_and_mismatches_are_ignored(eng):
+    """nele_prefetch only moves the upload earlier: same scores with, without, and with a
+    prefetch that does not match the following call."""
+    from nele_gan_b200.engine import pack
+    from nele_gan_b200.synth import make_batch
+    refs, degs = make_batch(6, [30001, 24000, 33536, 28111, 16000, 40007])
+    fr, offs, lens = pack(refs)
+    fd, _, _ = pack(degs)
+    base = eng.score_packed(fr, fd, offs, lens, mapped=False, no_dither=True)
+    eng.prefetch(fr, fd, offs, lens)
+    eng.prefetch(fr, fd, offs, lens)                                   # two calls ahead
+    a = eng.score_packed(fr, fd, offs, lens, mapped=False, no_dither=True)
+    b = eng.score_packed(fr, fd, offs, lens, mapped=False, no_dither=True)
+    same = lambda u, v: np.allclose(u, v, rtol=1e-7, atol=0, equal_nan=True)   # run-to-run noise of the FP32 eigen-solver is ~1e-9
+    assert same(a.scores, base.scores) and same(b.scores, base.scores)
+    fr2, offs2, lens2 = pack(refs[:3])
+    fd2, _, _ = pack(degs[:3])
+    eng.prefetch(fr, fd, offs, lens)                                   # stale: a different batch follows
+    c = eng.score_packed(fr2, fd2, offs2, lens2, mapped=False, no_dither=True)
+    assert same(c.scores, base.scores[:3])
+    d = eng.score_packed(fr, fd, offs, lens, mapped=False, no_dither=True)
+    assert same(d.scores, base.scores)
