@@ -831,18 +831,32 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
         any |= live[i];
       }
       if (!any) continue;
-      for (int c = lane; c < kSDim; c += 32) {
-        if (s_done[c]) continue;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      // 4 rows x 2 columns per lane: 2 + 2 shared-memory loads (the row values as two 128-bit
+      // broadcasts) per 8 FP64 FMAs
+      for (int c = lane; c < kSDim; c += 64) {
+        const int c1 = c + 32;
+        const bool h0 = !s_done[c], h1 = (c1 < kSDim) && !s_done[c1];
+        if (!h0 && !h1) continue;
+        const int c1s = (c1 < kSDim) ? c1 : c;
+        double acc0[4] = {0.0, 0.0, 0.0, 0.0}, acc1[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 8
         for (int m = 0; m < kCholW; ++m) {
-          const double lc = s_panel[m * kSDim + c];
+          const double l0 = s_panel[m * kSDim + c], l1 = s_panel[m * kSDim + c1s];
+          const double2 r01 = *reinterpret_cast<const double2*>(&s_panel[m * kSDim + a0]);
+          const double2 r23 = *reinterpret_cast<const double2*>(&s_panel[m * kSDim + a0 + 2]);
+          const double rr[4] = {r01.x, r01.y, r23.x, r23.y};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i] = fma(s_panel[m * kSDim + a0 + i], lc, acc[i]);
+          for (int i = 0; i < 4; ++i) {
+            acc0[i] = fma(rr[i], l0, acc0[i]);
+            acc1[i] = fma(rr[i], l1, acc1[i]);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (live[i]) W[(int64_t)(a0 + i) * kSDim + c] = As[(int64_t)(a0 + i) * kSDim + c] - acc[i];
+          if (live[i]) {
+            if (h0) W[(int64_t)(a0 + i) * kSDim + c] = As[(int64_t)(a0 + i) * kSDim + c] - acc0[i];
+            if (h1) W[(int64_t)(a0 + i) * kSDim + c1] = As[(int64_t)(a0 + i) * kSDim + c1] - acc1[i];
+          }
       }
     }
     __syncthreads();
