@@ -56,6 +56,9 @@ extern "C" {
 #define NELE_FLAG_STOI_CLASSIC  0x40u /* NELE_METRIC_ESTOI computes classic STOI, pystoi.stoi(..., extended=False) */
 #define NELE_FLAG_SIIB_KNN      0x80u /* NELE_METRIC_SIIB uses pysiib's k-nearest-neighbour (Kraskov) estimator,
                                          SIIB(x, y, fs, gauss=False), instead of SIIB^Gauss */
+#define NELE_FLAG_HASQI_V2      0x100u /* NELE_METRIC_HASPI computes HASQI version 2, hasqi_v2() of pyhaspi2.py:32-74, on the
+                                          version-1 pipeline: scores[.][1] = Combined, haspi_raw[.][0..5] = {CepCorr,
+                                          BMsync5, Dloud, Dslope, Nonlin, Linear}.  Never mapped. */
 
 /* error codes (function return values) */
 #define NELE_OK              0

@@ -23,7 +23,7 @@ import numpy as np
 
 from . import engine as _eng
 
-__all__ = ["haspi_v2", "haspi", "SIIB", "stoi", "score_batch", "score_tensors", "read_batch_all",
+__all__ = ["haspi_v2", "haspi", "hasqi_v2", "SIIB", "stoi", "score_batch", "score_tensors", "read_batch_all",
            "SIIB_Wrapper_harvard", "SIIB_Wrapper_raw_harvard", "mapping_SIIB_harvard",
            "HASPI_Wrapper_harvard", "HASPI_Wrapper_raw_harvard", "mapping_HASPI_harvard",
            "ESTOI_Wrapper_harvard", "ESTOI_Wrapper_raw_harvard", "mapping_ESTOI_harvard",
@@ -89,6 +89,27 @@ def haspi(x, fx, y, fy, HL=np.zeros(6), alpha=-1.0, seed=None):
     raw = r.haspi_raw[0, :4].copy()
     arg = -9.047 + 14.816 * raw[0] + 4.616 * raw[3]                       # pyhaspi2.py:146-149
     return np.float64(1.0 / (1.0 + np.exp(alpha * arg))), raw            # :152
+
+
+def hasqi_v2(x, fx, y, fy, HL=np.zeros(6), seed=None):
+    """pyhaspi2.py:32-74 (HASQI version 2).  Returns ``(Combined, Nonlin, Linear, raw)`` with
+    ``raw = [CepCorr, BMsync5, Dloud, Dslope]``.  Not called by NELE-GAN; same ear model and
+    noise convention as :func:`haspi`."""
+    if fx != fy:
+        raise ValueError("hasqi_v2: the engine needs fx == fy (got %r, %r)" % (fx, fy))
+    if fx > 24000:
+        raise NotImplementedError  # pyhaspi2.py:819-820
+    x, y = _f32(x), _f32(y)
+    L = min(len(x), len(y))
+    if seed is None:
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+    hl = np.asarray(HL, dtype=np.float64)
+    r = _engine().score_batch([x[:L]], [y[:L]], fs=int(fx), metrics=("haspi",), mapped=False, seed=seed,
+                              hl=None if not hl.any() else hl, hasqi=True)
+    if r.metric_status("haspi")[0] == _eng.ST_BELOW_THR:
+        raise Exception('Function eb_melcor: Signal below threshold, outputs set to 0.')  # pyhaspi2.py:722-723
+    raw = r.haspi_raw[0]
+    return np.float64(r.haspi[0]), np.float64(raw[4]), np.float64(raw[5]), [raw[0], raw[1], raw[2], raw[3]]
 
 
 # ------------------------------------------------------------------- SIIB

@@ -275,10 +275,11 @@ struct EarLane {
   // = (out + e)/(env + e) with e = 1e-30, so bm = glp gain (ur c + ui s) (out + e) / (env + e),
   // env = glp gain |u| the compressed envelope.  (cs, sn) is the carrier the caller demodulated
   // with, i.e. the reference's (coscf, sincf).
-  NELE_HD float sample_bm(T xr, T xi, T cs, T sn, float& bm) {
+  NELE_HD float sample_bm(T xr, T xi, T cs, T sn, float& bm, float& ps_out) {
     const float pc = (float)fc.step(kc, xr, xi);
     T ur, ui;
     const float ps = (float)fs.step_ri(ks, xr, xi, ur, ui);
+    ps_out = ps;  // squared magnitude of the (unnormalised) signal-path output, for HASQI's average levels
     float le = fmaf(NELE_10_OVER_LOG2_10, fast_lg2(pc), ctl_db);
     le = fminf(fmaxf(le, thr_low), 100.0f);
     const float g = fast_ex2(fmaf(thr_low - le, crfac_l2, ohc_l2));

@@ -67,11 +67,12 @@ struct nele_engine {
   int rs_fs = 0, rs_up = 1, rs_down = 1;
   int st_fs = 0, st_up = 1, st_down = 1, st_K = 0;
   double hl_cached[6] = {-1, -1, -1, -1, -1, -1};
+  bool hl_ref_cached = false;
 
   // workspace (grow-only)
   DevBuf in_ref[2], in_deg[2], geom, sgeom, dither;  // inputs double-buffered: chunk k + 1 uploads while chunk k computes
   DevBuf x24, mid, bw, shift, envlp, rowsel, nsel, cep, cepmean, modsum;            // HASPI
-  DevBuf v1_bm, v1_segsum, v1_cov, v1_msx, v1_xsum, v1_cepcorr, v1_cov3, v1_status;  // HASPI version 1
+  DevBuf v1_bm, v1_segsum, v1_cov, v1_msx, v1_xsum, v1_cepcorr, v1_cov3, v1_status, v1_cave, v1_ave, v1_sync5;  // HASPI version 1
   DevBuf x10, st_energy, st_kept, st_nkept, st_tob;                                 // ESTOI
   DevBuf sb_wrapdb, sb_M, sb_wact, sb_mean, sb_xdb, sb_act, sb_aidx, sb_src, sb_Fa, sb_Pact, sb_perflag, sb_lograw, sb_logspec;      // SIIB, per chunk
   DevBuf sb_base, sb_Sxx, sb_Sxy, sb_Syy, sb_Lc, sb_G, sb_perm;                     // SIIB, per sub-chunk
@@ -204,7 +205,7 @@ extern "C" int nele_create(int device, nele_engine** out) {
   e->serial = !(p && p[0] == '1');
   e->all_bufs = {&e->bands, &e->rs_taps, &e->st_taps, &e->in_ref[0], &e->in_ref[1], &e->in_deg[0], &e->in_deg[1], &e->geom, &e->sgeom, &e->dither,
                  &e->x24, &e->mid, &e->bw, &e->shift, &e->envlp, &e->rowsel, &e->nsel, &e->cep, &e->cepmean, &e->modsum,
-                 &e->v1_bm, &e->v1_segsum, &e->v1_cov, &e->v1_msx, &e->v1_xsum, &e->v1_cepcorr, &e->v1_cov3, &e->v1_status,
+                 &e->v1_bm, &e->v1_segsum, &e->v1_cov, &e->v1_msx, &e->v1_xsum, &e->v1_cepcorr, &e->v1_cov3, &e->v1_status, &e->v1_cave, &e->v1_ave, &e->v1_sync5,
                  &e->x10, &e->st_energy, &e->st_kept, &e->st_nkept, &e->st_tob,
                  &e->sb_wrapdb, &e->sb_M, &e->sb_wact, &e->sb_mean, &e->sb_xdb, &e->sb_act, &e->sb_aidx, &e->sb_src, &e->sb_Fa, &e->sb_Pact, &e->sb_perflag, &e->sb_lograw, &e->sb_logspec,
                  &e->sb_base, &e->sb_Sxx, &e->sb_Sxy, &e->sb_Syy, &e->sb_Lc, &e->sb_G, &e->sb_perm,
@@ -282,12 +283,21 @@ extern "C" int nele_set_profiling(nele_engine* e, int on) {
   return NELE_OK;
 }
 
-static int ensure_tables(nele_engine* e, int fs, bool haspi_rate_ok, const double* hl, cudaStream_t s) {
+static int ensure_tables(nele_engine* e, int fs, bool haspi_rate_ok, const double* hl, bool ref_gets_hl, cudaStream_t s) {
   double h[6] = {0, 0, 0, 0, 0, 0};
   if (hl) memcpy(h, hl, sizeof(h));
-  if (!e->bands.p || memcmp(h, e->hl_cached, sizeof(h)) != 0) {
+  if (!e->bands.p || memcmp(h, e->hl_cached, sizeof(h)) != 0 || e->hl_ref_cached != ref_gets_hl) {
     BandConst bc[kBands];
     host::make_band_consts(h, bc);
+    if (ref_gets_hl)  // hasqi_v2 calls eb_EarModel with itype = 2: the reference signal gets the audiogram too (pyhaspi2.py:1162-1165)
+      for (int k = 0; k < kBands; ++k) {
+        bc[k].attn_ohc[0] = bc[k].attn_ohc[1];
+        bc[k].bwmin[0] = bc[k].bwmin[1];
+        bc[k].lowknee[0] = bc[k].lowknee[1];
+        bc[k].cr[0] = bc[k].cr[1];
+        bc[k].attn_ihc[0] = bc[k].attn_ihc[1];
+      }
+    e->hl_ref_cached = ref_gets_hl;
     RESERVE(e, e->bands, sizeof(bc));
     CU(e, cudaMemcpyAsync(e->bands.p, bc, sizeof(bc), cudaMemcpyHostToDevice, s));
     CU(e, cudaStreamSynchronize(s));
@@ -472,8 +482,9 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
   const bool siib_rate_ok = fs == 16000;  // audio_util.py:131,159,187 assert it; the wrapper's R = fs / 200 presumes it
   const bool dev_in = flags & NELE_FLAG_DEVICE_INPUT;
   const bool mapped = flags & NELE_FLAG_MAPPED;
-  const bool haspi_v1 = do_haspi && (flags & NELE_FLAG_HASPI_V1);
-  int rc = ensure_tables(e, fs, haspi_rate_ok, hl, s);
+  const bool hasqi = do_haspi && (flags & NELE_FLAG_HASQI_V2);
+  const bool haspi_v1 = do_haspi && ((flags & NELE_FLAG_HASPI_V1) || hasqi);  // HASQI runs on the version-1 pipeline
+  int rc = ensure_tables(e, fs, haspi_rate_ok, hl, hasqi, s);
   if (rc != NELE_OK) return rc;
 
   if (dither && !(flags & NELE_FLAG_NO_DITHER)) {
@@ -692,6 +703,9 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
         RESERVE(e, e->v1_cepcorr, (size_t)cn * sizeof(double));
         RESERVE(e, e->v1_cov3, (size_t)cn * 3 * sizeof(double));
         RESERVE(e, e->v1_status, (size_t)cn * sizeof(int32_t));
+        RESERVE(e, e->v1_cave, (size_t)cn * 2 * kBands * sizeof(double));
+        RESERVE(e, e->v1_ave, (size_t)cn * 2 * kBands * sizeof(double));
+        RESERVE(e, e->v1_sync5, (size_t)cn * sizeof(double));
       }
       hb.ref = d_ref;
       hb.deg = d_deg;
@@ -730,8 +744,12 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
         vb.cepcorr = (double*)e->v1_cepcorr.p;
         vb.cov3 = (double*)e->v1_cov3.p;
         vb.status = (int32_t*)e->v1_status.p;
+        vb.ave = (double*)e->v1_ave.p;
+        vb.sync5 = (double*)e->v1_sync5.p;
+        vb.hasqi = hasqi ? 1 : 0;
+        hb.cave = hasqi ? (double*)e->v1_cave.p : nullptr;
         e->last_launches += haspi_v1_run(g, hb, vb, cn, max_n24, e->f64, kt, s);
-        e->last_launches += haspi_v1_finish(g, vb, cn, (double*)e->out_haspi.p, (double*)e->out_raw.p, (int32_t*)e->out_hst.p, kt, s);
+        e->last_launches += haspi_v1_finish(g, hb, vb, cn, (double*)e->out_haspi.p, (double*)e->out_raw.p, (int32_t*)e->out_hst.p, kt, s);
       }
     }
     // ---- ESTOI

@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_control_kernel(PairGeom 
   }
   b.bw[((int64_t)pair * 2 + q) * kBands + lane] =
       bw_from_control(acc, (double)cl.k.gain, N, bc.bwmin[q], bc.bw1);
+  if (b.cave) b.cave[((int64_t)pair * 2 + q) * kBands + lane] = (double)cl.k.gain * sqrt(acc / (double)N);
 }
 
 // group-delay shifts, always from BWx (pyhaspi2.py:1239-1240)

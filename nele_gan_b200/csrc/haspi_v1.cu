@@ -32,6 +32,7 @@ __constant__ float c1_lagh[kMaxLag + 1];    // 1 / xcorr(halfwindow, halfwindow)
 __constant__ float c1_norm[4];              // 1/sum(w), 1/sum(hw), 1/sum(w^2), 1/sum(hw^2)
 __constant__ float c1_cepm[kBands * kNumCep];
 __constant__ IhcConst c1_ihc;
+__constant__ float c1_fsync5[kBands];        // eb_AveCovary2 fsync[4]: sqrt(fc^10 / (fc^10 + cf^10)), fc = 3500 Hz
 
 __host__ __device__ inline int v1_nseg(int n24) {  // pyhaspi2.py:686-687
   if (n24 < kSegHalf) return 0;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(kEar1Warps * 32) haspi_ear_v1_kernel(PairGeom 
   const bool noisy = !b.no_dither;
   const uint64_t gp = (uint64_t)(b.pair_base + pair);
   int rp = (shift == 0) ? 0 : 2 * kEar1Chunk - shift;
+  double pw_x = 0.0, pw_y = 0.0;  // HASQI: sum of the squared signal-path envelope (before compression)
   const int nchunks = (N + kEar1Chunk - 1) / kEar1Chunk;
   for (int c = 0; c < nchunks; ++c) {
     const int i0 = c * kEar1Chunk;
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(kEar1Warps * 32) haspi_ear_v1_kernel(PairGeom 
     for (int blk = 0; blk < 3; ++blk) {
       const int ib = i0 + blk * kSegHalf;
       if (ib >= N) break;
-      float ar_x = 0.f, af_x = 0.f, ar_y = 0.f, af_y = 0.f;
+      float ar_x = 0.f, af_x = 0.f, ar_y = 0.f, af_y = 0.f, pwp_x = 0.f, pwp_y = 0.f;
 #pragma unroll 4
       for (int p = 0; p < kSegHalf; ++p) {
         const int i = ib + p;
@@ -106,8 +108,11 @@ __global__ void __launch_bounds__(kEar1Warps * 32) haspi_ear_v1_kernel(PairGeom 
         float vx = 0.f, vy = 0.f, bx = 0.f, by = 0.f;
         if (i >= shift && i < N) {
           car.advance();
-          vx = Lx.sample_bm(xs * car.c, xs * car.s, car.c, car.s, bx);
-          vy = Ly.sample_bm(ys * car.c, ys * car.s, car.c, car.s, by);
+          float px, py;
+          vx = Lx.sample_bm(xs * car.c, xs * car.s, car.c, car.s, bx, px);
+          vy = Ly.sample_bm(ys * car.c, ys * car.s, car.c, car.s, by, py);
+          pwp_x += px;
+          pwp_y += py;
           if (noisy) {  // added before the delay compensation: the zero-filled head stays silent
             float z0, z1;
             philox_normal2(b.seed ^ 0x9e3779b97f4a7c15ull, gp, (uint32_t)(i - shift), (uint32_t)lane, z0, z1);
@@ -130,7 +135,24 @@ __global__ void __launch_bounds__(kEar1Warps * 32) haspi_ear_v1_kernel(PairGeom 
       sfx[m] = af_x;
       sry[m] = ar_y;
       sfy[m] = af_y;
+      pw_x += (double)pwp_x;
+      pw_y += (double)pwp_y;
     }
+  }
+  if (v.hasqi) {
+    // eb_EarModel averages the envelope over all N samples of the band (pyhaspi2.py:1211-1212);
+    // the delayed time axis of this lane stopped `shift` samples short: run the signal path on.
+    float tx = 0.f, ty = 0.f;
+    for (int t = N - shift; t < N; ++t) {
+      car.advance();
+      const T xs = (T)midx[t], ys = (T)midy[t];
+      tx += (float)Lx.fs.step(Lx.ks, xs * car.c, xs * car.s);
+      ty += (float)Ly.fs.step(Ly.ks, ys * car.c, ys * car.s);
+    }
+    pw_x += (double)tx;
+    pw_y += (double)ty;
+    v.ave[((int64_t)pair * 2 + 0) * kBands + lane] = (double)Lx.ks.gain * sqrt(pw_x / (double)N);
+    v.ave[((int64_t)pair * 2 + 1) * kBands + lane] = (double)Ly.ks.gain * sqrt(pw_y / (double)N);
   }
 }
 
@@ -405,6 +427,8 @@ __global__ void __launch_bounds__(kLevThreads) haspi_lev3_kernel(PairGeom g, Has
   __syncthreads();
   const double e0 = s_edge[0], e1 = s_edge[1];
   double ss[3] = {0.0, 0.0, 0.0}, ws[3] = {0.0, 0.0, 0.0};
+  double f5 = 0.0, s5 = 0.0;  // eb_AveCovary2 (pyhaspi2.py:161-218): fsync-weighted covariance of the audible cells
+  const double fw = (double)c1_fsync5[lane];
   for (int s = wib; s < nseg; s += NW) {
     const double xs = xsum[s];
     if (xs < -1.0e299) continue;
@@ -412,6 +436,8 @@ __global__ void __launch_bounds__(kLevThreads) haspi_lev3_kernel(PairGeom g, Has
     const double rms = sqrt((double)msx[(int64_t)s * kBands + lane]);
     if (rms > 2.5) {  // pyhaspi2.py:486-488
       const double c = (double)cov[(int64_t)s * kBands + lane];
+      f5 += fw * c;
+      s5 += fw;
 #pragma unroll
       for (int k = 0; k < 3; ++k)
         if (k == grp) {
@@ -437,6 +463,10 @@ __global__ void __launch_bounds__(kLevThreads) haspi_lev3_kernel(PairGeom g, Has
     const double nc = warp_sum((w != 0.0) ? 1.0 : 0.0);
     if (lane == 0) v.cov3[3 * pair + wib] = tot / nc;  // 0 / 0 = NaN like the reference
   }
+  if (v.hasqi) {
+    const double a = block_sum(f5, red), c = block_sum(s5, red);
+    if (tid == 0) v.sync5[pair] = a / c;
+  }
 }
 
 __global__ void haspi_v1_score_kernel(HaspiV1Buffers v, int n, double* intel, double* raw10, int32_t* status) {
@@ -458,6 +488,57 @@ __global__ void haspi_v1_score_kernel(HaspiV1Buffers v, int n, double* intel, do
   raw[2] = c1;
   raw[3] = c2;
   status[pair] = 0;
+}
+
+// HASQI version 2 (pyhaspi2.py:32-74): one warp per pair, lane = band
+__global__ void __launch_bounds__(128) hasqi_score_kernel(HaspiBuffers b, HaspiV1Buffers v, int n, double* out, double* raw10,
+                                                           int32_t* status) {
+  const int pair = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (pair >= n) return;
+  double* raw = raw10 + (int64_t)pair * kNumMod;
+  if (v.status[pair] != 0) {
+    if (lane == 0) {
+      for (int m = 0; m < kNumMod; ++m) raw[m] = nan("");
+      out[pair] = nan("");
+      status[pair] = 1;
+    }
+    return;
+  }
+  const BandConst bc = b.bands[lane];
+  double lin[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {  // eb_aveSL (pyhaspi2.py:1135-1152); itype = 2: x gets the audiogram of y (:1162-1165)
+    const double env = v.ave[((int64_t)pair * 2 + q) * kBands + lane], ctl = b.cave[((int64_t)pair * 2 + q) * kBands + lane];
+    double le = 65.0 + 20.0 * log10(fmax(ctl, 1.0e-30));
+    le = fmin(fmax(le, bc.lowknee[1]), 100.0);
+    const double gain = -bc.attn_ohc[1] - (le - bc.lowknee[1]) * (1.0 - 1.0 / bc.cr[1]);
+    double ls = fmax(65.0 + 20.0 * log10(fmax(env, 1.0e-30)), 0.0);
+    const double sl = fmax(ls + gain - bc.attn_ihc[1], 0.0);
+    lin[q] = pow(10.0, sl / 20.0);
+  }
+  // eb_SpectDiff (pyhaspi2.py:220-251): dloud[1] = nbands std(x - y), dslope[1] = nbands std of the first differences
+  const double x = lin[0] / warp_sum(lin[0]), y = lin[1] / warp_sum(lin[1]);
+  const double d = x - y;
+  const double md = warp_sum(d) / kBands;
+  const double dloud = kBands * sqrt(warp_sum((d - md) * (d - md)) / kBands);
+  const double dn = __shfl_down_sync(0xffffffffu, d, 1) - d;  // (x[i+1] - x[i]) - (y[i+1] - y[i]), lanes 0..30
+  const double e = (lane < kBands - 1) ? dn : 0.0;
+  const double me = warp_sum(e) / (kBands - 1);
+  const double dslope = kBands * sqrt(warp_sum((lane < kBands - 1) ? (e - me) * (e - me) : 0.0) / (kBands - 1));
+  if (lane == 0) {
+    const double cep = v.cepcorr[pair], sync5 = v.sync5[pair];
+    const double Dloud = fmin(fmax(1.0 - dloud / 2.5, 0.0), 1.0), Dslope = fmin(fmax(1.0 - dslope, 0.0), 1.0);
+    const double nonlin = cep * cep * sync5, linear = 0.579 * Dloud + 0.421 * Dslope;
+    out[pair] = nonlin * linear;
+    raw[0] = cep;
+    raw[1] = sync5;
+    raw[2] = Dloud;
+    raw[3] = Dslope;
+    raw[4] = nonlin;
+    raw[5] = linear;
+    for (int m = 6; m < kNumMod; ++m) raw[m] = nan("");
+    status[pair] = 0;
+  }
 }
 
 // ------------------------------------------------------------- launchers
@@ -496,6 +577,14 @@ void haspi_v1_upload_tables(const float* cepm, cudaStream_t s) {
   cudaMemcpyToSymbolAsync(c1_cepm, cepm, sizeof(float) * kBands * kNumCep, 0, cudaMemcpyHostToDevice, s);
   const IhcConst ih = make_ihc_const();
   cudaMemcpyToSymbolAsync(c1_ihc, &ih, sizeof(ih), 0, cudaMemcpyHostToDevice, s);
+  double cf[kBands];
+  host::center_freqs(cf);
+  float fs5[kBands];
+  for (int k = 0; k < kBands; ++k) {
+    const double fc10 = pow(3500.0, 10.0);
+    fs5[k] = (float)sqrt(fc10 / (fc10 + pow(cf[k], 10.0)));
+  }
+  cudaMemcpyToSymbolAsync(c1_fsync5, fs5, sizeof(fs5), 0, cudaMemcpyHostToDevice, s);
   cudaFuncSetAttribute(haspi_ear_v1_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kEar1Warps * 4 * kEar1Chunk * sizeof(double)));
   cudaFuncSetAttribute(haspi_bmcov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -526,14 +615,20 @@ int haspi_v1_run(const PairGeom& g, const HaspiBuffers& b, const HaspiV1Buffers&
   return launches;
 }
 
-int haspi_v1_finish(const PairGeom& g, const HaspiV1Buffers& v, int n, double* intel, double* raw10, int32_t* status,
-                    KernelTimer* kt, cudaStream_t s) {
+int haspi_v1_finish(const PairGeom& g, const HaspiBuffers& b, const HaspiV1Buffers& v, int n, double* intel, double* raw10,
+                    int32_t* status, KernelTimer* kt, cudaStream_t s) {
   kt_begin(kt, "haspi_lev3", s);
   haspi_lev3_kernel<<<n, kLevThreads, 0, s>>>(g, v);
   kt_end(kt, s);
-  kt_begin(kt, "haspi_v1_score", s);
-  haspi_v1_score_kernel<<<(n + 127) / 128, 128, 0, s>>>(v, n, intel, raw10, status);
-  kt_end(kt, s);
+  if (v.hasqi) {
+    kt_begin(kt, "hasqi_score", s);
+    hasqi_score_kernel<<<(n + 3) / 4, 128, 0, s>>>(b, v, n, intel, raw10, status);
+    kt_end(kt, s);
+  } else {
+    kt_begin(kt, "haspi_v1_score", s);
+    haspi_v1_score_kernel<<<(n + 127) / 128, 128, 0, s>>>(v, n, intel, raw10, status);
+    kt_end(kt, s);
+  }
   return 2;
 }
 

@@ -25,6 +25,7 @@ struct HaspiBuffers {
   double* mid;           // [2][tot24]
   int64_t tot24;
   double* bw;            // [n][2][32]
+  double* cave;          // [n][2][32] RMS of the control envelope (eb_EarModel xcave / ycave), or null
   int32_t* shift;        // [n][32]
   float* envlp;          // [2][totsub][32]
   int64_t totsub;
@@ -83,14 +84,17 @@ struct HaspiV1Buffers {
   double* xsum;      // [totblk] segment loudness of eb_3LevelCovary (-1e300 = below threshold)
   double* cepcorr;   // [n]
   double* cov3;      // [n][3]
+  double* ave;       // [n][2][32] RMS of the signal-path envelope before compression (xave / yave), HASQI only
+  double* sync5;     // [n] eb_AveCovary2 syncov[4], HASQI only
+  int hasqi;         // compute the HASQI extras
   int32_t* status;   // [n] 0 ok, 1 below threshold
 };
 void haspi_v1_upload_tables(const float* cepm, cudaStream_t s);
 // prep / control / shift kernels of haspi_run, then the v1 ear kernel and back-end
 int haspi_v1_run(const PairGeom& g, const HaspiBuffers& b, const HaspiV1Buffers& v, int n, int max_n24, bool f64,
                  KernelTimer* kt, cudaStream_t s);
-int haspi_v1_finish(const PairGeom& g, const HaspiV1Buffers& v, int n, double* intel, double* raw10, int32_t* status,
-                    KernelTimer* kt, cudaStream_t s);
+int haspi_v1_finish(const PairGeom& g, const HaspiBuffers& b, const HaspiV1Buffers& v, int n, double* intel, double* raw10,
+                    int32_t* status, KernelTimer* kt, cudaStream_t s);
 // front half of haspi_run (prep, control, shift), shared by both versions
 int haspi_run_front(const PairGeom& g, const HaspiBuffers& b, int n, bool f64, KernelTimer* kt, cudaStream_t s);
 

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libnele_score.so")
 
 METRIC_HASPI, METRIC_SIIB, METRIC_ESTOI = 1, 2, 4
 METRIC_ALL = 7
-FLAG_MAPPED, FLAG_DEVICE_INPUT, FLAG_NO_DITHER, FLAG_SIIB_NO_TILE, FLAG_KEEP_STAGES, FLAG_HASPI_V1, FLAG_STOI_CLASSIC, FLAG_SIIB_KNN = 1, 2, 4, 8, 16, 32, 64, 128
+FLAG_MAPPED, FLAG_DEVICE_INPUT, FLAG_NO_DITHER, FLAG_SIIB_NO_TILE, FLAG_KEEP_STAGES, FLAG_HASPI_V1, FLAG_STOI_CLASSIC, FLAG_SIIB_KNN, FLAG_HASQI_V2 = 1, 2, 4, 8, 16, 32, 64, 128, 256
 ST_OK, ST_BELOW_THR, ST_TOO_SHORT, ST_BAD_RATE, ST_UNSUPPORTED, ST_SKIPPED = 0, 1, 2, 3, 4, 0xFF
 _METRIC_BITS = {"haspi": METRIC_HASPI, "siib": METRIC_SIIB, "estoi": METRIC_ESTOI, "stoi": METRIC_ESTOI}
 COL_SIIB, COL_HASPI, COL_ESTOI = 0, 1, 2
@@ -136,7 +136,7 @@ class Engine:
     # ------------------------------------------------------------------ low level
     def score_packed(self, ref, deg, offs, lens, fs=16000, metrics=METRIC_ALL, mapped=True, dither=None,
                      seed=0, no_dither=False, hl=None, siib_no_tile=False, keep_stages=False,
-                     device_input=False, stream=None, out=None, haspi_v1=False, stoi_classic=False, siib_knn=False):
+                     device_input=False, stream=None, out=None, haspi_v1=False, stoi_classic=False, siib_knn=False, hasqi=False):
         """``ref``/``deg``: flat float32 numpy arrays, or raw pointers (ints, e.g.
         ``tensor.data_ptr()``; device pointers when ``device_input``).  ``offs``
         int64[n], ``lens`` int32[n] are host numpy arrays."""
@@ -152,7 +152,8 @@ class Engine:
         flags = (FLAG_MAPPED if mapped else 0) | (FLAG_NO_DITHER if no_dither else 0) | \
                 (FLAG_SIIB_NO_TILE if siib_no_tile else 0) | (FLAG_KEEP_STAGES if keep_stages else 0) | \
                 (FLAG_DEVICE_INPUT if device_input else 0) | (FLAG_HASPI_V1 if haspi_v1 else 0) | \
-                (FLAG_STOI_CLASSIC if stoi_classic else 0) | (FLAG_SIIB_KNN if siib_knn else 0)
+                (FLAG_STOI_CLASSIC if stoi_classic else 0) | (FLAG_SIIB_KNN if siib_knn else 0) | \
+                (FLAG_HASQI_V2 if hasqi else 0)
         pd, drows = None, 0
         if dither is not None:
             dither = np.ascontiguousarray(dither, dtype=np.float32)

@@ -53,6 +53,7 @@ def test_constants_match_header():
     assert vals["NELE_FLAG_HASPI_V1"] == engine.FLAG_HASPI_V1
     assert vals["NELE_FLAG_STOI_CLASSIC"] == engine.FLAG_STOI_CLASSIC
     assert vals["NELE_FLAG_SIIB_KNN"] == engine.FLAG_SIIB_KNN
+    assert vals["NELE_FLAG_HASQI_V2"] == engine.FLAG_HASQI_V2
     assert vals["NELE_ST_UNSUPPORTED"] == engine.ST_UNSUPPORTED
     assert vals["NELE_ST_TOO_SHORT"] == engine.ST_TOO_SHORT
 

@@ -98,3 +98,26 @@ def test_too_short_is_below_threshold(eng):
     x = (0.01 * np.random.default_rng(0).standard_normal(100)).astype(np.float32)
     r = eng.score_batch([x], [x], metrics=("haspi",), mapped=False, no_dither=True, haspi_v1=True)
     assert r.metric_status("haspi")[0] == 1 and np.isnan(r.haspi[0])
+
+
+@pytest.mark.parametrize("name", ["bundled_22050"] + CASES)
+def test_hasqi_v2_against_the_reference(eng, golden, name):
+    """hasqi_v2 (pyhaspi2.py:32-74) on the version-1 pipeline, against the outputs of the unmodified
+    reference with the BM noise forced to zero (tests/golden/hasqi_ref.npz)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "hasqi_ref.npz"))
+    g = golden[name]
+    fs = int(g["fs"])
+    r = eng.score_batch([g["x"]], [g["y"]], fs=fs, metrics=("haspi",), mapped=False, no_dither=True, hasqi=True)
+    assert r.metric_status("haspi")[0] == 0
+    comb, nonlin, lin = z[name + "/hq_zero"]
+    assert abs(r.haspi[0] - comb) < TOL
+    assert np.abs(r.haspi_raw[0, :4] - z[name + "/hq_zero_raw"]).max() < TOL
+    assert abs(r.haspi_raw[0, 4] - nonlin) < TOL and abs(r.haspi_raw[0, 5] - lin) < TOL
+
+
+def test_hasqi_api_and_identity(eng, golden):
+    from nele_gan_b200 import api
+    g = golden["synth_0_24000"]
+    comb, nonlin, lin, raw = api.hasqi_v2(g["x"], 16000, g["x"], 16000, seed=1)
+    assert abs(lin - 1.0) < 1e-6 and abs(raw[0] - 1.0) < 1e-4 and comb > 0.95 and len(raw) == 4

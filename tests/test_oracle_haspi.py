@@ -79,3 +79,19 @@ def test_below_threshold_raises():
     with pytest.raises(Exception):
         # a constant-ish tiny signal normalises fine; silence in x must raise
         haspi_np.cep_coef(np.zeros((100, 32)), np.zeros((100, 32)))
+
+
+@pytest.mark.parametrize("name", ["bundled_22050", "toy_train_multienh", "toy_test_clean", "synth_2_48000"])
+def test_hasqi_v2_zero_noise(golden, name):
+    """oracle hasqi_v2 against the outputs of the unmodified reference (tests/golden/hasqi_ref.npz)."""
+    import os
+    from oracle import haspi_np
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "hasqi_ref.npz"))
+    g = golden[name]
+    fs = int(g["fs"])
+    st = {}
+    comb, nonlin, lin, raw = haspi_np.hasqi_v2(g["x"], fs, g["y"], fs, noise=None, stages=st)
+    assert np.abs(st["xsl"] - z[name + "/xsl"]).max() < 1e-6
+    assert np.abs(st["ysl"] - z[name + "/ysl"]).max() < 1e-6
+    assert np.allclose([comb, nonlin, lin], z[name + "/hq_zero"], rtol=0, atol=1e-7)
+    assert np.allclose(raw, z[name + "/hq_zero_raw"], rtol=0, atol=1e-7)
