@@ -180,11 +180,24 @@ struct SiibKnnBuffers {
 void siib_knn_setup();
 int siib_run_knn(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers& kb, int n, int64_t max_F, KernelTimer* kt,
                  cudaStream_t s);
+// tridiagonalisation-based KLT for full-rank pairs: siib_eig.cu
+struct SiibEigBuffers {
+  double* d;       // [sub][448] diagonal of T
+  double* e;       // [sub][448] sub-diagonal of T
+  double* tau;     // [sub][448] Householder scalars
+  double* lam;     // [sub][448] eigenvalues, ascending
+  double* znorm;   // [sub][448] squared norms of the unnormalised eigenvectors of T
+  float* scratch;  // [sub][420][448] per-thread D- sequence (aliases G: dead before G is written)
+  float* zt;       // [sub][420][448] eigenvectors of T, entry-major
+};
+int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, KernelTimer* kt,
+                 cudaStream_t s);
 void siib_upload_tables(const float* win, const float* decay, const float* g2t, const float* tw, cudaStream_t s);
 int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_tile, KernelTimer* kt, cudaStream_t s);
 // kb != nullptr: k-NN estimator instead of the Gaussian quadratic forms
 // max_unique: upper bound over the pairs of the number of distinct frames, min(F, L / gcd(L, 200))
-int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, int n, int64_t max_F, int64_t max_unique,
-             KernelTimer* kt, cudaStream_t s);
+// eb != nullptr: pairs of rank > 112 take the tridiagonalisation path instead of the cluster Jacobi
+int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, const SiibEigBuffers* eb, int n, int64_t max_F,
+             int64_t max_unique, KernelTimer* kt, cudaStream_t s);
 
 }  // namespace nele

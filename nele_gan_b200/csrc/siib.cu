@@ -719,13 +719,20 @@ __global__ void __launch_bounds__(kExpThreads) siib_expand_kernel(SiibGeom g, Si
 constexpr int kCholThreads = 448;
 constexpr int kCholW = 32;
 
-__global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, SiibBuffers b) {
+__global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, SiibBuffers b, int skip_nonperiodic) {
   const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   constexpr int NW = kCholThreads / 32;
   const int Nf = b.Fa[pair] - (kSStack - 1);
   float* __restrict__ G = b.G + (int64_t)lp * kSDim * kSLd;
   if (Nf < 2) {
     if (tid == 0) b.rank[pair] = 0;
+    return;
+  }
+  if (skip_nonperiodic && !b.perflag[2 * pair]) {
+    // A tiled signal that does not repeat its frames has a full-rank covariance (almost surely):
+    // such pairs go straight to the tridiagonalisation path (siib_eig.cu), which needs no factor
+    // and treats a numerically singular matrix the same way (eigenvalues <= 1e-10 lambda_max).
+    if (tid == 0) b.rank[pair] = kSDim;
     return;
   }
   const double* __restrict__ A0 = b.Sxx + (int64_t)lp * kSDim * kSDim;
@@ -1350,8 +1357,8 @@ int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_til
   return 1;
 }
 
-int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, int n, int64_t max_F, int64_t max_unique,
-             KernelTimer* kt, cudaStream_t s) {
+int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, const SiibEigBuffers* eb, int n, int64_t max_F,
+             int64_t max_unique, KernelTimer* kt, cudaStream_t s) {
   int launches = 0;
   kt_begin(kt, "siib_vad", s);
   siib_vad_kernel<<<n, kVad2Threads, 0, s>>>(g, b);
@@ -1381,7 +1388,7 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, 
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "siib_chol", s);
-  siib_chol_kernel<<<n, kCholThreads, kCholW * kSDim * sizeof(double), s>>>(g, b);
+  siib_chol_kernel<<<n, kCholThreads, kCholW * kSDim * sizeof(double), s>>>(g, b, eb ? 1 : 0);
   kt_end(kt, s);
   ++launches;
   {
@@ -1391,22 +1398,26 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, 
     siib_jacobi2_kernel<1, kJ2WarpsSmall><<<n, kJ2WarpsSmall * 32, smem, s>>>(g, b, 2, 2 * kJ2MaxSb);
     kt_end(kt, s);
     ++launches;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(4 * n);
-    cfg.blockDim = dim3(kJ2Warps * 32);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 4;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    kt_begin(kt, "siib_jacobi_cluster", s);
-    cudaLaunchKernelEx(&cfg, siib_jacobi2_kernel<4, kJ2Warps>, g, b, 2 * kJ2MaxSb + 1, kSDim);
-    kt_end(kt, s);
-    ++launches;
+    if (eb) {
+      launches += siib_run_eig(g, b, *eb, n, 2 * kJ2MaxSb + 1, kt, s);
+    } else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(4 * n);
+      cfg.blockDim = dim3(kJ2Warps * 32);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 4;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      kt_begin(kt, "siib_jacobi_cluster", s);
+      cudaLaunchKernelEx(&cfg, siib_jacobi2_kernel<4, kJ2Warps>, g, b, 2 * kJ2MaxSb + 1, kSDim);
+      kt_end(kt, s);
+      ++launches;
+    }
   }
   if (kb) return launches + siib_run_knn(g, b, *kb, n, max_F, kt, s);
   kt_begin(kt, "siib_quad", s);

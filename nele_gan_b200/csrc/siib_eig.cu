@@ -1,0 +1,410 @@
+// Full-rank KLT of SIIB: eigen-decomposition of the 420 x 420 covariance Sxx by Householder
+// tridiagonalisation instead of the one-sided Jacobi of siib.cu (which needs 10-11 sweeps of
+// 88 k rotations whatever the preconditioning; scripts/exp_jacobi_sweeps.py).  Used for pairs whose
+// numerical rank (pivoted Cholesky, siib_chol_kernel) exceeds 112; rank-deficient pairs keep the
+// one-CTA Jacobi on the Cholesky factor.  The numerical recipe was validated on the CPU against
+// numpy.linalg.eigh (scripts/exp_tridiag_eig.py: orthogonality <= 3e-8, SIIB equal to 1e-14).
+//
+//   siib_tridiag_kernel  per pair CTA, thread = row: A = Q T Q^T in FP64.  Work matrix in the
+//                        Lc buffer (a copy of Sxx), read and updated row-wise so that every access
+//                        of the symmetric matrix is coalesced; the Householder vector of step k
+//                        stays in row k (columns > k + 1), as LAPACK keeps it in column k.
+//   siib_trieig_kernel   per pair CTA, thread = eigenvalue: bisection with a division-free Sturm
+//                        count (three-term recurrence, periodic rescaling), then the eigenvector
+//                        of T from the twisted factorisation (dlar1v): the twist index is the
+//                        minimum of |gamma|, the entries come from the two recurrences run from
+//                        the ends towards the twist (their growing, i.e. stable, direction) with
+//                        an explicit exponent, so no O(n) per-thread storage is needed
+//   siib_backtf_kernel   per (pair, 64 eigenvectors) CTA, 4 lanes per vector: u = H_0 ... H_{n-3} z
+//                        with the vector in registers, reflectors staged through shared memory;
+//                        writes G[j] = sqrt(lambda_j) u_j, the format siib_quad_kernel reads
+#include <stdlib.h>
+
+#include "kernels.h"
+
+namespace nele {
+
+constexpr int kEDim = 420, kELd = 448, kEThreads = 448;
+constexpr int kTriPrefetch = 8;   // rows of look-ahead of the L2 prefetch in the fused pass
+
+// ------------------------------------------------------------ tridiagonalisation
+// Step k: reflector v from row k, p = tau S v, w = p - (tau/2)(p.v) v, S -= v w^T + w v^T.
+// The rank-2 update of step k and the matrix-vector product of step k + 1 are one pass over the
+// trailing matrix (row k + 1 is updated first, it defines the next reflector): every element is
+// read and written once per step, 16 B instead of 24 B of traffic.
+__device__ __forceinline__ void householder(double x, double alpha, double sig, int tid, int k, bool own, double& vi,
+                                            double& beta, double& tau) {
+  if (sig == 0.0) {  // nothing to annihilate
+    beta = alpha;
+    tau = 0.0;
+    vi = 0.0;
+    return;
+  }
+  const double nrm = sqrt(alpha * alpha + sig);
+  beta = alpha >= 0.0 ? -nrm : nrm;
+  tau = (beta - alpha) / beta;
+  vi = (tid == k + 1) ? 1.0 : (tid > k + 1 && own) ? x / (alpha - beta) : 0.0;
+}
+
+__global__ void __launch_bounds__(kEThreads) siib_tridiag_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_lo, int pf_rows) {
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x;
+  if (b.rank[pair] < rank_lo) return;
+  const double* __restrict__ A0 = b.Sxx + (int64_t)lp * kEDim * kEDim;
+  double* __restrict__ A = b.Lc + (int64_t)lp * kEDim * kEDim;
+  double* __restrict__ dd = eb.d + (int64_t)lp * kELd;
+  double* __restrict__ ee = eb.e + (int64_t)lp * kELd;
+  double* __restrict__ tt = eb.tau + (int64_t)lp * kELd;
+  __shared__ double s_v[2][kELd], s_w[kELd];
+  __shared__ double red[32];
+  __shared__ double s_alpha;
+  const bool own = tid < kEDim;
+  const bool pf_lane = (tid & 15) == 0;  // one prefetch per 128-byte line of a row
+  double* Ac = A + tid;  // column tid, read row-wise: element (j, tid) at Ac[j * kEDim]
+  // ---- step 0: reflector from row 0 of Sxx, p by a plain pass that also copies Sxx into the work matrix
+  double x = (own && tid > 0) ? A0[tid] : 0.0;
+  double sig = block_sum((tid > 1) ? x * x : 0.0, red);
+  if (tid == 1) s_alpha = x;
+  __syncthreads();
+  double vi, beta, tau;
+  householder(x, s_alpha, sig, tid, 0, own, vi, beta, tau);
+  s_v[0][tid] = vi;
+  if (own) A[tid] = (tid > 1) ? vi : A0[tid];
+  if (tid == 0) {
+    dd[0] = A0[0];
+    ee[0] = beta;
+    tt[0] = tau;
+  }
+  __syncthreads();
+  double p = 0.0;
+  if (own) {
+    double p0 = 0.0, p1 = 0.0;
+    for (int j = 1; j < kEDim; ++j) {
+      const double a = A0[(int64_t)j * kEDim + tid];
+      Ac[(int64_t)j * kEDim] = a;
+      if (j & 1) p0 = fma(a, s_v[0][j], p0);
+      else p1 = fma(a, s_v[0][j], p1);
+    }
+    p = (tid > 0) ? tau * (p0 + p1) : 0.0;
+  }
+  for (int k = 0; k < kEDim - 2; ++k) {
+    const double* vcur = s_v[k & 1];
+    double* vnext = s_v[(k + 1) & 1];
+    // w of step k
+    const double pv = block_sum(p * vi, red);
+    const double w = p - (0.5 * tau * pv) * vi;
+    s_w[tid] = w;
+    __syncthreads();
+    if (k == kEDim - 3) {  // last reflector: only the 2 x 2 trailing block is left to update
+      if (own && tid > k)
+        for (int j = k + 1; j < kEDim; ++j) Ac[(int64_t)j * kEDim] -= vcur[j] * w + s_w[j] * vi;
+      break;
+    }
+    // row k + 1 first: it defines the reflector of step k + 1
+    double xn = 0.0;
+    if (own && tid > k) {
+      xn = Ac[(int64_t)(k + 1) * kEDim] - vcur[k + 1] * w - s_w[k + 1] * vi;
+      Ac[(int64_t)(k + 1) * kEDim] = xn;
+    }
+    if (tid <= k + 1) xn = (tid == k + 1) ? xn : 0.0;  // keep the diagonal entry for d[k + 1] in its owner only
+    const double diag = xn;
+    const double xr = (tid > k + 1) ? xn : 0.0;
+    const double sgn = block_sum((tid > k + 2) ? xr * xr : 0.0, red);
+    if (tid == k + 2) s_alpha = xr;
+    if (tid == k + 1) dd[k + 1] = diag;
+    __syncthreads();
+    double vn, betan, taun;
+    householder(xr, s_alpha, sgn, tid, k + 1, own, vn, betan, taun);
+    vnext[tid] = vn;
+    if (own && tid > k + 2) Ac[(int64_t)(k + 1) * kEDim] = vn;  // the reflector stays in row k + 1
+    if (tid == 0) {
+      ee[k + 1] = betan;
+      tt[k + 1] = taun;
+    }
+    __syncthreads();
+    // fused pass over rows j >= k + 2: finish the update of step k, accumulate p of step k + 1
+    double pn = 0.0;
+    if (own && tid > k + 1) {
+      double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+      int j = k + 2;
+      for (; j + 8 <= kEDim; j += 8) {  // eight independent loads in flight per thread
+        double a[8];
+        if (pf_lane && j + 8 + pf_rows <= kEDim) {  // pull the rows two iterations ahead into the L2 / L1 path
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Ac + (int64_t)(j + pf_rows + u) * kEDim));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = Ac[(int64_t)(j + u) * kEDim];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          a[u] -= vcur[j + u] * w + s_w[j + u] * vi;
+          Ac[(int64_t)(j + u) * kEDim] = a[u];
+        }
+        q0 = fma(a[0], vnext[j], q0);
+        q1 = fma(a[1], vnext[j + 1], q1);
+        q2 = fma(a[2], vnext[j + 2], q2);
+        q3 = fma(a[3], vnext[j + 3], q3);
+        q0 = fma(a[4], vnext[j + 4], q0);
+        q1 = fma(a[5], vnext[j + 5], q1);
+        q2 = fma(a[6], vnext[j + 6], q2);
+        q3 = fma(a[7], vnext[j + 7], q3);
+      }
+      for (; j < kEDim; ++j) {
+        double a0 = Ac[(int64_t)j * kEDim];
+        a0 -= vcur[j] * w + s_w[j] * vi;
+        Ac[(int64_t)j * kEDim] = a0;
+        q0 = fma(a0, vnext[j], q0);
+      }
+      pn = taun * ((q0 + q1) + (q2 + q3));
+    }
+    p = pn;
+    vi = vn;
+    tau = taun;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    dd[kEDim - 2] = A[(int64_t)(kEDim - 2) * kEDim + (kEDim - 2)];
+    dd[kEDim - 1] = A[(int64_t)(kEDim - 1) * kEDim + (kEDim - 1)];
+    ee[kEDim - 2] = A[(int64_t)(kEDim - 2) * kEDim + (kEDim - 1)];
+    tt[kEDim - 2] = 0.0;
+  }
+}
+
+// --------------------------------------------------- eigenpairs of the tridiagonal
+// number of eigenvalues of T (scaled so that |entries| <= 1) below x: sign changes of the
+// three-term recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}, rescaled every 8 steps
+__device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2, double x) {
+  double pm = 1.0, p = d[0] - x;
+  int cnt = (p < 0.0) ? 1 : 0;
+  for (int i0 = 1; i0 < kEDim; i0 += 8) {
+    const int i1 = min(i0 + 8, kEDim);
+    for (int i = i0; i < i1; ++i) {
+      const double pn = fma(d[i] - x, p, -e2[i - 1] * pm);
+      cnt += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;  // a sign change = one more eigenvalue below x
+      pm = p;
+      p = pn;
+    }
+    const double m = fmax(fabs(p), fabs(pm));
+    if (m > 1.0e100 || (m < 1.0e-100 && m > 0.0)) {
+      const double sc = 1.0 / m;
+      p *= sc;
+      pm *= sc;
+    }
+  }
+  return cnt;
+}
+
+// value with an explicit binary exponent, kept near 1
+struct Scaled {
+  double m;
+  int ex;
+  __device__ __forceinline__ void norm() {
+    int k;
+    m = frexp(m, &k);
+    ex += k;
+  }
+};
+
+__global__ void __launch_bounds__(kEThreads) siib_trieig_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_lo) {
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x;
+  if (b.rank[pair] < rank_lo) return;
+  __shared__ double s_d[kEDim], s_e[kEDim], s_e2[kEDim];
+  __shared__ double red[32];
+  const double* __restrict__ dd = eb.d + (int64_t)lp * kELd;
+  const double* __restrict__ ee = eb.e + (int64_t)lp * kELd;
+  // scale T by 1 / max|entry| (Sturm recurrence stays in range); eigenvalues scale back at the end
+  double mx = 0.0;
+  if (tid < kEDim) mx = fmax(fabs(dd[tid]), (tid < kEDim - 1) ? fabs(ee[tid]) : 0.0);
+  const double scale = block_max(mx, red);
+  const double inv = scale > 0.0 ? 1.0 / scale : 0.0;
+  if (tid < kEDim) {
+    s_d[tid] = dd[tid] * inv;
+    const double ev = (tid < kEDim - 1) ? ee[tid] * inv : 0.0;
+    s_e[tid] = ev;
+    s_e2[tid] = ev * ev;
+  }
+  __syncthreads();
+  if (tid >= kEDim) return;  // no block-wide barrier below
+  // ---- bisection: eigenvalue number tid (ascending) inside the Gershgorin interval [-3, 3]
+  double lo = -3.0, hi = 3.0;
+  for (int it = 0; it < 58; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (sturm_count(s_d, s_e2, mid) > tid) hi = mid;
+    else lo = mid;
+  }
+  const double lam = 0.5 * (lo + hi);
+  eb.lam[(int64_t)lp * kELd + tid] = lam * scale;
+  // ---- eigenvector: twisted factorisation of T - lam I
+  // backward pass: dm_i (D- of the U D U^T factorisation from the bottom), kept in FP32 scratch
+  float* __restrict__ scr = eb.scratch + (int64_t)lp * kEDim * kELd + tid;  // [i][thread]
+  const double tiny = 1.0e-300;
+  {
+    double dm = s_d[kEDim - 1] - lam;
+    scr[(int64_t)(kEDim - 1) * kELd] = (float)dm;
+    for (int i = kEDim - 2; i >= 0; --i) {
+      if (dm == 0.0) dm = tiny;
+      dm = (s_d[i] - lam) - s_e2[i] / dm;
+      scr[(int64_t)i * kELd] = (float)dm;
+    }
+  }
+  // forward pass: dp_i, gamma_i = dp_i + dm_i - (d_i - lam); the scaled forward recurrence
+  // z_{i+1} = -z_i dp_i / e_i is carried along and snapshotted at the running minimum of |gamma|
+  int kt = 0;
+  Scaled zk = {1.0, 0};
+  {
+    double dp = s_d[0] - lam, best = 1.0e300;
+    Scaled z = {1.0, 0};
+    for (int i = 0; i < kEDim; ++i) {
+      const double gam = dp + (double)scr[(int64_t)i * kELd] - (s_d[i] - lam);
+      if (fabs(gam) < best) {
+        best = fabs(gam);
+        kt = i;
+        zk = z;
+      }
+      if (i == kEDim - 1) break;
+      if (dp == 0.0) dp = tiny;
+      const double ei = s_e[i] != 0.0 ? s_e[i] : tiny;
+      z.m = -z.m * dp / ei;
+      z.norm();
+      dp = (s_d[i + 1] - lam) - s_e2[i] / dp;
+    }
+  }
+  // value of the backward recurrence z_i = -z_{i+1} dm_{i+1} / e_i at the twist index
+  Scaled zb = {1.0, 0};
+  {
+    double dm = s_d[kEDim - 1] - lam;
+    for (int i = kEDim - 2; i >= kt; --i) {
+      if (dm == 0.0) dm = tiny;
+      const double ei = s_e[i] != 0.0 ? s_e[i] : tiny;
+      zb.m = -zb.m * dm / ei;
+      zb.norm();
+      dm = (s_d[i] - lam) - s_e2[i] / dm;
+    }
+  }
+  // write z (z_kt = 1) and its squared norm; entries below 2^-126 flush to zero in FP32
+  double nrm2 = 0.0;
+  {
+    double dp = s_d[0] - lam;
+    Scaled z = {1.0, 0};
+    for (int i = 0; i <= kt; ++i) {
+      const double v = ldexp(z.m / zk.m, z.ex - zk.ex);
+      eb.zt[((int64_t)lp * kEDim + i) * kELd + tid] = (float)v;
+      nrm2 += v * v;
+      if (i == kt) break;
+      if (dp == 0.0) dp = tiny;
+      const double ei = s_e[i] != 0.0 ? s_e[i] : tiny;
+      z.m = -z.m * dp / ei;
+      z.norm();
+      dp = (s_d[i + 1] - lam) - s_e2[i] / dp;
+    }
+  }
+  {
+    double dm = s_d[kEDim - 1] - lam;
+    Scaled z = {1.0, 0};
+    for (int i = kEDim - 1; i > kt; --i) {
+      const double v = ldexp(z.m / zb.m, z.ex - zb.ex);
+      eb.zt[((int64_t)lp * kEDim + i) * kELd + tid] = (float)v;
+      nrm2 += v * v;
+      if (dm == 0.0) dm = tiny;
+      const double ei = s_e[i - 1] != 0.0 ? s_e[i - 1] : tiny;
+      z.m = -z.m * dm / ei;
+      z.norm();
+      dm = (s_d[i - 1] - lam) - s_e2[i - 1] / dm;
+    }
+  }
+  eb.znorm[(int64_t)lp * kELd + tid] = nrm2;
+}
+
+// ------------------------------------------------------------ back-transformation
+constexpr int kBtVec = 64, kBtThreads = 4 * kBtVec, kBtRows = kEDim / 4;  // 105 rows per lane, rows i = 4 m + part
+constexpr int kBtPanel = 16;                                               // reflectors staged per barrier
+constexpr int kBtChunk = 15;                                               // rows per lane skipped / processed together
+
+__global__ void __launch_bounds__(kBtThreads) siib_backtf_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_lo) {
+  const int lp = blockIdx.y, pair = b.pair_lo + lp, tid = threadIdx.x;
+  if (b.rank[pair] < rank_lo) return;
+  const int j = blockIdx.x * kBtVec + (tid >> 2), part = tid & 3;
+  const bool live = j < kEDim;
+  __shared__ float s_v[kBtPanel][kEDim];
+  __shared__ float s_tau[kBtPanel];
+  const double* __restrict__ A = b.Lc + (int64_t)lp * kEDim * kEDim;
+  const double* __restrict__ tt = eb.tau + (int64_t)lp * kELd;
+  float u[kBtRows];
+#pragma unroll
+  for (int m = 0; m < kBtRows; ++m) u[m] = live ? eb.zt[((int64_t)lp * kEDim + 4 * m + part) * kELd + j] : 0.f;
+  // reflectors k = n-3 .. 0 in panels of 16 (k descending inside a panel)
+  for (int k1 = kEDim - 3; k1 >= 0; k1 -= kBtPanel) {
+    const int nk = min(kBtPanel, k1 + 1);
+    __syncthreads();
+    for (int idx = tid; idx < nk * kEDim; idx += kBtThreads) {
+      const int kk = idx / kEDim, i = idx % kEDim, k = k1 - kk;
+      s_v[kk][i] = (i == k + 1) ? 1.f : (i > k + 1) ? (float)A[(int64_t)k * kEDim + i] : 0.f;
+    }
+    if (tid < nk) s_tau[tid] = (float)tt[k1 - tid];
+    __syncthreads();
+    for (int kk = 0; kk < nk; ++kk) {
+      const float tau = s_tau[kk];
+      if (tau == 0.f) continue;
+      const float* v = s_v[kk] + part;
+      // reflector k is zero in rows <= k: skip whole 15-row chunks (rows 60 c .. 60 c + 59) below it
+      const int c0 = (k1 - kk + 1) / (4 * kBtChunk);
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < kBtRows / kBtChunk; ++c) {
+        if (c < c0) continue;
+#pragma unroll
+        for (int m = c * kBtChunk; m < (c + 1) * kBtChunk; ++m) dot = fmaf(v[4 * m], u[m], dot);
+      }
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      const float cf = -tau * dot;
+#pragma unroll
+      for (int c = 0; c < kBtRows / kBtChunk; ++c) {
+        if (c < c0) continue;
+#pragma unroll
+        for (int m = c * kBtChunk; m < (c + 1) * kBtChunk; ++m) u[m] = fmaf(cf, v[4 * m], u[m]);
+      }
+    }
+  }
+  if (!live) return;
+  // column j of G = sqrt(lambda_j) u_j / |z_j|; eigenvalues at or below 1e-10 lambda_max carry no information
+  const double lam = eb.lam[(int64_t)lp * kELd + j], lmax = eb.lam[(int64_t)lp * kELd + kEDim - 1];
+  const double nz = eb.znorm[(int64_t)lp * kELd + j];
+  const float sc = (lam > 1.0e-10 * lmax && nz > 0.0) ? (float)sqrt(lam / nz) : 0.f;
+  float* __restrict__ G = b.G + (int64_t)lp * kEDim * kELd + (int64_t)j * kELd;
+#pragma unroll
+  for (int m = 0; m < kBtRows; ++m) G[4 * m + part] = sc * u[m];
+  if (part == 0)
+    for (int i = kEDim; i < kELd; ++i) G[i] = 0.f;
+}
+
+// rank <- 420 for the pairs that took this path (siib_quad_kernel loops over `rank` columns)
+__global__ void siib_eig_finish_kernel(SiibBuffers b, int n, int rank_lo) {
+  const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lp >= n) return;
+  const int pair = b.pair_lo + lp;
+  if (b.rank[pair] >= rank_lo) {
+    b.rank[pair] = kEDim;
+    b.sweeps[pair] = -1;  // marks "tridiagonal path" in the siib.rank stage
+  }
+}
+
+int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, KernelTimer* kt,
+                 cudaStream_t s) {
+  kt_begin(kt, "siib_tridiag", s);
+  static const int pf_rows = [] { const char* p = getenv("NELE_TRIDIAG_PF"); return p ? atoi(p) : kTriPrefetch; }();
+  siib_tridiag_kernel<<<n, kEThreads, 0, s>>>(g, b, eb, rank_lo, pf_rows);
+  kt_end(kt, s);
+  kt_begin(kt, "siib_trieig", s);
+  siib_trieig_kernel<<<n, kEThreads, 0, s>>>(g, b, eb, rank_lo);
+  kt_end(kt, s);
+  kt_begin(kt, "siib_backtf", s);
+  siib_backtf_kernel<<<dim3((kEDim + kBtVec - 1) / kBtVec, n), kBtThreads, 0, s>>>(g, b, eb, rank_lo);
+  kt_end(kt, s);
+  kt_begin(kt, "siib_eig_finish", s);
+  siib_eig_finish_kernel<<<(n + 127) / 128, 128, 0, s>>>(b, n, rank_lo);
+  kt_end(kt, s);
+  return 4;
+}
+
+}  // namespace nele
