@@ -28,10 +28,14 @@ constexpr int kEDim = 420, kELd = 448, kEThreads = 448;
 constexpr int kTriPrefetch = 8;   // rows of look-ahead of the L2 prefetch in the fused pass
 
 // ------------------------------------------------------------ tridiagonalisation
-// Step k: reflector v from row k, p = tau S v, w = p - (tau/2)(p.v) v, S -= v w^T + w v^T.
-// The rank-2 update of step k and the matrix-vector product of step k + 1 are one pass over the
-// trailing matrix (row k + 1 is updated first, it defines the next reflector): every element is
-// read and written once per step, 16 B instead of 24 B of traffic.
+// Blocked as LAPACK's dsytrd / dlatrd: inside a panel of kTriB steps the trailing matrix is only
+// *read* (one coalesced pass per step for p = S v); the rank-2 updates of the panel are kept as the
+// n x kTriB matrices V, W in shared memory and applied to whatever is touched on the fly
+// (S_cur = S_panel - V W^T - W V^T), and the trailing matrix is rewritten once per panel.  Traffic
+// per element and step: 8 B + 16 B / kTriB instead of 16 B for the step-by-step form -- the kernel
+// is HBM bound (ncu: 4.4 TB/s).
+constexpr int kTriB = 12;
+
 __device__ __forceinline__ void householder(double x, double alpha, double sig, int tid, int k, bool own, double& vi,
                                             double& beta, double& tau) {
   if (sig == 0.0) {  // nothing to annihilate
@@ -47,121 +51,104 @@ __device__ __forceinline__ void householder(double x, double alpha, double sig, 
 }
 
 __global__ void __launch_bounds__(kEThreads) siib_tridiag_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_lo, int pf_rows) {
-  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x;
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  constexpr int NW = kEThreads / 32;
   if (b.rank[pair] < rank_lo) return;
   const double* __restrict__ A0 = b.Sxx + (int64_t)lp * kEDim * kEDim;
   double* __restrict__ A = b.Lc + (int64_t)lp * kEDim * kEDim;
   double* __restrict__ dd = eb.d + (int64_t)lp * kELd;
   double* __restrict__ ee = eb.e + (int64_t)lp * kELd;
   double* __restrict__ tt = eb.tau + (int64_t)lp * kELd;
-  __shared__ double s_v[2][kELd], s_w[kELd];
+  extern __shared__ __align__(16) double s_vw[];  // V[kTriB][448], W[kTriB][448]
+  double* sV = s_vw;
+  double* sW = s_vw + kTriB * kELd;
   __shared__ double red[32];
+  __shared__ double s_part[NW][2 * kTriB];
+  __shared__ double s_tot[2 * kTriB];
   __shared__ double s_alpha;
   const bool own = tid < kEDim;
-  const bool pf_lane = (tid & 15) == 0;  // one prefetch per 128-byte line of a row
-  double* Ac = A + tid;  // column tid, read row-wise: element (j, tid) at Ac[j * kEDim]
-  // ---- step 0: reflector from row 0 of Sxx, p by a plain pass that also copies Sxx into the work matrix
-  double x = (own && tid > 0) ? A0[tid] : 0.0;
-  double sig = block_sum((tid > 1) ? x * x : 0.0, red);
-  if (tid == 1) s_alpha = x;
-  __syncthreads();
-  double vi, beta, tau;
-  householder(x, s_alpha, sig, tid, 0, own, vi, beta, tau);
-  s_v[0][tid] = vi;
-  if (own) A[tid] = (tid > 1) ? vi : A0[tid];
-  if (tid == 0) {
-    dd[0] = A0[0];
-    ee[0] = beta;
-    tt[0] = tau;
-  }
-  __syncthreads();
-  double p = 0.0;
-  if (own) {
-    double p0 = 0.0, p1 = 0.0;
-    for (int j = 1; j < kEDim; ++j) {
-      const double a = A0[(int64_t)j * kEDim + tid];
-      Ac[(int64_t)j * kEDim] = a;
-      if (j & 1) p0 = fma(a, s_v[0][j], p0);
-      else p1 = fma(a, s_v[0][j], p1);
-    }
-    p = (tid > 0) ? tau * (p0 + p1) : 0.0;
-  }
-  for (int k = 0; k < kEDim - 2; ++k) {
-    const double* vcur = s_v[k & 1];
-    double* vnext = s_v[(k + 1) & 1];
-    // w of step k
-    const double pv = block_sum(p * vi, red);
-    const double w = p - (0.5 * tau * pv) * vi;
-    s_w[tid] = w;
-    __syncthreads();
-    if (k == kEDim - 3) {  // last reflector: only the 2 x 2 trailing block is left to update
-      if (own && tid > k)
-        for (int j = k + 1; j < kEDim; ++j) Ac[(int64_t)j * kEDim] -= vcur[j] * w + s_w[j] * vi;
-      break;
-    }
-    // row k + 1 first: it defines the reflector of step k + 1
-    double xn = 0.0;
-    if (own && tid > k) {
-      xn = Ac[(int64_t)(k + 1) * kEDim] - vcur[k + 1] * w - s_w[k + 1] * vi;
-      Ac[(int64_t)(k + 1) * kEDim] = xn;
-    }
-    if (tid <= k + 1) xn = (tid == k + 1) ? xn : 0.0;  // keep the diagonal entry for d[k + 1] in its owner only
-    const double diag = xn;
-    const double xr = (tid > k + 1) ? xn : 0.0;
-    const double sgn = block_sum((tid > k + 2) ? xr * xr : 0.0, red);
-    if (tid == k + 2) s_alpha = xr;
-    if (tid == k + 1) dd[k + 1] = diag;
-    __syncthreads();
-    double vn, betan, taun;
-    householder(xr, s_alpha, sgn, tid, k + 1, own, vn, betan, taun);
-    vnext[tid] = vn;
-    if (own && tid > k + 2) Ac[(int64_t)(k + 1) * kEDim] = vn;  // the reflector stays in row k + 1
-    if (tid == 0) {
-      ee[k + 1] = betan;
-      tt[k + 1] = taun;
-    }
-    __syncthreads();
-    // fused pass over rows j >= k + 2: finish the update of step k, accumulate p of step k + 1
-    double pn = 0.0;
-    if (own && tid > k + 1) {
-      double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
-      int j = k + 2;
-      for (; j + 8 <= kEDim; j += 8) {  // eight independent loads in flight per thread
-        double a[8];
-        if (pf_lane && j + 8 + pf_rows <= kEDim) {  // pull the rows two iterations ahead into the L2 / L1 path
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(Ac + (int64_t)(j + pf_rows + u) * kEDim));
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) a[u] = Ac[(int64_t)(j + u) * kEDim];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          a[u] -= vcur[j + u] * w + s_w[j + u] * vi;
-          Ac[(int64_t)(j + u) * kEDim] = a[u];
-        }
-        q0 = fma(a[0], vnext[j], q0);
-        q1 = fma(a[1], vnext[j + 1], q1);
-        q2 = fma(a[2], vnext[j + 2], q2);
-        q3 = fma(a[3], vnext[j + 3], q3);
-        q0 = fma(a[4], vnext[j + 4], q0);
-        q1 = fma(a[5], vnext[j + 5], q1);
-        q2 = fma(a[6], vnext[j + 6], q2);
-        q3 = fma(a[7], vnext[j + 7], q3);
+  (void)pf_rows;
+  for (int k0 = 0; k0 < kEDim - 2; k0 += kTriB) {
+    const double* __restrict__ Ain = (k0 == 0) ? A0 : A;  // the matrix as of the start of the panel
+    const int nb = min(kTriB, kEDim - 2 - k0);
+    for (int m = 0; m < nb; ++m) {
+      const int k = k0 + m;
+      // row k of the current matrix: panel-start values minus the updates of the steps before
+      double x = (own && tid >= k) ? Ain[(int64_t)k * kEDim + tid] : 0.0;
+      for (int mm = 0; mm < m; ++mm) x -= sV[mm * kELd + k] * sW[mm * kELd + tid] + sW[mm * kELd + k] * sV[mm * kELd + tid];
+      if (tid == k) dd[k] = x;
+      const double xr = (own && tid > k) ? x : 0.0;
+      const double sig = block_sum((tid > k + 1) ? xr * xr : 0.0, red);
+      if (tid == k + 1) s_alpha = xr;
+      __syncthreads();
+      double vi, beta, tau;
+      householder(xr, s_alpha, sig, tid, k, own, vi, beta, tau);
+      sV[m * kELd + tid] = vi;
+      if (own && tid > k + 1) A[(int64_t)k * kEDim + tid] = vi;  // the reflector stays in row k of the work matrix
+      if (tid == 0) {
+        ee[k] = beta;
+        tt[k] = tau;
       }
-      for (; j < kEDim; ++j) {
-        double a0 = Ac[(int64_t)j * kEDim];
-        a0 -= vcur[j] * w + s_w[j] * vi;
-        Ac[(int64_t)j * kEDim] = a0;
-        q0 = fma(a0, vnext[j], q0);
+      __syncthreads();
+      // p = S_panel v: one coalesced read-only pass over rows j > k
+      double p = 0.0;
+      if (own && tid > k) {
+        const double* __restrict__ col = Ain + tid;
+        const double* __restrict__ v = sV + m * kELd;
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+        int j = k + 1;
+        for (; j + 8 <= kEDim; j += 8) {
+          double a[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) a[u] = __ldg(col + (int64_t)(j + u) * kEDim);
+          p0 = fma(a[0], v[j], p0);
+          p1 = fma(a[1], v[j + 1], p1);
+          p2 = fma(a[2], v[j + 2], p2);
+          p3 = fma(a[3], v[j + 3], p3);
+          p0 = fma(a[4], v[j + 4], p0);
+          p1 = fma(a[5], v[j + 5], p1);
+          p2 = fma(a[6], v[j + 6], p2);
+          p3 = fma(a[7], v[j + 7], p3);
+        }
+        for (; j < kEDim; ++j) p0 = fma(__ldg(col + (int64_t)j * kEDim), v[j], p0);
+        p = (p0 + p1) + (p2 + p3);
       }
-      pn = taun * ((q0 + q1) + (q2 + q3));
+      // corrections for the steps of this panel: p -= V (W^T v) + W (V^T v)
+      if (m > 0) {
+        for (int mm = 0; mm < m; ++mm) {
+          const double aw = warp_sum(sW[mm * kELd + tid] * vi), av = warp_sum(sV[mm * kELd + tid] * vi);
+          if (lane == 0) {
+            s_part[wib][2 * mm] = aw;
+            s_part[wib][2 * mm + 1] = av;
+          }
+        }
+        __syncthreads();
+        if (tid < 2 * m) {
+          double t = 0.0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) t += s_part[w][tid];
+          s_tot[tid] = t;
+        }
+        __syncthreads();
+        for (int mm = 0; mm < m; ++mm) p -= sV[mm * kELd + tid] * s_tot[2 * mm] + sW[mm * kELd + tid] * s_tot[2 * mm + 1];
+      }
+      p = (own && tid > k) ? tau * p : 0.0;
+      const double pv = block_sum(p * vi, red);
+      sW[m * kELd + tid] = p - (0.5 * tau * pv) * vi;
+      __syncthreads();
     }
-    p = pn;
-    vi = vn;
-    tau = taun;
+    // trailing update of the panel: rows and columns beyond its last step
+    const int kl = k0 + nb - 1;
+    if (own && tid > kl) {
+      for (int j = kl + 1; j < kEDim; ++j) {
+        double a = Ain[(int64_t)j * kEDim + tid];
+#pragma unroll 4
+        for (int mm = 0; mm < nb; ++mm) a -= sV[mm * kELd + j] * sW[mm * kELd + tid] + sW[mm * kELd + j] * sV[mm * kELd + tid];
+        A[(int64_t)j * kEDim + tid] = a;
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (tid == 0) {
     dd[kEDim - 2] = A[(int64_t)(kEDim - 2) * kEDim + (kEDim - 2)];
     dd[kEDim - 1] = A[(int64_t)(kEDim - 1) * kEDim + (kEDim - 1)];
@@ -393,7 +380,12 @@ int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& 
                  cudaStream_t s) {
   kt_begin(kt, "siib_tridiag", s);
   static const int pf_rows = [] { const char* p = getenv("NELE_TRIDIAG_PF"); return p ? atoi(p) : kTriPrefetch; }();
-  siib_tridiag_kernel<<<n, kEThreads, 0, s>>>(g, b, eb, rank_lo, pf_rows);
+  static const bool tri_attr = [] {
+    cudaFuncSetAttribute(siib_tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTriB * kELd * (int)sizeof(double));
+    return true;
+  }();
+  (void)tri_attr;
+  siib_tridiag_kernel<<<n, kEThreads, 2 * kTriB * kELd * sizeof(double), s>>>(g, b, eb, rank_lo, pf_rows);
   kt_end(kt, s);
   kt_begin(kt, "siib_trieig", s);
   siib_trieig_kernel<<<n, kEThreads, 0, s>>>(g, b, eb, rank_lo);
