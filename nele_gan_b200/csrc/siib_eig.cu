@@ -303,53 +303,88 @@ __global__ void __launch_bounds__(kEThreads) siib_trieig_kernel(SiibGeom g, Siib
 }
 
 // ------------------------------------------------------------ back-transformation
-constexpr int kBtVec = 64, kBtThreads = 4 * kBtVec, kBtRows = kEDim / 4;  // 105 rows per lane, rows i = 4 m + part
-constexpr int kBtPanel = 16;                                               // reflectors staged per barrier
-constexpr int kBtChunk = 15;                                               // rows per lane skipped / processed together
+// Lane = eigenvector (32 per CTA), warp w of 8 holds its rows i = 8 m + w (m = 0..52, padded to 56)
+// in registers: every element of a reflector is read by all 32 lanes at once (one shared-memory
+// wavefront per 128-bit word; a 4-lanes-per-vector layout tried first was bound by shared-memory
+// bandwidth), and 16 warps per SM hide the latency of the dependent dot -> update chain (the
+// kernel is latency bound: fewer, fatter warps were slower).  The eight partial dot products of a
+// vector meet in shared memory, one block barrier per reflector.  A reflector is staged as
+// [w][m]; its all-zero head (rows <= k) is skipped in chunks of 64 rows, uniformly over the CTA.
+constexpr int kBtVec = 32, kBtParts = 8, kBtThreads = kBtParts * 32;
+constexpr int kBtRows = 56;                   // rows per warp (14 x 4), 8 * 56 = 448 >= 420
+constexpr int kBtLd = kBtParts * kBtRows;     // staged reflector length
+constexpr int kBtPanel = 16;                  // reflectors staged per panel
+constexpr int kBtChunk = 2;                   // 128-bit words per skippable chunk
 
-__global__ void __launch_bounds__(kBtThreads) siib_backtf_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_lo) {
-  const int lp = blockIdx.y, pair = b.pair_lo + lp, tid = threadIdx.x;
+__global__ void __launch_bounds__(kBtThreads, 2) siib_backtf_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_lo) {
+  const int lp = blockIdx.y, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (b.rank[pair] < rank_lo) return;
-  const int j = blockIdx.x * kBtVec + (tid >> 2), part = tid & 3;
+  const int j = blockIdx.x * kBtVec + lane;
   const bool live = j < kEDim;
-  __shared__ float s_v[kBtPanel][kEDim];
+  __shared__ __align__(16) float s_v[kBtPanel][kBtLd];
   __shared__ float s_tau[kBtPanel];
+  __shared__ float s_dot[2][kBtParts][32];
   const double* __restrict__ A = b.Lc + (int64_t)lp * kEDim * kEDim;
   const double* __restrict__ tt = eb.tau + (int64_t)lp * kELd;
   float u[kBtRows];
 #pragma unroll
-  for (int m = 0; m < kBtRows; ++m) u[m] = live ? eb.zt[((int64_t)lp * kEDim + 4 * m + part) * kELd + j] : 0.f;
+  for (int m = 0; m < kBtRows; ++m) {
+    const int i = kBtParts * m + w;
+    u[m] = (live && i < kEDim) ? eb.zt[((int64_t)lp * kEDim + i) * kELd + j] : 0.f;
+  }
+  int par = 0;
   // reflectors k = n-3 .. 0 in panels of 16 (k descending inside a panel)
   for (int k1 = kEDim - 3; k1 >= 0; k1 -= kBtPanel) {
     const int nk = min(kBtPanel, k1 + 1);
     __syncthreads();
-    for (int idx = tid; idx < nk * kEDim; idx += kBtThreads) {
-      const int kk = idx / kEDim, i = idx % kEDim, k = k1 - kk;
-      s_v[kk][i] = (i == k + 1) ? 1.f : (i > k + 1) ? (float)A[(int64_t)k * kEDim + i] : 0.f;
+    for (int kk = 0; kk < nk; ++kk) {
+      const int k = k1 - kk;
+      const double* __restrict__ row = A + (int64_t)k * kEDim;
+#pragma unroll
+      for (int i = tid; i < kBtLd; i += kBtThreads) {
+        const float v = (i == k + 1) ? 1.f : (i > k + 1 && i < kEDim) ? (float)__ldg(row + i) : 0.f;
+        s_v[kk][(i & (kBtParts - 1)) * kBtRows + (i >> 3)] = v;
+      }
     }
     if (tid < nk) s_tau[tid] = (float)tt[k1 - tid];
     __syncthreads();
     for (int kk = 0; kk < nk; ++kk) {
       const float tau = s_tau[kk];
       if (tau == 0.f) continue;
-      const float* v = s_v[kk] + part;
-      // reflector k is zero in rows <= k: skip whole 15-row chunks (rows 60 c .. 60 c + 59) below it
-      const int c0 = (k1 - kk + 1) / (4 * kBtChunk);
+      const float4* v4 = reinterpret_cast<const float4*>(s_v[kk] + w * kBtRows);
+      // reflector k is zero in rows <= k, i.e. in the words q < (k + 1) / 32 of every warp
+      const int c0 = ((k1 - kk + 1) >> 5) / kBtChunk;
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < kBtRows / 4 / kBtChunk; ++c) {
+        if (c < c0) continue;
+#pragma unroll
+        for (int q = c * kBtChunk; q < (c + 1) * kBtChunk; ++q) {
+          const float4 vv = v4[q];
+          d0 = fmaf(vv.x, u[4 * q], d0);
+          d1 = fmaf(vv.y, u[4 * q + 1], d1);
+          d2 = fmaf(vv.z, u[4 * q + 2], d2);
+          d3 = fmaf(vv.w, u[4 * q + 3], d3);
+        }
+      }
+      s_dot[par][w][lane] = (d0 + d1) + (d2 + d3);
+      __syncthreads();
       float dot = 0.f;
 #pragma unroll
-      for (int c = 0; c < kBtRows / kBtChunk; ++c) {
-        if (c < c0) continue;
-#pragma unroll
-        for (int m = c * kBtChunk; m < (c + 1) * kBtChunk; ++m) dot = fmaf(v[4 * m], u[m], dot);
-      }
-      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      for (int t = 0; t < kBtParts; ++t) dot += s_dot[par][t][lane];
+      par ^= 1;
       const float cf = -tau * dot;
 #pragma unroll
-      for (int c = 0; c < kBtRows / kBtChunk; ++c) {
+      for (int c = 0; c < kBtRows / 4 / kBtChunk; ++c) {
         if (c < c0) continue;
 #pragma unroll
-        for (int m = c * kBtChunk; m < (c + 1) * kBtChunk; ++m) u[m] = fmaf(cf, v[4 * m], u[m]);
+        for (int q = c * kBtChunk; q < (c + 1) * kBtChunk; ++q) {
+          const float4 vv = v4[q];
+          u[4 * q] = fmaf(cf, vv.x, u[4 * q]);
+          u[4 * q + 1] = fmaf(cf, vv.y, u[4 * q + 1]);
+          u[4 * q + 2] = fmaf(cf, vv.z, u[4 * q + 2]);
+          u[4 * q + 3] = fmaf(cf, vv.w, u[4 * q + 3]);
+        }
       }
     }
   }
@@ -360,9 +395,10 @@ __global__ void __launch_bounds__(kBtThreads) siib_backtf_kernel(SiibGeom g, Sii
   const float sc = (lam > 1.0e-10 * lmax && nz > 0.0) ? (float)sqrt(lam / nz) : 0.f;
   float* __restrict__ G = b.G + (int64_t)lp * kEDim * kELd + (int64_t)j * kELd;
 #pragma unroll
-  for (int m = 0; m < kBtRows; ++m) G[4 * m + part] = sc * u[m];
-  if (part == 0)
-    for (int i = kEDim; i < kELd; ++i) G[i] = 0.f;
+  for (int m = 0; m < kBtRows; ++m) {
+    const int i = kBtParts * m + w;
+    G[i] = (i < kEDim) ? sc * u[m] : 0.f;
+  }
 }
 
 // rank <- 420 for the pairs that took this path (siib_quad_kernel loops over `rank` columns)
