@@ -188,8 +188,11 @@ struct SiibEigBuffers {
   double* lam;     // [sub][448] eigenvalues, ascending
   double* znorm;   // [sub][448] squared norms of the unnormalised eigenvectors of T
   float* scratch;  // [sub][420][448] per-thread D- sequence (aliases G: dead before G is written)
-  float* zt;       // [sub][420][448] eigenvectors of T, entry-major
+  float* zt;       // [sub][420][448] eigenvectors of T, entry-major (low-rank path: scratch + V)
+  double* gram;    // [sub][112][112] zero-padded Gram matrix L^T L of the low-rank pairs
 };
+int siib_run_small_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_hi, KernelTimer* kt,
+                       cudaStream_t s);
 int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, KernelTimer* kt,
                  cudaStream_t s);
 void siib_upload_tables(const float* win, const float* decay, const float* g2t, const float* tw, cudaStream_t s);

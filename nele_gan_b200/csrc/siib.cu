@@ -1394,10 +1394,14 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, 
   {
     // r <= 112: one CTA per pair, everything in shared memory; larger ranks: 4-CTA clusters
     const size_t smem = (size_t)2 * kJ2MaxSb * kSLd * sizeof(float);
-    kt_begin(kt, "siib_jacobi", s);
-    siib_jacobi2_kernel<1, kJ2WarpsSmall><<<n, kJ2WarpsSmall * 32, smem, s>>>(g, b, 2, 2 * kJ2MaxSb);
-    kt_end(kt, s);
-    ++launches;
+    if (eb) {
+      launches += siib_run_small_eig(g, b, *eb, n, 2 * kJ2MaxSb, kt, s);
+    } else {
+      kt_begin(kt, "siib_jacobi", s);
+      siib_jacobi2_kernel<1, kJ2WarpsSmall><<<n, kJ2WarpsSmall * 32, smem, s>>>(g, b, 2, 2 * kJ2MaxSb);
+      kt_end(kt, s);
+      ++launches;
+    }
     if (eb) {
       launches += siib_run_eig(g, b, *eb, n, 2 * kJ2MaxSb + 1, kt, s);
     } else {

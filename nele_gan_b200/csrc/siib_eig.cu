@@ -436,3 +436,394 @@ int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& 
 }
 
 }  // namespace nele
+
+// ====================================================================================
+// Low-rank pairs (periodic tilings: numerical rank r <= 112 of 420, siib_chol_kernel).
+// With Sxx = L L^T (L: 420 x r, FP32 copy in G), the non-zero eigenpairs of Sxx follow from the
+// r x r Gram matrix M = L^T L = V Lambda V^T:  sqrt(lambda_j) u_j = L v_j.  M is zero padded to
+// 112 x 112 and goes through the same recipe as the full-rank case, but entirely on one SM
+// (the FP64 matrix is 100 KB of shared memory); this replaces the one-CTA Jacobi on the 448-long
+// columns of L (8-9 sweeps, 7.2 us per pair at bench size).
+//
+//   siib_gram_kernel      per pair CTA, 16 x 16 threads x 7 x 7 register tile: M in FP64
+//   siib_smalleig_kernel  per pair CTA, thread = row / eigenvalue / eigenvector: unblocked
+//                         Householder tridiagonalisation in shared memory, bisection + twisted
+//                         factorisation, back-transformation with the vector in registers -> V
+//   siib_lv_kernel        per (pair, 32-row tile) CTA: G <- L V in place
+namespace nele {
+
+constexpr int kSN = 112, kSNp = kSN + 1;  // padded Gram dimension, shared-memory row stride
+
+__global__ void __launch_bounds__(256) siib_gram_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_hi) {
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int r = b.rank[pair];
+  if (r < 2 || r > rank_hi) return;
+  const float* __restrict__ G = b.G + (int64_t)lp * kEDim * kELd;
+  __shared__ float sL[kSN][33];
+  double acc[7][7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) acc[i][j] = 0.0;
+  for (int row0 = 0; row0 < kEDim; row0 += 32) {
+    __syncthreads();
+    for (int idx = tid; idx < kSN * 32; idx += 256) {
+      const int c = idx >> 5, rr = idx & 31;
+      sL[c][rr] = (c < r && row0 + rr < kEDim) ? G[(int64_t)c * kELd + row0 + rr] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+      double a[7], c[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        a[i] = (double)sL[7 * ty + i][rr];
+        c[i] = (double)sL[7 * tx + i][rr];
+      }
+#pragma unroll
+      for (int i = 0; i < 7; ++i)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc[i][j] = fma(a[i], c[j], acc[i][j]);
+    }
+  }
+  double* __restrict__ M = eb.gram + (int64_t)lp * kSN * kSN;
+#pragma unroll
+  for (int i = 0; i < 7; ++i)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) M[(7 * ty + i) * kSN + 7 * tx + j] = acc[i][j];
+}
+
+__device__ __forceinline__ int sturm_count_n(const double* __restrict__ d, const double* __restrict__ e2, int n, double x) {
+  double pm = 1.0, p = d[0] - x;
+  int cnt = (p < 0.0) ? 1 : 0;
+  for (int i0 = 1; i0 < n; i0 += 8) {
+    const int i1 = min(i0 + 8, n);
+    for (int i = i0; i < i1; ++i) {
+      const double pn = fma(d[i] - x, p, -e2[i - 1] * pm);
+      cnt += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
+      pm = p;
+      p = pn;
+    }
+    const double m = fmax(fabs(p), fabs(pm));
+    if (m > 1.0e100 || (m < 1.0e-100 && m > 0.0)) {
+      const double sc = 1.0 / m;
+      p *= sc;
+      pm *= sc;
+    }
+  }
+  return cnt;
+}
+
+// unblocked Householder tridiagonalisation of the padded Gram matrix in shared memory
+// (thread = row = column); d, e, tau and the reflectors (in the eliminated rows) go back to global
+__global__ void __launch_bounds__(128) siib_smalltri_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_hi) {
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x;
+  const int r = b.rank[pair];
+  if (r < 2 || r > rank_hi) return;
+  extern __shared__ __align__(16) double s_A[];  // [112][113]
+  __shared__ double s_v[128], s_w[128];
+  __shared__ double red[32];
+  __shared__ double s_alpha;
+  double* __restrict__ M = eb.gram + (int64_t)lp * kSN * kSN;
+  double* __restrict__ dd = eb.d + (int64_t)lp * kELd;
+  double* __restrict__ ee = eb.e + (int64_t)lp * kELd;
+  double* __restrict__ tt = eb.tau + (int64_t)lp * kELd;
+  for (int idx = tid; idx < kSN * kSN; idx += 128) s_A[(idx / kSN) * kSNp + idx % kSN] = M[idx];
+  __syncthreads();
+  const bool own = tid < kSN;
+  for (int k = 0; k < kSN - 2; ++k) {
+    const double x = (own && tid > k) ? s_A[k * kSNp + tid] : 0.0;
+    const double sig = block_sum((tid > k + 1) ? x * x : 0.0, red);
+    if (tid == k + 1) s_alpha = x;
+    if (tid == k) dd[k] = s_A[k * kSNp + k];
+    __syncthreads();
+    double vi, beta, tau;
+    householder(x, s_alpha, sig, tid, k, own, vi, beta, tau);
+    s_v[tid] = vi;
+    if (own && tid > k + 1) s_A[k * kSNp + tid] = vi;  // the reflector stays in row k
+    if (tid == 0) {
+      ee[k] = beta;
+      tt[k] = tau;
+    }
+    __syncthreads();
+    if (tau == 0.0) continue;
+    double p = 0.0;
+    if (own && tid > k) {
+      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+      int j = k + 1;
+      for (; j + 4 <= kSN; j += 4) {
+        p0 = fma(s_A[j * kSNp + tid], s_v[j], p0);
+        p1 = fma(s_A[(j + 1) * kSNp + tid], s_v[j + 1], p1);
+        p2 = fma(s_A[(j + 2) * kSNp + tid], s_v[j + 2], p2);
+        p3 = fma(s_A[(j + 3) * kSNp + tid], s_v[j + 3], p3);
+      }
+      for (; j < kSN; ++j) p0 = fma(s_A[j * kSNp + tid], s_v[j], p0);
+      p = tau * ((p0 + p1) + (p2 + p3));
+    }
+    const double pv = block_sum(p * vi, red);
+    const double w = p - (0.5 * tau * pv) * vi;
+    s_w[tid] = w;
+    __syncthreads();
+    if (own && tid > k) {
+#pragma unroll 4
+      for (int j = k + 1; j < kSN; ++j) s_A[j * kSNp + tid] -= s_v[j] * w + s_w[j] * vi;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    dd[kSN - 2] = s_A[(kSN - 2) * kSNp + (kSN - 2)];
+    dd[kSN - 1] = s_A[(kSN - 1) * kSNp + (kSN - 1)];
+    ee[kSN - 2] = s_A[(kSN - 2) * kSNp + (kSN - 1)];
+    ee[kSN - 1] = 0.0;
+    tt[kSN - 2] = 0.0;
+  }
+  for (int idx = tid; idx < kSN * kSN; idx += 128) M[idx] = s_A[(idx / kSN) * kSNp + idx % kSN];
+}
+
+// eigenpairs of the 112 x 112 tridiagonal (as siib_trieig_kernel): thread = eigenvalue, descending,
+// so that the <= r non-zero ones fill the first columns (siib_quad_kernel reads `rank` of them)
+__global__ void __launch_bounds__(128) siib_smallvec_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_hi) {
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x;
+  const int r = b.rank[pair];
+  if (r < 2 || r > rank_hi) return;
+  __shared__ double s_d[kSN], s_e[kSN], s_e2[kSN];
+  __shared__ double red[32];
+  const double* __restrict__ dd = eb.d + (int64_t)lp * kELd;
+  const double* __restrict__ ee = eb.e + (int64_t)lp * kELd;
+  const bool own = tid < kSN;
+  double mx = own ? fmax(fabs(dd[tid]), (tid < kSN - 1) ? fabs(ee[tid]) : 0.0) : 0.0;
+  const double scale = block_max(mx, red);
+  const double inv = scale > 0.0 ? 1.0 / scale : 0.0;
+  if (own) {
+    s_d[tid] = dd[tid] * inv;
+    const double ev = (tid < kSN - 1) ? ee[tid] * inv : 0.0;
+    s_e[tid] = ev;
+    s_e2[tid] = ev * ev;
+  }
+  __syncthreads();
+  if (!own) return;
+  float* __restrict__ scr = eb.zt + (int64_t)lp * kEDim * kELd;  // [i][128] D- sequence, then [i][128] z
+  double lo = -3.0, hi = 3.0;
+  for (int it = 0; it < 58; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (sturm_count_n(s_d, s_e2, kSN, mid) > kSN - 1 - tid) hi = mid;
+    else lo = mid;
+  }
+  const double lam = 0.5 * (lo + hi);
+  const double tiny = 1.0e-300;
+  float* dmv = scr + tid;             // dmv[i * 128]
+  float* zv = scr + kSN * 128 + tid;  // zv[i * 128]
+  double nrm2 = 0.0;
+  {
+    double dm = s_d[kSN - 1] - lam;
+    dmv[(kSN - 1) * 128] = (float)dm;
+    for (int i = kSN - 2; i >= 0; --i) {
+      if (dm == 0.0) dm = tiny;
+      dm = (s_d[i] - lam) - s_e2[i] / dm;
+      dmv[i * 128] = (float)dm;
+    }
+  }
+  int kt = 0;
+  Scaled zk = {1.0, 0};
+  {
+    double dp = s_d[0] - lam, best = 1.0e300;
+    Scaled z = {1.0, 0};
+    for (int i = 0; i < kSN; ++i) {
+      const double gam = dp + (double)dmv[i * 128] - (s_d[i] - lam);
+      if (fabs(gam) < best) {
+        best = fabs(gam);
+        kt = i;
+        zk = z;
+      }
+      if (i == kSN - 1) break;
+      if (dp == 0.0) dp = tiny;
+      const double ei = s_e[i] != 0.0 ? s_e[i] : tiny;
+      z.m = -z.m * dp / ei;
+      z.norm();
+      dp = (s_d[i + 1] - lam) - s_e2[i] / dp;
+    }
+  }
+  Scaled zb = {1.0, 0};
+  {
+    double dm = s_d[kSN - 1] - lam;
+    for (int i = kSN - 2; i >= kt; --i) {
+      if (dm == 0.0) dm = tiny;
+      const double ei = s_e[i] != 0.0 ? s_e[i] : tiny;
+      zb.m = -zb.m * dm / ei;
+      zb.norm();
+      dm = (s_d[i] - lam) - s_e2[i] / dm;
+    }
+  }
+  {
+    double dp = s_d[0] - lam;
+    Scaled z = {1.0, 0};
+    for (int i = 0; i <= kt; ++i) {
+      const double v = ldexp(z.m / zk.m, z.ex - zk.ex);
+      zv[i * 128] = (float)v;
+      nrm2 += v * v;
+      if (i == kt) break;
+      if (dp == 0.0) dp = tiny;
+      const double ei = s_e[i] != 0.0 ? s_e[i] : tiny;
+      z.m = -z.m * dp / ei;
+      z.norm();
+      dp = (s_d[i + 1] - lam) - s_e2[i] / dp;
+    }
+  }
+  {
+    double dm = s_d[kSN - 1] - lam;
+    Scaled z = {1.0, 0};
+    for (int i = kSN - 1; i > kt; --i) {
+      const double v = ldexp(z.m / zb.m, z.ex - zb.ex);
+      zv[i * 128] = (float)v;
+      nrm2 += v * v;
+      if (dm == 0.0) dm = tiny;
+      const double ei = s_e[i - 1] != 0.0 ? s_e[i - 1] : tiny;
+      z.m = -z.m * dm / ei;
+      z.norm();
+      dm = (s_d[i - 1] - lam) - s_e2[i - 1] / dm;
+    }
+  }
+  eb.lam[(int64_t)lp * kELd + tid] = lam * scale;
+  eb.znorm[(int64_t)lp * kELd + tid] = nrm2;
+}
+
+// back-transformation u = H_0 ... H_{n-3} z of the 112 eigenvectors: thread = vector (in registers),
+// reflectors broadcast from shared memory (FP32 copy), zero heads skipped in chunks of 16 rows
+__global__ void __launch_bounds__(128) siib_smallback_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_hi) {
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x;
+  const int r = b.rank[pair];
+  if (r < 2 || r > rank_hi) return;
+  extern __shared__ __align__(16) float s_R[];  // [112][112] reflectors, row k = v_k (1 at k + 1, 0 before)
+  __shared__ float s_tau[kSN];
+  const double* __restrict__ M = eb.gram + (int64_t)lp * kSN * kSN;
+  for (int idx = tid; idx < kSN * kSN; idx += 128) {
+    const int k = idx / kSN, i = idx % kSN;
+    s_R[idx] = (i == k + 1) ? 1.f : (i > k + 1) ? (float)M[idx] : 0.f;
+  }
+  if (tid < kSN) s_tau[tid] = (float)eb.tau[(int64_t)lp * kELd + tid];
+  __syncthreads();
+  if (tid >= kSN) return;
+  float* __restrict__ scr = eb.zt + (int64_t)lp * kEDim * kELd;
+  float* __restrict__ Vout = scr + 2 * kSN * 128;  // [c][112] unit eigenvectors of M
+  float u[kSN];
+  {
+    const float* zv = scr + kSN * 128 + tid;
+#pragma unroll
+    for (int i = 0; i < kSN; ++i) u[i] = zv[i * 128];
+  }
+  for (int k = kSN - 3; k >= 0; --k) {
+    const float tau = s_tau[k];
+    if (tau == 0.f) continue;
+    const float4* v4 = reinterpret_cast<const float4*>(s_R + k * kSN);
+    const int c0 = (k + 1) >> 4;  // 16-row chunks that are entirely zero (rows <= k)
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kSN / 16; ++c) {
+      if (c < c0) continue;
+#pragma unroll
+      for (int q = 4 * c; q < 4 * c + 4; ++q) {
+        const float4 vv = v4[q];
+        d0 = fmaf(vv.x, u[4 * q], d0);
+        d1 = fmaf(vv.y, u[4 * q + 1], d1);
+        d2 = fmaf(vv.z, u[4 * q + 2], d2);
+        d3 = fmaf(vv.w, u[4 * q + 3], d3);
+      }
+    }
+    const float cf = -tau * ((d0 + d1) + (d2 + d3));
+#pragma unroll
+    for (int c = 0; c < kSN / 16; ++c) {
+      if (c < c0) continue;
+#pragma unroll
+      for (int q = 4 * c; q < 4 * c + 4; ++q) {
+        const float4 vv = v4[q];
+        u[4 * q] = fmaf(cf, vv.x, u[4 * q]);
+        u[4 * q + 1] = fmaf(cf, vv.y, u[4 * q + 1]);
+        u[4 * q + 2] = fmaf(cf, vv.z, u[4 * q + 2]);
+        u[4 * q + 3] = fmaf(cf, vv.w, u[4 * q + 3]);
+      }
+    }
+  }
+  const double lam = eb.lam[(int64_t)lp * kELd + tid], lmax = eb.lam[(int64_t)lp * kELd];
+  const double nrm2 = eb.znorm[(int64_t)lp * kELd + tid];
+  const float sc = (lam > 1.0e-10 * lmax && nrm2 > 0.0) ? (float)(1.0 / sqrt(nrm2)) : 0.f;
+#pragma unroll
+  for (int c = 0; c < kSN; ++c) Vout[c * kSN + tid] = sc * u[c];
+}
+
+// G <- L V in place, one 32-row tile per CTA: out[j][row] = sum_c L[c][row] V[c][j]
+__global__ void __launch_bounds__(128) siib_lv_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_hi) {
+  const int lp = blockIdx.y, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int r = b.rank[pair];
+  if (r < 2 || r > rank_hi) return;
+  const int row0 = blockIdx.x * 32;
+  float* __restrict__ G = b.G + (int64_t)lp * kEDim * kELd;
+  const float* __restrict__ V = eb.zt + (int64_t)lp * kEDim * kELd + 2 * kSN * 128;
+  extern __shared__ __align__(16) float s_lv[];
+  float* sL = s_lv;              // [112][33]
+  float* sV = s_lv + kSN * 33;   // [112][112]
+  for (int idx = tid; idx < kSN * 32; idx += 128) {
+    const int c = idx >> 5, rr = idx & 31;
+    sL[c * 33 + rr] = (c < r && row0 + rr < kELd) ? G[(int64_t)c * kELd + row0 + rr] : 0.f;
+  }
+  for (int idx = tid; idx < kSN * kSN; idx += 128) sV[idx] = V[idx];
+  __syncthreads();
+  float acc[28];
+#pragma unroll
+  for (int t = 0; t < 28; ++t) acc[t] = 0.f;
+  for (int c = 0; c < kSN; ++c) {
+    const float a = sL[c * 33 + lane];
+    const float4* v4 = reinterpret_cast<const float4*>(sV + c * kSN + 28 * w);
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      const float4 vv = v4[q];
+      acc[4 * q] = fmaf(a, vv.x, acc[4 * q]);
+      acc[4 * q + 1] = fmaf(a, vv.y, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(a, vv.z, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(a, vv.w, acc[4 * q + 3]);
+    }
+  }
+  if (row0 + lane < kELd) {
+#pragma unroll
+    for (int t = 0; t < 28; ++t) G[(int64_t)(28 * w + t) * kELd + row0 + lane] = acc[t];
+  }
+}
+
+__global__ void siib_small_finish_kernel(SiibBuffers b, int n, int rank_hi) {
+  const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lp >= n) return;
+  const int pair = b.pair_lo + lp;
+  const int r = b.rank[pair];
+  if (r >= 2 && r <= rank_hi) b.sweeps[pair] = -2;  // marks "Gram path" in the siib.rank stage
+}
+
+int siib_run_small_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_hi, KernelTimer* kt,
+                       cudaStream_t s) {
+  static const bool attr = [] {
+    cudaFuncSetAttribute(siib_smalltri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSN * kSNp * (int)sizeof(double));
+    cudaFuncSetAttribute(siib_smallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSN * kSN * (int)sizeof(float));
+    cudaFuncSetAttribute(siib_lv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kSN * 33 + kSN * kSN) * (int)sizeof(float));
+    return true;
+  }();
+  (void)attr;
+  kt_begin(kt, "siib_gram", s);
+  siib_gram_kernel<<<n, 256, 0, s>>>(g, b, eb, rank_hi);
+  kt_end(kt, s);
+  kt_begin(kt, "siib_smalltri", s);
+  siib_smalltri_kernel<<<n, 128, kSN * kSNp * sizeof(double), s>>>(g, b, eb, rank_hi);
+  kt_end(kt, s);
+  kt_begin(kt, "siib_smallvec", s);
+  siib_smallvec_kernel<<<n, 128, 0, s>>>(g, b, eb, rank_hi);
+  kt_end(kt, s);
+  kt_begin(kt, "siib_smallback", s);
+  siib_smallback_kernel<<<n, 128, kSN * kSN * sizeof(float), s>>>(g, b, eb, rank_hi);
+  kt_end(kt, s);
+  kt_begin(kt, "siib_lv", s);
+  siib_lv_kernel<<<dim3(kELd / 32, n), 128, (kSN * 33 + kSN * kSN) * sizeof(float), s>>>(g, b, eb, rank_hi);
+  kt_end(kt, s);
+  kt_begin(kt, "siib_small_finish", s);
+  siib_small_finish_kernel<<<(n + 127) / 128, 128, 0, s>>>(b, n, rank_hi);
+  kt_end(kt, s);
+  return 6;
+}
+
+}  // namespace nele
