@@ -185,6 +185,10 @@ __global__ void __launch_bounds__(kKsgThreads) siib_ksg_kernel(SiibGeom g, SiibB
     }
     const double rx = block_max(hi_x, red) + block_max(-lo_x, red);
     const double ry = block_max(hi_y, red) + block_max(-lo_y, red);
+    if (!(rx > 0.0)) {  // a component of the numerical null space (zero column of G): no information
+      if (tid == 0) out[comp] = 0.0;
+      return;
+    }
     if (ry > rx) {
       const float* t = gx;
       gx = gy;
