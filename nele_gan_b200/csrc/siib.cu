@@ -1223,7 +1223,7 @@ __global__ void __launch_bounds__(NWARP * 32) siib_jacobi2_kernel(SiibGeom g, Si
 
 // ------------------------------------------------------- quadratic forms + score
 constexpr int kQuadThreads = 448;
-constexpr int kQuadJ = 24;  // eigenvectors per pass over Sxy / Syy (each pass re-reads 1.4 MB); 96 = 4 x 24
+constexpr int kQuadJ = 16;  // eigenvectors per pass over Sxy / Syy (each pass re-reads 1.4 MB); 24 per pass was slower (104 registers, one CTA per SM)
 
 __global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, SiibBuffers b) {
   const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
