@@ -1278,17 +1278,16 @@ __global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, Sii
 #pragma unroll 4
       for (int c = 0; c < kSDim; ++c) {
         const float sxy = __ldg(Sxy + (int64_t)c * kSDim + tid), syy = __ldg(Syy + (int64_t)c * kSDim + tid);
+        const float4 u0 = *reinterpret_cast<const float4*>(&s_u[c][0]);
+        const float4 u1 = *reinterpret_cast<const float4*>(&s_u[c][4]);
+        const float4 u2 = *reinterpret_cast<const float4*>(&s_u[c][8]);
+        const float4 u3 = *reinterpret_cast<const float4*>(&s_u[c][12]);
+        const float uu[kQuadJ] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w,
+                                  u2.x, u2.y, u2.z, u2.w, u3.x, u3.y, u3.z, u3.w};
 #pragma unroll
-        for (int q = 0; q < kQuadJ / 4; ++q) {
-          const float4 uq = *reinterpret_cast<const float4*>(&s_u[c][4 * q]);
-          axy[4 * q] = fmaf(sxy, uq.x, axy[4 * q]);
-          ayy[4 * q] = fmaf(syy, uq.x, ayy[4 * q]);
-          axy[4 * q + 1] = fmaf(sxy, uq.y, axy[4 * q + 1]);
-          ayy[4 * q + 1] = fmaf(syy, uq.y, ayy[4 * q + 1]);
-          axy[4 * q + 2] = fmaf(sxy, uq.z, axy[4 * q + 2]);
-          ayy[4 * q + 2] = fmaf(syy, uq.z, ayy[4 * q + 2]);
-          axy[4 * q + 3] = fmaf(sxy, uq.w, axy[4 * q + 3]);
-          ayy[4 * q + 3] = fmaf(syy, uq.w, ayy[4 * q + 3]);
+        for (int jj = 0; jj < kQuadJ; ++jj) {
+          axy[jj] = fmaf(sxy, uu[jj], axy[jj]);
+          ayy[jj] = fmaf(syy, uu[jj], ayy[jj]);
         }
       }
       // (u^T S)_i u_i
