@@ -78,7 +78,7 @@ struct nele_engine {
   DevBuf sb_base, sb_Sxx, sb_Sxy, sb_Syy, sb_Lc, sb_G, sb_perm;                     // SIIB, per sub-chunk
   DevBuf sb_rank, sb_sweeps, sb_lambda, sb_rho;
   DevBuf kn_xk, kn_info, kn_digamma;  // SIIB k-NN estimator
-  DevBuf eg_vec, eg_zt, eg_gram;             // SIIB tridiagonal eigen-solver: 5 x [sub][448] doubles, [sub][420][448] floats
+  DevBuf eg_vec, eg_zt, eg_gram, eg_refl;             // SIIB tridiagonal eigen-solver: 5 x [sub][448] doubles, [sub][420][448] floats
   DevBuf out_haspi, out_raw, out_hst, out_estoi, out_est, out_siib, out_sst;
   std::vector<DevBuf*> all_bufs;
   char *h_geom = nullptr, *h_sgeom = nullptr;  // pinned staging of the geometry blobs (read by blob_copy_kernel)
@@ -210,7 +210,7 @@ extern "C" int nele_create(int device, nele_engine** out) {
                  &e->x10, &e->st_energy, &e->st_kept, &e->st_nkept, &e->st_tob,
                  &e->sb_wrapdb, &e->sb_M, &e->sb_wact, &e->sb_mean, &e->sb_xdb, &e->sb_act, &e->sb_aidx, &e->sb_src, &e->sb_Fa, &e->sb_Pact, &e->sb_perflag, &e->sb_lograw, &e->sb_logspec,
                  &e->sb_base, &e->sb_Sxx, &e->sb_Sxy, &e->sb_Syy, &e->sb_Lc, &e->sb_G, &e->sb_perm,
-                 &e->sb_rank, &e->sb_sweeps, &e->sb_lambda, &e->sb_rho, &e->kn_xk, &e->kn_info, &e->kn_digamma, &e->eg_vec, &e->eg_zt, &e->eg_gram,
+                 &e->sb_rank, &e->sb_sweeps, &e->sb_lambda, &e->sb_rho, &e->kn_xk, &e->kn_info, &e->kn_digamma, &e->eg_vec, &e->eg_zt, &e->eg_gram, &e->eg_refl,
                  &e->out_haspi, &e->out_raw, &e->out_hst, &e->out_estoi, &e->out_est, &e->out_siib, &e->out_sst};
 #define CUC(call)                                                                             \
   do {                                                                                        \
@@ -874,6 +874,8 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
         egb.scratch = (float*)e->sb_G.p;
         RESERVE(e, e->eg_gram, (size_t)sub * 112 * 112 * sizeof(double));
         egb.gram = (double*)e->eg_gram.p;
+        RESERVE(e, e->eg_refl, (size_t)sub * 420 * 448 * sizeof(float));
+        egb.refl = (float*)e->eg_refl.p;
       }
       SiibKnnBuffers kb;
       memset(&kb, 0, sizeof(kb));

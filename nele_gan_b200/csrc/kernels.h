@@ -190,6 +190,7 @@ struct SiibEigBuffers {
   float* scratch;  // [sub][420][448] per-thread D- sequence (aliases G: dead before G is written)
   float* zt;       // [sub][420][448] eigenvectors of T, entry-major (low-rank path: scratch + V)
   double* gram;    // [sub][112][112] zero-padded Gram matrix L^T L of the low-rank pairs
+  float* refl;     // [sub][420][448] Householder vectors in FP32 (row k = reflector k)
 };
 int siib_run_small_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_hi, KernelTimer* kt,
                        cudaStream_t s);

@@ -25,7 +25,6 @@
 namespace nele {
 
 constexpr int kEDim = 420, kELd = 448, kEThreads = 448;
-constexpr int kTriPrefetch = 8;   // rows of look-ahead of the L2 prefetch in the fused pass
 
 // ------------------------------------------------------------ tridiagonalisation
 // Blocked as LAPACK's dsytrd / dlatrd: inside a panel of kTriB steps the trailing matrix is only
@@ -50,7 +49,7 @@ __device__ __forceinline__ void householder(double x, double alpha, double sig, 
   vi = (tid == k + 1) ? 1.0 : (tid > k + 1 && own) ? x / (alpha - beta) : 0.0;
 }
 
-__global__ void __launch_bounds__(kEThreads) siib_tridiag_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_lo, int pf_rows) {
+__global__ void __launch_bounds__(kEThreads) siib_tridiag_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_lo) {
   const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   constexpr int NW = kEThreads / 32;
   if (b.rank[pair] < rank_lo) return;
@@ -67,9 +66,9 @@ __global__ void __launch_bounds__(kEThreads) siib_tridiag_kernel(SiibGeom g, Sii
   __shared__ double s_tot[2 * kTriB];
   __shared__ double s_alpha;
   const bool own = tid < kEDim;
-  (void)pf_rows;
   for (int k0 = 0; k0 < kEDim - 2; k0 += kTriB) {
-    const double* __restrict__ Ain = (k0 == 0) ? A0 : A;  // the matrix as of the start of the panel
+    const double* Ain = (k0 == 0) ? A0 : A;  // the matrix as of the start of the panel (aliases the work matrix:
+                                             // read with ld.global.cg, never through the non-coherent path)
     const int nb = min(kTriB, kEDim - 2 - k0);
     for (int m = 0; m < nb; ++m) {
       const int k = k0 + m;
@@ -85,6 +84,7 @@ __global__ void __launch_bounds__(kEThreads) siib_tridiag_kernel(SiibGeom g, Sii
       householder(xr, s_alpha, sig, tid, k, own, vi, beta, tau);
       sV[m * kELd + tid] = vi;
       if (own && tid > k + 1) A[(int64_t)k * kEDim + tid] = vi;  // the reflector stays in row k of the work matrix
+      eb.refl[((int64_t)lp * kEDim + k) * kELd + tid] = (float)vi;  // FP32 copy for the back-transformation (0 in rows <= k, 1 at k + 1)
       if (tid == 0) {
         ee[k] = beta;
         tt[k] = tau;
@@ -93,14 +93,14 @@ __global__ void __launch_bounds__(kEThreads) siib_tridiag_kernel(SiibGeom g, Sii
       // p = S_panel v: one coalesced read-only pass over rows j > k
       double p = 0.0;
       if (own && tid > k) {
-        const double* __restrict__ col = Ain + tid;
+        const double* col = Ain + tid;
         const double* __restrict__ v = sV + m * kELd;
         double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
         int j = k + 1;
         for (; j + 8 <= kEDim; j += 8) {
           double a[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) a[u] = __ldg(col + (int64_t)(j + u) * kEDim);
+          for (int u = 0; u < 8; ++u) a[u] = __ldcg(col + (int64_t)(j + u) * kEDim);
           p0 = fma(a[0], v[j], p0);
           p1 = fma(a[1], v[j + 1], p1);
           p2 = fma(a[2], v[j + 2], p2);
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kEThreads) siib_tridiag_kernel(SiibGeom g, Sii
           p2 = fma(a[6], v[j + 6], p2);
           p3 = fma(a[7], v[j + 7], p3);
         }
-        for (; j < kEDim; ++j) p0 = fma(__ldg(col + (int64_t)j * kEDim), v[j], p0);
+        for (; j < kEDim; ++j) p0 = fma(__ldcg(col + (int64_t)j * kEDim), v[j], p0);
         p = (p0 + p1) + (p2 + p3);
       }
       // corrections for the steps of this panel: p -= V (W^T v) + W (V^T v)
@@ -140,9 +140,21 @@ __global__ void __launch_bounds__(kEThreads) siib_tridiag_kernel(SiibGeom g, Sii
     // trailing update of the panel: rows and columns beyond its last step
     const int kl = k0 + nb - 1;
     if (own && tid > kl) {
-      for (int j = kl + 1; j < kEDim; ++j) {
+      int j = kl + 1;
+      for (; j + 4 <= kEDim; j += 4) {  // four independent loads in flight (the pass is latency bound otherwise)
+        double a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = __ldcg(Ain + (int64_t)(j + u) * kEDim + tid);
+        for (int mm = 0; mm < nb; ++mm) {
+          const double wt = sW[mm * kELd + tid], vt = sV[mm * kELd + tid];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a[u] -= sV[mm * kELd + j + u] * wt + sW[mm * kELd + j + u] * vt;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) A[(int64_t)(j + u) * kEDim + tid] = a[u];
+      }
+      for (; j < kEDim; ++j) {
         double a = Ain[(int64_t)j * kEDim + tid];
-#pragma unroll 4
         for (int mm = 0; mm < nb; ++mm) a -= sV[mm * kELd + j] * sW[mm * kELd + tid] + sW[mm * kELd + j] * sV[mm * kELd + tid];
         A[(int64_t)j * kEDim + tid] = a;
       }
@@ -324,7 +336,7 @@ __global__ void __launch_bounds__(kBtThreads, 2) siib_backtf_kernel(SiibGeom g, 
   __shared__ __align__(16) float s_v[kBtPanel][kBtLd];
   __shared__ float s_tau[kBtPanel];
   __shared__ float s_dot[2][kBtParts][32];
-  const double* __restrict__ A = b.Lc + (int64_t)lp * kEDim * kEDim;
+  const float* __restrict__ R = eb.refl + (int64_t)lp * kEDim * kELd;
   const double* __restrict__ tt = eb.tau + (int64_t)lp * kELd;
   float u[kBtRows];
 #pragma unroll
@@ -338,13 +350,9 @@ __global__ void __launch_bounds__(kBtThreads, 2) siib_backtf_kernel(SiibGeom g, 
     const int nk = min(kBtPanel, k1 + 1);
     __syncthreads();
     for (int kk = 0; kk < nk; ++kk) {
-      const int k = k1 - kk;
-      const double* __restrict__ row = A + (int64_t)k * kEDim;
+      const float* __restrict__ row = R + (int64_t)(k1 - kk) * kELd;
 #pragma unroll
-      for (int i = tid; i < kBtLd; i += kBtThreads) {
-        const float v = (i == k + 1) ? 1.f : (i > k + 1 && i < kEDim) ? (float)__ldg(row + i) : 0.f;
-        s_v[kk][(i & (kBtParts - 1)) * kBtRows + (i >> 3)] = v;
-      }
+      for (int i = tid; i < kBtLd; i += kBtThreads) s_v[kk][(i & (kBtParts - 1)) * kBtRows + (i >> 3)] = __ldg(row + i);
     }
     if (tid < nk) s_tau[tid] = (float)tt[k1 - tid];
     __syncthreads();
@@ -415,13 +423,12 @@ __global__ void siib_eig_finish_kernel(SiibBuffers b, int n, int rank_lo) {
 int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, KernelTimer* kt,
                  cudaStream_t s) {
   kt_begin(kt, "siib_tridiag", s);
-  static const int pf_rows = [] { const char* p = getenv("NELE_TRIDIAG_PF"); return p ? atoi(p) : kTriPrefetch; }();
   static const bool tri_attr = [] {
     cudaFuncSetAttribute(siib_tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTriB * kELd * (int)sizeof(double));
     return true;
   }();
   (void)tri_attr;
-  siib_tridiag_kernel<<<n, kEThreads, 2 * kTriB * kELd * sizeof(double), s>>>(g, b, eb, rank_lo, pf_rows);
+  siib_tridiag_kernel<<<n, kEThreads, 2 * kTriB * kELd * sizeof(double), s>>>(g, b, eb, rank_lo);
   kt_end(kt, s);
   kt_begin(kt, "siib_trieig", s);
   siib_trieig_kernel<<<n, kEThreads, 0, s>>>(g, b, eb, rank_lo);
