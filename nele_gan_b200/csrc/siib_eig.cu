@@ -20,6 +20,8 @@
 //                        writes G[j] = sqrt(lambda_j) u_j, the format siib_quad_kernel reads
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace nele {
@@ -33,7 +35,7 @@ constexpr int kEDim = 420, kELd = 448, kEThreads = 448;
 // (S_cur = S_panel - V W^T - W V^T), and the trailing matrix is rewritten once per panel.  Traffic
 // per element and step: 8 B + 16 B / kTriB instead of 16 B for the step-by-step form -- the kernel
 // is HBM bound (ncu: 4.4 TB/s).
-constexpr int kTriB = 12;
+constexpr int kTriB = 8;
 
 __device__ __forceinline__ void householder(double x, double alpha, double sig, int tid, int k, bool own, double& vi,
                                             double& beta, double& tau) {
@@ -49,10 +51,14 @@ __device__ __forceinline__ void householder(double x, double alpha, double sig, 
   vi = (tid == k + 1) ? 1.0 : (tid > k + 1 && own) ? x / (alpha - beta) : 0.0;
 }
 
-__global__ void __launch_bounds__(kEThreads) siib_tridiag_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_lo) {
-  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+__global__ void __launch_bounds__(kEThreads, 3) siib_tridiag_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_lo, int n_pairs) {
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   constexpr int NW = kEThreads / 32;
-  if (b.rank[pair] < rank_lo) return;
+  // persistent CTAs: the grid is sized so that the work matrices of the resident CTAs fit in the L2
+  for (int lp = blockIdx.x; lp < n_pairs; lp += gridDim.x) {
+  const int pair = b.pair_lo + lp;
+  if (b.rank[pair] < rank_lo) continue;
+  __syncthreads();
   const double* __restrict__ A0 = b.Sxx + (int64_t)lp * kEDim * kEDim;
   double* __restrict__ A = b.Lc + (int64_t)lp * kEDim * kEDim;
   double* __restrict__ dd = eb.d + (int64_t)lp * kELd;
@@ -166,6 +172,7 @@ __global__ void __launch_bounds__(kEThreads) siib_tridiag_kernel(SiibGeom g, Sii
     dd[kEDim - 1] = A[(int64_t)(kEDim - 1) * kEDim + (kEDim - 1)];
     ee[kEDim - 2] = A[(int64_t)(kEDim - 2) * kEDim + (kEDim - 1)];
     tt[kEDim - 2] = 0.0;
+  }
   }
 }
 
@@ -428,7 +435,8 @@ int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& 
     return true;
   }();
   (void)tri_attr;
-  siib_tridiag_kernel<<<n, kEThreads, 2 * kTriB * kELd * sizeof(double), s>>>(g, b, eb, rank_lo);
+  static const int tri_grid = [] { const char* p = getenv("NELE_TRIDIAG_GRID"); return p ? atoi(p) : 1 << 30; }();
+  siib_tridiag_kernel<<<std::min(n, tri_grid), kEThreads, 2 * kTriB * kELd * sizeof(double), s>>>(g, b, eb, rank_lo, n);
   kt_end(kt, s);
   kt_begin(kt, "siib_trieig", s);
   siib_trieig_kernel<<<n, kEThreads, 0, s>>>(g, b, eb, rank_lo);
