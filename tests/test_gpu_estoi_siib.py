@@ -185,3 +185,25 @@ def test_profiling_lists_every_kernel(eng):
         assert k in kt and kt[k][0] > 0 and kt[k][1] >= 1
     ms, launches = eng.last_timing()
     assert launches == sum(v[1] for v in kt.values())
+
+
+def test_siib_klt_dispatch_paths(eng):
+    """Every KLT route against the oracle (components with a numerically non-zero eigenvalue):
+    non-repeating tiling -> tridiagonalisation of Sxx; exactly repeating tiling of low rank ->
+    Cholesky + Gram matrix; repeating tiling with a long period (rank > 112) -> Cholesky, then
+    tridiagonalisation.  `siib.rank` stage: [rank, marker] with marker -1 / -2 for the two paths."""
+    from nele_gan_b200.synth import make_pair
+    cases = ((7, 36123, -1), (8, 40000, -2), (9, 50000, -2), (10, 44100, None), (11, 30000, -2))
+    xs, ys = zip(*[make_pair(i, L)[:2] for i, L, _ in cases])
+    r = eng.score_batch(list(xs), list(ys), metrics=("siib",), mapped=False, keep_stages=True)
+    for n, (i, L, marker) in enumerate(cases):
+        st = {}
+        _oracle_siib(xs[n], ys[n], st)
+        nonnull = st["lam"] > 1e-9 * st["lam"].max()
+        want = 80.0 / 15 * float(np.sum(st["I_ch"][nonnull]))
+        rk = eng.stage("siib.rank", n)
+        assert abs(r.siib[n] - want) < 2e-3 * want, (L, r.siib[n], want, rk[:2])
+        if marker is not None:
+            assert rk[1] == marker, (L, rk[:2])
+        if marker == -2:
+            assert rk[0] == int(nonnull.sum())
