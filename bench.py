@@ -279,10 +279,16 @@ def main():
         r = step_host()
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    # the same loop with plain blocking calls (no nele_prefetch): every upload is exposed
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        r = step_host()
+    barrier()
+    ms_e2e_blocking = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([ms_dev, ms_e2e, ms_e2e_blocking], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    ms_dev, ms_e2e, ms_e2e_blocking = float(t[0]), float(t[1]), float(t[2])
     ok = int(np.sum((r.status & 0xFFFFFF) == 0))
 
     if rank == 0:
@@ -313,6 +319,7 @@ def main():
             "e2e": {"value": audio_s * world / (ms_e2e / a.steps * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h_ref.numel() * 4 * 2), "d2h_bytes_per_step": int(n * (14 * 8 + 4)),
                     "ms_per_step": ms_e2e / a.steps,
+                    "ms_per_step_blocking_calls": ms_e2e_blocking / a.steps,
                     "pipelining": "upload of step k+1 (nele_prefetch) overlaps the kernels of step k; every step's H2D and D2H copies are inside the timed region"},
             "gpu_launches": int(launches),
             "clocks": clocks,
