@@ -233,38 +233,56 @@ constexpr int kEarWarps = 4;          // warps per CTA in the lane = band kernel
 constexpr int kEarChunkMax = 576;     // delay-line capacity of the main pass (kEarChunk)
 constexpr int kCtlChunk = 256;
 
+// One warp per pair, lane = band; the clean and the processed signal run side by side in a thread
+// (two independent recurrence chains, one shared carrier), as in the main pass.
 template <typename T>
-__global__ void __launch_bounds__(kEarWarps * 32) haspi_control_kernel(PairGeom g, HaspiBuffers b, int n_items) {
+__global__ void __launch_bounds__(kEarWarps * 32) haspi_control_kernel(PairGeom g, HaspiBuffers b, int n_pairs) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int item = blockIdx.x * kEarWarps + wib;
-  if (item >= n_items) return;
-  const int pair = item >> 1, q = item & 1;
-  const double* __restrict__ mid = b.mid + (int64_t)q * b.tot24 + g.off24[pair];
+  const int pair = blockIdx.x * kEarWarps + wib;
+  if (pair >= n_pairs) return;
+  const double* __restrict__ midx = b.mid + g.off24[pair];
+  const double* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
   const int N = g.n24[pair];
-  __shared__ double s_buf[kEarWarps][kCtlChunk];
-  double* buf = s_buf[wib];
+  __shared__ T s_buf[kEarWarps][2][kCtlChunk];
+  T* bx = s_buf[wib][0];
+  T* by = s_buf[wib][1];
   const BandConst bc = b.bands[lane];
-  ControlLane<T> cl;
-  cl.init(bc);
-  double acc = 0.0;
+  Carrier<T> car;
+  car.init(bc.cf);
+  const GtCoef<T> k = make_gt<T>(bc.bw1, bc.erb);
+  Gt4<T> fx, fy;
+  fx.reset();
+  fy.reset();
+  double accx = 0.0, accy = 0.0;
   for (int base = 0; base < N; base += kCtlChunk) {
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < kCtlChunk / 32; ++k) {
-      const int t = base + k * 32 + lane;
-      buf[k * 32 + lane] = (t < N) ? mid[t] : 0.0;
+    for (int q = 0; q < kCtlChunk / 32; ++q) {
+      const int t = base + q * 32 + lane;
+      bx[q * 32 + lane] = (t < N) ? (T)midx[t] : (T)0;
+      by[q * 32 + lane] = (t < N) ? (T)midy[t] : (T)0;
     }
     __syncwarp();
-    cl.car.seed_before(base);
+    car.seed_before(base);
     const int m = min(kCtlChunk, N - base);
-    T part = (T)0;
+    T px = (T)0, py = (T)0;
 #pragma unroll 4
-    for (int k = 0; k < m; ++k) part += cl.step((T)buf[k]);
-    acc += (double)part;
+    for (int q = 0; q < m; ++q) {
+      car.advance();
+      const T xs = bx[q], ys = by[q];
+      px += fx.step(k, xs * car.c, xs * car.s);
+      py += fy.step(k, ys * car.c, ys * car.s);
+    }
+    accx += (double)px;
+    accy += (double)py;
   }
-  b.bw[((int64_t)pair * 2 + q) * kBands + lane] =
-      bw_from_control(acc, (double)cl.k.gain, N, bc.bwmin[q], bc.bw1);
-  if (b.cave) b.cave[((int64_t)pair * 2 + q) * kBands + lane] = (double)cl.k.gain * sqrt(acc / (double)N);
+  const int64_t o = (int64_t)pair * 2 * kBands + lane;
+  b.bw[o] = bw_from_control(accx, (double)k.gain, N, bc.bwmin[0], bc.bw1);
+  b.bw[o + kBands] = bw_from_control(accy, (double)k.gain, N, bc.bwmin[1], bc.bw1);
+  if (b.cave) {
+    b.cave[o] = (double)k.gain * sqrt(accx / (double)N);
+    b.cave[o + kBands] = (double)k.gain * sqrt(accy / (double)N);
+  }
 }
 
 // group-delay shifts, always from BWx (pyhaspi2.py:1239-1240)
@@ -763,10 +781,10 @@ int haspi_run_front(const PairGeom& g, const HaspiBuffers& b, int n, bool f64, K
   haspi_prep_kernel<<<dim3(n, 2), kPrepThreads, (kPrepSpan + kPrepSpan / 8 + 8) * sizeof(double), s>>>(g, b);
   kt_end(kt, s);
   ++launches;
-  const int items = 2 * n, ctas = (items + kEarWarps - 1) / kEarWarps;
+  const int ctas = (n + kEarWarps - 1) / kEarWarps;
   kt_begin(kt, "haspi_control", s);
-  if (f64) haspi_control_kernel<double><<<ctas, kEarWarps * 32, 0, s>>>(g, b, items);
-  else haspi_control_kernel<float><<<ctas, kEarWarps * 32, 0, s>>>(g, b, items);
+  if (f64) haspi_control_kernel<double><<<ctas, kEarWarps * 32, 0, s>>>(g, b, n);
+  else haspi_control_kernel<float><<<ctas, kEarWarps * 32, 0, s>>>(g, b, n);
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "haspi_shift", s);
