@@ -124,6 +124,7 @@ def kernel_bytes_per_pair(name, L16, Nf=1950, rank=420):
         "siib_chol": 420 * 420 * 8 + rank * 448 * 4,
         "siib_jacobi": 2 * rank * 448 * 4,
         "siib_quad": rank * 448 * 4 + 2 * 420 * 420 * 4,
+        "siib_projquad": rank * 448 * 4 + 2 * 128 * F,
     }
     return table.get(name)
 

@@ -840,6 +840,8 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       sb.Fa = (int32_t*)e->sb_Fa.p;
       sb.Pact = (int32_t*)e->sb_Pact.p;
       sb.perflag = (int32_t*)e->sb_perflag.p;
+      static const bool no_proj = [] { const char* p = getenv("NELE_SIIB_QUADFORM"); return p && p[0] == '1'; }();
+      sb.no_proj = no_proj ? 1 : 0;
       sb.lograw = (float*)e->sb_lograw.p;
       sb.logspec = (float*)e->sb_logspec.p;
       sb.totF = tFa + 1;

@@ -429,6 +429,15 @@ __device__ __forceinline__ CovSpan cov_span(const SiibBuffers& b, int pair, int 
   }
   return s;
 }
+// Pairs whose x and y features are both verified periodic take the projection route: the 2 P
+// distinct stacked frames are projected on the eigenvectors and rho comes from the weighted
+// sample moments of the two KLT-domain series (siib_projquad_kernel), which is what the
+// quadratic forms u^T Sxy u, u^T Syy u evaluate -- so the yy / xy lag products and the expanded
+// Sxy, Syy are never formed for them.
+__device__ __forceinline__ bool siib_projected(const SiibBuffers& b, int pair, int Nf) {
+  const int P = b.Pact[pair];
+  return !b.no_proj && b.perflag[2 * pair] && b.perflag[2 * pair + 1] && P > 0 && Nf >= 2 * P;
+}
 
 constexpr int kCovWarps = 8;
 constexpr int kCovTile = 64;                        // frames per staged tile
@@ -558,7 +567,7 @@ __global__ void __launch_bounds__(kCov32Warps * 32) siib_cov32_kernel(SiibGeom g
   const int task = kCovTasks64 + blockIdx.x * kCov32Warps + wib;
   const int Fa = b.Fa[pair];
   const int Nf = Fa - (kSStack - 1);
-  if (Nf < 1) return;
+  if (Nf < 1 || siib_projected(b, pair, Nf)) return;
   __shared__ __align__(16) float s_x[4][kCovRows][kSLanes];  // [0], [1]: x, y rows weighted (A side); [2], [3]: plain
   const CovSpan span = cov_span(b, pair, Nf, true);
   const bool active = task < kCovTasks;
@@ -675,7 +684,7 @@ __global__ void __launch_bounds__(kExpThreads) siib_expand_kernel(SiibGeom g, Si
   float* __restrict__ Sxy = b.Sxy + (int64_t)lp * kSDim * kSDim;
   float* __restrict__ Syy = b.Syy + (int64_t)lp * kSDim * kSDim;
   const double* __restrict__ base = b.base + (int64_t)lp * kSBlocks * (kSLanes * kSLanes);
-  const int ndiag = kSBlocks * kSBands * kSBands;
+  const int ndiag = (siib_projected(b, pair, Nf) ? 15 : kSBlocks) * kSBands * kSBands;  // xx blocks only / all 59
   for (int it = tid; it < ndiag; it += kExpThreads) {
     const int blk = it / (kSBands * kSBands), rem = it % (kSBands * kSBands);
     const int j1 = rem / kSBands, j2 = rem % kSBands;
@@ -1238,6 +1247,7 @@ __global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, Sii
     }
     return;
   }
+  if (siib_projected(b, pair, Nf)) return;  // siib_projquad_kernel scores this pair
   const int r = b.rank[pair];
   const float* __restrict__ G = b.G + (int64_t)lp * kSDim * kSLd;
   const float* __restrict__ Sxy = b.Sxy + (int64_t)lp * kSDim * kSDim;
@@ -1336,6 +1346,176 @@ __global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, Sii
   }
 }
 
+// -------------------------------------------------- projection route (periodic pairs)
+// rho_j of a pair whose stacked frames repeat (siib_projected): with the summation plan of
+// cov_span only the first 2 P stacked frames are distinct, so
+//   u^T Sxy u = sum_t w(t) xk(t) yk(t) - (sum_t w xk)(sum_t w yk) / Nf,   xk(t) = u^T xs(t),
+// and likewise for xx and yy: 2 P x r dot products of length 420 per signal instead of two
+// r x 420 x 420 quadratic forms over matrices that then need not exist.  Stacked frame t is the
+// contiguous slab logspec[t .. t + 14][28], so for one band j a thread that owns 8 consecutive
+// frames slides a 22-value register window past the 15 stack offsets: 59 shared-memory loads
+// feed 960 FMAs.
+//   CTA = pair, 128 threads: thread (tc, tt) = components 4 tc .. 4 tc + 3 of a 32-component tile,
+//   frames 8 tt .. 8 tt + 7 of a 128-frame tile.  sU [420][32] holds the unit eigenvectors with
+//   the 16-byte chunks XOR-swizzled by the row (the fill writes along a column), the slabs
+//   [28][142] are stored with an (i + i / 8) skew so that lanes 8 frames apart hit distinct banks.
+constexpr int kPqThreads = 128, kPqC = 32, kPqT = 128, kPqF = 8;
+constexpr int kPqRows = kPqT + kSStack - 1;               // 142 feature rows per time tile
+constexpr int kPqLd = kPqRows + (kPqRows >> 3) + 2;        // 161: skewed row length, odd
+constexpr int kPqSmem = (kSDim * kPqC + 2 * kSBands * kPqLd) * (int)sizeof(float);
+
+__global__ void __launch_bounds__(kPqThreads) siib_projquad_kernel(SiibGeom g, SiibBuffers b) {
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  const int Fa = b.Fa[pair];
+  const int Nf = Fa - (kSStack - 1);
+  if (b.M[pair] <= 0 || (double)Fa / 80.0 < 20.0 || Nf < 2) return;  // siib_quad_kernel reports these
+  if (!siib_projected(b, pair, Nf)) return;
+  const CovSpan span = cov_span(b, pair, Nf, true);
+  const int r = b.rank[pair];
+  extern __shared__ __align__(16) float s_pq[];
+  float* sU = s_pq;                       // [420][32], chunk c / 4 of row i at chunk (c / 4) ^ (i & 7)
+  float* sX = sU + kSDim * kPqC;          // [28][kPqLd]
+  float* sY = sX + kSBands * kPqLd;
+  __shared__ float s_nrm[kPqC];
+  __shared__ double s_info[kSDim];
+  const float* __restrict__ G = b.G + (int64_t)lp * kSDim * kSLd;
+  const float* __restrict__ X = b.logspec + (g.offF[pair]) * kSLanes;
+  const float* __restrict__ Y = b.logspec + (b.totF + g.offF[pair]) * kSLanes;
+  float* __restrict__ lam_out = b.lambda + (int64_t)pair * kSDim;
+  float* __restrict__ rho_out = b.rho + (int64_t)pair * kSDim;
+  const int tt = tid & 15, tc = tid >> 4;
+  for (int c0 = 0; c0 < r; c0 += kPqC) {
+    __syncthreads();
+    for (int c = wib; c < kPqC; c += kPqThreads / 32) {
+      float ss = 0.f;
+      if (c0 + c < r) {
+        const float* col = G + (int64_t)(c0 + c) * kSLd;
+        for (int i = lane; i < kSDim; i += 32) ss = fmaf(col[i], col[i], ss);
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) s_nrm[c] = ss;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kSDim * kPqC; idx += kPqThreads) {
+      const int c = idx / kSDim, i = idx % kSDim;
+      const float nn = s_nrm[c];
+      const float v = (c0 + c < r && nn > 0.f) ? G[(int64_t)(c0 + c) * kSLd + i] * rsqrtf(nn) : 0.f;
+      sU[i * kPqC + ((((c >> 2) ^ (i & 7)) << 2) | (c & 3))] = v;
+    }
+    double m1x[4], m1y[4], mxx[4], myy[4], mxy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m1x[i] = m1y[i] = mxx[i] = myy[i] = mxy[i] = 0.0;
+    for (int t0 = 0; t0 < span.ne; t0 += kPqT) {
+      __syncthreads();
+      for (int idx = tid; idx < kPqRows * kSLanes; idx += kPqThreads) {
+        const int row = idx / kSLanes, j = idx % kSLanes;
+        if (j < kSBands) {
+          const bool ok = t0 + row < Fa;
+          const int at = j * kPqLd + row + (row >> 3);
+          sX[at] = ok ? X[(int64_t)(t0 + row) * kSLanes + j] : 0.f;
+          sY[at] = ok ? Y[(int64_t)(t0 + row) * kSLanes + j] : 0.f;
+        }
+      }
+      __syncthreads();
+      float ax[4][kPqF], ay[4][kPqF];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int f = 0; f < kPqF; ++f) ax[i][f] = ay[i][f] = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < kSBands; ++j) {
+        // frames 8 tt + o, o = 0..21, live at 9 tt + o + o / 8 of the skewed row
+        const float* xr = sX + j * kPqLd + 9 * tt;
+        const float* yr = sY + j * kPqLd + 9 * tt;
+        float xw[kPqF + kSStack - 1], yw[kPqF + kSStack - 1];
+#pragma unroll
+        for (int o = 0; o < kPqF + kSStack - 1; ++o) {
+          xw[o] = xr[o + (o >> 3)];
+          yw[o] = yr[o + (o >> 3)];
+        }
+#pragma unroll
+        for (int k = 0; k < kSStack; ++k) {
+          const int row = k * kSBands + j;
+          const float4 uu = *reinterpret_cast<const float4*>(sU + row * kPqC + ((tc ^ (row & 7)) << 2));
+          const float uc[4] = {uu.x, uu.y, uu.z, uu.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int f = 0; f < kPqF; ++f) {
+              ax[i][f] = fmaf(uc[i], xw[k + f], ax[i][f]);
+              ay[i][f] = fmaf(uc[i], yw[k + f], ay[i][f]);
+            }
+        }
+      }
+      // weighted moments of the 8 frames of this thread, then of the 16 frame groups
+      float wt[kPqF];
+#pragma unroll
+      for (int f = 0; f < kPqF; ++f) {
+        const int t = t0 + kPqF * tt + f;
+        wt[f] = (t < span.ne) ? (float)span.w(t) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float p1x = 0.f, p1y = 0.f, pxx = 0.f, pyy = 0.f, pxy = 0.f;
+#pragma unroll
+        for (int f = 0; f < kPqF; ++f) {
+          const float wx = wt[f] * ax[i][f], wy = wt[f] * ay[i][f];
+          p1x += wx;
+          p1y += wy;
+          pxx = fmaf(wx, ax[i][f], pxx);
+          pyy = fmaf(wy, ay[i][f], pyy);
+          pxy = fmaf(wx, ay[i][f], pxy);
+        }
+        double d1x = (double)p1x, d1y = (double)p1y, dxx = (double)pxx, dyy = (double)pyy, dxy = (double)pxy;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          d1x += __shfl_xor_sync(0xffffffffu, d1x, o);
+          d1y += __shfl_xor_sync(0xffffffffu, d1y, o);
+          dxx += __shfl_xor_sync(0xffffffffu, dxx, o);
+          dyy += __shfl_xor_sync(0xffffffffu, dyy, o);
+          dxy += __shfl_xor_sync(0xffffffffu, dxy, o);
+        }
+        m1x[i] += d1x;
+        m1y[i] += d1y;
+        mxx[i] += dxx;
+        myy[i] += dyy;
+        mxy[i] += dxy;
+      }
+    }
+    if (tt == 0) {
+      const double inv_nf = 1.0 / (double)Nf;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + 4 * tc + i;
+        if (c >= r) continue;
+        const double cxx = mxx[i] - m1x[i] * m1x[i] * inv_nf, cyy = myy[i] - m1y[i] * m1y[i] * inv_nf;
+        const double cxy = mxy[i] - m1x[i] * m1y[i] * inv_nf;
+        double rho = 0.0;
+        if (cxx > 0.0 && cyy > 0.0) rho = cxy / sqrt(cxx * cyy);
+        if (rho > 1.0) rho = 1.0;
+        if (rho < -1.0) rho = -1.0;
+        const double pr = 0.75 * rho;
+        s_info[c] = -0.5 * log2(1.0 - pr * pr);
+        lam_out[c] = s_nrm[4 * tc + i];
+        rho_out[c] = (float)rho;
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = r + tid; j < kSDim; j += kPqThreads) {
+    lam_out[j] = 0.f;
+    rho_out[j] = 0.f;
+  }
+  if (tid == 0) {
+    double info = 0.0;
+    for (int c = 0; c < r; ++c) info += s_info[c];
+    const double R = 1.0 / 200.0 * 16000.0;
+    const double v = R / (double)kSStack * info;
+    b.score[pair] = v > 0.0 ? v : 0.0;
+    b.status[pair] = 0;
+  }
+}
+
 // ------------------------------------------------------------- launchers
 void siib_upload_tables(const float* win, const float* decay, const float* g2t, const float* tw, cudaStream_t s) {
   cudaMemcpyToSymbolAsync(g_siib_win, win, sizeof(float) * kSWin, 0, cudaMemcpyHostToDevice, s);
@@ -1344,6 +1524,7 @@ void siib_upload_tables(const float* win, const float* decay, const float* g2t, 
   cudaMemcpyToSymbolAsync(g_siib_tw, tw, sizeof(float) * 2 * kSWin, 0, cudaMemcpyHostToDevice, s);
   cudaFuncSetAttribute(siib_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpecSmem));
   cudaFuncSetAttribute(siib_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholW * kSDim * (int)sizeof(double));
+  cudaFuncSetAttribute(siib_projquad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPqSmem);
   cudaFuncSetAttribute(siib_jacobi2_kernel<1, kJ2WarpsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kJ2MaxSb * kSLd * (int)sizeof(float));
   cudaFuncSetAttribute(siib_jacobi2_kernel<4, kJ2Warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kJ2MaxSb * kSLd * (int)sizeof(float));
   siib_knn_setup();
@@ -1428,6 +1609,12 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, 
   siib_quad_kernel<<<n, kQuadThreads, 0, s>>>(g, b);
   kt_end(kt, s);
   ++launches;
+  if (!b.no_proj) {
+    kt_begin(kt, "siib_projquad", s);
+    siib_projquad_kernel<<<n, kPqThreads, kPqSmem, s>>>(g, b);
+    kt_end(kt, s);
+    ++launches;
+  }
   return launches;
 }
 

@@ -181,7 +181,7 @@ def test_profiling_lists_every_kernel(eng):
     eng.score_batch([x], [y], mapped=False)
     kt = eng.kernel_times()
     eng.set_profiling(False)
-    for k in ("haspi_ear", "estoi_tob", "siib_cov", "siib_chol", "siib_gram", "siib_tridiag", "siib_backtf", "siib_quad"):
+    for k in ("haspi_ear", "estoi_tob", "siib_cov", "siib_chol", "siib_gram", "siib_tridiag", "siib_backtf", "siib_quad", "siib_projquad"):
         assert k in kt and kt[k][0] > 0 and kt[k][1] >= 1
     ms, launches = eng.last_timing()
     assert launches == sum(v[1] for v in kt.values())
