@@ -15,6 +15,9 @@
  *   pystoi.stoi(x, y, fs, extended=True)(intel.py:126,133) nele_score_batch, NELE_METRIC_ESTOI
  *   intel.py:57-140  *_Wrapper[_raw]_harvard(x, y, fs)    nele_score_batch, NELE_FLAG_MAPPED on/off
  *   audio_util.py:145-203,281-321 read_batch_*            one nele_score_batch call per list
+ *   audio_util.py:422-457  Sp_and_phase_Speech / _Noise   nele_features (the data loaders' feature front-end,
+ *     (compute_band_E :30-50, STFT :52-57, NoisePSD        dataloader.py:30-84)
+ *      :117-122 -> noise_est/imcra.py:487-577)
  *
  * Conventions: plain pointers and sizes, no ownership transfer.  The caller
  * owns inputs and outputs; the engine owns a grow-only device workspace.  One
@@ -180,6 +183,33 @@ int nele_last_timing(const nele_engine* e, double* kernel_ms, int64_t* launches)
  * summed milliseconds and number of launches.  Off by default. */
 int nele_set_profiling(nele_engine* e, int on);
 int nele_kernel_time(const nele_engine* e, int idx, const char** name, double* ms, int64_t* launches);
+
+/*
+ * Feature front-end of the generator / discriminator data loaders (dataloader.py:30-84): for each of
+ * n waveforms the centred 512 / 256 STFT with a periodic Hann window and reflect padding
+ * (librosa.stft as audio_util.py:52-57 calls it), its magnitude and phase, and the 64 band energies
+ * of compute_band_E (audio_util.py:30-50) raised to `power` (dataloader.py:14: 1/6).
+ *
+ *   Sp_and_phase_Speech(signal, power, Normalization)  (audio_util.py:422-437): flags = 0
+ *   Sp_and_phase_Noise(signal, power, Normalization)   (audio_util.py:439-457): NELE_FEAT_NOISE -- the band
+ *       energies are those of the IMCRA noise PSD, NoisePSD = imcra_est(nfft=512).estimate
+ *       (audio_util.py:117-122, noise_est/imcra.py:487-577 and :362-484), one fresh estimator per waveform
+ *
+ *   wav, offs, lens   concatenated float32 waveforms, waveform i at [offs[i], offs[i] + lens[i]); lens[i] >= 257
+ *                     (reflect padding needs more than n_fft / 2 samples, as in librosa).  offs / lens on the host.
+ *   frames            T_i = 1 + lens[i] / 256; F_i = sum of T_j over j < i  (nele_feature_frames)
+ *   band              float32 [sum T][64]: rows F_i .. F_i + T_i of waveform i -- bandE[T, 64] of the reference
+ *   mag, phase, psd   NULL or float32 [257 * sum T]: waveform i's [257][T_i] matrix (the reference's layout) at
+ *                     257 * F_i; psd (NELE_FEAT_NOISE only) is the noise PSD NoisePSD returns
+ *   flags             NELE_FEAT_NOISE; NELE_FEAT_DEVICE_IO: wav and every output are device pointers;
+ *                     NELE_FEAT_NO_POWER: Normalization=False, band energies not raised to `power`
+ */
+#define NELE_FEAT_NOISE     0x1u
+#define NELE_FEAT_DEVICE_IO 0x2u
+#define NELE_FEAT_NO_POWER  0x4u
+int64_t nele_feature_frames(int32_t len);
+int nele_features(nele_engine* e, const float* wav, const int64_t* offs, const int32_t* lens, int n, uint32_t flags,
+                  double power, float* band, float* mag, float* phase, float* psd, void* stream);
 
 #ifdef __cplusplus
 }

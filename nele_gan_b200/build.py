@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnele_score.so")
-SOURCES = ["engine.cu", "haspi.cu", "haspi_v1.cu", "estoi.cu", "siib.cu", "siib_knn.cu", "siib_eig.cu"]
+SOURCES = ["engine.cu", "haspi.cu", "haspi_v1.cu", "estoi.cu", "siib.cu", "siib_knn.cu", "siib_eig.cu", "features.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--shared"]
 

@@ -80,6 +80,7 @@ struct nele_engine {
   DevBuf kn_xk, kn_info, kn_digamma;  // SIIB k-NN estimator
   DevBuf eg_vec, eg_zt, eg_gram, eg_refl;             // SIIB tridiagonal eigen-solver: 5 x [sub][448] doubles, [sub][420][448] floats
   DevBuf out_haspi, out_raw, out_hst, out_estoi, out_est, out_siib, out_sst;
+  DevBuf ft_wav, ft_geom, ft_band, ft_mag, ft_phase, ft_psd;   // feature front-end (nele_features)
   std::vector<DevBuf*> all_bufs;
   char *h_geom = nullptr, *h_sgeom = nullptr;  // pinned staging of the geometry blobs (read by blob_copy_kernel)
   size_t h_geom_cap = 0, h_sgeom_cap = 0;
@@ -211,7 +212,8 @@ extern "C" int nele_create(int device, nele_engine** out) {
                  &e->sb_wrapdb, &e->sb_M, &e->sb_wact, &e->sb_mean, &e->sb_xdb, &e->sb_act, &e->sb_aidx, &e->sb_src, &e->sb_Fa, &e->sb_Pact, &e->sb_perflag, &e->sb_lograw, &e->sb_logspec,
                  &e->sb_base, &e->sb_Sxx, &e->sb_Sxy, &e->sb_Syy, &e->sb_Lc, &e->sb_G, &e->sb_perm,
                  &e->sb_rank, &e->sb_sweeps, &e->sb_lambda, &e->sb_rho, &e->kn_xk, &e->kn_info, &e->kn_digamma, &e->eg_vec, &e->eg_zt, &e->eg_gram, &e->eg_refl,
-                 &e->out_haspi, &e->out_raw, &e->out_hst, &e->out_estoi, &e->out_est, &e->out_siib, &e->out_sst};
+                 &e->out_haspi, &e->out_raw, &e->out_hst, &e->out_estoi, &e->out_est, &e->out_siib, &e->out_sst,
+                 &e->ft_wav, &e->ft_geom, &e->ft_band, &e->ft_mag, &e->ft_phase, &e->ft_psd};
 #define CUC(call)                                                                             \
   do {                                                                                        \
     cudaError_t _r = (call);                                                                  \
@@ -1019,6 +1021,113 @@ extern "C" int nele_prefetch(nele_engine* e, const float* ref, const float* deg,
   e->pf[slot].n = n;
   e->pf[slot].tot = plans[0].tot;
   e->pf[slot].seq = ++e->pf_seq;
+  return NELE_OK;
+}
+
+// ------------------------------------------------------------------ feature front-end
+extern "C" int64_t nele_feature_frames(int32_t len) { return len < 0 ? 0 : 1 + (int64_t)len / 256; }
+
+extern "C" int nele_features(nele_engine* e, const float* wav, const int64_t* offs, const int32_t* lens, int n,
+                             uint32_t flags, double power, float* band, float* mag, float* phase, float* psd,
+                             void* stream) {
+  if (!e) return NELE_E_ARG;
+  if (n < 0 || (n > 0 && (!wav || !offs || !lens || !band)))
+    return fail(e, NELE_E_ARG, "nele_features: null pointer or negative n");
+  if (flags & ~(NELE_FEAT_NOISE | NELE_FEAT_DEVICE_IO | NELE_FEAT_NO_POWER))
+    return fail(e, NELE_E_ARG, "nele_features: bad flags 0x%x", flags);
+  const bool noise = flags & NELE_FEAT_NOISE, dev_io = flags & NELE_FEAT_DEVICE_IO, normalize = !(flags & NELE_FEAT_NO_POWER);
+  if (psd && !noise) return fail(e, NELE_E_ARG, "nele_features: psd requested without NELE_FEAT_NOISE");
+  for (int i = 0; i < n; ++i)
+    if (lens[i] <= 256 || offs[i] < 0)   // librosa: reflect padding by n_fft / 2 needs a longer signal
+      return fail(e, NELE_E_ARG, "nele_features: waveform %d has length %d / offset %lld (need more than 256 samples)", i,
+                  lens[i], (long long)offs[i]);
+  e->last_kernel_ms = 0.0;
+  e->last_launches = 0;
+  e->kstats.clear();
+  e->kt.count = 0;
+  e->kt.enabled = e->profiling && e->kt_events;
+  KernelTimer* kt = e->kt.enabled ? &e->kt : nullptr;
+  if (n == 0) return NELE_OK;
+  CU(e, cudaSetDevice(e->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+
+  const int64_t kMaxFrames = 4 << 20;   // frames per chunk: bounds the [257][T] workspaces at 4.3 GB each
+  int64_t frame0 = 0;                   // frames of the waveforms before this chunk
+  for (int first = 0; first < n;) {
+    int last = first;
+    int64_t frames = 0, lo = INT64_MAX, hi = 0;
+    std::vector<int64_t> h_off, h_foff;
+    std::vector<int2> h_tiles;
+    while (last < n && (last == first || frames + nele_feature_frames(lens[last]) <= kMaxFrames)) {
+      const int T = (int)nele_feature_frames(lens[last]);
+      h_foff.push_back(frames);
+      for (int t0 = 0; t0 < T; t0 += 8) h_tiles.push_back(make_int2(last - first, t0));
+      frames += T;
+      lo = std::min(lo, offs[last]);
+      hi = std::max(hi, offs[last] + lens[last]);
+      ++last;
+    }
+    const int cn = last - first;
+    // geometry blob: offsets (relative to the staged span for host input), lengths, frame offsets, tiles
+    const size_t g_off = 0, g_foff = g_off + 8 * (size_t)cn, g_tiles = g_foff + 8 * (size_t)cn,
+                 g_len = g_tiles + 8 * h_tiles.size(), g_bytes = g_len + 4 * (size_t)cn;
+    std::vector<char> blob(g_bytes);
+    for (int i = 0; i < cn; ++i) h_off.push_back(dev_io ? offs[first + i] : offs[first + i] - lo);
+    memcpy(&blob[g_off], h_off.data(), 8 * (size_t)cn);
+    memcpy(&blob[g_foff], h_foff.data(), 8 * (size_t)cn);
+    memcpy(&blob[g_tiles], h_tiles.data(), 8 * h_tiles.size());
+    memcpy(&blob[g_len], lens + first, 4 * (size_t)cn);
+    RESERVE(e, e->ft_geom, g_bytes);
+    CU(e, cudaMemcpyAsync(e->ft_geom.p, blob.data(), g_bytes, cudaMemcpyHostToDevice, s));
+    CU(e, cudaStreamSynchronize(s));   // blob is a local vector
+    const char* gp = (const char*)e->ft_geom.p;
+
+    const float* d_wav = wav;
+    float *d_band = band + frame0 * 64, *d_mag = mag ? mag + frame0 * 257 : nullptr,
+          *d_phase = phase ? phase + frame0 * 257 : nullptr, *d_psd = psd ? psd + frame0 * 257 : nullptr;
+    const size_t mbytes = (size_t)frames * 257 * sizeof(float);
+    if (!dev_io) {
+      RESERVE(e, e->ft_wav, (size_t)(hi - lo) * sizeof(float));
+      CU(e, cudaMemcpyAsync(e->ft_wav.p, wav + lo, (size_t)(hi - lo) * sizeof(float), cudaMemcpyHostToDevice, s));
+      d_wav = (const float*)e->ft_wav.p;
+      RESERVE(e, e->ft_band, (size_t)frames * 64 * sizeof(float));
+      d_band = (float*)e->ft_band.p;
+      if (mag || noise) {
+        RESERVE(e, e->ft_mag, mbytes);
+        d_mag = (float*)e->ft_mag.p;
+      }
+      if (phase) {
+        RESERVE(e, e->ft_phase, mbytes);
+        d_phase = (float*)e->ft_phase.p;
+      }
+      if (psd) {
+        RESERVE(e, e->ft_psd, mbytes);
+        d_psd = (float*)e->ft_psd.p;
+      }
+    } else if (noise && !d_mag) {
+      RESERVE(e, e->ft_mag, mbytes);
+      d_mag = (float*)e->ft_mag.p;
+    }
+    CU(e, cudaEventRecord(e->ev0, s));
+    e->last_launches += features_run(d_wav, (const int64_t*)(gp + g_off), (const int32_t*)(gp + g_len),
+                                     (const int64_t*)(gp + g_foff), (const int2*)(gp + g_tiles), cn, (int)h_tiles.size(),
+                                     noise, (float)power, normalize, d_band, d_mag, d_phase, d_psd, kt, s);
+    CU(e, cudaGetLastError());
+    CU(e, cudaEventRecord(e->ev1, s));
+    if (!dev_io) {
+      CU(e, cudaMemcpyAsync(band + frame0 * 64, d_band, (size_t)frames * 64 * sizeof(float), cudaMemcpyDeviceToHost, s));
+      if (mag) CU(e, cudaMemcpyAsync(mag + frame0 * 257, d_mag, mbytes, cudaMemcpyDeviceToHost, s));
+      if (phase) CU(e, cudaMemcpyAsync(phase + frame0 * 257, d_phase, mbytes, cudaMemcpyDeviceToHost, s));
+      if (psd) CU(e, cudaMemcpyAsync(psd + frame0 * 257, d_psd, mbytes, cudaMemcpyDeviceToHost, s));
+    }
+    CU(e, cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CU(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->last_kernel_ms += ms;
+    collect_kernel_times(e);
+    frame0 += frames;
+    first = last;
+  }
   return NELE_OK;
 }
 

@@ -1,0 +1,394 @@
+// Feature front-end of NELE-GAN's generator / discriminator data loaders (SURVEY.md section 8f,
+// rank 3): what dataloader.py:30-84 computes per utterance through audio_util.py:422-457 --
+//
+//   Sp_and_phase_Speech : librosa.stft(512 / 256, periodic Hann, centred, reflect padding) ->
+//                         |F|, angle(F), compute_band_E(|F|) ** power        (audio_util.py:30-57, 422-437)
+//   Sp_and_phase_Noise  : the same STFT, then the IMCRA noise PSD of noise_est/imcra.py
+//                         (imcra_est.estimate, :487-577, driving imcra.update, :362-484) ->
+//                         compute_band_E(sqrt(PSD)) ** power                (audio_util.py:117-122, 439-457)
+//
+// Two kernels.  feat_stft: one CTA per 8 consecutive frames of one utterance; the frames are
+// paired into four 512-point complex FFTs (frame a + i frame b), radix-8 Stockham in FP64 through
+// shared memory (the reference transforms in float64 and stores complex64, so the spectra are
+// rounded to float32 from the same precision), split into the two real spectra, magnitude / phase
+// written in the reference's [257][T] layout, band energies with the reference's exact
+// accumulation order.  feat_imcra: one CTA per utterance, thread = frequency bin, the frame
+// recursion in FP64 with the spectra staged 32 frames at a time through shared memory; the 3-tap
+// frequency smoothing goes through shared memory, the minimum store is a register ring; the noise
+// band energies are formed in the same pass, so the PSD only goes to HBM when the caller asks.
+#include <math.h>
+
+#include "kernels.h"
+
+namespace nele {
+
+namespace {
+
+constexpr int kNfft = 512, kHop = 256, kBins = 257, kFeatBands = 64;
+constexpr int kTileFrames = 8;
+
+// audio_util.py:23
+__constant__ int c_gmt[kFeatBands] = {0,  3,  4,  5,  6,  7,  8,  9,  10,  11,  12,  13,  14,  15,  16,  17,
+                                      18, 19, 20, 21, 22, 23, 24, 25, 26,  28,  30,  32,  34,  36,  38,  41,
+                                      43, 46, 49, 52, 55, 58, 62, 66, 70,  74,  79,  83,  88,  93,  99,  105,
+                                      111, 117, 124, 131, 139, 147, 156, 165, 174, 184, 195, 206, 218, 230, 243, 257};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 mul_mi(double2 a) { return make_double2(a.y, -a.x); }  // a * (-i)
+
+// 4-point DFT, natural order in and out
+__device__ __forceinline__ void fft4(double2& a0, double2& a1, double2& a2, double2& a3) {
+  double2 s0 = cadd(a0, a2), s1 = csub(a0, a2), s2 = cadd(a1, a3), s3 = mul_mi(csub(a1, a3));
+  a0 = cadd(s0, s2);
+  a2 = csub(s0, s2);
+  a1 = cadd(s1, s3);
+  a3 = csub(s1, s3);
+}
+
+// 8-point DFT (forward, exp(-2 pi i r q / 8)), natural order in and out
+__device__ __forceinline__ void fft8(double2* v) {
+  const double c = 0.70710678118654752440;
+  fft4(v[0], v[2], v[4], v[6]);
+  fft4(v[1], v[3], v[5], v[7]);
+  double2 o1 = make_double2(c * (v[3].x + v[3].y), c * (v[3].y - v[3].x));    // * W8
+  double2 o2 = mul_mi(v[5]);                                                  // * W8^2
+  double2 o3 = make_double2(c * (v[7].y - v[7].x), -c * (v[7].x + v[7].y));   // * W8^3
+  double2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+  v[0] = cadd(e0, o0);
+  v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1);
+  v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2);
+  v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3);
+  v[7] = csub(e3, o3);
+}
+
+// compute_band_E (audio_util.py:30-50) for one band from the squared magnitudes `sq` (float32, as
+// numpy squares them): band b collects frac * sq over the bins of band b - 1, then (1 - frac) * sq
+// over its own bins -- in that order, float32 products accumulated in float64.  d_wown[k] =
+// float32(1 - frac), d_wnext[k] = float32(frac) of bin k (numpy multiplies the float32 square by the
+// python float as a float32).
+__device__ float d_wown[kBins], d_wnext[kBins];
+
+__device__ __forceinline__ float band_energy(const float* sq, int b) {
+  double acc = 0.0;
+  if (b > 0)
+    for (int k = c_gmt[b - 1]; k < c_gmt[b]; ++k) acc += (double)__fmul_rn(__ldg(&d_wnext[k]), sq[k]);
+  if (b < kFeatBands - 1)
+    for (int k = c_gmt[b]; k < c_gmt[b + 1]; ++k) acc += (double)__fmul_rn(__ldg(&d_wown[k]), sq[k]);
+  return (float)acc;
+}
+
+// bandE ** power in float32 (audio_util.py:432): numpy calls powf; the double pow rounded to
+// float32 is the correctly rounded value, which glibc's powf returns too.
+__device__ __forceinline__ float band_power(float v, float power, int normalize) {
+  return normalize ? (float)pow((double)v, (double)power) : v;
+}
+
+struct StftSmem {
+  double2 buf[4][kNfft];
+  double2 tw[kNfft];
+  float mag[kTileFrames][kBins + 3];
+  float ph[kTileFrames][kBins + 3];
+};
+
+__global__ void __launch_bounds__(256) feat_stft_kernel(const float* __restrict__ wav, const int64_t* __restrict__ offs,
+                                                         const int32_t* __restrict__ lens,
+                                                         const int64_t* __restrict__ foff, const int2* __restrict__ tiles,
+                                                         float power, int normalize, float* __restrict__ band,
+                                                         float* __restrict__ mag, float* __restrict__ phase) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  StftSmem& sm = *reinterpret_cast<StftSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int2 tile = tiles[blockIdx.x];
+  const int u = tile.x, t0 = tile.y;
+  const int L = lens[u];
+  const int T = 1 + L / kHop;
+  const float* x = wav + offs[u];
+
+  for (int m = tid; m < kNfft; m += 256) {
+    double s, c;
+    sincospi((double)m / 256.0, &s, &c);
+    sm.tw[m] = make_double2(c, -s);
+  }
+  __syncthreads();
+  // windowed frames: FFT q takes frame 2q as its real and frame 2q + 1 as its imaginary part
+  for (int e = tid; e < kTileFrames * kNfft; e += 256) {
+    int f = e >> 9, n = e & 511;
+    int t = t0 + f;
+    double v = 0.0;
+    if (t < T) {
+      int p = t * kHop + n - kNfft / 2;   // centred frame, reflect padding (np.pad(..., mode='reflect'))
+      if (p < 0) p = -p;
+      if (p >= L) p = 2 * (L - 1) - p;
+      v = (0.5 - 0.5 * sm.tw[n].x) * (double)x[p];
+    }
+    double* dst = reinterpret_cast<double*>(&sm.buf[f >> 1][n]);
+    dst[f & 1] = v;
+  }
+  __syncthreads();
+  {
+    const int q = tid >> 6, j = tid & 63;
+    double2 v[8];
+#pragma unroll
+    for (int stage = 0; stage < 3; ++stage) {
+      const int Ns = stage == 0 ? 1 : (stage == 1 ? 8 : 64);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = sm.buf[q][j + r * 64];
+      if (stage > 0) {
+        const int k = (j & (Ns - 1)) * (64 / Ns);
+#pragma unroll
+        for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], sm.tw[k * r]);
+      }
+      fft8(v);
+      __syncthreads();
+      const int base = (j / Ns) * Ns * 8 + (j & (Ns - 1));
+#pragma unroll
+      for (int r = 0; r < 8; ++r) sm.buf[q][base + r * Ns] = v[r];
+      __syncthreads();
+    }
+  }
+  // split Z = A + iB into the spectra of the two real frames, round to complex64, |.| and angle
+  for (int e = tid; e < 4 * kBins; e += 256) {
+    int q = e / kBins, k = e - q * kBins;
+    double2 zk = sm.buf[q][k], zn = sm.buf[q][(kNfft - k) & (kNfft - 1)];
+    float are = (float)(0.5 * (zk.x + zn.x)), aim = (float)(0.5 * (zk.y - zn.y));
+    float bre = (float)(0.5 * (zk.y + zn.y)), bim = (float)(-0.5 * (zk.x - zn.x));
+    if (k == 0 || k == kBins - 1) aim = 0.f, bim = 0.f;   // a real FFT returns +0 there
+    // np.abs(complex64) = hypotf; glibc evaluates it as the rounded double sqrt of the exact sum of squares
+    sm.mag[2 * q][k] = (float)sqrt((double)are * are + (double)aim * aim);
+    sm.mag[2 * q + 1][k] = (float)sqrt((double)bre * bre + (double)bim * bim);
+    sm.ph[2 * q][k] = atan2f(aim, are);
+    sm.ph[2 * q + 1][k] = atan2f(bim, bre);
+  }
+  __syncthreads();
+  const int64_t fo = foff[u];
+  const int64_t mbase = (int64_t)kBins * fo;
+  for (int e = tid; e < kBins * kTileFrames; e += 256) {
+    int k = e >> 3, f = e & 7;
+    int t = t0 + f;
+    if (t < T) {
+      if (mag) mag[mbase + (int64_t)k * T + t] = sm.mag[f][k];
+      if (phase) phase[mbase + (int64_t)k * T + t] = sm.ph[f][k];
+    }
+  }
+  if (band) {
+    __syncthreads();
+    // square in place (float32, as X[iT, k] ** 2), then the 64 bands of each frame
+    for (int e = tid; e < kBins * kTileFrames; e += 256) {
+      int f = e / kBins, k = e - f * kBins;
+      float a = sm.mag[f][k];
+      sm.mag[f][k] = __fmul_rn(a, a);
+    }
+    __syncthreads();
+    for (int e = tid; e < kFeatBands * kTileFrames; e += 256) {
+      int f = e >> 6, b = e & 63;
+      int t = t0 + f;
+      if (t < T) band[(fo + t) * kFeatBands + b] = band_power(band_energy(sm.mag[f], b), power, normalize);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- IMCRA
+constexpr int kImcraThreads = 288;
+constexpr int kImcraTile = 32;
+constexpr int kIS = 15, kU = 8, kV = 15;   // noise_est/imcra.py:181,192,194 (imcra_est passes IS = 15)
+
+struct ImcraSmem {
+  float tile[kBins][kImcraTile + 1];
+  double P[kBins + 2], I[kBins + 2], IP[kBins + 2];
+  float nsq[kBins + 3];
+};
+
+// fsmooth (noise_est/imcra.py:336-337) with w = 1: sym_hanning(3) = [0.5, 1, 0.5], truncated at the
+// edges and normalised per row (:262-272).  `a` has one guard cell on each side (index k + 1 = bin k).
+__device__ __forceinline__ double fsmooth3(const double* a, int k) {
+  if (k == 0) return (1.0 / 1.5) * a[1] + (0.5 / 1.5) * a[2];
+  if (k == kBins - 1) return (0.5 / 1.5) * a[k] + (1.0 / 1.5) * a[k + 1];
+  return 0.25 * a[k] + 0.5 * a[k + 1] + 0.25 * a[k + 2];
+}
+
+__global__ void __launch_bounds__(kImcraThreads) feat_imcra_kernel(const float* __restrict__ mag,
+                                                                    const int64_t* __restrict__ foff,
+                                                                    const int32_t* __restrict__ lens, float power,
+                                                                    int normalize, float* __restrict__ band,
+                                                                    float* __restrict__ psd) {
+  __shared__ ImcraSmem sm;
+  const int u = blockIdx.x, k = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool live = k < kBins;
+  const int T = 1 + lens[u] / kHop;
+  const int64_t fo = foff[u];
+  const float* M = mag + (int64_t)kBins * fo;
+  float* PSD = psd ? psd + (int64_t)kBins * fo : nullptr;
+
+  // imcra defaults (:181-228), imcra_est defaults (:492)
+  const double alpha_s = 0.9, alpha_d = 0.85, Bmin = 3.2, Gamma0 = 4.6, Gamma1 = 3.0, zeta0 = 1.67, beta = 1.47;
+  const double alpha_dd = 0.92, xi_min = 0.056234132519034911 /* 10 ** (-25 / 20) */, p_up = 0.9;
+
+  double G = 1.0, Gamma = 1.0, Lam = 1e-6;
+  float Lam32 = 0.f;
+  double S = 0, tS = 0, Smin = 0, tSmin = 0, Smin_sw = 0, tSmin_sw = 0, ovLam = 0;
+  double store[kU], tstore[kU];
+#pragma unroll
+  for (int i = 0; i < kU; ++i) store[i] = tstore[i] = 0.0;
+  int jcnt = 0, ucnt = 0;
+  if (k < kBins + 2) sm.P[k] = sm.I[k] = sm.IP[k] = 0.0;
+
+  for (int tb = 0; tb < T; tb += kImcraTile) {
+    __syncthreads();
+    for (int row = warp; row < kBins; row += kImcraThreads / 32) {
+      int t = tb + lane;
+      sm.tile[row][lane] = t < T ? M[(int64_t)row * T + t] : 0.f;
+    }
+    __syncthreads();
+    const int nt = min(kImcraTile, T - tb);
+    for (int tt = 0; tt < nt; ++tt) {
+      const int l = tb + tt;
+      float P32 = 0.f;
+      double P = 0, xi = 0;
+      if (live) {
+        float a = sm.tile[k][tt];
+        P32 = __fmul_rn(a, a);
+        P = (double)P32;
+        // decision-directed a-priori SNR (:544-557)
+        double xi_G = G * G * Gamma;
+        Gamma = P / Lam;
+        xi = alpha_dd * xi_G + (1.0 - alpha_dd) * fmax(Gamma - 1.0, 1e-6);
+        xi = fmax(xi, xi_min);
+        G = xi / (1.0 + xi);
+        sm.P[k + 1] = P;
+      }
+      __syncthreads();
+      double Sf = 0;
+      if (live) {
+        Sf = fsmooth3(sm.P, k);
+        if (l == 0) {   // init_params (:339-360)
+          S = tS = Smin = tSmin = Smin_sw = tSmin_sw = Sf;
+          ovLam = P;
+          Lam32 = P32;
+        }
+        S = alpha_s * S + (1.0 - alpha_s) * Sf;
+        Smin = fmin(Smin, S);
+        Smin_sw = fmin(Smin_sw, S);
+      }
+      if (l < kIS) {
+        // initial segment (:384-399): python scalars times float32 arrays -- a float32 recursion
+        if (live) {
+          Lam32 = __fadd_rn(__fmul_rn(0.85f, Lam32), __fmul_rn(0.15f, P32));
+          Lam = (double)Lam32;
+        }
+      } else {
+        double Iv = 0;
+        if (live) {
+          double Gmin = P / (Bmin * Smin), zeta = S / (Bmin * Smin);   // :411-414
+          Iv = (Gmin < Gamma0 && zeta < zeta0) ? 1.0 : 0.0;
+          sm.I[k + 1] = Iv;
+          sm.IP[k + 1] = Iv * P;
+        }
+        __syncthreads();
+        if (live) {
+          double norm = fsmooth3(sm.I, k), tSf = fsmooth3(sm.IP, k);   // :420-422
+          if (norm > 0) tSf = tSf / norm;
+          tS = alpha_s * tS + (1.0 - alpha_s) * tSf;
+          tSmin = fmin(tSmin, tS);
+          tSmin_sw = fmin(tSmin_sw, tS);
+          double tG = P / (Bmin * tSmin), tz = S / (Bmin * tSmin);      // :429-430
+          double q = 0.0;
+          if (tz < zeta0) {
+            if (tG <= 1.0) q = 1.0;
+            else if (tG < Gamma1) q = (Gamma1 - tG) / (Gamma1 - 1.0);
+          }
+          double p = 0.0;                                              // post_speech_prob (:23-38)
+          if (q < 1.0) {
+            double nu = Gamma * xi / (1.0 + xi);
+            p = 1.0 / (1.0 + (q / (1.0 - q)) * (1.0 + xi) * exp(-nu));
+          }
+          p = fmin(p, p_up);
+          double ta = alpha_d + (1.0 - alpha_d) * p;                   // :443-447
+          ovLam = ta * ovLam + (1.0 - ta) * P;
+          Lam = beta * ovLam;
+        }
+        if (++jcnt == kV) {   // minimum store (:451-482); a ring: the minimum does not depend on the order
+          if (live) {
+            const int slot = ucnt & (kU - 1), cnt = min(ucnt + 1, kU);
+            double m1 = INFINITY, m2 = INFINITY;
+#pragma unroll
+            for (int i = 0; i < kU; ++i) {
+              if (i == slot) store[i] = Smin_sw, tstore[i] = tSmin_sw;
+              if (i < cnt) m1 = fmin(m1, store[i]), m2 = fmin(m2, tstore[i]);
+            }
+            Smin = m1;
+            tSmin = m2;
+            Smin_sw = S;
+            tSmin_sw = tS;
+          }
+          jcnt = 0;
+          ++ucnt;
+        }
+      }
+      if (live) {
+        float lam = (float)Lam;   // N_PSD is float32 (:531,568)
+        sm.tile[k][tt] = lam;
+        float s = sqrtf(lam);     // compute_band_E(np.sqrt(estPSD)) squares the root again (audio_util.py:447)
+        sm.nsq[k] = __fmul_rn(s, s);
+      }
+      __syncthreads();
+      if (band && k < kFeatBands) band[(fo + l) * kFeatBands + k] = band_power(band_energy(sm.nsq, k), power, normalize);
+    }
+    if (PSD) {
+      __syncthreads();
+      for (int row = warp; row < kBins; row += kImcraThreads / 32) {
+        int t = tb + lane;
+        if (t < T) PSD[(int64_t)row * T + t] = sm.tile[row][lane];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int features_run(const float* wav, const int64_t* offs, const int32_t* lens, const int64_t* foff, const int2* tiles,
+                 int n, int ntiles, bool noise, float power, bool normalize, float* band, float* mag, float* phase,
+                 float* psd, KernelTimer* kt, cudaStream_t s) {
+  static bool ready = false;   // per process and device context: tables + the shared-memory opt-in
+  if (!ready) {
+    static const int gmt[kFeatBands] = {0,  3,  4,  5,  6,  7,  8,  9,  10,  11,  12,  13,  14,  15,  16,  17,
+                                        18, 19, 20, 21, 22, 23, 24, 25, 26,  28,  30,  32,  34,  36,  38,  41,
+                                        43, 46, 49, 52, 55, 58, 62, 66, 70,  74,  79,  83,  88,  93,  99,  105,
+                                        111, 117, 124, 131, 139, 147, 156, 165, 174, 184, 195, 206, 218, 230, 243, 257};
+    float wown[kBins], wnext[kBins];
+    for (int i = 0; i < kFeatBands - 1; ++i) {
+      const int size = gmt[i + 1] - gmt[i];
+      for (int j = 0; j < size; ++j) {
+        const double frac = (double)j / size;
+        wown[gmt[i] + j] = (float)(1.0 - frac);
+        wnext[gmt[i] + j] = (float)frac;
+      }
+    }
+    cudaMemcpyToSymbolAsync(d_wown, wown, sizeof(wown), 0, cudaMemcpyHostToDevice, s);
+    cudaMemcpyToSymbolAsync(d_wnext, wnext, sizeof(wnext), 0, cudaMemcpyHostToDevice, s);
+    cudaStreamSynchronize(s);
+    cudaFuncSetAttribute(feat_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem));
+    ready = true;
+  }
+  int launches = 0;
+  kt_begin(kt, "feat_stft", s);
+  feat_stft_kernel<<<ntiles, 256, sizeof(StftSmem), s>>>(wav, offs, lens, foff, tiles, power, normalize ? 1 : 0,
+                                                         noise ? nullptr : band, mag, phase);
+  kt_end(kt, s);
+  ++launches;
+  if (noise) {
+    kt_begin(kt, "feat_imcra", s);
+    feat_imcra_kernel<<<n, kImcraThreads, 0, s>>>(mag, foff, lens, power, normalize ? 1 : 0, band, psd);
+    kt_end(kt, s);
+    ++launches;
+  }
+  return launches;
+}
+
+}  // namespace nele

@@ -205,4 +205,12 @@ int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_til
 int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, const SiibEigBuffers* eb, int n, int64_t max_F,
              int64_t max_unique, KernelTimer* kt, cudaStream_t s);
 
+// --------------------------------------------------------------- feature front-end (features.cu)
+// STFT magnitude / phase / 64 band energies, and for noise inputs the IMCRA noise PSD
+// (audio_util.py:422-457).  foff: frame offsets [n]; tiles: (waveform, first frame) per CTA of
+// feat_stft.  All pointers are device pointers; mag must be non-null when noise is set.
+int features_run(const float* wav, const int64_t* offs, const int32_t* lens, const int64_t* foff, const int2* tiles,
+                 int n, int ntiles, bool noise, float power, bool normalize, float* band, float* mag, float* phase,
+                 float* psd, KernelTimer* kt, cudaStream_t s);
+
 }  // namespace nele

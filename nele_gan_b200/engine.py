@@ -22,7 +22,9 @@ _METRIC_BITS = {"haspi": METRIC_HASPI, "siib": METRIC_SIIB, "estoi": METRIC_ESTO
 COL_SIIB, COL_HASPI, COL_ESTOI = 0, 1, 2
 
 SYMBOLS = ("nele_abi_version", "nele_create", "nele_destroy", "nele_last_error", "nele_score_batch", "nele_prefetch",
-           "nele_get_stage", "nele_last_timing", "nele_set_profiling", "nele_kernel_time")
+           "nele_get_stage", "nele_last_timing", "nele_set_profiling", "nele_kernel_time", "nele_feature_frames",
+           "nele_features")
+FEAT_NOISE, FEAT_DEVICE_IO, FEAT_NO_POWER = 0x1, 0x2, 0x4
 
 
 class NeleError(RuntimeError):
@@ -67,6 +69,11 @@ def load_library(path=None):
         lib.nele_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                          C.POINTER(C.c_int64)]
         lib.nele_kernel_time.restype = C.c_int
+        lib.nele_feature_frames.argtypes = [C.c_int32]
+        lib.nele_feature_frames.restype = C.c_int64
+        lib.nele_features.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_double,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.nele_features.restype = C.c_int
         if path is None:
             _lib = lib
         return lib
@@ -208,6 +215,61 @@ class Engine:
         fr, offs, lens = pack(refs)
         fd, _, _ = pack(degs)
         return self.score_packed(fr, fd, offs, lens, fs=fs, metrics=metrics, mapped=mapped, **kw)
+
+    # ------------------------------------------------------------- feature front-end
+    def features_packed(self, wav, offs, lens, power=1.0 / 6.0, noise=False, normalization=True, want_mag=True,
+                        want_phase=True, want_psd=False, device_io=False, out=None, stream=None):
+        """``nele_features`` (audio_util.py:422-457 for a batch).  Host mode: ``wav`` flat float32 numpy
+        array -> dict of numpy arrays ``band`` [sum T, 64], ``mag`` / ``phase`` / ``psd`` flat
+        [257 * sum T] (waveform i's [257, T_i] matrix at 257 * foff[i]) and ``foff`` / ``frames``.
+        Device mode (``device_io``): ``wav`` and ``out = (band, mag, phase, psd)`` are raw device
+        pointers (ints or None)."""
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        n = int(lens.shape[0])
+        frames = 1 + lens.astype(np.int64) // 256
+        foff = np.concatenate(([0], np.cumsum(frames)[:-1])).astype(np.int64) if n else np.zeros(0, np.int64)
+        tot = int(frames.sum())
+        flags = (FEAT_NOISE if noise else 0) | (FEAT_DEVICE_IO if device_io else 0) | (0 if normalization else FEAT_NO_POWER)
+        res = {"foff": foff, "frames": frames}
+        if device_io:
+            pw = int(wav)
+            ptrs = [None if p is None else int(p) for p in out]
+        else:
+            wav = np.ascontiguousarray(wav, dtype=np.float32)
+            pw = wav.ctypes.data
+            res["band"] = np.empty((tot, 64), dtype=np.float32)
+            if want_mag:
+                res["mag"] = np.empty(257 * tot, dtype=np.float32)
+            if want_phase:
+                res["phase"] = np.empty(257 * tot, dtype=np.float32)
+            if want_psd and noise:
+                res["psd"] = np.empty(257 * tot, dtype=np.float32)
+            ptrs = [res[k].ctypes.data if k in res else None for k in ("band", "mag", "phase", "psd")]
+        rc = self._lib.nele_features(self._h, pw, offs.ctypes.data, lens.ctypes.data, n, flags, float(power), ptrs[0],
+                                     ptrs[1], ptrs[2], ptrs[3], None if stream is None else int(stream))
+        self._check(rc, "nele_features")
+        return res
+
+    def features(self, signals, power=1.0 / 6.0, noise=False, normalization=True, want_psd=False):
+        """Per-signal ``(bandE [T, 64], mag [257, T], phase [257, T])`` tuples (plus the noise PSD
+        [257, T] when ``want_psd``) for a list of 1-D signals -- the return values of
+        ``Sp_and_phase_Speech`` / ``Sp_and_phase_Noise`` (audio_util.py:422-457)."""
+        signals = [np.asarray(x, dtype=np.float32) for x in signals]
+        if not signals:
+            return []
+        flat, offs, lens = pack(signals)
+        r = self.features_packed(flat, offs, lens, power=power, noise=noise, normalization=normalization,
+                                 want_psd=want_psd)
+        out = []
+        for i in range(len(signals)):
+            T, fo = int(r["frames"][i]), int(r["foff"][i])
+            item = [r["band"][fo:fo + T], r["mag"][257 * fo:257 * (fo + T)].reshape(257, T),
+                    r["phase"][257 * fo:257 * (fo + T)].reshape(257, T)]
+            if want_psd and noise:
+                item.append(r["psd"][257 * fo:257 * (fo + T)].reshape(257, T))
+            out.append(tuple(item))
+        return out
 
     def last_timing(self):
         """(kernel milliseconds, kernel launches) of the last call."""

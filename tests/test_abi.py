@@ -25,7 +25,8 @@ def declared_functions():
 def test_header_declares_the_boundary():
     names = declared_functions()
     for need in ("nele_create", "nele_destroy", "nele_score_batch", "nele_last_error", "nele_get_stage",
-                 "nele_last_timing", "nele_abi_version", "nele_set_profiling", "nele_kernel_time"):
+                 "nele_last_timing", "nele_abi_version", "nele_set_profiling", "nele_kernel_time", "nele_features",
+                 "nele_feature_frames"):
         assert need in names
 
 
