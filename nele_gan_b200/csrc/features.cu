@@ -84,17 +84,22 @@ __device__ __forceinline__ float band_energy(const float* sq, int b) {
   return (float)acc;
 }
 
-// bandE ** power in float32 (audio_util.py:432): numpy calls powf; the double pow rounded to
-// float32 is the correctly rounded value, which glibc's powf returns too.
+// bandE ** power in float32 (audio_util.py:432): numpy calls powf too (CUDA's is within 4 ulp; the
+// correctly rounded double pow costs ten times as much -- it was the largest item of feat_stft).
 __device__ __forceinline__ float band_power(float v, float power, int normalize) {
-  return normalize ? (float)pow((double)v, (double)power) : v;
+  return normalize ? powf(v, power) : v;
 }
 
-struct StftSmem {
-  double2 buf[4][kNfft];
-  double2 tw[kNfft];
+// exp(-2 pi i m / 512), m = 0..511 (host-computed, uploaded once; 8 KB, L1-resident)
+__device__ double2 d_tw512[kNfft];
+
+struct StftMagPh {
   float mag[kTileFrames][kBins + 3];
   float ph[kTileFrames][kBins + 3];
+};
+union StftSmem {   // the spectra are consumed into registers before magnitude / phase overwrite them
+  double2 buf[4][kNfft];
+  StftMagPh o;
 };
 
 __global__ void __launch_bounds__(256) feat_stft_kernel(const float* __restrict__ wav, const int64_t* __restrict__ offs,
@@ -102,21 +107,18 @@ __global__ void __launch_bounds__(256) feat_stft_kernel(const float* __restrict_
                                                          const int64_t* __restrict__ foff, const int2* __restrict__ tiles,
                                                          float power, int normalize, float* __restrict__ band,
                                                          float* __restrict__ mag, float* __restrict__ phase) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  StftSmem& sm = *reinterpret_cast<StftSmem*>(smem_raw);
+  __shared__ __align__(16) StftSmem sm;
+  __shared__ int nonzero[kTileFrames];   // an all-zero frame (digital silence) must come out exactly zero:
+                                         // paired with a live frame it would pick up that frame's roundoff
   const int tid = threadIdx.x;
+  if (tid < kTileFrames) nonzero[tid] = 0;
+  __syncthreads();
   const int2 tile = tiles[blockIdx.x];
   const int u = tile.x, t0 = tile.y;
   const int L = lens[u];
   const int T = 1 + L / kHop;
   const float* x = wav + offs[u];
 
-  for (int m = tid; m < kNfft; m += 256) {
-    double s, c;
-    sincospi((double)m / 256.0, &s, &c);
-    sm.tw[m] = make_double2(c, -s);
-  }
-  __syncthreads();
   // windowed frames: FFT q takes frame 2q as its real and frame 2q + 1 as its imaginary part
   for (int e = tid; e < kTileFrames * kNfft; e += 256) {
     int f = e >> 9, n = e & 511;
@@ -126,7 +128,8 @@ __global__ void __launch_bounds__(256) feat_stft_kernel(const float* __restrict_
       int p = t * kHop + n - kNfft / 2;   // centred frame, reflect padding (np.pad(..., mode='reflect'))
       if (p < 0) p = -p;
       if (p >= L) p = 2 * (L - 1) - p;
-      v = (0.5 - 0.5 * sm.tw[n].x) * (double)x[p];
+      v = (0.5 - 0.5 * __ldg(&d_tw512[n].x)) * (double)x[p];
+      if (v != 0.0) nonzero[f] = 1;
     }
     double* dst = reinterpret_cast<double*>(&sm.buf[f >> 1][n]);
     dst[f & 1] = v;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(256) feat_stft_kernel(const float* __restrict_
       if (stage > 0) {
         const int k = (j & (Ns - 1)) * (64 / Ns);
 #pragma unroll
-        for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], sm.tw[k * r]);
+        for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], __ldg(&d_tw512[k * r]));
       }
       fft8(v);
       __syncthreads();
@@ -154,17 +157,42 @@ __global__ void __launch_bounds__(256) feat_stft_kernel(const float* __restrict_
     }
   }
   // split Z = A + iB into the spectra of the two real frames, round to complex64, |.| and angle
-  for (int e = tid; e < 4 * kBins; e += 256) {
-    int q = e / kBins, k = e - q * kBins;
-    double2 zk = sm.buf[q][k], zn = sm.buf[q][(kNfft - k) & (kNfft - 1)];
-    float are = (float)(0.5 * (zk.x + zn.x)), aim = (float)(0.5 * (zk.y - zn.y));
-    float bre = (float)(0.5 * (zk.y + zn.y)), bim = (float)(-0.5 * (zk.x - zn.x));
-    if (k == 0 || k == kBins - 1) aim = 0.f, bim = 0.f;   // a real FFT returns +0 there
-    // np.abs(complex64) = hypotf; glibc evaluates it as the rounded double sqrt of the exact sum of squares
-    sm.mag[2 * q][k] = (float)sqrt((double)are * are + (double)aim * aim);
-    sm.mag[2 * q + 1][k] = (float)sqrt((double)bre * bre + (double)bim * bim);
-    sm.ph[2 * q][k] = atan2f(aim, are);
-    sm.ph[2 * q + 1][k] = atan2f(bim, bre);
+  {
+    float rm[5][2], rp[5][2];
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int e = tid + it * 256;
+      if (e < 4 * kBins) {
+        int q = e / kBins, k = e - q * kBins;
+        double2 zk = sm.buf[q][k], zn = sm.buf[q][(kNfft - k) & (kNfft - 1)];
+        float are = (float)(0.5 * (zk.x + zn.x)), aim = (float)(0.5 * (zk.y - zn.y));
+        float bre = (float)(0.5 * (zk.y + zn.y)), bim = (float)(-0.5 * (zk.x - zn.x));
+        if (k == 0 || k == kBins - 1) aim = 0.f, bim = 0.f;   // a real FFT returns +0 there
+        if (!nonzero[2 * q]) are = aim = 0.f;
+        if (!nonzero[2 * q + 1]) bre = bim = 0.f;
+        // np.abs(complex64) = hypotf; glibc evaluates it as the rounded double sqrt of the exact sum of squares
+        rm[it][0] = (float)sqrt((double)are * are + (double)aim * aim);
+        rm[it][1] = (float)sqrt((double)bre * bre + (double)bim * bim);
+        if (phase) {
+          rp[it][0] = atan2f(aim, are);
+          rp[it][1] = atan2f(bim, bre);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int e = tid + it * 256;
+      if (e < 4 * kBins) {
+        int q = e / kBins, k = e - q * kBins;
+        sm.o.mag[2 * q][k] = rm[it][0];
+        sm.o.mag[2 * q + 1][k] = rm[it][1];
+        if (phase) {
+          sm.o.ph[2 * q][k] = rp[it][0];
+          sm.o.ph[2 * q + 1][k] = rp[it][1];
+        }
+      }
+    }
   }
   __syncthreads();
   const int64_t fo = foff[u];
@@ -173,8 +201,8 @@ __global__ void __launch_bounds__(256) feat_stft_kernel(const float* __restrict_
     int k = e >> 3, f = e & 7;
     int t = t0 + f;
     if (t < T) {
-      if (mag) mag[mbase + (int64_t)k * T + t] = sm.mag[f][k];
-      if (phase) phase[mbase + (int64_t)k * T + t] = sm.ph[f][k];
+      if (mag) mag[mbase + (int64_t)k * T + t] = sm.o.mag[f][k];
+      if (phase) phase[mbase + (int64_t)k * T + t] = sm.o.ph[f][k];
     }
   }
   if (band) {
@@ -182,14 +210,14 @@ __global__ void __launch_bounds__(256) feat_stft_kernel(const float* __restrict_
     // square in place (float32, as X[iT, k] ** 2), then the 64 bands of each frame
     for (int e = tid; e < kBins * kTileFrames; e += 256) {
       int f = e / kBins, k = e - f * kBins;
-      float a = sm.mag[f][k];
-      sm.mag[f][k] = __fmul_rn(a, a);
+      float a = sm.o.mag[f][k];
+      sm.o.mag[f][k] = __fmul_rn(a, a);
     }
     __syncthreads();
     for (int e = tid; e < kFeatBands * kTileFrames; e += 256) {
       int f = e >> 6, b = e & 63;
       int t = t0 + f;
-      if (t < T) band[(fo + t) * kFeatBands + b] = band_power(band_energy(sm.mag[f], b), power, normalize);
+      if (t < T) band[(fo + t) * kFeatBands + b] = band_power(band_energy(sm.o.mag[f], b), power, normalize);
     }
   }
 }
@@ -202,7 +230,6 @@ constexpr int kIS = 15, kU = 8, kV = 15;   // noise_est/imcra.py:181,192,194 (im
 struct ImcraSmem {
   float tile[kBins][kImcraTile + 1];
   double P[kBins + 2], I[kBins + 2], IP[kBins + 2];
-  float nsq[kBins + 3];
 };
 
 // fsmooth (noise_est/imcra.py:336-337) with w = 1: sym_hanning(3) = [0.5, 1, 0.5], truncated at the
@@ -213,7 +240,7 @@ __device__ __forceinline__ double fsmooth3(const double* a, int k) {
   return 0.25 * a[k] + 0.5 * a[k + 1] + 0.25 * a[k + 2];
 }
 
-__global__ void __launch_bounds__(kImcraThreads) feat_imcra_kernel(const float* __restrict__ mag,
+__global__ void __launch_bounds__(kImcraThreads, 3) feat_imcra_kernel(const float* __restrict__ mag,
                                                                     const int64_t* __restrict__ foff,
                                                                     const int32_t* __restrict__ lens, float power,
                                                                     int normalize, float* __restrict__ band,
@@ -282,10 +309,12 @@ __global__ void __launch_bounds__(kImcraThreads) feat_imcra_kernel(const float* 
           Lam32 = __fadd_rn(__fmul_rn(0.85f, Lam32), __fmul_rn(0.15f, P32));
           Lam = (double)Lam32;
         }
+        __syncthreads();   // the next frame overwrites sm.P (the other branch has its own barrier)
       } else {
         double Iv = 0;
         if (live) {
-          double Gmin = P / (Bmin * Smin), zeta = S / (Bmin * Smin);   // :411-414
+          const double rmin = 1.0 / (Bmin * Smin);                    // :411-414, one reciprocal for both ratios
+          double Gmin = P * rmin, zeta = S * rmin;
           Iv = (Gmin < Gamma0 && zeta < zeta0) ? 1.0 : 0.0;
           sm.I[k + 1] = Iv;
           sm.IP[k + 1] = Iv * P;
@@ -297,7 +326,8 @@ __global__ void __launch_bounds__(kImcraThreads) feat_imcra_kernel(const float* 
           tS = alpha_s * tS + (1.0 - alpha_s) * tSf;
           tSmin = fmin(tSmin, tS);
           tSmin_sw = fmin(tSmin_sw, tS);
-          double tG = P / (Bmin * tSmin), tz = S / (Bmin * tSmin);      // :429-430
+          const double trmin = 1.0 / (Bmin * tSmin);                  // :429-430
+          double tG = P * trmin, tz = S * trmin;
           double q = 0.0;
           if (tz < zeta0) {
             if (tG <= 1.0) q = 1.0;
@@ -305,8 +335,8 @@ __global__ void __launch_bounds__(kImcraThreads) feat_imcra_kernel(const float* 
           }
           double p = 0.0;                                              // post_speech_prob (:23-38)
           if (q < 1.0) {
-            double nu = Gamma * xi / (1.0 + xi);
-            p = 1.0 / (1.0 + (q / (1.0 - q)) * (1.0 + xi) * exp(-nu));
+            const double nu = Gamma * G;   // Gamma xi / (1 + xi), G = xi / (1 + xi) from above
+            p = q > 0.0 ? (1.0 - q) / ((1.0 - q) + q * (1.0 + xi) * exp(-nu)) : 1.0;
           }
           p = fmin(p, p_up);
           double ta = alpha_d + (1.0 - alpha_d) * p;                   // :443-447
@@ -331,20 +361,33 @@ __global__ void __launch_bounds__(kImcraThreads) feat_imcra_kernel(const float* 
           ++ucnt;
         }
       }
-      if (live) {
-        float lam = (float)Lam;   // N_PSD is float32 (:531,568)
-        sm.tile[k][tt] = lam;
-        float s = sqrtf(lam);     // compute_band_E(np.sqrt(estPSD)) squares the root again (audio_util.py:447)
-        sm.nsq[k] = __fmul_rn(s, s);
-      }
-      __syncthreads();
-      if (band && k < kFeatBands) band[(fo + l) * kFeatBands + k] = band_power(band_energy(sm.nsq, k), power, normalize);
+      if (live) sm.tile[k][tt] = (float)Lam;   // N_PSD is float32 (:531,568); the cell has been consumed
     }
+    __syncthreads();
     if (PSD) {
-      __syncthreads();
       for (int row = warp; row < kBins; row += kImcraThreads / 32) {
         int t = tb + lane;
         if (t < T) PSD[(int64_t)row * T + t] = sm.tile[row][lane];
+      }
+      __syncthreads();
+    }
+    if (band) {
+      // noise band energies of the tile's frames, all threads: compute_band_E(np.sqrt(estPSD)) squares the
+      // float32 root again (audio_util.py:445-447)
+      if (live)
+        for (int tt = 0; tt < nt; ++tt) {
+          float r = sqrtf(sm.tile[k][tt]);
+          sm.tile[k][tt] = __fmul_rn(r, r);
+        }
+      __syncthreads();
+      for (int e = threadIdx.x; e < nt * kFeatBands; e += kImcraThreads) {
+        const int tt = e >> 6, b = e & 63;
+        double acc = 0.0;
+        if (b > 0)
+          for (int kk = c_gmt[b - 1]; kk < c_gmt[b]; ++kk) acc += (double)__fmul_rn(__ldg(&d_wnext[kk]), sm.tile[kk][tt]);
+        if (b < kFeatBands - 1)
+          for (int kk = c_gmt[b]; kk < c_gmt[b + 1]; ++kk) acc += (double)__fmul_rn(__ldg(&d_wown[kk]), sm.tile[kk][tt]);
+        band[(fo + tb + tt) * kFeatBands + b] = band_power((float)acc, power, normalize);
       }
     }
   }
@@ -372,13 +415,19 @@ int features_run(const float* wav, const int64_t* offs, const int32_t* lens, con
     }
     cudaMemcpyToSymbolAsync(d_wown, wown, sizeof(wown), 0, cudaMemcpyHostToDevice, s);
     cudaMemcpyToSymbolAsync(d_wnext, wnext, sizeof(wnext), 0, cudaMemcpyHostToDevice, s);
+    static double2 tw[kNfft];
+    for (int m = 0; m < kNfft; ++m) {
+      // exact octant symmetries so that the table is as symmetric as pocketfft's
+      const double a = 2.0 * 3.14159265358979323846 * m / kNfft;
+      tw[m] = make_double2(m == 128 || m == 384 ? 0.0 : cos(a), m == 0 || m == 256 ? 0.0 : -sin(a));
+    }
+    cudaMemcpyToSymbolAsync(d_tw512, tw, sizeof(tw), 0, cudaMemcpyHostToDevice, s);
     cudaStreamSynchronize(s);
-    cudaFuncSetAttribute(feat_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem));
     ready = true;
   }
   int launches = 0;
   kt_begin(kt, "feat_stft", s);
-  feat_stft_kernel<<<ntiles, 256, sizeof(StftSmem), s>>>(wav, offs, lens, foff, tiles, power, normalize ? 1 : 0,
+  feat_stft_kernel<<<ntiles, 256, 0, s>>>(wav, offs, lens, foff, tiles, power, normalize ? 1 : 0,
                                                          noise ? nullptr : band, mag, phase);
   kt_end(kt, s);
   ++launches;
