@@ -334,6 +334,7 @@ static int ensure_tables(nele_engine* e, int fs, bool haspi_rate_ok, const doubl
     RESERVE(e, e->st_taps, pt.taps.size() * sizeof(double));
     CU(e, cudaMemcpyAsync(e->st_taps.p, pt.taps.data(), pt.taps.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     CU(e, cudaStreamSynchronize(s));
+    estoi_upload_polytaps(pt.taps.data(), pt.up, pt.K, s);
     e->st_fs = fs;
     e->st_up = pt.up;
     e->st_down = pt.down;

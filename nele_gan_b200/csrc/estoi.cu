@@ -15,6 +15,8 @@
 //                          normalisation and the correlation sum
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace nele {
@@ -79,6 +81,85 @@ __global__ void __launch_bounds__(kRsThreads) estoi_resample_kernel(EstoiGeom g,
   for (int j = 0; j < kRsJ; ++j) {
     const int mj = m + j * nthr;
     if (mj < n_out) dst[mj] = (float)acc[j];
+  }
+}
+
+// 16 -> 10 kHz fast path (up = 5, down = 8, 2K + 1 <= 128 taps per branch; K = 59 for pystoi's
+// filter).  Warp = output phase (t mod 5, i.e. one polyphase branch: the tap of a step is one
+// broadcast read), lane = group of 20 outputs; a thread owns the four outputs t = 20 v + phi + 5 j
+// of its group, whose inputs sit 8 apart, so the inputs slide through a 32-register ring: per tap
+// one tap load, one new input and four FP64 FMAs (the generic kernel re-reads and re-converts four
+// inputs per tap).  Inputs are staged as FP64 with a (u + u / 32) skew -- lanes 32 samples apart
+// hit distinct banks -- and the taps are zero padded to 128 so the ring indices are static.
+constexpr int kRfG = 32, kRfThreads = 5 * kRfG, kRfTile = 20 * kRfG, kRfNt = 128;
+constexpr int kRfSpan = 32 * kRfG + 126;
+__constant__ double c_rf_tap[5][kRfNt];   // zero padded branches (estoi_upload_polytaps); a warp reads one entry per step
+
+constexpr int kRfTilesPerCta = 4;
+constexpr int kRfPre = (kRfSpan + kRfThreads - 1) / kRfThreads;   // staged inputs per thread and tile
+
+__global__ void __launch_bounds__(kRfThreads, 4) estoi_resample58_kernel(EstoiGeom g, EstoiBuffers b) {
+  const int pair = blockIdx.y, q = blockIdx.z, tid = threadIdx.x;
+  const int n_out = g.n10[pair];
+  const int Tfirst = blockIdx.x * (kRfTilesPerCta * kRfTile);
+  if (Tfirst >= n_out) return;
+  const float* __restrict__ src = (q == 0 ? b.ref : b.deg) + g.off16[pair];
+  const int L = g.len16[pair];
+  float* __restrict__ dst = b.x10 + (int64_t)q * b.tot10 + g.off10[pair];
+  __shared__ double s_in[kRfSpan + kRfSpan / 32 + 2];
+  __shared__ float s_out[kRfTile];
+  const int phi = tid >> 5, v = tid & 31;
+  const double* __restrict__ tp = c_rf_tap[(8 * phi) % 5];
+  const int u0 = 32 * v + (8 * phi) / 5 + (kRfNt - 1);   // staged index of x[n + K] for the first output
+  // staged index i <-> x[inbase + i]; output t with n = floor(8 t / 5) reads x[n + K - kk], kk = 0..127.
+  // The inputs of the next tile are fetched into registers while the current one is computed.
+  float pre[kRfPre];
+  auto fetch = [&](int T0) {
+    const int inbase = (T0 / 5) * 8 + b.K - (kRfNt - 1);
+#pragma unroll
+    for (int c = 0; c < kRfPre; ++c) {
+      const int j = inbase + tid + c * kRfThreads;
+      pre[c] = (j >= 0 && j < L) ? __ldg(src + j) : 0.f;
+    }
+  };
+  fetch(Tfirst);
+  for (int tile = 0; tile < kRfTilesPerCta; ++tile) {
+    const int T0 = Tfirst + tile * kRfTile;
+    if (T0 >= n_out) break;
+#pragma unroll
+    for (int c = 0; c < kRfPre; ++c) {
+      const int i = tid + c * kRfThreads;
+      if (i < kRfSpan) s_in[i + (i >> 5)] = (double)pre[c];
+    }
+    __syncthreads();
+    if (tile + 1 < kRfTilesPerCta && T0 + kRfTile < n_out) fetch(T0 + kRfTile);
+    double w[32];
+#pragma unroll
+    for (int i = 1; i <= 24; ++i) {
+      const int u = u0 + i;
+      w[32 - i] = s_in[u + (u >> 5)];
+    }
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 1
+    for (int kk0 = 0; kk0 < kRfNt; kk0 += 32) {
+#pragma unroll
+      for (int sft = 0; sft < 32; ++sft) {
+        const int u = u0 - kk0 - sft;
+        w[sft] = s_in[u + (u >> 5)];
+        const double t = tp[kk0 + sft];
+        a0 = fma(t, w[sft], a0);
+        a1 = fma(t, w[(sft + 24) & 31], a1);   // loaded 8 steps ago: x 8 samples later
+        a2 = fma(t, w[(sft + 16) & 31], a2);
+        a3 = fma(t, w[(sft + 8) & 31], a3);
+      }
+    }
+    const int tl = 20 * v + phi;
+    s_out[tl] = (float)a0;
+    s_out[tl + 5] = (float)a1;
+    s_out[tl + 10] = (float)a2;
+    s_out[tl + 15] = (float)a3;
+    __syncthreads();   // also: every read of s_in is done before the next tile overwrites it
+    for (int t = tid; t < kRfTile && T0 + t < n_out; t += kRfThreads) dst[T0 + t] = s_out[t];
   }
 }
 
@@ -366,6 +447,21 @@ void estoi_upload_tables(const float* win, const int* lo, const int* hi, const f
   cudaStreamSynchronize(s);
 }
 
+// taps [up][2K + 1] of the polyphase resampler (host_tables.hpp make_estoi_polytaps): the 16 -> 10 kHz
+// fast path keeps them zero padded in constant memory
+static bool g_rf_taps_ok = false;
+void estoi_upload_polytaps(const double* taps, int up, int K, cudaStream_t s) {
+  g_rf_taps_ok = false;
+  const int nt = 2 * K + 1;
+  if (up != 5 || nt > kRfNt) return;
+  static double padded[5][kRfNt];
+  for (int r = 0; r < 5; ++r)
+    for (int k = 0; k < kRfNt; ++k) padded[r][k] = k < nt ? taps[r * nt + k] : 0.0;
+  cudaMemcpyToSymbolAsync(c_rf_tap, padded, sizeof(padded), 0, cudaMemcpyHostToDevice, s);
+  cudaStreamSynchronize(s);
+  g_rf_taps_ok = true;
+}
+
 int estoi_run(const EstoiGeom& g, const EstoiBuffers& b, int n, int max_n10, int max_nfa, bool classic, KernelTimer* kt,
               cudaStream_t s) {
   int launches = 0;
@@ -377,8 +473,12 @@ int estoi_run(const EstoiGeom& g, const EstoiBuffers& b, int n, int max_n10, int
   const size_t smem = (size_t)span * sizeof(float) + (taps_in_smem ? tap_bytes : 0);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(estoi_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static const bool generic_only = getenv("NELE_ESTOI_RESAMPLE_GENERIC") != nullptr;   // A/B switch
   kt_begin(kt, "estoi_resample", s);
-  estoi_resample_kernel<<<dim3((max_n10 + tile - 1) / tile, n, 2), kRsThreads, smem, s>>>(g, b, span, groups, taps_in_smem);
+  if (b.up == 5 && b.down == 8 && g_rf_taps_ok && !generic_only)
+    estoi_resample58_kernel<<<dim3((max_n10 + kRfTilesPerCta * kRfTile - 1) / (kRfTilesPerCta * kRfTile), n, 2), kRfThreads, 0, s>>>(g, b);
+  else
+    estoi_resample_kernel<<<dim3((max_n10 + tile - 1) / tile, n, 2), kRsThreads, smem, s>>>(g, b, span, groups, taps_in_smem);
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "estoi_vad", s);

@@ -123,6 +123,7 @@ struct EstoiBuffers {
   int32_t* status;   // [n]
 };
 void estoi_upload_tables(const float* win, const int* lo, const int* hi, const float* tw, cudaStream_t s);
+void estoi_upload_polytaps(const double* taps, int up, int K, cudaStream_t s);
 int estoi_run(const EstoiGeom& g, const EstoiBuffers& b, int n, int max_n10, int max_nfa, bool classic, KernelTimer* kt,
               cudaStream_t s);
 
