@@ -65,7 +65,7 @@ constexpr int kPrepThreads = 256;
 constexpr int kPrepGroups = 85;                       // 3 threads x 4 outputs each = 12 outputs per group
 constexpr int kPrepSpan = kPrepGroups * 8 + 128 + 16;  // staged inputs per tile
 
-__global__ void __launch_bounds__(kPrepThreads) haspi_prep_kernel(PairGeom g, HaspiBuffers b) {
+__global__ void __launch_bounds__(kPrepThreads, 4) haspi_prep_kernel(PairGeom g, HaspiBuffers b) {
   const int pair = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
   const float* __restrict__ src = (q == 0 ? b.ref : b.deg) + g.off16[pair];
   const int L = g.len16[pair];
@@ -111,15 +111,29 @@ __global__ void __launch_bounds__(kPrepThreads) haspi_prep_kernel(PairGeom g, Ha
     const int n_out = (int)(((int64_t)L * 3) / 2);  // int(L * ratio); the tail up to N is zero (fix_length)
     const int v_loc = tid / 3, phi = tid % 3;
     const bool worker = tid < kPrepGroups * 3;
+    // the inputs of the next tile are fetched into registers while the current one is computed
+    constexpr int kPre = (kPrepSpan + kPrepThreads - 1) / kPrepThreads;
+    float pre[kPre];
+    auto fetch = [&](int tile0) {
+      const int in0 = (tile0 / 12) * 8 - 63;
+#pragma unroll
+      for (int c = 0; c < kPre; ++c) {
+        const int jx = in0 + tid + c * kPrepThreads;
+        pre[c] = (jx >= 0 && jx < L) ? __ldg(src + jx) : 0.f;
+      }
+    };
+    fetch(0);
     for (int tile0 = 0; tile0 < N; tile0 += kPrepGroups * 12) {
       // inputs needed: n in [8 V0 - 63, 8 (V0 + groups) + 1 + 64 + 6], V0 = tile0 / 12
       const int in0 = (tile0 / 12) * 8 - 63;
       __syncthreads();
-      for (int u = tid; u < kPrepSpan; u += kPrepThreads) {
-        const int jx = in0 + u;
-        s_xin[u + (u >> 3)] = (jx >= 0 && jx < L) ? (double)src[jx] : 0.0;
+#pragma unroll
+      for (int c = 0; c < kPre; ++c) {
+        const int u = tid + c * kPrepThreads;
+        if (u < kPrepSpan) s_xin[u + (u >> 3)] = (double)pre[c];
       }
       __syncthreads();
+      if (tile0 + kPrepGroups * 12 < N) fetch(tile0 + kPrepGroups * 12);
       if (worker) {
         const int t0 = tile0 + 12 * v_loc + phi;       // first of the four outputs
         const int n = (2 * t0) / 3, r = (2 * t0) % 3;  // t0 = 12 v + phi -> n = 8 v + {0, 0, 1}
@@ -189,8 +203,31 @@ __global__ void __launch_bounds__(kPrepThreads) haspi_prep_kernel(PairGeom g, Ha
   //    is re-run from its exact initial state.
   const int Lc = (N + kPrepThreads - 1) / kPrepThreads;
   const int t0 = min(tid * Lc, N), t1 = min(t0 + Lc, N);
+  // A thread's chunk is contiguous, so lanes are Lc samples apart: the samples go through a
+  // per-warp shared-memory tile, eight per lane and round, moved with 32-byte row segments (four
+  // chunks per warp instruction) instead of one sector per lane and instruction.
+  __shared__ float s_tx[kPrepThreads / 32][32][9];
+  __shared__ double s_tm[kPrepThreads / 32][32][9];
+  const int lane = tid & 31, wib = tid >> 5;
+  float (*tx)[9] = s_tx[wib];
+  double (*tm)[9] = s_tm[wib];
+  const int rounds = (Lc + 7) / 8;
+  const int crow = lane >> 3, ccol = lane & 7;   // cooperative moves: rows 4 i + crow, column ccol
   MidState st = {0.0, 0.0, 0.0};
-  for (int t = t0; t < t1; ++t) mid_step(st, (double)(float)((double)x24[t] * scale));
+  for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = 4 * i + crow;
+      const int r0 = min((wib * 32 + row) * Lc, N), r1 = min(r0 + Lc, N);
+      const int t = r0 + 8 * r + ccol;
+      tx[row][ccol] = (t < r1) ? x24[t] : 0.f;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (t0 + 8 * r + i < t1) mid_step(st, (double)(float)((double)tx[lane][i] * scale));
+    __syncwarp();
+  }
   s_loc[tid][0] = st.z0;
   s_loc[tid][1] = st.z1;
   s_loc[tid][2] = st.z2;
@@ -221,10 +258,34 @@ __global__ void __launch_bounds__(kPrepThreads) haspi_prep_kernel(PairGeom g, Ha
   st.z0 = s_loc[tid][0];
   st.z1 = s_loc[tid][1];
   st.z2 = s_loc[tid][2];
-  for (int t = t0; t < t1; ++t) {
-    const float v = (float)((double)x24[t] * scale);
-    x24[t] = v;
-    mid[t] = mid_step(st, (double)v);
+  for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = 4 * i + crow;
+      const int r0 = min((wib * 32 + row) * Lc, N), r1 = min(r0 + Lc, N);
+      const int t = r0 + 8 * r + ccol;
+      tx[row][ccol] = (t < r1) ? x24[t] : 0.f;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (t0 + 8 * r + i < t1) {
+        const float v = (float)((double)tx[lane][i] * scale);
+        tx[lane][i] = v;
+        tm[lane][i] = mid_step(st, (double)v);
+      }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = 4 * i + crow;
+      const int r0 = min((wib * 32 + row) * Lc, N), r1 = min(r0 + Lc, N);
+      const int t = r0 + 8 * r + ccol;
+      if (t < r1) {
+        x24[t] = tx[row][ccol];
+        mid[t] = tm[row][ccol];
+      }
+    }
+    __syncwarp();
   }
 }
 
