@@ -545,7 +545,10 @@ __global__ void __launch_bounds__(128) siib_smalltri_kernel(SiibGeom g, SiibBuff
   double* __restrict__ tt = eb.tau + (int64_t)lp * kELd;
   for (int idx = tid; idx < kSN * kSN; idx += 128) s_A[(idx / kSN) * kSNp + idx % kSN] = M[idx];
   __syncthreads();
-  const bool own = tid < kSN;
+  // rows / columns >= r are zero padding: nothing to annihilate there (tau = 0), so the inner loops
+  // stop at n = r rounded up to a multiple of four
+  const int n = min(kSN, (r + 3) & ~3);
+  const bool own = tid < n;
   for (int k = 0; k < kSN - 2; ++k) {
     const double x = (own && tid > k) ? s_A[k * kSNp + tid] : 0.0;
     const double sig = block_sum((tid > k + 1) ? x * x : 0.0, red);
@@ -566,13 +569,13 @@ __global__ void __launch_bounds__(128) siib_smalltri_kernel(SiibGeom g, SiibBuff
     if (own && tid > k) {
       double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
       int j = k + 1;
-      for (; j + 4 <= kSN; j += 4) {
+      for (; j + 4 <= n; j += 4) {
         p0 = fma(s_A[j * kSNp + tid], s_v[j], p0);
         p1 = fma(s_A[(j + 1) * kSNp + tid], s_v[j + 1], p1);
         p2 = fma(s_A[(j + 2) * kSNp + tid], s_v[j + 2], p2);
         p3 = fma(s_A[(j + 3) * kSNp + tid], s_v[j + 3], p3);
       }
-      for (; j < kSN; ++j) p0 = fma(s_A[j * kSNp + tid], s_v[j], p0);
+      for (; j < n; ++j) p0 = fma(s_A[j * kSNp + tid], s_v[j], p0);
       p = tau * ((p0 + p1) + (p2 + p3));
     }
     const double pv = block_sum(p * vi, red);
@@ -581,7 +584,7 @@ __global__ void __launch_bounds__(128) siib_smalltri_kernel(SiibGeom g, SiibBuff
     __syncthreads();
     if (own && tid > k) {
 #pragma unroll 4
-      for (int j = k + 1; j < kSN; ++j) s_A[j * kSNp + tid] -= s_v[j] * w + s_w[j] * vi;
+      for (int j = k + 1; j < n; ++j) s_A[j * kSNp + tid] -= s_v[j] * w + s_w[j] * vi;
     }
     __syncthreads();
   }

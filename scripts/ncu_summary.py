@@ -33,7 +33,7 @@ def main(path, header=""):
         for w, _ in WANT:
             try:
                 i = hdr.index(w)
-                v = float(r[i]) * SCALE.get(units[i], 1)
+                v = float(r[i]) * (1 if _.startswith('st_') else SCALE.get(units[i], 1))   # stall ratios carry the unit 'inst'
                 vals.append('%8.2f' % v)
             except Exception:
                 vals.append('%8s' % '-')
