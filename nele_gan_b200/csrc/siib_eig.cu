@@ -469,10 +469,18 @@ namespace nele {
 
 constexpr int kSN = 112, kSNp = kSN + 1;  // padded Gram dimension, shared-memory row stride
 
-__global__ void __launch_bounds__(256) siib_gram_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_hi) {
-  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+// M = L^T L is symmetric: a thread owns one 7 x 7 tile (ty, tx) of the lower triangle (136 tiles for
+// the 16 x 16 tile grid, 160 threads) and stores it to both halves; tiles beyond the rank are zero.
+constexpr int kGramThreads = 160;
+
+__global__ void __launch_bounds__(kGramThreads) siib_gram_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_hi) {
+  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x;
   const int r = b.rank[pair];
   if (r < 2 || r > rank_hi) return;
+  int ty = 0;
+  while ((ty + 1) * (ty + 2) / 2 <= tid) ++ty;   // tid = ty (ty + 1) / 2 + tx, tx <= ty
+  const int tx = tid - ty * (ty + 1) / 2;
+  const bool work = tid < 136 && 7 * tx < r;     // 7 tx <= 7 ty: a tile left of the rank boundary has live columns
   const float* __restrict__ G = b.G + (int64_t)lp * kEDim * kELd;
   __shared__ float sL[kSN][33];
   double acc[7][7];
@@ -482,30 +490,36 @@ __global__ void __launch_bounds__(256) siib_gram_kernel(SiibGeom g, SiibBuffers 
     for (int j = 0; j < 7; ++j) acc[i][j] = 0.0;
   for (int row0 = 0; row0 < kEDim; row0 += 32) {
     __syncthreads();
-    for (int idx = tid; idx < kSN * 32; idx += 256) {
+    for (int idx = tid; idx < kSN * 32; idx += kGramThreads) {
       const int c = idx >> 5, rr = idx & 31;
       sL[c][rr] = (c < r && row0 + rr < kEDim) ? G[(int64_t)c * kELd + row0 + rr] : 0.f;
     }
     __syncthreads();
+    if (work && 7 * ty < r) {
 #pragma unroll 4
-    for (int rr = 0; rr < 32; ++rr) {
-      double a[7], c[7];
+      for (int rr = 0; rr < 32; ++rr) {
+        double a[7], c[7];
 #pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        a[i] = (double)sL[7 * ty + i][rr];
-        c[i] = (double)sL[7 * tx + i][rr];
+        for (int i = 0; i < 7; ++i) {
+          a[i] = (double)sL[7 * ty + i][rr];
+          c[i] = (double)sL[7 * tx + i][rr];
+        }
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+#pragma unroll
+          for (int j = 0; j < 7; ++j) acc[i][j] = fma(a[i], c[j], acc[i][j]);
       }
-#pragma unroll
-      for (int i = 0; i < 7; ++i)
-#pragma unroll
-        for (int j = 0; j < 7; ++j) acc[i][j] = fma(a[i], c[j], acc[i][j]);
     }
   }
+  if (tid >= 136) return;
   double* __restrict__ M = eb.gram + (int64_t)lp * kSN * kSN;
 #pragma unroll
   for (int i = 0; i < 7; ++i)
 #pragma unroll
-    for (int j = 0; j < 7; ++j) M[(7 * ty + i) * kSN + 7 * tx + j] = acc[i][j];
+    for (int j = 0; j < 7; ++j) {
+      M[(7 * ty + i) * kSN + 7 * tx + j] = acc[i][j];
+      if (tx != ty) M[(7 * tx + j) * kSN + 7 * ty + i] = acc[i][j];
+    }
 }
 
 __device__ __forceinline__ int sturm_count_n(const double* __restrict__ d, const double* __restrict__ e2, int n, double x) {
@@ -824,7 +838,7 @@ int siib_run_small_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuf
   }();
   (void)attr;
   kt_begin(kt, "siib_gram", s);
-  siib_gram_kernel<<<n, 256, 0, s>>>(g, b, eb, rank_hi);
+  siib_gram_kernel<<<n, kGramThreads, 0, s>>>(g, b, eb, rank_hi);
   kt_end(kt, s);
   kt_begin(kt, "siib_smalltri", s);
   siib_smalltri_kernel<<<n, 128, kSN * kSNp * sizeof(double), s>>>(g, b, eb, rank_hi);
