@@ -805,7 +805,9 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
           done = true;
           s_done[tid] = 1;
         } else {
-          double s0 = As[(int64_t)astar * kSDim + tid], s1 = 0.0;
+          // after the first panel only the lower triangle of the work matrix is maintained: row astar up
+          // to the diagonal, column astar below it
+          double s0 = (k0 == 0 || tid <= astar) ? As[(int64_t)astar * kSDim + tid] : As[(int64_t)tid * kSDim + astar], s1 = 0.0;
           int m = 0;
           for (; m + 2 <= j; m += 2) {
             s0 = fma(-s_panel[m * kSDim + tid], s_panel[m * kSDim + astar], s0);
@@ -837,7 +839,8 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
         break;
       }
     }
-    // trailing update with the finished panel: W[a][c] = As[a][c] - sum_m Lp[m][a] Lp[m][c]
+    // trailing update with the finished panel: W[a][c] = As[a][c] - sum_m Lp[m][a] Lp[m][c], c <= a (the matrix is
+    // symmetric: half the flops and half the traffic of the full update)
     for (int a0 = 4 * wib; a0 < kSDim; a0 += 4 * NW) {
       bool live[4];
       bool any = false;
@@ -849,15 +852,15 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
       if (!any) continue;
       // 4 rows x 2 columns per lane: 2 + 2 shared-memory loads (the row values as two 128-bit
       // broadcasts) per 8 FP64 FMAs
-      for (int c = lane; c < kSDim; c += 64) {
-        const int c1 = c + 32;
-        const bool h0 = !s_done[c], h1 = (c1 < kSDim) && !s_done[c1];
+      for (int cb = 0; cb <= a0 + 3; cb += 64) {   // lower triangle: columns <= row
+        const int c = cb + lane, c1 = c + 32;
+        const bool h0 = c <= a0 + 3 && !s_done[c], h1 = (c1 <= a0 + 3) && !s_done[c1];
         if (!h0 && !h1) continue;
-        const int c1s = (c1 < kSDim) ? c1 : c;
+        const int cs = min(c, kSDim - 1), c1s = min(c1, kSDim - 1);
         double acc0[4] = {0.0, 0.0, 0.0, 0.0}, acc1[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 8
         for (int m = 0; m < kCholW; ++m) {
-          const double l0 = s_panel[m * kSDim + c], l1 = s_panel[m * kSDim + c1s];
+          const double l0 = s_panel[m * kSDim + cs], l1 = s_panel[m * kSDim + c1s];
           const double2 r01 = *reinterpret_cast<const double2*>(&s_panel[m * kSDim + a0]);
           const double2 r23 = *reinterpret_cast<const double2*>(&s_panel[m * kSDim + a0 + 2]);
           const double rr[4] = {r01.x, r01.y, r23.x, r23.y};
@@ -870,8 +873,8 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (live[i]) {
-            if (h0) W[(int64_t)(a0 + i) * kSDim + c] = As[(int64_t)(a0 + i) * kSDim + c] - acc0[i];
-            if (h1) W[(int64_t)(a0 + i) * kSDim + c1] = As[(int64_t)(a0 + i) * kSDim + c1] - acc1[i];
+            if (h0 && c <= a0 + i) W[(int64_t)(a0 + i) * kSDim + c] = As[(int64_t)(a0 + i) * kSDim + c] - acc0[i];
+            if (h1 && c1 <= a0 + i) W[(int64_t)(a0 + i) * kSDim + c1] = As[(int64_t)(a0 + i) * kSDim + c1] - acc1[i];
           }
       }
     }

@@ -797,12 +797,12 @@ __global__ void __launch_bounds__(128) siib_lv_kernel(SiibGeom g, SiibBuffers b,
     const int c = idx >> 5, rr = idx & 31;
     sL[c * 33 + rr] = (c < r && row0 + rr < kELd) ? G[(int64_t)c * kELd + row0 + rr] : 0.f;
   }
-  for (int idx = tid; idx < kSN * kSN; idx += 128) sV[idx] = V[idx];
+  for (int idx = tid; idx < r * kSN; idx += 128) sV[idx] = V[idx];   // columns of L beyond the rank are zero
   __syncthreads();
   float acc[28];
 #pragma unroll
   for (int t = 0; t < 28; ++t) acc[t] = 0.f;
-  for (int c = 0; c < kSN; ++c) {
+  for (int c = 0; c < r; ++c) {
     const float a = sL[c * 33 + lane];
     const float4* v4 = reinterpret_cast<const float4*>(sV + c * kSN + 28 * w);
 #pragma unroll
