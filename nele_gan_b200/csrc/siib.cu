@@ -858,6 +858,13 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
         if (!h0 && !h1) continue;
         const int cs = min(c, kSDim - 1), c1s = min(c1, kSDim - 1);
         double acc0[4] = {0.0, 0.0, 0.0, 0.0}, acc1[4] = {0.0, 0.0, 0.0, 0.0};
+        // the old values are requested before the product loop, so their latency hides behind it
+        double old0[4], old1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          old0[i] = (live[i] && h0 && c <= a0 + i) ? As[(int64_t)(a0 + i) * kSDim + c] : 0.0;
+          old1[i] = (live[i] && h1 && c1 <= a0 + i) ? As[(int64_t)(a0 + i) * kSDim + c1] : 0.0;
+        }
 #pragma unroll 8
         for (int m = 0; m < kCholW; ++m) {
           const double l0 = s_panel[m * kSDim + cs], l1 = s_panel[m * kSDim + c1s];
@@ -873,8 +880,8 @@ __global__ void __launch_bounds__(kCholThreads) siib_chol_kernel(SiibGeom g, Sii
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (live[i]) {
-            if (h0 && c <= a0 + i) W[(int64_t)(a0 + i) * kSDim + c] = As[(int64_t)(a0 + i) * kSDim + c] - acc0[i];
-            if (h1 && c1 <= a0 + i) W[(int64_t)(a0 + i) * kSDim + c1] = As[(int64_t)(a0 + i) * kSDim + c1] - acc1[i];
+            if (h0 && c <= a0 + i) W[(int64_t)(a0 + i) * kSDim + c] = old0[i] - acc0[i];
+            if (h1 && c1 <= a0 + i) W[(int64_t)(a0 + i) * kSDim + c1] = old1[i] - acc1[i];
           }
       }
     }
