@@ -661,19 +661,46 @@ __global__ void __launch_bounds__(kExpThreads) siib_expand_kernel(SiibGeom g, Si
   const int Nf = Fa - (kSStack - 1);
   if (Nf < 2) return;
   __shared__ double s_rs[2][kSDim];  // row sums of the stacked matrices
+  __shared__ float s_edge[2][2 * kSStack][kSLanes];   // frames 0..14 and Nf..Nf+14 of x and y: all the sliding terms
+  __shared__ double s_part[kExpThreads / 32][2][kSLanes];
   const float* __restrict__ X = b.logspec + (g.offF[pair]) * kSLanes;
   const float* __restrict__ Y = b.logspec + (b.totF + g.offF[pair]) * kSLanes;
-  // sums over t < Nf of band j (k = 0), then slide
-  for (int item = wib; item < 2 * kSBands; item += kExpThreads / 32) {
-    const int q = item / kSBands, j = item % kSBands;
-    const float* S = (q ? Y : X) + j;
-    double s = 0.0;
-    for (int t = lane; t < Nf; t += 32) s += (double)S[(int64_t)t * kSLanes];
-    s = warp_sum(s);
-    if (lane == 0) {
+  for (int idx = tid; idx < 2 * 2 * kSStack * kSLanes; idx += kExpThreads) {
+    const int q = idx / (2 * kSStack * kSLanes), rr = (idx / kSLanes) % (2 * kSStack), j = idx % kSLanes;
+    const int fr = rr < kSStack ? rr : Nf + (rr - kSStack);
+    s_edge[q][rr][j] = (fr < Fa) ? (q ? Y : X)[(int64_t)fr * kSLanes + j] : 0.f;
+  }
+  // sums over t < Nf of every band (k = 0): a warp reads whole 128-byte frame rows, lane = band
+  {
+    double sx = 0.0, sy = 0.0;
+    constexpr int NWp = kExpThreads / 32;
+    for (int t0 = wib; t0 < Nf; t0 += 8 * NWp) {   // sixteen independent loads in flight per lane
+      float vx[8], vy[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int t = t0 + u * NWp;
+        vx[u] = t < Nf ? X[(int64_t)t * kSLanes + lane] : 0.f;
+        vy[u] = t < Nf ? Y[(int64_t)t * kSLanes + lane] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        sx += (double)vx[u];
+        sy += (double)vy[u];
+      }
+    }
+    s_part[wib][0][lane] = sx;
+    s_part[wib][1][lane] = sy;
+  }
+  __syncthreads();
+  if (tid < 2 * kSLanes) {
+    const int q = tid / kSLanes, j = tid % kSLanes;
+    if (j < kSBands) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kExpThreads / 32; ++w) s += s_part[w][q][j];
       s_rs[q][j] = s;
-      for (int k = 1; k < kSStack; ++k) {
-        s += (double)S[(int64_t)(Nf + k - 1) * kSLanes] - (double)S[(int64_t)(k - 1) * kSLanes];
+      for (int k = 1; k < kSStack; ++k) {   // then slide by one frame per stack offset
+        s += (double)s_edge[q][kSStack + k - 1][j] - (double)s_edge[q][k - 1][j];
         s_rs[q][k * kSBands + j] = s;
       }
     }
@@ -684,33 +711,40 @@ __global__ void __launch_bounds__(kExpThreads) siib_expand_kernel(SiibGeom g, Si
   float* __restrict__ Sxy = b.Sxy + (int64_t)lp * kSDim * kSDim;
   float* __restrict__ Syy = b.Syy + (int64_t)lp * kSDim * kSDim;
   const double* __restrict__ base = b.base + (int64_t)lp * kSBlocks * (kSLanes * kSLanes);
-  const int ndiag = (siib_projected(b, pair, Nf) ? 15 : kSBlocks) * kSBands * kSBands;  // xx blocks only / all 59
-  for (int it = tid; it < ndiag; it += kExpThreads) {
-    const int blk = it / (kSBands * kSBands), rem = it % (kSBands * kSBands);
-    const int j1 = rem / kSBands, j2 = rem % kSBands;
+  // Every (block, j1, j2) diagonal is walked twice for the symmetric matrices: once with the lanes along j2,
+  // writing row segments of the upper block triangle, once with the lanes along j1, writing the mirrored
+  // element into the lower one -- so both stores are 28 consecutive values of a row (a lane-transposed store
+  // costs one L1 wavefront per element, which bound this kernel).
+  const bool proj = siib_projected(b, pair, Nf);
+  const int ndiag = (proj ? 15 : kSBlocks) * kSBands * kSBands;  // xx blocks only / all 59
+  const int nmir = (proj ? 15 : 30) * kSBands * kSBands;         // xx (and yy) blocks have a mirror image
+  for (int it = tid; it < ndiag + nmir; it += kExpThreads) {
+    const bool mirror = it >= ndiag;
+    const int idx = mirror ? it - ndiag : it;
+    const int blk = idx / (kSBands * kSBands), rem = idx % (kSBands * kSBands);
+    const int j1 = mirror ? rem % kSBands : rem / kSBands, j2 = mirror ? rem / kSBands : rem % kSBands;
     int ta, tb, d;
     block_desc(blk, ta, tb, d);
-    const float* A = (ta ? Y : X) + j1;
-    const float* B = (tb ? Y : X) + j2;
+    if (mirror && d == 0) continue;   // a diagonal block is its own mirror image
+    const float (*A)[kSLanes] = s_edge[ta];
+    const float (*B)[kSLanes] = s_edge[tb];
     int k1 = max(0, -d), k2 = max(0, d);
     double r = base[blk * (kSLanes * kSLanes) + j1 * kSLanes + j2];
     const int steps = kSStack - (d < 0 ? -d : d);
     for (int m = 0; m < steps; ++m) {
       const int a = k1 * kSBands + j1, c = k2 * kSBands + j2;
       const double v = r - s_rs[ta][a] * s_rs[tb][c] * inv_nf;
-      if (blk < 15) {
-        Sxx[(int64_t)a * kSDim + c] = v;
-        Sxx[(int64_t)c * kSDim + a] = v;
-      } else if (blk < 30) {
-        Syy[(int64_t)a * kSDim + c] = (float)v;
-        Syy[(int64_t)c * kSDim + a] = (float)v;
+      if (!mirror) {
+        if (blk < 15) Sxx[(int64_t)a * kSDim + c] = v;
+        else if (blk < 30) Syy[(int64_t)a * kSDim + c] = (float)v;
+        else Sxy[(int64_t)a * kSDim + c] = (float)v;
       } else {
-        Sxy[(int64_t)a * kSDim + c] = (float)v;
+        if (blk < 15) Sxx[(int64_t)c * kSDim + a] = v;
+        else Syy[(int64_t)c * kSDim + a] = (float)v;
       }
       if (m + 1 == steps) break;
       // slide the summation window by one frame
-      r += (double)A[(int64_t)(Nf + k1) * kSLanes] * (double)B[(int64_t)(Nf + k2) * kSLanes] -
-           (double)A[(int64_t)k1 * kSLanes] * (double)B[(int64_t)k2 * kSLanes];
+      r += (double)A[kSStack + k1][j1] * (double)B[kSStack + k2][j2] - (double)A[k1][j1] * (double)B[k2][j2];
       ++k1;
       ++k2;
     }
