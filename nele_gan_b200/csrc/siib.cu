@@ -361,8 +361,17 @@ __global__ void __launch_bounds__(128) siib_mask_kernel(SiibGeom g, SiibBuffers 
   float* __restrict__ X = b.logspec + ((int64_t)q * b.totF + g.offF[pair]) * kSLanes + lane;
   const float* __restrict__ R = b.lograw + ((int64_t)q * b.totF + g.offF[pair]) * kSLanes + lane;
   const int32_t* __restrict__ src = b.src + g.offF[pair];
+  // Every pass below takes the frames eight at a time with the loads issued first: the row of a frame is a
+  // two-level gather (first-occurrence map, then the row), and one frame per iteration leaves the warp
+  // waiting on that latency for most of its life.
   float fl = 3.0e38f;
-  for (int t = 0; t < Fa; ++t) fl = fminf(fl, R[(int64_t)src[t] * kSLanes]);
+  for (int t0 = 0; t0 < Fa; t0 += 8) {
+    float raw[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) raw[u] = R[(int64_t)src[min(t0 + u, Fa - 1)] * kSLanes];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) fl = fminf(fl, raw[u]);
+  }
   float hx[kSMaskT - 1], he[kSMaskT - 1];  // masked level and (level - floor) of the previous 15 frames
 #pragma unroll
   for (int d = 0; d < kSMaskT - 1; ++d) {
@@ -370,29 +379,55 @@ __global__ void __launch_bounds__(128) siib_mask_kernel(SiibGeom g, SiibBuffers 
     he[d] = 0.f;
   }
   double sum = 0.0;
-  for (int t = 0; t < Fa; ++t) {
-    float v = R[(int64_t)src[t] * kSLanes];
+  for (int t0 = 0; t0 < Fa; t0 += 8) {
+    float raw[8];
 #pragma unroll
-    for (int d = 0; d < kSMaskT - 1; ++d) v = fmaxf(v, fmaf(-c_siib_decay[d + 1], he[d], hx[d]));
+    for (int u = 0; u < 8; ++u) raw[u] = R[(int64_t)src[min(t0 + u, Fa - 1)] * kSLanes];
 #pragma unroll
-    for (int d = kSMaskT - 2; d > 0; --d) {
-      hx[d] = hx[d - 1];
-      he[d] = he[d - 1];
+    for (int u = 0; u < 8; ++u) {
+      const int t = t0 + u;
+      if (t < Fa) {
+        float v = raw[u];
+#pragma unroll
+        for (int d = 0; d < kSMaskT - 1; ++d) v = fmaxf(v, fmaf(-c_siib_decay[d + 1], he[d], hx[d]));
+#pragma unroll
+        for (int d = kSMaskT - 2; d > 0; --d) {
+          hx[d] = hx[d - 1];
+          he[d] = he[d - 1];
+        }
+        hx[0] = v;
+        he[0] = v - fl;
+        X[(int64_t)t * kSLanes] = v;
+        sum += (double)v;
+      }
     }
-    hx[0] = v;
-    he[0] = v - fl;
-    X[(int64_t)t * kSLanes] = v;
-    sum += (double)v;
   }
   const float mu = (Fa > 0) ? (float)(sum / (double)Fa) : 0.f;
-  for (int t = 0; t < Fa; ++t) X[(int64_t)t * kSLanes] = (lane < kSBands) ? X[(int64_t)t * kSLanes] - mu : 0.f;
+  for (int t0 = 0; t0 < Fa; t0 += 8) {
+    float cur[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cur[u] = X[(int64_t)min(t0 + u, Fa - 1) * kSLanes];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (t0 + u < Fa) X[(int64_t)(t0 + u) * kSLanes] = (lane < kSBands) ? cur[u] - mu : 0.f;
+  }
   // The raw frames of a tiled signal repeat with period P; the masked ones do so only once the
   // start-up transient of the recurrence has died out.  Verify (bit-exact) that everything from
   // the second period on repeats: the lag-product kernels then sum two periods instead of all.
   const int P = b.Pact[pair];
   int ok = (P > 0 && 2 * P + kSStack <= Fa) ? 1 : 0;
   if (ok)
-    for (int t = P; t + P < Fa; ++t) ok &= (X[(int64_t)t * kSLanes] == X[(int64_t)(t + P) * kSLanes]) ? 1 : 0;
+    for (int t0 = P; t0 + P < Fa; t0 += 8) {
+      float p0[8], p1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int t = min(t0 + u, Fa - P - 1);
+        p0[u] = X[(int64_t)t * kSLanes];
+        p1[u] = X[(int64_t)(t + P) * kSLanes];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ok &= (p0[u] == p1[u]) ? 1 : 0;
+    }
   ok = __all_sync(0xffffffffu, ok);
   if (lane == 0) b.perflag[2 * pair + q] = ok;
 }
