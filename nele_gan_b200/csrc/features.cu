@@ -398,7 +398,11 @@ __global__ void __launch_bounds__(kImcraThreads, 3) feat_imcra_kernel(const floa
 int features_run(const float* wav, const int64_t* offs, const int32_t* lens, const int64_t* foff, const int2* tiles,
                  int n, int ntiles, bool noise, float power, bool normalize, float* band, float* mag, float* phase,
                  float* psd, KernelTimer* kt, cudaStream_t s) {
-  static bool ready = false;   // per process and device context: tables + the shared-memory opt-in
+  // the tables live in __device__ memory, i.e. per device: one upload per device this process uses
+  static bool ready_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool ready = dev >= 0 && dev < 64 && ready_dev[dev];
   if (!ready) {
     static const int gmt[kFeatBands] = {0,  3,  4,  5,  6,  7,  8,  9,  10,  11,  12,  13,  14,  15,  16,  17,
                                         18, 19, 20, 21, 22, 23, 24, 25, 26,  28,  30,  32,  34,  36,  38,  41,
@@ -423,7 +427,7 @@ int features_run(const float* wav, const int64_t* offs, const int32_t* lens, con
     }
     cudaMemcpyToSymbolAsync(d_tw512, tw, sizeof(tw), 0, cudaMemcpyHostToDevice, s);
     cudaStreamSynchronize(s);
-    ready = true;
+    if (dev >= 0 && dev < 64) ready_dev[dev] = true;
   }
   int launches = 0;
   kt_begin(kt, "feat_stft", s);
