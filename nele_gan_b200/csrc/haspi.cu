@@ -346,6 +346,99 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_control_kernel(PairGeom 
   }
 }
 
+// ---- experimental: the control pass with the clean and the processed chain packed into
+// fma.rn.f32x2 (Blackwell's two-wide FP32 FMA: the same FMA-pipe throughput as two FFMA,
+// scripts/micro/ffma2.cu, but one issue slot).  The two chains share every coefficient here, so
+// each recurrence line becomes one packed instruction; the arithmetic per lane is the scalar
+// kernel's (fma.rn), the results agree to the last bit wherever the compiler contracts the scalar
+// expressions the same way.  Off by default (NELE_F32X2=1 switches it on for A/B timing).
+struct F2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ F2 f2_pack(float a, float b) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(F2 p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); }
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+  F2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return d;
+}
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+  F2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+  F2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+
+__global__ void __launch_bounds__(kEarWarps * 32) haspi_control_x2_kernel(PairGeom g, HaspiBuffers b, int n_pairs) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int pair = blockIdx.x * kEarWarps + wib;
+  if (pair >= n_pairs) return;
+  const double* __restrict__ midx = b.mid + g.off24[pair];
+  const double* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
+  const int N = g.n24[pair];
+  __shared__ float2 s_buf[kEarWarps][kCtlChunk];   // (x, y) sample pairs
+  float2* bxy = s_buf[wib];
+  const BandConst bc = b.bands[lane];
+  Carrier<float> car;
+  car.init(bc.cf);
+  const GtCoef<float> k = make_gt<float>(bc.bw1, bc.erb);
+  const F2 A = f2_pack(k.a, k.a), C1 = f2_pack(k.c1, k.c1), C2 = f2_pack(k.c2, k.c2);
+  const F2 Z = f2_pack(0.f, 0.f);
+  F2 r1 = Z, r2 = Z, r3 = Z, r4 = Z, rp = Z, i1 = Z, i2 = Z, i3 = Z, i4 = Z, ip = Z;
+  double accx = 0.0, accy = 0.0;
+  for (int base = 0; base < N; base += kCtlChunk) {
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < kCtlChunk / 32; ++q) {
+      const int t = base + q * 32 + lane;
+      bxy[q * 32 + lane] = (t < N) ? make_float2((float)midx[t], (float)midy[t]) : make_float2(0.f, 0.f);
+    }
+    __syncwarp();
+    car.seed_before(base);
+    const int m = min(kCtlChunk, N - base);
+    F2 p = Z;
+#pragma unroll 4
+    for (int q = 0; q < m; ++q) {
+      car.advance();
+      const float2 xy = bxy[q];
+      const F2 XY = f2_pack(xy.x, xy.y);
+      const F2 xr = f2_mul(XY, f2_pack(car.c, car.c)), xi = f2_mul(XY, f2_pack(car.s, car.s));
+      r1 = f2_fma(A, r1, xr);
+      i1 = f2_fma(A, i1, xi);
+      r2 = f2_fma(A, r2, r1);
+      i2 = f2_fma(A, i2, i1);
+      r3 = f2_fma(A, r3, r2);
+      i3 = f2_fma(A, i3, i2);
+      const F2 nr = f2_fma(A, r4, r3), ni = f2_fma(A, i4, i3);
+      const F2 ur = f2_fma(C2, rp, f2_fma(C1, r4, nr)), ui = f2_fma(C2, ip, f2_fma(C1, i4, ni));
+      rp = r4;
+      ip = i4;
+      r4 = nr;
+      i4 = ni;
+      p = f2_add(p, f2_fma(ur, ur, f2_mul(ui, ui)));
+    }
+    float px, py;
+    f2_unpack(p, px, py);
+    accx += (double)px;
+    accy += (double)py;
+  }
+  const int64_t o = (int64_t)pair * 2 * kBands + lane;
+  b.bw[o] = bw_from_control(accx, (double)k.gain, N, bc.bwmin[0], bc.bw1);
+  b.bw[o + kBands] = bw_from_control(accy, (double)k.gain, N, bc.bwmin[1], bc.bw1);
+  if (b.cave) {
+    b.cave[o] = (double)k.gain * sqrt(accx / (double)N);
+    b.cave[o + kBands] = (double)k.gain * sqrt(accy / (double)N);
+  }
+}
+
 // group-delay shifts, always from BWx (pyhaspi2.py:1239-1240)
 __global__ void haspi_shift_kernel(HaspiBuffers b, int n) {
   const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -451,6 +544,215 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_kernel(PairGeom g, H
       Lx.template accumulate<7>(vx[7], c_envfir); Ly.template accumulate<7>(vy[7], c_envfir);
       Lx.template accumulate<8>(vx[8], c_envfir); Ly.template accumulate<8>(vy[8], c_envfir);
       const float ox = Lx.emit(), oy = Ly.emit();
+      const int j = blk - 2;
+      if (j >= 0) {
+        outx[(int64_t)j * kBands + lane] = ox;
+        outy[(int64_t)j * kBands + lane] = oy;
+      }
+    }
+  }
+}
+
+// ---- experimental: the main pass with the clean and the processed chain packed into f32x2
+// instructions (see haspi_control_x2_kernel).  Every linear recurrence, the level arithmetic around
+// the MUFU calls and the FIR bookkeeping run two-wide; only lg2 / ex2 and the clamps stay scalar.
+// By the instruction count the loop drops from ~130 to ~75 issue slots per sample pair at the same
+// FMA-pipe time.  Off by default (NELE_F32X2=1).
+struct EarLane2 {
+  float kca, kcc1, kcc2, ctl_db;   // control filter: the same for both signals
+  F2 ksa, ksc1, ksc2, sig_db;      // signal filter: (x, y)
+  F2 cr1, cr2, cr3, cr4, crp, ci1, ci2, ci3, ci4, cip;
+  F2 sr1, sr2, sr3, sr4, srp, si1, si2, si3, si4, sip;
+  F2 zlp, v1, v2;
+  float m11, m12, m21, m22, g1, g2, r1inv;
+  float thr_x, thr_y;
+  F2 thr, crfac, ohc;
+  F2 acc[6];
+
+  __device__ __forceinline__ void init(const BandConst& b, double bwx, double bwy, const IhcConst& ih) {
+    const GtCoef<float> kc = make_gt<float>(b.bw1, b.erb);
+    const GtCoef<float> kx = make_gt<float>(bwx, b.erb), ky = make_gt<float>(bwy, b.erb);
+    kca = kc.a;
+    kcc1 = kc.c1;
+    kcc2 = kc.c2;
+    ksa = f2_pack(kx.a, ky.a);
+    ksc1 = f2_pack(kx.c1, ky.c1);
+    ksc2 = f2_pack(kx.c2, ky.c2);
+    const F2 z = f2_pack(0.f, 0.f);
+    cr1 = cr2 = cr3 = cr4 = crp = ci1 = ci2 = ci3 = ci4 = cip = z;
+    sr1 = sr2 = sr3 = sr4 = srp = si1 = si2 = si3 = si4 = sip = z;
+    zlp = v1 = v2 = z;
+    m11 = (float)ih.m11; m12 = (float)ih.m12; m21 = (float)ih.m21; m22 = (float)ih.m22;
+    g1 = (float)ih.g1; g2 = (float)ih.g2;
+    r1inv = (float)ih.r1inv;
+    thr_x = (float)b.lowknee[0];
+    thr_y = (float)b.lowknee[1];
+    thr = f2_pack(thr_x, thr_y);
+    crfac = f2_pack((float)((1.0 - 1.0 / b.cr[0]) * 3.3219280948873623 / 20.0),
+                    (float)((1.0 - 1.0 / b.cr[1]) * 3.3219280948873623 / 20.0));
+    ohc = f2_pack((float)(-b.attn_ohc[0] * 3.3219280948873623 / 20.0), (float)(-b.attn_ohc[1] * 3.3219280948873623 / 20.0));
+    ctl_db = (float)(65.0 + 20.0 * log10((double)kc.gain));
+    sig_db = f2_pack((float)(65.0 - b.attn_ihc[0] + 20.0 * log10((double)kx.gain)),
+                     (float)(65.0 - b.attn_ihc[1] + 20.0 * log10((double)ky.gain)));
+#pragma unroll
+    for (int d = 0; d < 6; ++d) acc[d] = z;
+  }
+
+  // one demodulated sample pair -> IHC-adapted envelopes (x, y) in dB SL; EarLane<float>::sample two-wide
+  __device__ __forceinline__ F2 sample(F2 xr, F2 xi) {
+    const F2 KA = f2_pack(kca, kca), KC1 = f2_pack(kcc1, kcc1), KC2 = f2_pack(kcc2, kcc2);
+    cr1 = f2_fma(KA, cr1, xr);
+    ci1 = f2_fma(KA, ci1, xi);
+    cr2 = f2_fma(KA, cr2, cr1);
+    ci2 = f2_fma(KA, ci2, ci1);
+    cr3 = f2_fma(KA, cr3, cr2);
+    ci3 = f2_fma(KA, ci3, ci2);
+    const F2 cnr = f2_fma(KA, cr4, cr3), cni = f2_fma(KA, ci4, ci3);
+    const F2 cur = f2_fma(KC2, crp, f2_fma(KC1, cr4, cnr)), cui = f2_fma(KC2, cip, f2_fma(KC1, ci4, cni));
+    crp = cr4;
+    cip = ci4;
+    cr4 = cnr;
+    ci4 = cni;
+    const F2 pc = f2_fma(cur, cur, f2_mul(cui, cui));
+    sr1 = f2_fma(ksa, sr1, xr);
+    si1 = f2_fma(ksa, si1, xi);
+    sr2 = f2_fma(ksa, sr2, sr1);
+    si2 = f2_fma(ksa, si2, si1);
+    sr3 = f2_fma(ksa, sr3, sr2);
+    si3 = f2_fma(ksa, si3, si2);
+    const F2 snr = f2_fma(ksa, sr4, sr3), sni = f2_fma(ksa, si4, si3);
+    const F2 sur = f2_fma(ksc2, srp, f2_fma(ksc1, sr4, snr)), sui = f2_fma(ksc2, sip, f2_fma(ksc1, si4, sni));
+    srp = sr4;
+    sip = si4;
+    sr4 = snr;
+    si4 = sni;
+    const F2 ps = f2_fma(sur, sur, f2_mul(sui, sui));
+    // eb_EnvCompressBM
+    const F2 C10 = f2_pack(NELE_10_OVER_LOG2_10, NELE_10_OVER_LOG2_10), NEG1 = f2_pack(-1.f, -1.f);
+    float pcx, pcy;
+    f2_unpack(pc, pcx, pcy);
+    float lx, ly;
+    f2_unpack(f2_fma(C10, f2_pack(fast_lg2(pcx), fast_lg2(pcy)), f2_pack(ctl_db, ctl_db)), lx, ly);
+    lx = fminf(fmaxf(lx, thr_x), 100.0f);
+    ly = fminf(fmaxf(ly, thr_y), 100.0f);
+    float ax, ay;
+    f2_unpack(f2_fma(f2_fma(f2_pack(lx, ly), NEG1, thr), crfac, ohc), ax, ay);   // (thrLow - le) crfac + ohc
+    const F2 G = f2_pack(fast_ex2(ax), fast_ex2(ay));
+    const F2 B0 = f2_pack(0.095107983402496f, 0.095107983402496f), K8 = f2_pack(0.809784033195007f, 0.809784033195007f);
+    const F2 glp = f2_fma(B0, G, zlp);
+    zlp = f2_fma(K8, glp, f2_mul(B0, G));
+    // eb_EnvSL2
+    float ex, ey;
+    f2_unpack(f2_mul(f2_mul(glp, glp), ps), ex, ey);
+    float v0x, v0y;
+    f2_unpack(f2_fma(C10, f2_pack(fast_lg2(ex), fast_lg2(ey)), sig_db), v0x, v0y);
+    const F2 V0 = f2_pack(fmaxf(v0x, 0.0f), fmaxf(v0y, 0.0f));
+    // eb_IHCadapt
+    const F2 n1 = f2_fma(f2_pack(g1, g1), V0, f2_fma(f2_pack(m12, m12), v2, f2_mul(f2_pack(m11, m11), v1)));
+    const F2 n2 = f2_fma(f2_pack(g2, g2), V0, f2_fma(f2_pack(m22, m22), v2, f2_mul(f2_pack(m21, m21), v1)));
+    v1 = n1;
+    v2 = n2;
+    float ox, oy;
+    f2_unpack(f2_mul(f2_fma(n1, NEG1, V0), f2_pack(r1inv, r1inv)), ox, oy);
+    return f2_pack(fmaxf(ox, 0.0f), fmaxf(oy, 0.0f));
+  }
+
+  template <int P>
+  __device__ __forceinline__ void accumulate(F2 v, const float* fir) {
+#pragma unroll
+    for (int d = 0; d < 6; ++d) acc[d] = f2_fma(f2_pack(fir[d * 9 + P], fir[d * 9 + P]), v, acc[d]);
+  }
+  __device__ __forceinline__ F2 emit() {
+    const F2 o = acc[0];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) acc[d] = acc[d + 1];
+    acc[5] = f2_pack(0.f, 0.f);
+    return o;
+  }
+};
+
+__global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_x2_kernel(PairGeom g, HaspiBuffers b, int n_pairs) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int pair = blockIdx.x * kEarWarps + wib;
+  if (pair >= n_pairs) return;
+  const double* __restrict__ midx = b.mid + g.off24[pair];
+  const double* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
+  const int N = g.n24[pair], nsub = g.nsub[pair];
+  float* __restrict__ outx = b.envlp + (g.offsub[pair]) * kBands;
+  float* __restrict__ outy = b.envlp + (b.totsub + g.offsub[pair]) * kBands;
+  extern __shared__ __align__(16) unsigned char s_ring_raw[];  // [kEarWarps][2 * kEarChunk] sample pairs (x, y)
+  float2* ring = reinterpret_cast<float2*>(s_ring_raw) + (size_t)wib * 2 * kEarChunk;
+
+  EarLane2 L2;
+  Carrier<float> car;
+  int shift;
+  {
+    const BandConst bc = b.bands[lane];
+    shift = b.shift[(int64_t)pair * kBands + lane];
+    car.init(bc.cf);
+    L2.init(bc, b.bw[((int64_t)pair * 2 + 0) * kBands + lane], b.bw[((int64_t)pair * 2 + 1) * kBands + lane], c_ihc);
+  }
+  int wshift = shift;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wshift = max(wshift, __shfl_xor_sync(0xffffffffu, wshift, o));
+  int rp = (shift == 0) ? 0 : 2 * kEarChunk - shift;
+  const int nblk = nsub + 2;
+  const int nchunks = (nblk * 9 + kEarChunk - 1) / kEarChunk;
+  const F2 zero = f2_pack(0.f, 0.f);
+  for (int c = 0; c < nchunks; ++c) {
+    const int i0 = c * kEarChunk;
+    float2* h = ring + (c & 1) * kEarChunk;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kEarChunk / 32; ++k) {
+      const int t = i0 + k * 32 + lane;
+      h[k * 32 + lane] = (t < N) ? make_float2((float)midx[t], (float)midy[t]) : make_float2(0.f, 0.f);
+    }
+    __syncwarp();
+    {
+      const int t = i0 - shift;
+      if (t >= 0) car.seed_before(t);
+      else if (t + kEarChunk > 0) car.seed_before(0);
+    }
+    const int blk_end = min((c + 1) * (kEarChunk / 9), nblk);
+    for (int blk = c * (kEarChunk / 9); blk < blk_end; ++blk) {
+      const int ib = blk * 9;
+      F2 v[9];
+      if (ib >= wshift && ib + 9 <= N) {
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+          const float2 xy = ring[rp];
+          rp = (rp + 1 == 2 * kEarChunk) ? 0 : rp + 1;
+          car.advance();
+          const F2 XY = f2_pack(xy.x, xy.y);
+          v[p] = L2.sample(f2_mul(XY, f2_pack(car.c, car.c)), f2_mul(XY, f2_pack(car.s, car.s)));
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+          const int i = ib + p;
+          const float2 xy = ring[rp];
+          rp = (rp + 1 == 2 * kEarChunk) ? 0 : rp + 1;
+          if (i >= shift && i < N) {
+            car.advance();
+            const F2 XY = f2_pack(xy.x, xy.y);
+            v[p] = L2.sample(f2_mul(XY, f2_pack(car.c, car.c)), f2_mul(XY, f2_pack(car.s, car.s)));
+          } else {
+            v[p] = zero;
+          }
+        }
+      }
+      L2.accumulate<0>(v[0], c_envfir);
+      L2.accumulate<1>(v[1], c_envfir);
+      L2.accumulate<2>(v[2], c_envfir);
+      L2.accumulate<3>(v[3], c_envfir);
+      L2.accumulate<4>(v[4], c_envfir);
+      L2.accumulate<5>(v[5], c_envfir);
+      L2.accumulate<6>(v[6], c_envfir);
+      L2.accumulate<7>(v[7], c_envfir);
+      L2.accumulate<8>(v[8], c_envfir);
+      float ox, oy;
+      f2_unpack(L2.emit(), ox, oy);
       const int j = blk - 2;
       if (j >= 0) {
         outx[(int64_t)j * kBands + lane] = ox;
@@ -844,7 +1146,12 @@ int haspi_run_front(const PairGeom& g, const HaspiBuffers& b, int n, bool f64, K
   ++launches;
   const int ctas = (n + kEarWarps - 1) / kEarWarps;
   kt_begin(kt, "haspi_control", s);
+  static const bool x2 = [] {
+    const char* p = getenv("NELE_F32X2");
+    return p && p[0] == '1';
+  }();
   if (f64) haspi_control_kernel<double><<<ctas, kEarWarps * 32, 0, s>>>(g, b, n);
+  else if (x2) haspi_control_x2_kernel<<<ctas, kEarWarps * 32, 0, s>>>(g, b, n);
   else haspi_control_kernel<float><<<ctas, kEarWarps * 32, 0, s>>>(g, b, n);
   kt_end(kt, s);
   ++launches;
@@ -859,7 +1166,12 @@ int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, boo
   int launches = haspi_run_front(g, b, n, f64, kt, s);
   kt_begin(kt, "haspi_ear", s);
   const int ear_ctas = (n + kEarWarps - 1) / kEarWarps;
+  static const bool x2 = [] {
+    const char* p = getenv("NELE_F32X2");
+    return p && p[0] == '1';
+  }();
   if (f64) haspi_ear_kernel<double><<<ear_ctas, kEarWarps * 32, kEarWarps * 4 * kEarChunk * sizeof(double), s>>>(g, b, n);
+  else if (x2) haspi_ear_x2_kernel<<<ear_ctas, kEarWarps * 32, kEarWarps * 4 * kEarChunk * sizeof(float), s>>>(g, b, n);
   else haspi_ear_kernel<float><<<ear_ctas, kEarWarps * 32, kEarWarps * 4 * kEarChunk * sizeof(float), s>>>(g, b, n);
   kt_end(kt, s);
   ++launches;
