@@ -318,6 +318,181 @@ struct EarLane {
   }
 };
 
+// Two FP32 values in one 64-bit register for Blackwell's two-wide FP32 instructions
+// (fma / mul / add .rn.f32x2); component-wise float arithmetic on the host (tests/host_emul).
+struct F2 {
+#if defined(__CUDA_ARCH__)
+  unsigned long long v;
+#else
+  float lo, hi;
+#endif
+};
+NELE_HD F2 f2_pack(float a, float b) {
+  F2 r;
+#if defined(__CUDA_ARCH__)
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+#else
+  r.lo = a;
+  r.hi = b;
+#endif
+  return r;
+}
+NELE_HD void f2_unpack(F2 p, float& a, float& b) {
+#if defined(__CUDA_ARCH__)
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v));
+#else
+  a = p.lo;
+  b = p.hi;
+#endif
+}
+NELE_HD F2 f2_fma(F2 a, F2 b, F2 c) {
+  F2 d;
+#if defined(__CUDA_ARCH__)
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+#else
+  d.lo = fmaf(a.lo, b.lo, c.lo);
+  d.hi = fmaf(a.hi, b.hi, c.hi);
+#endif
+  return d;
+}
+NELE_HD F2 f2_mul(F2 a, F2 b) {
+  F2 d;
+#if defined(__CUDA_ARCH__)
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+#else
+  d.lo = a.lo * b.lo;
+  d.hi = a.hi * b.hi;
+#endif
+  return d;
+}
+NELE_HD F2 f2_add(F2 a, F2 b) {
+  F2 d;
+#if defined(__CUDA_ARCH__)
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+#else
+  d.lo = a.lo + b.lo;
+  d.hi = a.hi + b.hi;
+#endif
+  return d;
+}
+
+// The main-pass lane of both signals of a pair, two-wide (experimental: haspi_ear_x2_kernel, NELE_F32X2=1).
+// Same arithmetic per component as EarLane<float>::sample; tests/host_emul/ear_x2_emul.cpp checks the two against
+// each other on the host.
+struct EarLane2 {
+  float kca, kcc1, kcc2, ctl_db;   // control filter: the same for both signals
+  F2 ksa, ksc1, ksc2, sig_db;      // signal filter: (x, y)
+  F2 cr1, cr2, cr3, cr4, crp, ci1, ci2, ci3, ci4, cip;
+  F2 sr1, sr2, sr3, sr4, srp, si1, si2, si3, si4, sip;
+  F2 zlp, v1, v2;
+  float m11, m12, m21, m22, g1, g2, r1inv;
+  float thr_x, thr_y;
+  F2 thr, crfac, ohc;
+  F2 acc[6];
+
+  NELE_HD void init(const BandConst& b, double bwx, double bwy, const IhcConst& ih) {
+    const GtCoef<float> kc = make_gt<float>(b.bw1, b.erb);
+    const GtCoef<float> kx = make_gt<float>(bwx, b.erb), ky = make_gt<float>(bwy, b.erb);
+    kca = kc.a;
+    kcc1 = kc.c1;
+    kcc2 = kc.c2;
+    ksa = f2_pack(kx.a, ky.a);
+    ksc1 = f2_pack(kx.c1, ky.c1);
+    ksc2 = f2_pack(kx.c2, ky.c2);
+    const F2 z = f2_pack(0.f, 0.f);
+    cr1 = cr2 = cr3 = cr4 = crp = ci1 = ci2 = ci3 = ci4 = cip = z;
+    sr1 = sr2 = sr3 = sr4 = srp = si1 = si2 = si3 = si4 = sip = z;
+    zlp = v1 = v2 = z;
+    m11 = (float)ih.m11; m12 = (float)ih.m12; m21 = (float)ih.m21; m22 = (float)ih.m22;
+    g1 = (float)ih.g1; g2 = (float)ih.g2;
+    r1inv = (float)ih.r1inv;
+    thr_x = (float)b.lowknee[0];
+    thr_y = (float)b.lowknee[1];
+    thr = f2_pack(thr_x, thr_y);
+    crfac = f2_pack((float)((1.0 - 1.0 / b.cr[0]) * 3.3219280948873623 / 20.0),
+                    (float)((1.0 - 1.0 / b.cr[1]) * 3.3219280948873623 / 20.0));
+    ohc = f2_pack((float)(-b.attn_ohc[0] * 3.3219280948873623 / 20.0), (float)(-b.attn_ohc[1] * 3.3219280948873623 / 20.0));
+    ctl_db = (float)(65.0 + 20.0 * log10((double)kc.gain));
+    sig_db = f2_pack((float)(65.0 - b.attn_ihc[0] + 20.0 * log10((double)kx.gain)),
+                     (float)(65.0 - b.attn_ihc[1] + 20.0 * log10((double)ky.gain)));
+#pragma unroll
+    for (int d = 0; d < 6; ++d) acc[d] = z;
+  }
+
+  // one demodulated sample pair -> IHC-adapted envelopes (x, y) in dB SL; EarLane<float>::sample two-wide
+  NELE_HD F2 sample(F2 xr, F2 xi) {
+    const F2 KA = f2_pack(kca, kca), KC1 = f2_pack(kcc1, kcc1), KC2 = f2_pack(kcc2, kcc2);
+    cr1 = f2_fma(KA, cr1, xr);
+    ci1 = f2_fma(KA, ci1, xi);
+    cr2 = f2_fma(KA, cr2, cr1);
+    ci2 = f2_fma(KA, ci2, ci1);
+    cr3 = f2_fma(KA, cr3, cr2);
+    ci3 = f2_fma(KA, ci3, ci2);
+    const F2 cnr = f2_fma(KA, cr4, cr3), cni = f2_fma(KA, ci4, ci3);
+    const F2 cur = f2_fma(KC2, crp, f2_fma(KC1, cr4, cnr)), cui = f2_fma(KC2, cip, f2_fma(KC1, ci4, cni));
+    crp = cr4;
+    cip = ci4;
+    cr4 = cnr;
+    ci4 = cni;
+    const F2 pc = f2_fma(cur, cur, f2_mul(cui, cui));
+    sr1 = f2_fma(ksa, sr1, xr);
+    si1 = f2_fma(ksa, si1, xi);
+    sr2 = f2_fma(ksa, sr2, sr1);
+    si2 = f2_fma(ksa, si2, si1);
+    sr3 = f2_fma(ksa, sr3, sr2);
+    si3 = f2_fma(ksa, si3, si2);
+    const F2 snr = f2_fma(ksa, sr4, sr3), sni = f2_fma(ksa, si4, si3);
+    const F2 sur = f2_fma(ksc2, srp, f2_fma(ksc1, sr4, snr)), sui = f2_fma(ksc2, sip, f2_fma(ksc1, si4, sni));
+    srp = sr4;
+    sip = si4;
+    sr4 = snr;
+    si4 = sni;
+    const F2 ps = f2_fma(sur, sur, f2_mul(sui, sui));
+    // eb_EnvCompressBM
+    const F2 C10 = f2_pack(NELE_10_OVER_LOG2_10, NELE_10_OVER_LOG2_10), NEG1 = f2_pack(-1.f, -1.f);
+    float pcx, pcy;
+    f2_unpack(pc, pcx, pcy);
+    float lx, ly;
+    f2_unpack(f2_fma(C10, f2_pack(fast_lg2(pcx), fast_lg2(pcy)), f2_pack(ctl_db, ctl_db)), lx, ly);
+    lx = fminf(fmaxf(lx, thr_x), 100.0f);
+    ly = fminf(fmaxf(ly, thr_y), 100.0f);
+    float ax, ay;
+    f2_unpack(f2_fma(f2_fma(f2_pack(lx, ly), NEG1, thr), crfac, ohc), ax, ay);   // (thrLow - le) crfac + ohc
+    const F2 G = f2_pack(fast_ex2(ax), fast_ex2(ay));
+    const F2 B0 = f2_pack(0.095107983402496f, 0.095107983402496f), K8 = f2_pack(0.809784033195007f, 0.809784033195007f);
+    const F2 glp = f2_fma(B0, G, zlp);
+    zlp = f2_fma(K8, glp, f2_mul(B0, G));
+    // eb_EnvSL2
+    float ex, ey;
+    f2_unpack(f2_mul(f2_mul(glp, glp), ps), ex, ey);
+    float v0x, v0y;
+    f2_unpack(f2_fma(C10, f2_pack(fast_lg2(ex), fast_lg2(ey)), sig_db), v0x, v0y);
+    const F2 V0 = f2_pack(fmaxf(v0x, 0.0f), fmaxf(v0y, 0.0f));
+    // eb_IHCadapt
+    const F2 n1 = f2_fma(f2_pack(g1, g1), V0, f2_fma(f2_pack(m12, m12), v2, f2_mul(f2_pack(m11, m11), v1)));
+    const F2 n2 = f2_fma(f2_pack(g2, g2), V0, f2_fma(f2_pack(m22, m22), v2, f2_mul(f2_pack(m21, m21), v1)));
+    v1 = n1;
+    v2 = n2;
+    float ox, oy;
+    f2_unpack(f2_mul(f2_fma(n1, NEG1, V0), f2_pack(r1inv, r1inv)), ox, oy);
+    return f2_pack(fmaxf(ox, 0.0f), fmaxf(oy, 0.0f));
+  }
+
+  template <int P>
+  NELE_HD void accumulate(F2 v, const float* fir) {
+#pragma unroll
+    for (int d = 0; d < 6; ++d) acc[d] = f2_fma(f2_pack(fir[d * 9 + P], fir[d * 9 + P]), v, acc[d]);
+  }
+  NELE_HD F2 emit() {
+    const F2 o = acc[0];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) acc[d] = acc[d + 1];
+    acc[5] = f2_pack(0.f, 0.f);
+    return o;
+  }
+};
+
+
 // h[k] = np.hanning(52)[k] / sum  -> fir[d*9 + p] = h[9(d-2) + 26 - p] (0 outside 0..51)
 inline void make_env_fir(float* fir /*[54]*/) {
   double h[kEnvTaps], s = 0.0;
