@@ -94,10 +94,14 @@ __global__ void __launch_bounds__(kRsThreads) estoi_resample_kernel(EstoiGeom g,
 constexpr int kRfG = 32, kRfThreads = 5 * kRfG, kRfTile = 20 * kRfG, kRfNt = 128;
 constexpr int kRfSpan = 32 * kRfG + 126;
 __constant__ double c_rf_tap[5][kRfNt];   // zero padded branches (estoi_upload_polytaps); a warp reads one entry per step
+__constant__ float c_rf_tapf[5][kRfNt];   // the same in FP32 (experimental NELE_RESAMPLE_F32=1)
 
 constexpr int kRfTilesPerCta = 4;
 constexpr int kRfPre = (kRfSpan + kRfThreads - 1) / kRfThreads;   // staged inputs per thread and tile
 
+// T = double: FP64 products and sums (default).  T = float (experimental, NELE_RESAMPLE_F32=1, not yet run on
+// hardware): FP32 throughout -- 119 taps of FP32 accumulation leave ~1e-6 relative error in the 10 kHz signal.
+template <typename T>
 __global__ void __launch_bounds__(kRfThreads, 4) estoi_resample58_kernel(EstoiGeom g, EstoiBuffers b) {
   const int pair = blockIdx.y, q = blockIdx.z, tid = threadIdx.x;
   const int n_out = g.n10[pair];
@@ -106,10 +110,12 @@ __global__ void __launch_bounds__(kRfThreads, 4) estoi_resample58_kernel(EstoiGe
   const float* __restrict__ src = (q == 0 ? b.ref : b.deg) + g.off16[pair];
   const int L = g.len16[pair];
   float* __restrict__ dst = b.x10 + (int64_t)q * b.tot10 + g.off10[pair];
-  __shared__ double s_in[kRfSpan + kRfSpan / 32 + 2];
+  __shared__ T s_in[kRfSpan + kRfSpan / 32 + 2];
   __shared__ float s_out[kRfTile];
   const int phi = tid >> 5, v = tid & 31;
-  const double* __restrict__ tp = c_rf_tap[(8 * phi) % 5];
+  const T* __restrict__ tp;
+  if constexpr (sizeof(T) == 8) tp = c_rf_tap[(8 * phi) % 5];
+  else tp = c_rf_tapf[(8 * phi) % 5];
   const int u0 = 32 * v + (8 * phi) / 5 + (kRfNt - 1);   // staged index of x[n + K] for the first output
   // staged index i <-> x[inbase + i]; output t with n = floor(8 t / 5) reads x[n + K - kk], kk = 0..127.
   // The inputs of the next tile are fetched into registers while the current one is computed.
@@ -129,24 +135,24 @@ __global__ void __launch_bounds__(kRfThreads, 4) estoi_resample58_kernel(EstoiGe
 #pragma unroll
     for (int c = 0; c < kRfPre; ++c) {
       const int i = tid + c * kRfThreads;
-      if (i < kRfSpan) s_in[i + (i >> 5)] = (double)pre[c];
+      if (i < kRfSpan) s_in[i + (i >> 5)] = (T)pre[c];
     }
     __syncthreads();
     if (tile + 1 < kRfTilesPerCta && T0 + kRfTile < n_out) fetch(T0 + kRfTile);
-    double w[32];
+    T w[32];
 #pragma unroll
     for (int i = 1; i <= 24; ++i) {
       const int u = u0 + i;
       w[32 - i] = s_in[u + (u >> 5)];
     }
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll 1
     for (int kk0 = 0; kk0 < kRfNt; kk0 += 32) {
 #pragma unroll
       for (int sft = 0; sft < 32; ++sft) {
         const int u = u0 - kk0 - sft;
         w[sft] = s_in[u + (u >> 5)];
-        const double t = tp[kk0 + sft];
+        const T t = tp[kk0 + sft];
         a0 = fma(t, w[sft], a0);
         a1 = fma(t, w[(sft + 24) & 31], a1);   // loaded 8 steps ago: x 8 samples later
         a2 = fma(t, w[(sft + 16) & 31], a2);
@@ -458,6 +464,10 @@ void estoi_upload_polytaps(const double* taps, int up, int K, cudaStream_t s) {
   for (int r = 0; r < 5; ++r)
     for (int k = 0; k < kRfNt; ++k) padded[r][k] = k < nt ? taps[r * nt + k] : 0.0;
   cudaMemcpyToSymbolAsync(c_rf_tap, padded, sizeof(padded), 0, cudaMemcpyHostToDevice, s);
+  static float paddedf[5][kRfNt];
+  for (int r = 0; r < 5; ++r)
+    for (int k = 0; k < kRfNt; ++k) paddedf[r][k] = (float)padded[r][k];
+  cudaMemcpyToSymbolAsync(c_rf_tapf, paddedf, sizeof(paddedf), 0, cudaMemcpyHostToDevice, s);
   cudaStreamSynchronize(s);
   g_rf_taps_ok = true;
 }
@@ -476,7 +486,12 @@ int estoi_run(const EstoiGeom& g, const EstoiBuffers& b, int n, int max_n10, int
   static const bool generic_only = getenv("NELE_ESTOI_RESAMPLE_GENERIC") != nullptr;   // A/B switch
   kt_begin(kt, "estoi_resample", s);
   if (b.up == 5 && b.down == 8 && g_rf_taps_ok && !generic_only)
-    estoi_resample58_kernel<<<dim3((max_n10 + kRfTilesPerCta * kRfTile - 1) / (kRfTilesPerCta * kRfTile), n, 2), kRfThreads, 0, s>>>(g, b);
+  {
+    static const bool f32 = [] { const char* p = getenv("NELE_RESAMPLE_F32"); return p && p[0] == '1'; }();
+    const dim3 grid((max_n10 + kRfTilesPerCta * kRfTile - 1) / (kRfTilesPerCta * kRfTile), n, 2);
+    if (f32) estoi_resample58_kernel<float><<<grid, kRfThreads, 0, s>>>(g, b);
+    else estoi_resample58_kernel<double><<<grid, kRfThreads, 0, s>>>(g, b);
+  }
   else
     estoi_resample_kernel<<<dim3((max_n10 + tile - 1) / tile, n, 2), kRsThreads, smem, s>>>(g, b, span, groups, taps_in_smem);
   kt_end(kt, s);

@@ -27,6 +27,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "host_tables.hpp"
 #include "kernels.h"
 #include "philox.cuh"
@@ -65,7 +67,12 @@ constexpr int kPrepThreads = 256;
 constexpr int kPrepGroups = 85;                       // 3 threads x 4 outputs each = 12 outputs per group
 constexpr int kPrepSpan = kPrepGroups * 8 + 128 + 16;  // staged inputs per tile
 
+// F32 (experimental, NELE_RESAMPLE_F32=1, not yet run on hardware): the 16 -> 24 kHz polyphase products and sums in
+// FP32 instead of FP64 (the output is stored as float32 either way; 128 taps of FP32 accumulation leave ~1e-6
+// relative error).  Everything else -- RMS, level match, middle ear -- stays FP64.
+template <bool F32>
 __global__ void __launch_bounds__(kPrepThreads, 4) haspi_prep_kernel(PairGeom g, HaspiBuffers b) {
+  using RT = typename std::conditional<F32, float, double>::type;
   const int pair = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
   const float* __restrict__ src = (q == 0 ? b.ref : b.deg) + g.off16[pair];
   const int L = g.len16[pair];
@@ -101,12 +108,13 @@ __global__ void __launch_bounds__(kPrepThreads, 4) haspi_prep_kernel(PairGeom g,
     // tap is fetched once for four FP64 FMAs and the inputs slide through an 8-register window.
     // Inputs are staged in shared memory as FP64 with a (a + a/8) skew: lanes 8 samples apart hit
     // distinct banks.
-    __shared__ double s_tap[3][130];
-    extern __shared__ double s_xin[];  // skewed tile of inputs
+    __shared__ RT s_tap[3][130];
+    extern __shared__ double s_xin_raw[];  // skewed tile of inputs
+    RT* s_xin = reinterpret_cast<RT*>(s_xin_raw);
     for (int k = tid; k < 3 * 128; k += kPrepThreads) {
       const int r = k / 128, m = k % 128;  // m = 0..127 <-> offset m - 63
       // taps[r][0..63] weigh x[n - i]; taps[r][64..127] weigh x[n + 1 + k]
-      s_tap[r][m] = (m <= 63) ? b.rs_taps[r * 128 + (63 - m)] : b.rs_taps[r * 128 + 64 + (m - 64)];
+      s_tap[r][m] = (RT)((m <= 63) ? b.rs_taps[r * 128 + (63 - m)] : b.rs_taps[r * 128 + 64 + (m - 64)]);
     }
     const int n_out = (int)(((int64_t)L * 3) / 2);  // int(L * ratio); the tail up to N is zero (fix_length)
     const int v_loc = tid / 3, phi = tid % 3;
@@ -130,7 +138,7 @@ __global__ void __launch_bounds__(kPrepThreads, 4) haspi_prep_kernel(PairGeom g,
 #pragma unroll
       for (int c = 0; c < kPre; ++c) {
         const int u = tid + c * kPrepThreads;
-        if (u < kPrepSpan) s_xin[u + (u >> 3)] = (double)pre[c];
+        if (u < kPrepSpan) s_xin[u + (u >> 3)] = (RT)pre[c];
       }
       __syncthreads();
       if (tile0 + kPrepGroups * 12 < N) fetch(tile0 + kPrepGroups * 12);
@@ -138,9 +146,9 @@ __global__ void __launch_bounds__(kPrepThreads, 4) haspi_prep_kernel(PairGeom g,
         const int t0 = tile0 + 12 * v_loc + phi;       // first of the four outputs
         const int n = (2 * t0) / 3, r = (2 * t0) % 3;  // t0 = 12 v + phi -> n = 8 v + {0, 0, 1}
         const int base = n - 63 - in0;                 // staged index of x[n - 63]
-        const double* __restrict__ tp = s_tap[r];
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        double w[8];
+        const RT* __restrict__ tp = s_tap[r];
+        RT a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        RT w[8];
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
           const int u = base + k;
@@ -152,14 +160,14 @@ __global__ void __launch_bounds__(kPrepThreads, 4) haspi_prep_kernel(PairGeom g,
           for (int sft = 0; sft < 8; ++sft) {
             const int u = base + m0 + sft + 7;
             w[(sft + 7) & 7] = s_xin[u + (u >> 3)];
-            const double tm = tp[m0 + sft];
+            const RT tm = tp[m0 + sft];
             a0 = fma(tm, w[sft & 7], a0);
             a1 = fma(tm, w[(sft + 2) & 7], a1);
             a2 = fma(tm, w[(sft + 4) & 7], a2);
             a3 = fma(tm, w[(sft + 6) & 7], a3);
           }
         }
-        const double acc[4] = {a0, a1, a2, a3};
+        const double acc[4] = {(double)a0, (double)a1, (double)a2, (double)a3};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int t = t0 + 3 * j;
@@ -1003,7 +1011,9 @@ void haspi_upload_tables(const float* cepm, const int* nhalf, const int* off, co
 int haspi_run_front(const PairGeom& g, const HaspiBuffers& b, int n, bool f64, KernelTimer* kt, cudaStream_t s) {
   int launches = 0;
   kt_begin(kt, "haspi_prep", s);
-  haspi_prep_kernel<<<dim3(n, 2), kPrepThreads, (kPrepSpan + kPrepSpan / 8 + 8) * sizeof(double), s>>>(g, b);
+  static const bool rs_f32 = [] { const char* p = getenv("NELE_RESAMPLE_F32"); return p && p[0] == '1'; }();
+  if (rs_f32) haspi_prep_kernel<true><<<dim3(n, 2), kPrepThreads, (kPrepSpan + kPrepSpan / 8 + 8) * sizeof(double), s>>>(g, b);
+  else haspi_prep_kernel<false><<<dim3(n, 2), kPrepThreads, (kPrepSpan + kPrepSpan / 8 + 8) * sizeof(double), s>>>(g, b);
   kt_end(kt, s);
   ++launches;
   const int ctas = (n + kEarWarps - 1) / kEarWarps;
