@@ -86,3 +86,24 @@ def test_band_matrix_is_compute_band_E():
                 s[i + 1] += frac * tmp
         out[t] = s
     assert rel(features_np.compute_band_E(X), out) < 1e-6
+
+
+def test_host_mirror_rejects_cpu_tensors_and_has_the_reference_names():
+    """nele_gan_b200/features.py: same names as audio_util.py:422-457, no CPU path."""
+    torch = pytest.importorskip("torch")
+    from nele_gan_b200 import features as F
+    for name in ("Sp_and_phase_Speech", "Sp_and_phase_Noise", "speech_features", "noise_features", "features_tensors"):
+        assert callable(getattr(F, name))
+    assert F.power_law == 1 / 6                                   # dataloader.py:14
+    with pytest.raises(ValueError):
+        F.features_tensors(torch.zeros(2, 4000))                  # CPU tensor: the engine has no CPU path
+    import inspect
+    src = inspect.getsource(F)
+    assert "oracle" not in src.replace("``oracle/``", "")         # the product never imports the oracle
+
+
+def test_frame_bookkeeping_matches_librosa_centred_framing():
+    """T = 1 + L // 256 (centred frames, hop 256): what nele_feature_frames and the Python binding assume."""
+    from oracle import features_np
+    for L in (257, 511, 512, 513, 4000, 48000):
+        assert features_np.stft(np.zeros(L, np.float32)).shape == (257, 1 + L // 256)
