@@ -1052,7 +1052,12 @@ extern "C" int nele_features(nele_engine* e, const float* wav, const int64_t* of
   CU(e, cudaSetDevice(e->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
 
-  const int64_t kMaxFrames = 4 << 20;   // frames per chunk: bounds the [257][T] workspaces at 4.3 GB each
+  // frames per chunk: bounds the [257][T] workspaces at 4.3 GB each (NELE_FEAT_MAX_FRAMES: test knob for the chunk loop)
+  static const int64_t kMaxFrames = [] {
+    const char* p = getenv("NELE_FEAT_MAX_FRAMES");
+    const long long v = p ? atoll(p) : 0;
+    return (int64_t)(v > 0 ? v : (4 << 20));
+  }();
   int64_t frame0 = 0;                   // frames of the waveforms before this chunk
   for (int first = 0; first < n;) {
     int last = first;
