@@ -67,9 +67,10 @@ constexpr int kPrepThreads = 256;
 constexpr int kPrepGroups = 85;                       // 3 threads x 4 outputs each = 12 outputs per group
 constexpr int kPrepSpan = kPrepGroups * 8 + 128 + 16;  // staged inputs per tile
 
-// F32 (experimental, NELE_RESAMPLE_F32=1, not yet run on hardware): the 16 -> 24 kHz polyphase products and sums in
-// FP32 instead of FP64 (the output is stored as float32 either way; 128 taps of FP32 accumulation leave ~1e-6
-// relative error).  Everything else -- RMS, level match, middle ear -- stays FP64.
+// F32 (default; NELE_RESAMPLE_F32=0 selects FP64): the 16 -> 24 kHz polyphase products and sums in FP32 instead of
+// FP64 (the output is stored as float32 either way; 128 taps of FP32 accumulation leave ~1e-6 relative error,
+// measured on a B200: HASPI moves by 8e-7, 12.4 -> 9.6 ms per 4096 x 3 s).  Everything else -- RMS, level match,
+// middle ear -- stays FP64.
 template <bool F32>
 __global__ void __launch_bounds__(kPrepThreads, 4) haspi_prep_kernel(PairGeom g, HaspiBuffers b) {
   using RT = typename std::conditional<F32, float, double>::type;
@@ -354,74 +355,6 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_control_kernel(PairGeom 
   }
 }
 
-// ---- experimental: the control pass with the clean and the processed chain packed into
-// fma.rn.f32x2 (Blackwell's two-wide FP32 FMA: the same FMA-pipe throughput as two FFMA,
-// scripts/micro/ffma2.cu, but one issue slot).  The two chains share every coefficient here, so
-// each recurrence line becomes one packed instruction; the arithmetic per lane is the scalar
-// kernel's (fma.rn), the results agree to the last bit wherever the compiler contracts the scalar
-// expressions the same way.  Off by default (NELE_F32X2=1 switches it on for A/B timing).
-__global__ void __launch_bounds__(kEarWarps * 32) haspi_control_x2_kernel(PairGeom g, HaspiBuffers b, int n_pairs) {
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int pair = blockIdx.x * kEarWarps + wib;
-  if (pair >= n_pairs) return;
-  const double* __restrict__ midx = b.mid + g.off24[pair];
-  const double* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
-  const int N = g.n24[pair];
-  __shared__ float2 s_buf[kEarWarps][kCtlChunk];   // (x, y) sample pairs
-  float2* bxy = s_buf[wib];
-  const BandConst bc = b.bands[lane];
-  Carrier<float> car;
-  car.init(bc.cf);
-  const GtCoef<float> k = make_gt<float>(bc.bw1, bc.erb);
-  const F2 A = f2_pack(k.a, k.a), C1 = f2_pack(k.c1, k.c1), C2 = f2_pack(k.c2, k.c2);
-  const F2 Z = f2_pack(0.f, 0.f);
-  F2 r1 = Z, r2 = Z, r3 = Z, r4 = Z, rp = Z, i1 = Z, i2 = Z, i3 = Z, i4 = Z, ip = Z;
-  double accx = 0.0, accy = 0.0;
-  for (int base = 0; base < N; base += kCtlChunk) {
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < kCtlChunk / 32; ++q) {
-      const int t = base + q * 32 + lane;
-      bxy[q * 32 + lane] = (t < N) ? make_float2((float)midx[t], (float)midy[t]) : make_float2(0.f, 0.f);
-    }
-    __syncwarp();
-    car.seed_before(base);
-    const int m = min(kCtlChunk, N - base);
-    F2 p = Z;
-#pragma unroll 4
-    for (int q = 0; q < m; ++q) {
-      car.advance();
-      const float2 xy = bxy[q];
-      const F2 XY = f2_pack(xy.x, xy.y);
-      const F2 xr = f2_mul(XY, f2_pack(car.c, car.c)), xi = f2_mul(XY, f2_pack(car.s, car.s));
-      r1 = f2_fma(A, r1, xr);
-      i1 = f2_fma(A, i1, xi);
-      r2 = f2_fma(A, r2, r1);
-      i2 = f2_fma(A, i2, i1);
-      r3 = f2_fma(A, r3, r2);
-      i3 = f2_fma(A, i3, i2);
-      const F2 nr = f2_fma(A, r4, r3), ni = f2_fma(A, i4, i3);
-      const F2 ur = f2_fma(C2, rp, f2_fma(C1, r4, nr)), ui = f2_fma(C2, ip, f2_fma(C1, i4, ni));
-      rp = r4;
-      ip = i4;
-      r4 = nr;
-      i4 = ni;
-      p = f2_add(p, f2_fma(ur, ur, f2_mul(ui, ui)));
-    }
-    float px, py;
-    f2_unpack(p, px, py);
-    accx += (double)px;
-    accy += (double)py;
-  }
-  const int64_t o = (int64_t)pair * 2 * kBands + lane;
-  b.bw[o] = bw_from_control(accx, (double)k.gain, N, bc.bwmin[0], bc.bw1);
-  b.bw[o + kBands] = bw_from_control(accy, (double)k.gain, N, bc.bwmin[1], bc.bw1);
-  if (b.cave) {
-    b.cave[o] = (double)k.gain * sqrt(accx / (double)N);
-    b.cave[o + kBands] = (double)k.gain * sqrt(accy / (double)N);
-  }
-}
-
 // group-delay shifts, always from BWx (pyhaspi2.py:1239-1240)
 __global__ void haspi_shift_kernel(HaspiBuffers b, int n) {
   const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -536,11 +469,14 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_kernel(PairGeom g, H
   }
 }
 
-// ---- experimental: the main pass with the clean and the processed chain packed into f32x2
-// instructions (see haspi_control_x2_kernel).  Every linear recurrence, the level arithmetic around
-// the MUFU calls and the FIR bookkeeping run two-wide; only lg2 / ex2 and the clamps stay scalar.
-// By the instruction count the loop drops from ~130 to ~75 issue slots per sample pair at the same
-// FMA-pipe time.  Off by default (NELE_F32X2=1).
+// ---- the main pass with the clean and the processed chain packed into fma.rn.f32x2 (Blackwell's
+// two-wide FP32 FMA: the same FMA-pipe throughput as two FFMA, scripts/micro/ffma2.cu, but one issue
+// slot).  Every linear recurrence, the level arithmetic around the MUFU calls and the FIR
+// bookkeeping run two-wide; only lg2 / ex2 and the clamps stay scalar: ~130 -> ~75 issue slots per
+// sample pair at the same FMA-pipe time.  Measured on a B200 (round 2): 45.1 -> 40.6 ms per
+// 4096 x 3 s, HASPI equal to 2.7e-6; default since then (NELE_F32X2=0 selects the scalar kernel).
+// The control pass was packed the same way and was *slower* (4.15 -> 4.65 ms per 1024 pairs: it
+// has no MUFU / clamp work to overlap, so packing only lengthens the dependency chain): removed.
 __global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_x2_kernel(PairGeom g, HaspiBuffers b, int n_pairs) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int pair = blockIdx.x * kEarWarps + wib;
@@ -1011,19 +947,14 @@ void haspi_upload_tables(const float* cepm, const int* nhalf, const int* off, co
 int haspi_run_front(const PairGeom& g, const HaspiBuffers& b, int n, bool f64, KernelTimer* kt, cudaStream_t s) {
   int launches = 0;
   kt_begin(kt, "haspi_prep", s);
-  static const bool rs_f32 = [] { const char* p = getenv("NELE_RESAMPLE_F32"); return p && p[0] == '1'; }();
+  static const bool rs_f32 = [] { const char* p = getenv("NELE_RESAMPLE_F32"); return !(p && p[0] == '0'); }();
   if (rs_f32) haspi_prep_kernel<true><<<dim3(n, 2), kPrepThreads, (kPrepSpan + kPrepSpan / 8 + 8) * sizeof(double), s>>>(g, b);
   else haspi_prep_kernel<false><<<dim3(n, 2), kPrepThreads, (kPrepSpan + kPrepSpan / 8 + 8) * sizeof(double), s>>>(g, b);
   kt_end(kt, s);
   ++launches;
   const int ctas = (n + kEarWarps - 1) / kEarWarps;
   kt_begin(kt, "haspi_control", s);
-  static const bool x2 = [] {
-    const char* p = getenv("NELE_F32X2");
-    return p && p[0] == '1';
-  }();
   if (f64) haspi_control_kernel<double><<<ctas, kEarWarps * 32, 0, s>>>(g, b, n);
-  else if (x2) haspi_control_x2_kernel<<<ctas, kEarWarps * 32, 0, s>>>(g, b, n);
   else haspi_control_kernel<float><<<ctas, kEarWarps * 32, 0, s>>>(g, b, n);
   kt_end(kt, s);
   ++launches;
@@ -1038,9 +969,9 @@ int haspi_run(const PairGeom& g, const HaspiBuffers& b, int n, int max_nsub, boo
   int launches = haspi_run_front(g, b, n, f64, kt, s);
   kt_begin(kt, "haspi_ear", s);
   const int ear_ctas = (n + kEarWarps - 1) / kEarWarps;
-  static const bool x2 = [] {
+  static const bool x2 = [] {  // packed main pass (default); NELE_F32X2=0 selects the scalar kernel for A/B checks
     const char* p = getenv("NELE_F32X2");
-    return p && p[0] == '1';
+    return !(p && p[0] == '0');
   }();
   if (f64) haspi_ear_kernel<double><<<ear_ctas, kEarWarps * 32, kEarWarps * 4 * kEarChunk * sizeof(double), s>>>(g, b, n);
   else if (x2) haspi_ear_x2_kernel<<<ear_ctas, kEarWarps * 32, kEarWarps * 4 * kEarChunk * sizeof(float), s>>>(g, b, n);

@@ -198,6 +198,8 @@ int siib_run_small_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuf
                        cudaStream_t s);
 int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, KernelTimer* kt,
                  cudaStream_t s);
+// FP32 lower-triangle tridiagonalisation (siib_klt.cu): same outputs as siib_tridiag_kernel
+int siib_launch_tridiag32(const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, cudaStream_t s);
 void siib_upload_tables(const float* win, const float* decay, const float* g2t, const float* tw, cudaStream_t s);
 int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_tile, KernelTimer* kt, cudaStream_t s);
 // kb != nullptr: k-NN estimator instead of the Gaussian quadratic forms

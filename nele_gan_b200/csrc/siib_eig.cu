@@ -463,6 +463,11 @@ __global__ void siib_eig_finish_kernel(SiibBuffers b, int n, int rank_lo) {
 int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, KernelTimer* kt,
                  cudaStream_t s) {
   kt_begin(kt, "siib_tridiag", s);
+  // default: FP32 lower-triangle kernel (siib_klt.cu); NELE_TRIDIAG_F64=1 selects the FP64 kernel above (A/B checks)
+  static const bool tri_f64 = [] { const char* p = getenv("NELE_TRIDIAG_F64"); return p && p[0] == '1'; }();
+  if (!tri_f64) {
+    siib_launch_tridiag32(b, eb, n, rank_lo, s);
+  } else {
   static const bool tri_attr = [] {
     cudaFuncSetAttribute(siib_tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTriB * kELd * (int)sizeof(double));
     return true;
@@ -471,6 +476,7 @@ int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& 
   static const int tri_grid = [] { const char* p = getenv("NELE_TRIDIAG_GRID"); return p ? atoi(p) : 1 << 30; }();
   static const int tri_mv32 = [] { const char* p = getenv("NELE_TRIDIAG_MV32"); return (p && p[0] == '1') ? 1 : 0; }();
   siib_tridiag_kernel<<<std::min(n, tri_grid), kEThreads, 2 * kTriB * kELd * sizeof(double), s>>>(g, b, eb, rank_lo, n, tri_mv32);
+  }
   kt_end(kt, s);
   kt_begin(kt, "siib_trieig", s);
   siib_trieig_kernel<<<n, kEThreads, 0, s>>>(g, b, eb, rank_lo);
