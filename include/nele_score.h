@@ -22,7 +22,8 @@
  * Conventions: plain pointers and sizes, no ownership transfer.  The caller
  * owns inputs and outputs; the engine owns a grow-only device workspace.  One
  * engine per (process, device); calls on one engine are serialised by the
- * caller.  Every function returns 0 on success or a negative NELE_E_* code;
+ * engine (a mutex per handle), so threads may share a handle but gain nothing
+ * by it.  Every function returns 0 on success or a negative NELE_E_* code;
  * nele_last_error() gives the message.  Per-pair conditions that the
  * reference reports by raising (signal below threshold, too few frames) come
  * back in status[] and never abort the batch.
@@ -79,6 +80,12 @@ extern "C" {
 #define NELE_ST_BAD_RATE     3 /* sampling rate not supported for this metric: score = NaN */
 #define NELE_ST_UNSUPPORTED  4 /* SIIB k-NN estimator: more than 16384 KLT frames (score = NaN) */
 #define NELE_ST_SKIPPED      0xff /* metric not requested */
+/* informational bits above the three status bytes (a pair that carries one is still NELE_ST_OK) */
+#define NELE_INFO_SIIB_NULLSPACE 0x01000000 /* SIIB: the tiled signal repeats its frames exactly (utterance length a
+                                               multiple of the 200-sample hop, intel.py:71-75), cov(X) is rank deficient
+                                               and its null space was given zero information.  pysiib's float64 value is
+                                               1-13 % higher on such inputs: the sample correlations of eigh's
+                                               rounding-noise eigenvectors. */
 
 typedef struct nele_engine nele_engine;
 
@@ -140,6 +147,10 @@ int nele_score_batch(nele_engine* e, const float* ref, const float* deg, const i
  */
 int nele_prefetch(nele_engine* e, const float* ref, const float* deg, const int64_t* offs, const int32_t* lens, int n,
                   uint32_t flags);
+/* Drop every pending prefetch (e.g. when the step it was issued for is skipped).  A prefetch is matched by the
+ * buffer addresses and by a hash of offs[] / lens[], and expires by itself once two nele_score_batch calls have
+ * passed without consuming it. */
+int nele_prefetch_cancel(nele_engine* e);
 
 /*
  * Parity-test access to the per-stage tensors of the last nele_score_batch

@@ -24,6 +24,7 @@ import numpy as np
 from . import engine as _eng
 
 __all__ = ["haspi_v2", "haspi", "hasqi_v2", "SIIB", "stoi", "score_batch", "score_tensors", "read_batch_all",
+           "check_status", "MetricError", "SiibTooShort", "BadRate",
            "SIIB_Wrapper_harvard", "SIIB_Wrapper_raw_harvard", "mapping_SIIB_harvard",
            "HASPI_Wrapper_harvard", "HASPI_Wrapper_raw_harvard", "mapping_HASPI_harvard",
            "ESTOI_Wrapper_harvard", "ESTOI_Wrapper_raw_harvard", "mapping_ESTOI_harvard",
@@ -50,7 +51,9 @@ def haspi_v2(x, fx, y, fy, HL=np.zeros(6), seed=None):
     ``np.random`` so that ``np.random.seed`` makes calls reproducible, as it
     does for the reference)."""
     if fx != fy:
-        raise ValueError("haspi_v2: the engine needs fx == fy (got %r, %r)" % (fx, fy))
+        # the reference raises here too: it trims x and y to the same sample count, resamples each from its own
+        # rate and then fails in numpy ("operands could not be broadcast together", pyhaspi2.py:1185-1230)
+        raise ValueError("haspi_v2: fx and fy must be equal (got %r, %r)" % (fx, fy))
     if fx > 24000:
         raise NotImplementedError  # pyhaspi2.py:819-820
     x, y = _f32(x), _f32(y)
@@ -74,7 +77,9 @@ def haspi(x, fx, y, fy, HL=np.zeros(6), alpha=-1.0, seed=None):
     counter-based generator keyed by ``seed`` (default: drawn from
     ``np.random``, so ``np.random.seed`` makes calls reproducible)."""
     if fx != fy:
-        raise ValueError("haspi: the engine needs fx == fy (got %r, %r)" % (fx, fy))
+        # the reference raises here too: it trims x and y to the same sample count, resamples each from its own
+        # rate and then fails in numpy ("operands could not be broadcast together", pyhaspi2.py:1185-1230)
+        raise ValueError("haspi: fx and fy must be equal (got %r, %r)" % (fx, fy))
     if fx > 24000:
         raise NotImplementedError  # pyhaspi2.py:819-820
     x, y = _f32(x), _f32(y)
@@ -96,7 +101,9 @@ def hasqi_v2(x, fx, y, fy, HL=np.zeros(6), seed=None):
     ``raw = [CepCorr, BMsync5, Dloud, Dslope]``.  Not called by NELE-GAN; same ear model and
     noise convention as :func:`haspi`."""
     if fx != fy:
-        raise ValueError("hasqi_v2: the engine needs fx == fy (got %r, %r)" % (fx, fy))
+        # the reference raises here too: it trims x and y to the same sample count, resamples each from its own
+        # rate and then fails in numpy ("operands could not be broadcast together", pyhaspi2.py:1185-1230)
+        raise ValueError("hasqi_v2: fx and fy must be equal (got %r, %r)" % (fx, fy))
     if fx > 24000:
         raise NotImplementedError  # pyhaspi2.py:819-820
     x, y = _f32(x), _f32(y)
@@ -168,10 +175,63 @@ def mapping_ESTOI_harvard(x):     # intel.py:136-140
     return 1 / (1 + np.exp(-8.0 * (x - 0.25)))
 
 
+class MetricError(Exception):
+    """A pair of a batch could not be scored.  ``indices`` lists the failing pairs, ``metric`` and ``code`` the
+    engine status (include/nele_score.h, NELE_ST_*).  Subclasses the reference's own exception types where it has
+    one, so ``except ValueError`` / ``except Exception`` written against the reference still catch it."""
+
+    def __init__(self, msg, metric, code, indices):
+        super().__init__("%s (%s, %d of the batch: pairs %s%s)" % (msg, metric, len(indices), list(indices[:8]),
+                                                                  " ..." if len(indices) > 8 else ""))
+        self.metric, self.code, self.indices = metric, code, list(indices)
+
+
+class SiibTooShort(MetricError, ValueError):      # pysiib: ValueError
+    pass
+
+
+class BadRate(MetricError, NotImplementedError):   # pyhaspi2.py:819-820 / audio_util.py:131 assert
+    pass
+
+
+def check_status(r, metrics=("siib", "haspi", "estoi"), strict=True):
+    """Turn per-pair engine status into the reference's error behaviour for a batch.
+
+    The reference's wrappers raise out of the whole ``Parallel`` call when one utterance fails --
+    'Signal below threshold' (pyhaspi2.py:357-358), pysiib's 'at least 20 seconds of speech' -- and pystoi warns
+    and returns 1e-5 for fewer than 30 frames.  ``strict=True`` (default of every batched entry point) does the
+    same and names the failing pairs; ``strict=False`` leaves NaN in the scores and warns once per condition, so
+    NaN never reaches the discriminator's training records unnoticed."""
+    for m in metrics:
+        st = r.metric_status(m)
+        bad = np.nonzero((st != _eng.ST_OK) & (st != _eng.ST_SKIPPED))[0]
+        if not len(bad):
+            continue
+        for code in np.unique(st[bad]):
+            idx = bad[st[bad] == code]
+            if m == "estoi" and code == _eng.ST_TOO_SHORT:
+                warnings.warn('Not enough STFT frames to compute intermediate intelligibility measure after removing '
+                              'silent frames. Returning 1e-5. Please check you wav files (pairs %s)' % list(idx[:8]),
+                              RuntimeWarning)
+                continue
+            if code == _eng.ST_BELOW_THR:
+                err = MetricError('Function ebm_CepCoef: Signal below threshold', m, int(code), idx)
+            elif code == _eng.ST_TOO_SHORT:
+                err = SiibTooShort('stimuli must have at least 20 seconds of speech', m, int(code), idx)
+            elif code == _eng.ST_BAD_RATE:
+                err = BadRate('sampling rate not supported for this metric', m, int(code), idx)
+            else:
+                err = MetricError('engine status %d' % int(code), m, int(code), idx)
+            if strict:
+                raise err
+            warnings.warn("%s -- scores of these pairs are NaN" % err, RuntimeWarning)
+    return r
+
+
 def _one(metric, x, y, fs_, mapped):
     r = _engine().score_batch([_f32(x)], [_f32(y)], fs=int(fs_), metrics=(metric,), mapped=mapped,
                               seed=int(np.random.randint(0, 2 ** 31 - 1)))
-    return r
+    return check_status(r, (metric,))
 
 
 def SIIB_Wrapper_raw_harvard(x, y, fs):      # intel.py:57-77 (VAD, tile to >= 25 s, SIIB^Gauss)
@@ -199,24 +259,36 @@ def ESTOI_Wrapper_harvard(x, y, fs):         # intel.py:129-134
 
 
 # ------------------------------------------------------- batched forms
-def score_batch(refs, degs, fs=16000, metrics=("siib", "haspi", "estoi"), norm=True, seed=0, **kw):
+def score_batch(refs, degs, fs=16000, metrics=("siib", "haspi", "estoi"), norm=True, seed=0, strict=True, **kw):
     """All labels of a list of (clean, degraded) pairs in one engine call.
     Returns ``float64[n, 3]`` in the column order {SIIB, HASPI, ESTOI} that
-    train_nele.py:320-322 computes and audio_util.py:367-389 serialises."""
-    return _engine().score_batch(refs, degs, fs=fs, metrics=metrics, mapped=norm, seed=seed, **kw).scores
+    train_nele.py:320-322 computes and audio_util.py:367-389 serialises.
+    ``strict``: see :func:`check_status`."""
+    r = _engine().score_batch(refs, degs, fs=fs, metrics=metrics, mapped=norm, seed=seed, **kw)
+    return check_status(r, metrics, strict).scores
 
 
 def _load16k(path):
     """``librosa.load(path, sr=16000)`` for the 16 kHz PCM WAV files the
-    reference writes (train_nele.py:313) and asserts on (audio_util.py:131)."""
+    reference writes (train_nele.py:313) and asserts on (audio_util.py:131):
+    float32 in [-1, 1), channels averaged to mono as librosa does.  A file at
+    another rate is an error here (librosa would resample it; the reference's
+    callers assert ``sr == 16000`` right after, audio_util.py:131,159,187)."""
     from scipy.io import wavfile
     sr, x = wavfile.read(path)
-    assert sr == 16000
+    if sr != 16000:
+        raise ValueError("%s: sampling rate %d, the labelling path needs 16000 Hz (audio_util.py:131)" % (path, sr))
     if x.dtype == np.int16:
-        return x.astype(np.float32) / 32768.0
-    if x.dtype == np.int32:
-        return (x.astype(np.float64) / 2147483648.0).astype(np.float32)
-    return x.astype(np.float32)
+        x = x.astype(np.float32) / 32768.0
+    elif x.dtype == np.int32:
+        x = (x.astype(np.float64) / 2147483648.0).astype(np.float32)
+    elif x.dtype == np.uint8:
+        x = (x.astype(np.float32) - 128.0) / 128.0
+    else:
+        x = x.astype(np.float32)
+    if x.ndim == 2:                                   # librosa.load(mono=True): mean over channels
+        x = x.mean(axis=1, dtype=np.float32)
+    return x
 
 
 def _wave_name(enhanced_file, drc):
@@ -237,12 +309,13 @@ def _read_pairs(clean_root, noise_root, enhanced_list, drc):
     return refs, degs
 
 
-def _read_batch(metric, col, clean_root, noise_root, enhanced_list, norm, drc):
+def _read_batch(metric, col, clean_root, noise_root, enhanced_list, norm, drc, strict=True):
     if not len(enhanced_list):
         return []
     refs, degs = _read_pairs(clean_root, noise_root, list(enhanced_list), drc)
     r = _engine().score_batch(refs, degs, fs=fs, metrics=(metric,), mapped=bool(norm),
                               seed=int(np.random.randint(0, 2 ** 31 - 1)))
+    check_status(r, (metric,), strict)
     return [float(v) for v in r.scores[:, col]]
 
 
@@ -270,7 +343,7 @@ def read_batch_HASPI_DRC(clean_root, noise_root, enhanced_list):            # au
     return _read_batch("haspi", _eng.COL_HASPI, clean_root, noise_root, enhanced_list, True, True)
 
 
-def read_batch_all(clean_root, noise_root, enhanced_list, norm=True, drc=False, seed=None):
+def read_batch_all(clean_root, noise_root, enhanced_list, norm=True, drc=False, seed=None, strict=True):
     """The three read_batch_* calls of one sampling round (train_nele.py:320-322
     or :333-335) fused: the WAV files are read once and scored in one engine
     call.  Returns ``(siib, haspi, estoi)`` lists."""
@@ -279,12 +352,12 @@ def read_batch_all(clean_root, noise_root, enhanced_list, norm=True, drc=False, 
     refs, degs = _read_pairs(clean_root, noise_root, list(enhanced_list), drc)
     if seed is None:
         seed = int(np.random.randint(0, 2 ** 31 - 1))
-    s = _engine().score_batch(refs, degs, fs=fs, mapped=bool(norm), seed=seed).scores
+    s = check_status(_engine().score_batch(refs, degs, fs=fs, mapped=bool(norm), seed=seed), strict=strict).scores
     return [float(v) for v in s[:, 0]], [float(v) for v in s[:, 1]], [float(v) for v in s[:, 2]]
 
 
 def score_tensors(ref, deg, lengths=None, fs=16000, metrics=("siib", "haspi", "estoi"), norm=True, seed=0,
-                  pcm16=False, **kw):
+                  pcm16=False, strict=True, **kw):
     """In-loop tensor boundary (train_nele.py:303-322 without the WAV round trip):
     ``ref`` / ``deg`` are CUDA float32 torch tensors ``[n, Lmax]`` (clean, and
     enhanced + noise as audio_util.py:139 forms it), ``lengths`` the valid
@@ -318,7 +391,7 @@ def score_tensors(ref, deg, lengths=None, fs=16000, metrics=("siib", "haspi", "e
     torch.cuda.current_stream(ref.device).synchronize()   # the engine runs on its own stream
     r = eng.score_packed(ref.data_ptr(), deg.data_ptr(), offs, lens, fs=fs, metrics=metrics, mapped=bool(norm),
                          seed=seed, device_input=True, **kw)
-    return torch.from_numpy(r.scores)
+    return torch.from_numpy(check_status(r, metrics, strict).scores)
 
 
 def dropin_path():

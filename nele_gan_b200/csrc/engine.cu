@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <chrono>
 #include <map>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -54,8 +55,12 @@ struct nele_engine {
     int n = 0;
     int64_t tot = 0;
     uint64_t seq = 0;
+    uint64_t geom_hash = 0;   // FNV-1a of offs[] and lens[]: the same pointers with another layout must not match
+    uint64_t born = 0;        // value of `calls` when the prefetch was issued; dropped when two calls old
   } pf[2];
   uint64_t pf_seq = 0;
+  uint64_t calls = 0;         // nele_score_batch calls with host inputs so far
+  std::mutex mu;              // entry points on one engine are serialised (the workspace is shared)
   int next_slot = 0;  // staging slot the next call (or prefetch) starts with
   cudaEvent_t ev_fork = nullptr, ev_estoi = nullptr, ev_siib = nullptr;
   bool serial = true;                                  // one stream unless NELE_CONCURRENT=1
@@ -274,6 +279,7 @@ extern "C" void nele_destroy(nele_engine* e) {
 
 extern "C" int nele_set_profiling(nele_engine* e, int on) {
   if (!e) return NELE_E_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
   CU(e, cudaSetDevice(e->device));
   if (on && !e->kt_events) {
     for (int i = 0; i < KernelTimer::kMax; ++i) {
@@ -459,11 +465,27 @@ static int upload_chunk(nele_engine* e, const ChunkPlan& c, int slot, const floa
   return NELE_OK;
 }
 
+static uint64_t geom_hash(const int64_t* offs, const int32_t* lens, int n) {
+  uint64_t h = 1469598103934665603ULL;
+  auto mix = [&h](uint64_t v) {
+    for (int k = 0; k < 8; ++k) {
+      h ^= (v >> (8 * k)) & 0xff;
+      h *= 1099511628211ULL;
+    }
+  };
+  for (int i = 0; i < n; ++i) {
+    mix((uint64_t)offs[i]);
+    mix((uint64_t)(uint32_t)lens[i]);
+  }
+  return h;
+}
+
 extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* deg, const int64_t* offs,
                                 const int32_t* lens, int n, int fs, uint32_t metrics, uint32_t flags,
                                 const float* dither, int64_t dither_rows, uint64_t seed, const double* hl,
                                 double* scores, double* haspi_raw, int32_t* status, void* stream) {
   if (!e) return NELE_E_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
   if (n < 0 || (n > 0 && (!ref || !deg || !offs || !lens || !scores)))
     return fail(e, NELE_E_ARG, "nele_score_batch: null pointer or negative n");
   if ((metrics & ~NELE_METRIC_ALL) || metrics == 0) return fail(e, NELE_E_ARG, "nele_score_batch: bad metric mask 0x%x", metrics);
@@ -524,11 +546,18 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
               haspi_v1 ? kMaxChunkSamplesV1 : kMaxChunkSamples, plans);
   int slot0 = e->next_slot;
   if (!dev_in) {
-    // chunk 0 may already be on its way (nele_prefetch): take the oldest matching slot
+    // chunk 0 may already be on its way (nele_prefetch): take the oldest matching slot.  A prefetch matches by
+    // buffer addresses *and* layout (hash of offs / lens), and expires when two calls have gone by without
+    // consuming it (a skipped step, an exception in the caller): freed-and-reallocated host buffers at the same
+    // address then cannot pick up stale waveforms.  nele_prefetch_cancel drops pending prefetches explicitly.
+    ++e->calls;
+    const uint64_t gh = geom_hash(offs, lens, n);
+    for (int k = 0; k < 2; ++k)
+      if (e->pf[k].valid && e->calls - e->pf[k].born > 2) e->pf[k].valid = false;
     int hit = -1;
     for (int k = 0; k < 2; ++k)
       if (e->pf[k].valid && e->pf[k].ref == ref && e->pf[k].deg == deg && e->pf[k].n == n && e->pf[k].tot == plans[0].tot &&
-          (hit < 0 || e->pf[k].seq < e->pf[hit].seq))
+          e->pf[k].geom_hash == gh && (hit < 0 || e->pf[k].seq < e->pf[hit].seq))
         hit = k;
     if (hit >= 0) {
       slot0 = hit;
@@ -971,7 +1000,9 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
         int ss = NELE_ST_BAD_RATE;
         double v = kNaN;
         if (siib_rate_ok) {
-          ss = h_sst[i];
+          ss = h_sst[i] & 0xff;
+          st &= ~(int32_t)NELE_INFO_SIIB_NULLSPACE;
+          if (h_sst[i] & 0x100) st |= (int32_t)NELE_INFO_SIIB_NULLSPACE;
           v = h_siib[i];
           if (mapped && ss == NELE_ST_OK) v = 1.0 / (1.0 + exp(-0.06 * (v - 32.0)));  // intel.py:102-106
         }
@@ -997,6 +1028,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
 extern "C" int nele_prefetch(nele_engine* e, const float* ref, const float* deg, const int64_t* offs, const int32_t* lens,
                              int n, uint32_t flags) {
   if (!e) return NELE_E_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
   if (n <= 0 || !ref || !deg || !offs || !lens) return fail(e, NELE_E_ARG, "nele_prefetch: null pointer or n <= 0");
   if (flags & NELE_FLAG_DEVICE_INPUT) return NELE_OK;  // nothing to upload
   for (int i = 0; i < n; ++i)
@@ -1022,6 +1054,15 @@ extern "C" int nele_prefetch(nele_engine* e, const float* ref, const float* deg,
   e->pf[slot].n = n;
   e->pf[slot].tot = plans[0].tot;
   e->pf[slot].seq = ++e->pf_seq;
+  e->pf[slot].geom_hash = geom_hash(offs, lens, n);
+  e->pf[slot].born = e->calls;
+  return NELE_OK;
+}
+
+extern "C" int nele_prefetch_cancel(nele_engine* e) {
+  if (!e) return NELE_E_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  e->pf[0].valid = e->pf[1].valid = false;
   return NELE_OK;
 }
 
@@ -1032,6 +1073,7 @@ extern "C" int nele_features(nele_engine* e, const float* wav, const int64_t* of
                              uint32_t flags, double power, float* band, float* mag, float* phase, float* psd,
                              void* stream) {
   if (!e) return NELE_E_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
   if (n < 0 || (n > 0 && (!wav || !offs || !lens || !band)))
     return fail(e, NELE_E_ARG, "nele_features: null pointer or negative n");
   if (flags & ~(NELE_FEAT_NOISE | NELE_FEAT_DEVICE_IO | NELE_FEAT_NO_POWER))
@@ -1154,6 +1196,7 @@ extern "C" int nele_kernel_time(const nele_engine* e, int idx, const char** name
 
 extern "C" int nele_get_stage(nele_engine* e, const char* name, int pair, void* dst, size_t cap, size_t* nbytes) {
   if (!e || !name) return NELE_E_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
   if (!e->stages_valid) return fail(e, NELE_E_ARG, "nele_get_stage: no stages kept (call nele_score_batch with NELE_FLAG_KEEP_STAGES on a single-chunk batch)");
   if (pair < 0 || pair >= e->chunk_n) return fail(e, NELE_E_ARG, "nele_get_stage: pair %d out of range", pair);
   CU(e, cudaSetDevice(e->device));

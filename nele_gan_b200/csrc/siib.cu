@@ -1421,7 +1421,10 @@ __global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, Sii
     const double R = 1.0 / 200.0 * 16000.0;
     const double v = R / (double)kSStack * s_info;
     b.score[pair] = v > 0.0 ? v : 0.0;
-    b.status[pair] = 0;
+    // bit 8: the null space of a rank-deficient (exactly periodic) covariance was given zero information
+    // (NELE_INFO_SIIB_NULLSPACE).  sweeps: -1 tridiagonal path at full rank, -3 rank deficient, -2 Gram path.
+    const int sw = b.sweeps[pair];
+    b.status[pair] = (sw == -2 || sw == -3 || (sw >= 0 && r < kSDim)) ? 0x100 : 0;
   }
 }
 
@@ -1591,7 +1594,7 @@ __global__ void __launch_bounds__(kPqThreads) siib_projquad_kernel(SiibGeom g, S
     const double R = 1.0 / 200.0 * 16000.0;
     const double v = R / (double)kSStack * info;
     b.score[pair] = v > 0.0 ? v : 0.0;
-    b.status[pair] = 0;
+    b.status[pair] = 0x100;  // periodic pair, rank <= 112: null space dropped (NELE_INFO_SIIB_NULLSPACE)
   }
 }
 

@@ -440,7 +440,10 @@ __global__ void __launch_bounds__(kBtThreads, 2) siib_backtf_kernel(SiibGeom g, 
   // column j of G = sqrt(lambda_j) u_j / |z_j|; eigenvalues at or below 1e-10 lambda_max carry no information
   const double lam = eb.lam[(int64_t)lp * kELd + j], lmax = eb.lam[(int64_t)lp * kELd + kEDim - 1];
   const double nz = eb.znorm[(int64_t)lp * kELd + j];
-  const float sc = (lam > 1.0e-10 * lmax && nz > 0.0) ? (float)sqrt(lam / nz) : 0.f;
+  // a periodic tiling of rank r < 420 (pivoted Cholesky, FP64): only the r largest eigenvalues are non-zero in exact
+  // arithmetic; the FP32 tridiagonalisation leaves the others at +-1e-7 lambda_max, so the rank decides, not the value
+  const bool in_range = j >= kEDim - b.rank[pair];
+  const float sc = (in_range && lam > 1.0e-10 * lmax && nz > 0.0) ? (float)sqrt(lam / nz) : 0.f;
   float* __restrict__ G = b.G + (int64_t)lp * kEDim * kELd + (int64_t)j * kELd;
 #pragma unroll
   for (int m = 0; m < kBtRows; ++m) {
@@ -455,8 +458,8 @@ __global__ void siib_eig_finish_kernel(SiibBuffers b, int n, int rank_lo) {
   if (lp >= n) return;
   const int pair = b.pair_lo + lp;
   if (b.rank[pair] >= rank_lo) {
+    b.sweeps[pair] = (b.rank[pair] < kEDim) ? -3 : -1;  // marks "tridiagonal path" in the siib.rank stage (-3: rank deficient)
     b.rank[pair] = kEDim;
-    b.sweeps[pair] = -1;  // marks "tridiagonal path" in the siib.rank stage
   }
 }
 

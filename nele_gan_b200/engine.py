@@ -18,10 +18,12 @@ METRIC_HASPI, METRIC_SIIB, METRIC_ESTOI = 1, 2, 4
 METRIC_ALL = 7
 FLAG_MAPPED, FLAG_DEVICE_INPUT, FLAG_NO_DITHER, FLAG_SIIB_NO_TILE, FLAG_KEEP_STAGES, FLAG_HASPI_V1, FLAG_STOI_CLASSIC, FLAG_SIIB_KNN, FLAG_HASQI_V2 = 1, 2, 4, 8, 16, 32, 64, 128, 256
 ST_OK, ST_BELOW_THR, ST_TOO_SHORT, ST_BAD_RATE, ST_UNSUPPORTED, ST_SKIPPED = 0, 1, 2, 3, 4, 0xFF
+INFO_SIIB_NULLSPACE = 0x01000000   # informational bit above the three status bytes (include/nele_score.h)
 _METRIC_BITS = {"haspi": METRIC_HASPI, "siib": METRIC_SIIB, "estoi": METRIC_ESTOI, "stoi": METRIC_ESTOI}
 COL_SIIB, COL_HASPI, COL_ESTOI = 0, 1, 2
 
 SYMBOLS = ("nele_abi_version", "nele_create", "nele_destroy", "nele_last_error", "nele_score_batch", "nele_prefetch",
+           "nele_prefetch_cancel",
            "nele_get_stage", "nele_last_timing", "nele_set_profiling", "nele_kernel_time", "nele_feature_frames",
            "nele_features")
 FEAT_NOISE, FEAT_DEVICE_IO, FEAT_NO_POWER = 0x1, 0x2, 0x4
@@ -59,6 +61,8 @@ def load_library(path=None):
         lib.nele_score_batch.restype = C.c_int
         lib.nele_prefetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
         lib.nele_prefetch.restype = C.c_int
+        lib.nele_prefetch_cancel.argtypes = [C.c_void_p]
+        lib.nele_prefetch_cancel.restype = C.c_int
         lib.nele_get_stage.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t,
                                        C.POINTER(C.c_size_t)]
         lib.nele_get_stage.restype = C.c_int
@@ -113,6 +117,19 @@ class BatchResult:
     def metric_status(self, name):
         k = {"haspi": 0, "siib": 1, "estoi": 2}[name]
         return (self.status >> (8 * k)) & 0xFF
+
+    @property
+    def ok(self):
+        """Per pair: every requested metric is ST_OK (informational bits ignored)."""
+        st = np.stack([self.metric_status(m) for m in ("haspi", "siib", "estoi")], axis=1)
+        return np.all((st == ST_OK) | (st == ST_SKIPPED), axis=1)
+
+    @property
+    def siib_nullspace_dropped(self):
+        """Per pair: SIIB ignored the null space of a rank-deficient covariance -- the utterance length is a
+        multiple of the 200-sample hop, so the wrapper's tiling repeats exactly and pysiib's float64 value
+        carries 1-13 % of rounding-noise information."""
+        return (self.status & INFO_SIIB_NULLSPACE) != 0
 
 
 class Engine:
@@ -196,6 +213,10 @@ class Engine:
         rc = self._lib.nele_prefetch(self._h, pref, pdeg, offs.ctypes.data, lens.ctypes.data, int(lens.shape[0]),
                                      FLAG_HASPI_V1 if haspi_v1 else 0)
         self._check(rc, "nele_prefetch")
+
+    def prefetch_cancel(self):
+        """Drop pending prefetches (``nele_prefetch_cancel``)."""
+        self._check(self._lib.nele_prefetch_cancel(self._h), "nele_prefetch_cancel")
 
     # ----------------------------------------------------------------- high level
     def score_batch(self, refs, degs, fs=16000, metrics=("siib", "haspi", "estoi"), mapped=True, **kw):

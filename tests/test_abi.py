@@ -57,6 +57,7 @@ def test_constants_match_header():
     assert vals["NELE_FLAG_HASQI_V2"] == engine.FLAG_HASQI_V2
     assert vals["NELE_ST_UNSUPPORTED"] == engine.ST_UNSUPPORTED
     assert vals["NELE_ST_TOO_SHORT"] == engine.ST_TOO_SHORT
+    assert vals["NELE_INFO_SIIB_NULLSPACE"] == engine.INFO_SIIB_NULLSPACE
 
 
 def test_no_gpu_fails_loudly(lib_path):

@@ -19,7 +19,7 @@ def test_bench_size_batch_copies_agree_and_match_single_calls(eng):
     n, uniq = 4096, 64
     refs, degs = make_batch(n, 48000, seed=777_000, unique=uniq)
     r = eng.score_batch(refs, degs, mapped=False, no_dither=True)
-    assert (r.status == 0).all()
+    assert r.ok.all() and r.siib_nullspace_dropped.all()      # 48000 = 240 hops: periodic tiling, flagged
     s = r.scores.reshape(n // uniq, uniq, 3)
     spread = np.abs(s - s[0]).max(axis=0)                 # copies of the same pair, 64 places each
     assert spread[:, 0].max() < 1e-6 * np.abs(s[0][:, 0]).max()   # SIIB

@@ -92,3 +92,31 @@ def test_mappings_are_the_reference_logistics():
     assert abs(intel_np.mapping_HASPI_harvard(2.8) - 0.5) < 1e-15        # intel.py:116-120
     assert abs(intel_np.mapping_ESTOI_harvard(0.25) - 0.5) < 1e-15       # intel.py:136-140
     assert abs(intel_np.mapping_ESTOI_harvard(1.0) - 1 / (1 + np.exp(-6.0))) < 1e-15
+
+
+def test_siib_reference_value_on_periodic_tilings_is_rounding_noise():
+    """Evidence for the engine's one deliberate deviation.
+
+    intel.py:71-75 tiles a short utterance M times with np.hstack.  When its length is a multiple of the
+    200-sample hop the tiled signal repeats its frames exactly, cov(X) (420 x 420) has rank ~ 76-99, and
+    numpy's eigh returns arbitrary rounding-noise eigenvectors for the null space whose sample
+    correlations add a few percent to the float64 score.  That surplus is not a property of the
+    signals: a relative perturbation of 1e-13 of the inputs -- three orders of magnitude below float64's
+    own rounding of the int16-derived samples' products -- removes it.  The engine returns the sum over
+    the components with a numerically non-zero eigenvalue, i.e. the limit the reference formula itself
+    converges to under any perturbation."""
+    for i in range(4):
+        x, y, _ = make_pair(i, 48000)                      # bench.py's workload: 3.0 s = 240 hops
+        M, _ = intel_np.siib_tiling_factor(x, 16000)
+        xt, yt = np.tile(x.astype(np.float64), M), np.tile(y.astype(np.float64), M)
+        st = {}
+        full = pysiib_np.SIIB(xt, yt, 16000, gauss=True, stages=st)
+        nonnull = st["lam"] > 1e-9 * st["lam"].max()
+        assert 60 < nonnull.sum() < 112                    # rank of the periodic tiling
+        engine_value = 80.0 / 15 * float(np.sum(st["I_ch"][nonnull]))
+        rng = np.random.default_rng(1000 + i)
+        pert = pysiib_np.SIIB(xt * (1 + 1e-13 * rng.standard_normal(len(xt))),
+                              yt * (1 + 1e-13 * rng.standard_normal(len(yt))), 16000, gauss=True)
+        assert abs(full - engine_value) > 5e-3 * engine_value, (i, full, engine_value)     # 1 % .. 13 % of junk
+        assert abs(pert - engine_value) <= 5e-3 * engine_value, (i, pert, engine_value)    # measured 0.05 % .. 0.18 %
+        assert abs(pert - full) > 5e-3 * full                                               # float64 value moves under 1e-13
