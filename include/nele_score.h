@@ -222,6 +222,29 @@ int64_t nele_feature_frames(int32_t len);
 int nele_features(nele_engine* e, const float* wav, const int64_t* offs, const int32_t* lens, int n, uint32_t flags,
                   double power, float* band, float* mag, float* phase, float* psd, void* stream);
 
+/*
+ * In-loop boundary of a GAN sampling round (train_nele.py:286-314): from the generator's band energy gains to the
+ * degraded waveforms the metrics score, on the device -- SP_to_wav / Resyn / interp_band_gain / librosa.istft
+ * (audio_util.py:60-115, 458-461), the PCM-16 rounding of sf.write(..., 'PCM_16') (train_nele.py:313) and
+ * `enhanced + noise` (audio_util.py:196).  Every utterance is processed at its own length (reflect padding at its own
+ * ends), as the reference does one file at a time.
+ *
+ *   clean, noise   device float32, utterance i at [offs[i], offs[i] + lens[i]) (offs / lens on the host, lens[i] > 256)
+ *   alpha2, arow   device float32 [rows][64]: `mask * beta_2`, T_i = 1 + lens[i] / 256 rows per utterance starting at row
+ *                  arow[i] (host int64 [n]; NULL: packed back to back, arow[i] = sum of T_j over j < i).  A generator
+ *                  output padded to [n][Tmax][64] is passed with arow[i] = i * Tmax.
+ *   enh, deg       device float32 outputs at the same offsets (either may be NULL): the resynthesised signal before the
+ *                  PCM-16 rounding, and round16(enh) + noise
+ *   out_lens       host int32 [n]: 256 * (lens[i] / 256) valid samples -- len(librosa.istft(...)), to which
+ *                  audio_util.py:190-193 trims both signals; pass it as `lens` to nele_score_batch
+ *                  (NELE_FLAG_DEVICE_INPUT, ref = clean, deg = deg, same offs)
+ *   flags          NELE_RESYN_PCM16
+ */
+#define NELE_RESYN_PCM16 0x1u
+int nele_resyn(nele_engine* e, const float* clean, const float* noise, const int64_t* offs, const int32_t* lens, int n,
+               const float* alpha2, const int64_t* arow, uint32_t flags, float* enh, float* deg, int32_t* out_lens,
+               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,7 +81,7 @@ struct nele_engine {
   DevBuf x10, st_energy, st_kept, st_nkept, st_tob;                                 // ESTOI
   DevBuf sb_wrapdb, sb_M, sb_wact, sb_mean, sb_xdb, sb_act, sb_aidx, sb_src, sb_Fa, sb_Pact, sb_perflag, sb_lograw, sb_logspec;      // SIIB, per chunk
   DevBuf sb_base, sb_Sxx, sb_Sxy, sb_Syy, sb_Lc, sb_G, sb_perm;                     // SIIB, per sub-chunk
-  DevBuf sb_rank, sb_sweeps, sb_lambda, sb_rho;
+  DevBuf sb_rank, sb_sweeps, sb_lambda, sb_rho, sb_info;
   DevBuf kn_xk, kn_info, kn_digamma;  // SIIB k-NN estimator
   DevBuf eg_vec, eg_zt, eg_gram, eg_refl;             // SIIB tridiagonal eigen-solver: 5 x [sub][448] doubles, [sub][420][448] floats
   DevBuf out_haspi, out_raw, out_hst, out_estoi, out_est, out_siib, out_sst;
@@ -216,7 +216,7 @@ extern "C" int nele_create(int device, nele_engine** out) {
                  &e->x10, &e->st_energy, &e->st_kept, &e->st_nkept, &e->st_tob,
                  &e->sb_wrapdb, &e->sb_M, &e->sb_wact, &e->sb_mean, &e->sb_xdb, &e->sb_act, &e->sb_aidx, &e->sb_src, &e->sb_Fa, &e->sb_Pact, &e->sb_perflag, &e->sb_lograw, &e->sb_logspec,
                  &e->sb_base, &e->sb_Sxx, &e->sb_Sxy, &e->sb_Syy, &e->sb_Lc, &e->sb_G, &e->sb_perm,
-                 &e->sb_rank, &e->sb_sweeps, &e->sb_lambda, &e->sb_rho, &e->kn_xk, &e->kn_info, &e->kn_digamma, &e->eg_vec, &e->eg_zt, &e->eg_gram, &e->eg_refl,
+                 &e->sb_rank, &e->sb_sweeps, &e->sb_lambda, &e->sb_rho, &e->sb_info, &e->kn_xk, &e->kn_info, &e->kn_digamma, &e->eg_vec, &e->eg_zt, &e->eg_gram, &e->eg_refl,
                  &e->out_haspi, &e->out_raw, &e->out_hst, &e->out_estoi, &e->out_est, &e->out_siib, &e->out_sst,
                  &e->ft_wav, &e->ft_geom, &e->ft_band, &e->ft_mag, &e->ft_phase, &e->ft_psd};
 #define CUC(call)                                                                             \
@@ -864,6 +864,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       RESERVE(e, e->sb_sweeps, (size_t)cn * 17 * sizeof(int32_t));
       RESERVE(e, e->sb_lambda, (size_t)cn * 420 * sizeof(float));
       RESERVE(e, e->sb_rho, (size_t)cn * 420 * sizeof(float));
+      RESERVE(e, e->sb_info, (size_t)cn * 8 * sizeof(double));
       sb.mean = (double*)e->sb_mean.p;
       sb.xdb = (double*)e->sb_xdb.p;
       sb.act = (int32_t*)e->sb_act.p;
@@ -889,6 +890,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       sb.sweep_rot = (int32_t*)e->sb_sweeps.p + cn;
       sb.lambda = (float*)e->sb_lambda.p;
       sb.rho = (float*)e->sb_rho.p;
+      sb.info_part = (double*)e->sb_info.p;
       sb.score = (double*)e->out_siib.p;
       sb.status = (int32_t*)e->out_sst.p;
       CU(e, cudaMemsetAsync(e->sb_sweeps.p, 0, (size_t)cn * 17 * sizeof(int32_t), ss));
@@ -1176,6 +1178,63 @@ extern "C" int nele_features(nele_engine* e, const float* wav, const int64_t* of
     frame0 += frames;
     first = last;
   }
+  return NELE_OK;
+}
+
+// ------------------------------------------------------------------ resynthesis (in-loop boundary)
+extern "C" int nele_resyn(nele_engine* e, const float* clean, const float* noise, const int64_t* offs, const int32_t* lens,
+                          int n, const float* alpha2, const int64_t* arow, uint32_t flags, float* enh, float* deg,
+                          int32_t* out_lens, void* stream) {
+  if (!e) return NELE_E_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (n < 0 || (n > 0 && (!clean || !offs || !lens || !alpha2 || (!enh && !deg) || (deg && !noise))))
+    return fail(e, NELE_E_ARG, "nele_resyn: null pointer or negative n");
+  if (flags & ~NELE_RESYN_PCM16) return fail(e, NELE_E_ARG, "nele_resyn: bad flags 0x%x", flags);
+  for (int i = 0; i < n; ++i)
+    if (lens[i] <= 256 || offs[i] < 0)
+      return fail(e, NELE_E_ARG, "nele_resyn: waveform %d has length %d / offset %lld (need more than 256 samples)", i, lens[i],
+                  (long long)offs[i]);
+  e->last_kernel_ms = 0.0;
+  e->last_launches = 0;
+  e->kstats.clear();
+  e->kt.count = 0;
+  e->kt.enabled = e->profiling && e->kt_events;
+  KernelTimer* kt = e->kt.enabled ? &e->kt : nullptr;
+  if (n == 0) return NELE_OK;
+  CU(e, cudaSetDevice(e->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  std::vector<int64_t> h_foff(n);
+  std::vector<int2> h_tiles;
+  int64_t frames = 0;
+  for (int i = 0; i < n; ++i) {
+    const int T = (int)nele_feature_frames(lens[i]);
+    h_foff[i] = arow ? arow[i] : frames;
+    for (int t0 = 0; t0 < T - 1; t0 += 7) h_tiles.push_back(make_int2(i, t0));   // 8 frames -> 7 output hops per CTA
+    frames += T;
+    if (out_lens) out_lens[i] = 256 * (lens[i] / 256);   // len(librosa.istft(...)) = hop * (T - 1); audio_util.py:190-193 trims to it
+  }
+  const size_t g_off = 0, g_foff = g_off + 8 * (size_t)n, g_tiles = g_foff + 8 * (size_t)n,
+               g_len = g_tiles + 8 * h_tiles.size(), g_bytes = g_len + 4 * (size_t)n;
+  std::vector<char> blob(g_bytes);
+  memcpy(&blob[g_off], offs, 8 * (size_t)n);
+  memcpy(&blob[g_foff], h_foff.data(), 8 * (size_t)n);
+  memcpy(&blob[g_tiles], h_tiles.data(), 8 * h_tiles.size());
+  memcpy(&blob[g_len], lens, 4 * (size_t)n);
+  RESERVE(e, e->ft_geom, g_bytes);
+  CU(e, cudaMemcpyAsync(e->ft_geom.p, blob.data(), g_bytes, cudaMemcpyHostToDevice, s));
+  CU(e, cudaStreamSynchronize(s));   // blob is a local vector
+  const char* gp = (const char*)e->ft_geom.p;
+  CU(e, cudaEventRecord(e->ev0, s));
+  e->last_launches += resyn_run(clean, noise, (const int64_t*)(gp + g_off), (const int32_t*)(gp + g_len),
+                                (const int64_t*)(gp + g_foff), (const int2*)(gp + g_tiles), (int)h_tiles.size(), alpha2,
+                                flags & NELE_RESYN_PCM16, enh, deg, kt, s);
+  CU(e, cudaGetLastError());
+  CU(e, cudaEventRecord(e->ev1, s));
+  CU(e, cudaStreamSynchronize(s));
+  float ms = 0.f;
+  CU(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->last_kernel_ms += ms;
+  collect_kernel_times(e);
   return NELE_OK;
 }
 

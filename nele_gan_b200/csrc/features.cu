@@ -395,10 +395,8 @@ __global__ void __launch_bounds__(kImcraThreads, 3) feat_imcra_kernel(const floa
 
 }  // namespace
 
-int features_run(const float* wav, const int64_t* offs, const int32_t* lens, const int64_t* foff, const int2* tiles,
-                 int n, int ntiles, bool noise, float power, bool normalize, float* band, float* mag, float* phase,
-                 float* psd, KernelTimer* kt, cudaStream_t s) {
-  // the tables live in __device__ memory, i.e. per device: one upload per device this process uses
+// the tables live in __device__ memory, i.e. per device: one upload per device this process uses
+static void feat_tables_ready(cudaStream_t s) {
   static bool ready_dev[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -429,6 +427,130 @@ int features_run(const float* wav, const int64_t* offs, const int32_t* lens, con
     cudaStreamSynchronize(s);
     if (dev >= 0 && dev < 64) ready_dev[dev] = true;
   }
+}
+
+// ------------------------------------------------------------------------------------ resynthesis
+// The in-loop boundary of a GAN sampling round (train_nele.py:303-314): the generator's
+// band energy gains alpha2 [T][64] of one utterance -> interp_band_gain (audio_util.py:98-115) -> sqrt -> times the
+// clean STFT (Resyn, :84-96) -> librosa.istft(hop 256, win 512) (:60-65) -> the PCM-16 rounding of
+// sf.write(..., 'PCM_16') (train_nele.py:313) -> + noise (audio_util.py:196), written at the clean signal's offsets so
+// that nele_score_batch can take (clean, degraded) as device inputs.  One CTA = 8 consecutive frames of one utterance
+// (four 512-point complex FFTs in FP64, as feat_stft) = 7 output hops: every output sample is the windowed overlap-add
+// of exactly two frames divided by the summed squared window.  Utterances are processed at their own length (reflect
+// padding at their own ends), which is what the reference does one file at a time.
+constexpr int kResynHops = kTileFrames - 1;
+
+__device__ __forceinline__ void fft512_x4(double2 (*buf)[kNfft], int tid) {
+  const int q = tid >> 6, j = tid & 63;
+  double2 v[8];
+#pragma unroll
+  for (int stage = 0; stage < 3; ++stage) {
+    const int Ns = stage == 0 ? 1 : (stage == 1 ? 8 : 64);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = buf[q][j + r * 64];
+    if (stage > 0) {
+      const int k = (j & (Ns - 1)) * (64 / Ns);
+#pragma unroll
+      for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], __ldg(&d_tw512[k * r]));
+    }
+    fft8(v);
+    __syncthreads();
+    const int base = (j / Ns) * Ns * 8 + (j & (Ns - 1));
+#pragma unroll
+    for (int r = 0; r < 8; ++r) buf[q][base + r * Ns] = v[r];
+    __syncthreads();
+  }
+}
+
+// sqrt(interp_band_gain(E)[k]) (audio_util.py:98-115, :91): g[k] = (1 - frac) E[i] + frac E[i + 1] inside band i; the bins of
+// the last band (243..256) keep g = 1 (the reference's loop stops at NB_BANDS - 1); bins 0, 1 and 256 are forced
+__device__ __forceinline__ double resyn_gain(const float* __restrict__ E, int k) {
+  if (k <= 1) return 1e-2;          // sqrt(1e-4)
+  if (k == kBins - 1) return 0.1;   // sqrt(1e-2)
+  int i = 0;
+  while (i + 1 < kFeatBands && c_gmt[i + 1] <= k) ++i;      // band whose bins contain k
+  if (i >= kFeatBands - 1) return 1.0;
+  const double frac = (double)(k - c_gmt[i]) / (double)(c_gmt[i + 1] - c_gmt[i]);
+  return sqrt((1.0 - frac) * (double)E[i] + frac * (double)E[i + 1]);
+}
+
+__global__ void __launch_bounds__(256) feat_resyn_kernel(const float* __restrict__ clean, const float* __restrict__ noise,
+                                                          const int64_t* __restrict__ offs, const int32_t* __restrict__ lens,
+                                                          const int64_t* __restrict__ foff, const int2* __restrict__ tiles,
+                                                          const float* __restrict__ alpha2, int pcm16,
+                                                          float* __restrict__ enh, float* __restrict__ deg) {
+  __shared__ __align__(16) double2 buf[4][kNfft];
+  const int tid = threadIdx.x;
+  const int2 tile = tiles[blockIdx.x];
+  const int u = tile.x, t0 = tile.y;
+  const int L = lens[u];
+  const int T = 1 + L / kHop;
+  const float* x = clean + offs[u];
+  for (int e = tid; e < kTileFrames * kNfft; e += 256) {
+    const int f = e >> 9, n = e & 511, t = t0 + f;
+    double v = 0.0;
+    if (t < T) {
+      int p = t * kHop + n - kNfft / 2;
+      if (p < 0) p = -p;
+      if (p >= L) p = 2 * (L - 1) - p;
+      v = (0.5 - 0.5 * __ldg(&d_tw512[n].x)) * (double)x[p];
+    }
+    reinterpret_cast<double*>(&buf[f >> 1][n])[f & 1] = v;
+  }
+  __syncthreads();
+  fft512_x4(buf, tid);
+  // split Z = A + iB, round the two spectra to complex64 (what librosa.stft returns), apply the gains and put
+  // conj(A' + i B') back: a second forward transform then gives N conj(a' + i b')
+  for (int e = tid; e < 4 * kBins; e += 256) {
+    const int q = e / kBins, k = e - q * kBins, kn = (kNfft - k) & (kNfft - 1);
+    const double2 zk = buf[q][k], zn = buf[q][kn];
+    float are = (float)(0.5 * (zk.x + zn.x)), aim = (float)(0.5 * (zk.y - zn.y));
+    float bre = (float)(0.5 * (zk.y + zn.y)), bim = (float)(-0.5 * (zk.x - zn.x));
+    if (k == 0 || k == kBins - 1) aim = 0.f, bim = 0.f;
+    const int ta = t0 + 2 * q, tb = ta + 1;
+    const double ga = ta < T ? resyn_gain(alpha2 + (foff[u] + ta) * kFeatBands, k) : 0.0;
+    const double gb = tb < T ? resyn_gain(alpha2 + (foff[u] + tb) * kFeatBands, k) : 0.0;
+    const double ar = ga * (double)are, ai = ga * (double)aim, br = gb * (double)bre, bi = gb * (double)bim;
+    // Z'[k] = A' + i B' = (ar - bi) + i (ai + br); Z'[N - k] = conj(A') + i conj(B') = (ar + bi) + i (br - ai)
+    buf[q][k] = make_double2(ar - bi, -(ai + br));
+    if (k != 0 && k != kBins - 1) buf[q][kn] = make_double2(ar + bi, -(br - ai));
+  }
+  __syncthreads();
+  fft512_x4(buf, tid);
+  // overlap-add of frames h (second half) and h + 1 (first half), summed squared window, PCM-16, + noise
+  const int64_t o = offs[u];
+  for (int e = tid; e < kResynHops * kHop; e += 256) {
+    const int hh = e >> 8, p = e & 255, h = t0 + hh;
+    if (h >= T - 1) continue;
+    const int fa = hh, fb = hh + 1;
+    const double2 ra = buf[fa >> 1][p + kHop], rb = buf[fb >> 1][p];
+    const double ya = ((fa & 1) ? -ra.y : ra.x) * (1.0 / kNfft), yb = ((fb & 1) ? -rb.y : rb.x) * (1.0 / kNfft);
+    const double wa = 0.5 - 0.5 * __ldg(&d_tw512[p + kHop].x), wb = 0.5 - 0.5 * __ldg(&d_tw512[p].x);
+    // librosa.istft accumulates window * frame in a float32 buffer and divides by the float32 window sum
+    const float acc = (float)(wa * ya) + (float)(wb * yb);
+    const float ss = (float)(wa * wa) + (float)(wb * wb);
+    float y = acc / ss;
+    const int64_t sidx = (int64_t)h * kHop + p;
+    if (enh) enh[o + sidx] = y;
+    if (pcm16) y = fminf(fmaxf(rintf(y * 32768.f), -32768.f), 32767.f) * (1.f / 32768.f);
+    if (deg) deg[o + sidx] = y + noise[o + sidx];
+  }
+}
+
+int resyn_run(const float* clean, const float* noise, const int64_t* offs, const int32_t* lens, const int64_t* foff,
+              const int2* tiles, int ntiles, const float* alpha2, bool pcm16, float* enh, float* deg, KernelTimer* kt,
+              cudaStream_t s) {
+  feat_tables_ready(s);
+  kt_begin(kt, "feat_resyn", s);
+  feat_resyn_kernel<<<ntiles, 256, 0, s>>>(clean, noise, offs, lens, foff, tiles, alpha2, pcm16 ? 1 : 0, enh, deg);
+  kt_end(kt, s);
+  return 1;
+}
+
+int features_run(const float* wav, const int64_t* offs, const int32_t* lens, const int64_t* foff, const int2* tiles,
+                 int n, int ntiles, bool noise, float power, bool normalize, float* band, float* mag, float* phase,
+                 float* psd, KernelTimer* kt, cudaStream_t s) {
+  feat_tables_ready(s);
   int launches = 0;
   kt_begin(kt, "feat_stft", s);
   feat_stft_kernel<<<ntiles, 256, 0, s>>>(wav, offs, lens, foff, tiles, power, normalize ? 1 : 0,

@@ -170,6 +170,7 @@ struct SiibBuffers {
   float* rho;            // [n][420]
   double* score;         // [n]
   int32_t* status;       // [n]
+  double* info_part;     // [n][8] per-tile information sums of siib_launch_quadform
 };
 // k-NN (Kraskov) estimator of pysiib.SIIB(..., gauss=False): siib_knn.cu
 struct SiibKnnBuffers {
@@ -200,6 +201,10 @@ int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& 
                  cudaStream_t s);
 // FP32 lower-triangle tridiagonalisation (siib_klt.cu): same outputs as siib_tridiag_kernel
 int siib_launch_tridiag32(const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, cudaStream_t s);
+// back-transformation with the reflectors applied four at a time (siib_klt.cu): same inputs / output as siib_backtf_kernel
+int siib_launch_backtf4(const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, cudaStream_t s);
+// register-tiled quadratic forms + score (siib_klt.cu); info_part: [n_chunk][8] doubles of scratch
+int siib_launch_quadform(const SiibBuffers& b, double* info_part, int n, KernelTimer* kt, cudaStream_t s);
 void siib_upload_tables(const float* win, const float* decay, const float* g2t, const float* tw, cudaStream_t s);
 int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_tile, KernelTimer* kt, cudaStream_t s);
 // kb != nullptr: k-NN estimator instead of the Gaussian quadratic forms
@@ -215,5 +220,11 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, 
 int features_run(const float* wav, const int64_t* offs, const int32_t* lens, const int64_t* foff, const int2* tiles,
                  int n, int ntiles, bool noise, float power, bool normalize, float* band, float* mag, float* phase,
                  float* psd, KernelTimer* kt, cudaStream_t s);
+
+// Resynthesis of a sampling round (audio_util.py:60-115, train_nele.py:303-314): tiles = (utterance, first frame) per CTA,
+// 7 output hops each; alpha2 [sum T][64]; enh / deg written at the clean signal's offsets (either may be null)
+int resyn_run(const float* clean, const float* noise, const int64_t* offs, const int32_t* lens, const int64_t* foff,
+              const int2* tiles, int ntiles, const float* alpha2, bool pcm16, float* enh, float* deg, KernelTimer* kt,
+              cudaStream_t s);
 
 }  // namespace nele

@@ -37,6 +37,8 @@
 #include <algorithm>
 
 #include "fft400.cuh"
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace cg = cooperative_groups;
@@ -289,15 +291,21 @@ struct SpecSmem {
   cpx t[kSpecWarps][kSWin];
 };
 
+constexpr int kSpecIter = 8;  // frames per warp: the 29 KB of tables are staged once per 64 frames, not once per 8
+
 __global__ void __launch_bounds__(kSpecWarps * 32) siib_spec_kernel(SiibGeom g, SiibBuffers b) {
   const int pair = b.pair_lo + blockIdx.y, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int Fa = b.Fa[pair];
-  if (blockIdx.x * kSpecWarps >= Fa) return;
+  const int tbase = blockIdx.x * kSpecWarps * kSpecIter;
+  if (tbase >= Fa) return;
   {
     // nothing to do when every frame of this CTA is a copy of an earlier one (siib_vad_kernel):
     // leave before the 29 KB of tables are staged
-    const int tw = blockIdx.x * kSpecWarps + wib;
-    const int need = (tw < Fa) && (b.src[g.offF[pair] + tw] == tw);
+    int need = 0;
+    for (int it = 0; it < kSpecIter; ++it) {
+      const int tw = tbase + it * kSpecWarps + wib;
+      need |= (tw < Fa) && (b.src[g.offF[pair] + tw] == tw);
+    }
     if (!__syncthreads_or(need)) return;
   }
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -308,47 +316,50 @@ __global__ void __launch_bounds__(kSpecWarps * 32) siib_spec_kernel(SiibGeom g, 
   }
   for (int k = threadIdx.x; k < kSBins * kSLanes; k += kSpecWarps * 32) sm.g2t[k] = g_siib_g2t[k];
   __syncthreads();
-  const int t = blockIdx.x * kSpecWarps + wib;
-  if (t >= Fa) return;
-  if (b.src[g.offF[pair] + t] != t) return;  // a copy of an earlier frame (siib_vad_kernel)
   const float* __restrict__ x = b.ref + g.off16[pair];
   const float* __restrict__ y = b.deg + g.off16[pair];
   const int L = g.len16[pair];
   const float mx = (float)b.mean[2 * pair], my = (float)b.mean[2 * pair + 1];
-  const int64_t f = b.act[g.offF[pair] + t];
-  const int64_t base = (f * kSHop) % L;
   cpx* z = sm.z[wib];
   cpx* tt = sm.t[wib];
-  for (int i = lane; i < kSWin; i += 32) {
-    int64_t idx = base + i;
-    if (idx >= L) idx %= L;
-    const float w = sm.win[i];
-    z[i] = {w * (x[idx] - mx), w * (y[idx] - my)};
-  }
-  __syncwarp();
-  if (lane < 25) fft400_phase_a(lane, z, tt, sm.tw);
-  __syncwarp();
-  if (lane < 16) fft400_phase_b(lane, tt, z, sm.tw);
-  __syncwarp();
-  // power spectra of the two real signals, interleaved (px, py) into tt
-  float2* pw = reinterpret_cast<float2*>(tt);
-  for (int k = lane; k < kSBins; k += 32) {
-    const cpx a = z[k], c = z[(kSWin - k) % kSWin];
-    const float xr = a.x + c.x, xi = a.y - c.y, yr = a.y + c.y, yi = c.x - a.x;
-    pw[k] = make_float2(0.25f * (xr * xr + xi * xi), 0.25f * (yr * yr + yi * yi));
-  }
-  __syncwarp();
-  float ex = 0.f, ey = 0.f;
+  for (int it = 0; it < kSpecIter; ++it) {
+    const int t = tbase + it * kSpecWarps + wib;
+    if (t >= Fa) break;
+    if (b.src[g.offF[pair] + t] != t) continue;  // a copy of an earlier frame (siib_vad_kernel)
+    const int64_t f = b.act[g.offF[pair] + t];
+    const int64_t base = (f * kSHop) % L;
+    __syncwarp();
+    for (int i = lane; i < kSWin; i += 32) {
+      int64_t idx = base + i;
+      if (idx >= L) idx %= L;
+      const float w = sm.win[i];
+      z[i] = {w * (x[idx] - mx), w * (y[idx] - my)};
+    }
+    __syncwarp();
+    if (lane < 25) fft400_phase_a(lane, z, tt, sm.tw);
+    __syncwarp();
+    if (lane < 16) fft400_phase_b(lane, tt, z, sm.tw);
+    __syncwarp();
+    // power spectra of the two real signals, interleaved (px, py) into tt
+    float2* pw = reinterpret_cast<float2*>(tt);
+    for (int k = lane; k < kSBins; k += 32) {
+      const cpx a = z[k], c = z[(kSWin - k) % kSWin];
+      const float xr = a.x + c.x, xi = a.y - c.y, yr = a.y + c.y, yi = c.x - a.x;
+      pw[k] = make_float2(0.25f * (xr * xr + xi * xi), 0.25f * (yr * yr + yi * yi));
+    }
+    __syncwarp();
+    float ex = 0.f, ey = 0.f;
 #pragma unroll 4
-  for (int k = 0; k < kSBins; ++k) {
-    const float2 p = pw[k];
-    const float gk = sm.g2t[k * kSLanes + lane];
-    ex = fmaf(gk, p.x, ex);
-    ey = fmaf(gk, p.y, ey);
+    for (int k = 0; k < kSBins; ++k) {
+      const float2 p = pw[k];
+      const float gk = sm.g2t[k * kSLanes + lane];
+      ex = fmaf(gk, p.x, ex);
+      ey = fmaf(gk, p.y, ey);
+    }
+    const int64_t row = g.offF[pair] + t;
+    b.lograw[row * kSLanes + lane] = (lane < kSBands) ? logf(ex + (float)kEps) : 0.f;
+    b.lograw[(b.totF + row) * kSLanes + lane] = (lane < kSBands) ? logf(ey + (float)kEps) : 0.f;
   }
-  const int64_t row = g.offF[pair] + t;
-  b.lograw[row * kSLanes + lane] = (lane < kSBands) ? logf(ex + (float)kEps) : 0.f;
-  b.lograw[(b.totF + row) * kSLanes + lane] = (lane < kSBands) ? logf(ey + (float)kEps) : 0.f;
 }
 
 // --------------------------------------------------- forward masking + de-mean
@@ -1630,7 +1641,7 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, 
   if (max_F > 0) {
     kt_begin(kt, "siib_spec", s);
     // active index t <= frame f, and frames beyond the first period are copies: t < max_unique is enough
-    siib_spec_kernel<<<dim3((unsigned)((std::min(max_F, max_unique) + kSpecWarps - 1) / kSpecWarps), n), kSpecWarps * 32, sizeof(SpecSmem), s>>>(g, b);
+    siib_spec_kernel<<<dim3((unsigned)((std::min(max_F, max_unique) + kSpecWarps * kSpecIter - 1) / (kSpecWarps * kSpecIter)), n), kSpecWarps * 32, sizeof(SpecSmem), s>>>(g, b);
     kt_end(kt, s);
     ++launches;
   }
@@ -1687,10 +1698,16 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, 
     }
   }
   if (kb) return launches + siib_run_knn(g, b, *kb, n, max_F, kt, s);
-  kt_begin(kt, "siib_quad", s);
-  siib_quad_kernel<<<n, kQuadThreads, 0, s>>>(g, b);
-  kt_end(kt, s);
-  ++launches;
+  // default: register-tiled quadratic forms (siib_klt.cu); NELE_SIIB_QUAD_OLD=1 selects the thread-per-row kernel (A/B)
+  static const bool quad_old = [] { const char* p = getenv("NELE_SIIB_QUAD_OLD"); return p && p[0] == '1'; }();
+  if (quad_old) {
+    kt_begin(kt, "siib_quad", s);
+    siib_quad_kernel<<<n, kQuadThreads, 0, s>>>(g, b);
+    kt_end(kt, s);
+    ++launches;
+  } else {
+    launches += siib_launch_quadform(b, b.info_part, n, kt, s);
+  }
   if (!b.no_proj) {
     kt_begin(kt, "siib_projquad", s);
     siib_projquad_kernel<<<n, kPqThreads, kPqSmem, s>>>(g, b);

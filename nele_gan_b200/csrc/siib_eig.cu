@@ -485,7 +485,9 @@ int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& 
   siib_trieig_kernel<<<n, kEThreads, 0, s>>>(g, b, eb, rank_lo);
   kt_end(kt, s);
   kt_begin(kt, "siib_backtf", s);
-  siib_backtf_kernel<<<dim3((kEDim + kBtVec - 1) / kBtVec, n), kBtThreads, 0, s>>>(g, b, eb, rank_lo);
+  static const bool bt_old = [] { const char* p = getenv("NELE_BACKTF_OLD"); return p && p[0] == '1'; }();  // A/B: one reflector per barrier
+  if (bt_old) siib_backtf_kernel<<<dim3((kEDim + kBtVec - 1) / kBtVec, n), kBtThreads, 0, s>>>(g, b, eb, rank_lo);
+  else siib_launch_backtf4(b, eb, n, rank_lo, s);
   kt_end(kt, s);
   kt_begin(kt, "siib_eig_finish", s);
   siib_eig_finish_kernel<<<(n + 127) / 128, 128, 0, s>>>(b, n, rank_lo);

@@ -36,7 +36,7 @@
 namespace nele {
 namespace klt {
 
-constexpr int N = 420, LD = 448, NT = 256, NW = NT / 32, PB = 8, RG = 16, CB = 64;
+constexpr int N = 420, LD = 448, NT = 384, NW = NT / 32, PB = 8, RG = 16, CB = 64;
 constexpr int NE = (LD + NT - 1) / NT;  // vector elements per thread (j = tid, tid + 256)
 constexpr int JMAX = (N - 1) / RG;      // last row group
 
@@ -65,47 +65,37 @@ __device__ __forceinline__ float bsum(float v, float* red) {
   return t;
 }
 
-// tiles (J, C) of the lower triangle with rows > k, columns > k: row groups J = (k + 1) / 16 .. 26, column
-// blocks C = (k + 1) / 64 .. J / 4; warp w takes tiles w, w + 8, ... of that enumeration
-struct TileIter {
-  int J, C, cmin, rem;
-  __device__ __forceinline__ void init(int k, int wib) {
-    J = (k + 1) / RG;
-    cmin = (k + 1) / CB;
-    C = cmin;
-    rem = wib;
-  }
-  __device__ __forceinline__ bool next() {  // positions (J, C) on the next tile of this warp; false when done
-    while (J <= JMAX) {
-      const int avail = (J >> 2) - C + 1;
-      if (rem < avail) {
-        C += rem;
-        rem = NW;
-        return true;
-      }
-      rem -= avail;
-      ++J;
-      C = cmin;
-    }
-    return false;
-  }
-};
+// Tiles (J, C) of the lower triangle with rows > k, columns > k: row groups J = jmin .. 26 with jmin = (k + 1) / 16,
+// column blocks C = jmin / 4 .. J / 4.  The list depends on jmin only, so the 27 lists live in constant memory
+// (one byte per tile: J << 3 | C, at most 112 tiles), written by tile_tables_ready(); warp w takes entries w, w + NW, ...
+// (the first version enumerated the tiles with a stateful iterator: 11 % of the kernel's instructions).
+constexpr int kMaxTiles = 112;
+__constant__ unsigned char c_tiles[JMAX + 1][kMaxTiles];
+__constant__ int c_ntiles[JMAX + 1];
 
 // one tile of p = A v (A symmetric, lower triangle stored).  v: shared-memory vector (zero for indices <= k and
 // >= N), pw: this warp's partial result.
+// DIAG: the tile crosses the diagonal (elements right of it are masked, the diagonal counts once).  Other tiles load
+// through one base pointer with immediate row offsets and no predicates at all: rows <= k or >= N and columns <= k
+// that a tile at the edge of the trailing matrix also covers meet v = 0 (their products vanish, their own results
+// are never read) and hold finite numbers -- stale matrix entries, and zeros in the pad rows 420 .. 431.
 template <bool DIAG>
 __device__ __forceinline__ void mv_tile(const float* __restrict__ A, const float* __restrict__ v, float* __restrict__ pw, int J, int C,
-                                        int k, int lane) {
+                                        int lane) {
   const int j0 = RG * J, c0 = CB * C + 2 * lane;
-  const bool colok = c0 + 1 > k;
   float2 a[RG];
+  if (!DIAG) {
+    const float2* __restrict__ p = reinterpret_cast<const float2*>(A + (size_t)j0 * LD + c0);
 #pragma unroll
-  for (int r = 0; r < RG; ++r) {
-    const int j = j0 + r;
-    bool ok = colok && j > k && j < N;
-    if (DIAG) ok = ok && c0 <= j;
-    a[r] = ok ? __ldcg(reinterpret_cast<const float2*>(A + (size_t)j * LD + c0)) : make_float2(0.f, 0.f);
-    if (DIAG && c0 + 1 > j) a[r].y = 0.f;
+    for (int r = 0; r < RG; ++r) a[r] = __ldcg(p + r * (LD / 2));
+  } else {
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+      const int j = j0 + r;
+      const bool ok = j < N && c0 <= j;
+      a[r] = ok ? __ldcg(reinterpret_cast<const float2*>(A + (size_t)j * LD + c0)) : make_float2(0.f, 0.f);
+      if (c0 + 1 > j) a[r].y = 0.f;
+    }
   }
   const float2 vc = *reinterpret_cast<const float2*>(v + c0);
   float acc0 = 0.f, acc1 = 0.f;
@@ -165,18 +155,10 @@ __device__ __forceinline__ void mv_tile(const float* __restrict__ A, const float
 
 // one tile of the trailing update A -= V W^T + W V^T (rows and columns > kl, lower triangle); columns
 // kn .. kn + 7 (the next panel) are copied to s.col on the way
+// (non-diagonal tiles also update the stale entries and pad rows they cover: nobody reads those)
 template <bool DIAG>
-__device__ __forceinline__ void up_tile(float* __restrict__ A, Smem& s, int J, int C, int kl, int kn, int lane) {
+__device__ __forceinline__ void up_tile(float* __restrict__ A, Smem& s, int J, int C, int kn, int lane) {
   const int j0 = RG * J, c0 = CB * C + 2 * lane;
-  const bool colok = c0 > kl;  // kl is odd, c0 even: both columns of the lane are trailing columns
-  float2 a[RG];
-#pragma unroll
-  for (int r = 0; r < RG; ++r) {
-    const int j = j0 + r;
-    bool ok = colok && j > kl && j < N;
-    if (DIAG) ok = ok && c0 <= j;
-    a[r] = ok ? __ldcg(reinterpret_cast<const float2*>(A + (size_t)j * LD + c0)) : make_float2(0.f, 0.f);
-  }
   float2 vcx[PB], wcx[PB];
 #pragma unroll
   for (int mm = 0; mm < PB; ++mm) {
@@ -184,30 +166,41 @@ __device__ __forceinline__ void up_tile(float* __restrict__ A, Smem& s, int J, i
     wcx[mm] = *reinterpret_cast<const float2*>(&s.W[mm][c0]);
   }
   const bool tocol = (c0 & ~7) == kn;
+  // two halves of eight rows: the eight loads of a half are in flight together, and the tile's footprint stays
+  // inside the 80 registers that two CTAs of 384 threads per SM allow
+#pragma unroll 1
+  for (int h = 0; h < RG; h += RG / 2) {
+    float2 a[RG / 2];
 #pragma unroll
-  for (int r = 0; r < RG; ++r) {
-    const int j = j0 + r;
-    bool ok = colok && j > kl && j < N;
-    if (DIAG) ok = ok && c0 <= j;
-    const float4 v0 = *reinterpret_cast<const float4*>(&s.Vt[j][0]), v1 = *reinterpret_cast<const float4*>(&s.Vt[j][4]);
-    const float4 w0 = *reinterpret_cast<const float4*>(&s.Wt[j][0]), w1 = *reinterpret_cast<const float4*>(&s.Wt[j][4]);
-    const float vr[PB] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    const float wr[PB] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    float ax = a[r].x, ay = a[r].y;
-#pragma unroll
-    for (int mm = 0; mm < PB; ++mm) {
-      ax = fmaf(-vr[mm], wcx[mm].x, ax);
-      ax = fmaf(-wr[mm], vcx[mm].x, ax);
-      ay = fmaf(-vr[mm], wcx[mm].y, ay);
-      ay = fmaf(-wr[mm], vcx[mm].y, ay);
+    for (int r = 0; r < RG / 2; ++r) {
+      const int j = j0 + h + r;
+      const bool ok = DIAG ? (j < N && c0 <= j) : true;
+      a[r] = ok ? __ldcg(reinterpret_cast<const float2*>(A + (size_t)j * LD + c0)) : make_float2(0.f, 0.f);
     }
-    if (ok) {
-      const bool both = !DIAG || c0 + 1 <= j;
-      if (both) *reinterpret_cast<float2*>(A + (size_t)j * LD + c0) = make_float2(ax, ay);
-      else A[(size_t)j * LD + c0] = ax;
-      if (tocol) {
-        s.col[c0 - kn][j] = ax;
-        if (both) s.col[c0 + 1 - kn][j] = ay;
+#pragma unroll
+    for (int r = 0; r < RG / 2; ++r) {
+      const int j = j0 + h + r;
+      const bool ok = DIAG ? (j < N && c0 <= j) : true;
+      const float4 v0 = *reinterpret_cast<const float4*>(&s.Vt[j][0]), v1 = *reinterpret_cast<const float4*>(&s.Vt[j][4]);
+      const float4 w0 = *reinterpret_cast<const float4*>(&s.Wt[j][0]), w1 = *reinterpret_cast<const float4*>(&s.Wt[j][4]);
+      const float vr[PB] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      const float wr[PB] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      float ax = a[r].x, ay = a[r].y;
+#pragma unroll
+      for (int mm = 0; mm < PB; ++mm) {
+        ax = fmaf(-vr[mm], wcx[mm].x, ax);
+        ax = fmaf(-wr[mm], vcx[mm].x, ax);
+        ay = fmaf(-vr[mm], wcx[mm].y, ay);
+        ay = fmaf(-wr[mm], vcx[mm].y, ay);
+      }
+      if (ok) {
+        const bool both = !DIAG || c0 + 1 <= j;
+        if (both) *reinterpret_cast<float2*>(A + (size_t)j * LD + c0) = make_float2(ax, ay);
+        else A[(size_t)j * LD + c0] = ax;
+        if (tocol) {
+          s.col[c0 - kn][j] = ax;
+          if (both) s.col[c0 + 1 - kn][j] = ay;
+        }
       }
     }
   }
@@ -239,6 +232,7 @@ __global__ void __launch_bounds__(NT, 2) tridiag32_kernel(SiibBuffers b, SiibEig
         dst[c2] = make_float2((float)v.x, (float)v.y);
       }
     }
+    for (int idx = tid; idx < (RG * (JMAX + 1) - N) * LD; idx += NT) A[(size_t)N * LD + idx] = 0.f;   // pad rows 420 .. 431
     // columns of the first panel = rows of the symmetric input
     for (int idx = tid; idx < PB * LD; idx += NT) {
       const int q = idx / LD, j = idx % LD;
@@ -326,11 +320,11 @@ __global__ void __launch_bounds__(NT, 2) tridiag32_kernel(SiibBuffers b, SiibEig
             s.tot[tid] = t;
           }
           // ---- p = A v over the trailing lower triangle
-          TileIter it;
-          it.init(k, wib);
-          while (it.next()) {
-            if (CB * it.C + CB - 1 > RG * it.J) mv_tile<true>(A, s.V[m], s.pw[wib], it.J, it.C, k, lane);
-            else mv_tile<false>(A, s.V[m], s.pw[wib], it.J, it.C, k, lane);
+          const int jm = (k + 1) / RG, nt = c_ntiles[jm];
+          for (int t = wib; t < nt; t += NW) {
+            const int code = c_tiles[jm][t], J = code >> 3, C = code & 7;
+            if (CB * C + CB - 1 > RG * J) mv_tile<true>(A, s.V[m], s.pw[wib], J, C, lane);
+            else mv_tile<false>(A, s.V[m], s.pw[wib], J, C, lane);
           }
         }
         __syncthreads();
@@ -385,11 +379,11 @@ __global__ void __launch_bounds__(NT, 2) tridiag32_kernel(SiibBuffers b, SiibEig
       }
       __syncthreads();
       {
-        TileIter it;
-        it.init(kl, wib);
-        while (it.next()) {
-          if (CB * it.C + CB - 1 > RG * it.J) up_tile<true>(A, s, it.J, it.C, kl, kn, lane);
-          else up_tile<false>(A, s, it.J, it.C, kl, kn, lane);
+        const int jm = (kl + 1) / RG, nt = c_ntiles[jm];
+        for (int t = wib; t < nt; t += NW) {
+          const int code = c_tiles[jm][t], J = code >> 3, C = code & 7;
+          if (CB * C + CB - 1 > RG * J) up_tile<true>(A, s, J, C, kn, lane);
+          else up_tile<false>(A, s, J, C, kn, lane);
         }
       }
       __syncthreads();
@@ -405,12 +399,416 @@ __global__ void __launch_bounds__(NT, 2) tridiag32_kernel(SiibBuffers b, SiibEig
 
 }  // namespace klt
 
+// ------------------------------------------------------------------ quadratic forms
+// rho_j = u_j^T Sxy u_j / sqrt(lambda_j u_j^T Syy u_j) for the r eigenvectors of a pair, as one register-tiled
+// FP32 product per 64 eigenvectors: W = S^T G (420 x 420 x 64, Sxy and Syy side by side sharing the G
+// fragments) with the epilogue a_j = sum_i G[i][j] W[i][j] fused, so W never exists.  G[j] = sqrt(lambda_j) u_j
+// is what every KLT route leaves in b.G (column j contiguous); lambda_j = |G_j|^2 comes out of the same epilogue.
+// Replaces siib_quad_kernel (thread = row, 16 eigenvectors per pass: Sxy / Syy re-read 27 times per pair, 36 GB
+// of L2 traffic per 1024 pairs, 14.9 ms) -- here they are read 7 times by CTAs that run 64 FMAs per 5 shared loads.
+//   CTA = (64-eigenvector tile, pair), 256 threads = 16 (rows) x 16 (columns), thread tile 8 x 4 x 2 matrices,
+//   k-steps of 16 through double-buffered shared memory, next tile prefetched into registers.
+namespace qf {
+
+constexpr int N = 420, LD = 448, BM = 128, BN = 64, BK = 16, NT = 256;
+constexpr int KT = (N + BK - 1) / BK;   // 27 k-tiles
+constexpr int IB = (N + BM - 1) / BM;   // 4 row blocks
+constexpr int JT = (N + BN - 1) / BN;   // 7 eigenvector tiles
+
+struct Smem {
+  float Axy[2][BK][BM];
+  float Ayy[2][BK][BM];
+  float B[2][BK][BN];
+  float red[3][BN][17];
+  double wsum[NT / 32];
+};
+
+__device__ __forceinline__ bool pair_scored_here(const SiibBuffers& b, int pair, int& r) {
+  const int Fa = b.Fa[pair];
+  const int Nf = Fa - 14;
+  if (b.M[pair] <= 0 || (double)Fa / 80.0 < 20.0 || Nf < 2) return false;   // too short: quad_finish reports it
+  const int P = b.Pact[pair];
+  if (!b.no_proj && b.perflag[2 * pair] && b.perflag[2 * pair + 1] && P > 0 && Nf >= 2 * P) return false;  // siib_projquad_kernel
+  r = b.rank[pair];
+  return true;
+}
+
+__global__ void __launch_bounds__(NT, 2) quadform_kernel(SiibBuffers b, double* __restrict__ info_part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  const int lp = blockIdx.y, pair = b.pair_lo + lp, jt = blockIdx.x, j0 = jt * BN, tid = threadIdx.x;
+  const int ti = tid >> 4, tj = tid & 15, lane = tid & 31, wib = tid >> 5;
+  int r = 0;
+  if (!pair_scored_here(b, pair, r)) return;
+  float* __restrict__ lam_out = b.lambda + (int64_t)pair * N;
+  float* __restrict__ rho_out = b.rho + (int64_t)pair * N;
+  if (j0 >= r) {  // nothing beyond the rank
+    if (tid < BN && j0 + tid < N) {
+      lam_out[j0 + tid] = 0.f;
+      rho_out[j0 + tid] = 0.f;
+    }
+    if (tid == 0) info_part[(int64_t)pair * 8 + jt] = 0.0;
+    return;
+  }
+  const float* __restrict__ G = b.G + (int64_t)lp * N * LD;
+  const float* __restrict__ Sxy = b.Sxy + (int64_t)lp * N * N;
+  const float* __restrict__ Syy = b.Syy + (int64_t)lp * N * N;
+  // global -> register staging: A tiles 16 x 128 (two float4 per thread and matrix), B tile 16 x 64 (one float4)
+  const int arow = tid >> 5, acol = 4 * (tid & 31);
+  const int bj = tid >> 2, bc = 4 * (tid & 3);
+  const bool bj_ok = j0 + bj < r;
+  float4 rxy[2], ryy[2], rb;
+  auto fetch = [&](int i0, int kt) {
+    const int c0 = kt * BK;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + arow + 8 * h, i = i0 + acol;
+      const bool ok = c < N && i < N;
+      rxy[h] = ok ? __ldg(reinterpret_cast<const float4*>(Sxy + (int64_t)c * N + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ryy[h] = ok ? __ldg(reinterpret_cast<const float4*>(Syy + (int64_t)c * N + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int c = c0 + bc;
+    rb = (bj_ok && c < N) ? __ldg(reinterpret_cast<const float4*>(G + (int64_t)(j0 + bj) * LD + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      *reinterpret_cast<float4*>(&s.Axy[buf][arow + 8 * h][acol]) = rxy[h];
+      *reinterpret_cast<float4*>(&s.Ayy[buf][arow + 8 * h][acol]) = ryy[h];
+    }
+    s.B[buf][bc][bj] = rb.x;
+    s.B[buf][bc + 1][bj] = rb.y;
+    s.B[buf][bc + 2][bj] = rb.z;
+    s.B[buf][bc + 3][bj] = rb.w;
+  };
+  float pa[4] = {0.f, 0.f, 0.f, 0.f}, pc[4] = {0.f, 0.f, 0.f, 0.f}, pl[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int ib = 0; ib < IB; ++ib) {
+    const int i0 = ib * BM;
+    // accumulators as f32x2 pairs of rows (fma.rn.f32x2: two FMAs per issue slot, the same FMA-pipe rate): the
+    // scalar version of this loop sat at 73 % issue-slot and 61 % FMA-pipe utilisation, i.e. issue bound
+    F2 axy[4][4], ayy[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) axy[a][c] = ayy[a][c] = f2_pack(0.f, 0.f);
+    __syncthreads();
+    fetch(i0, 0);
+    stash(0);
+    __syncthreads();
+    for (int kt = 0; kt < KT; ++kt) {
+      const int cur = kt & 1;
+      if (kt + 1 < KT) fetch(i0, kt + 1);
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        const float4 x0 = *reinterpret_cast<const float4*>(&s.Axy[cur][k][8 * ti]);
+        const float4 x1 = *reinterpret_cast<const float4*>(&s.Axy[cur][k][8 * ti + 4]);
+        const float4 y0 = *reinterpret_cast<const float4*>(&s.Ayy[cur][k][8 * ti]);
+        const float4 y1 = *reinterpret_cast<const float4*>(&s.Ayy[cur][k][8 * ti + 4]);
+        const float4 bq = *reinterpret_cast<const float4*>(&s.B[cur][k][4 * tj]);
+        const F2 xa[4] = {f2_pack(x0.x, x0.y), f2_pack(x0.z, x0.w), f2_pack(x1.x, x1.y), f2_pack(x1.z, x1.w)};
+        const F2 ya[4] = {f2_pack(y0.x, y0.y), f2_pack(y0.z, y0.w), f2_pack(y1.x, y1.y), f2_pack(y1.z, y1.w)};
+        const F2 bb[4] = {f2_pack(bq.x, bq.x), f2_pack(bq.y, bq.y), f2_pack(bq.z, bq.z), f2_pack(bq.w, bq.w)};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            axy[a][c] = f2_fma(xa[a], bb[c], axy[a][c]);
+            ayy[a][c] = f2_fma(ya[a], bb[c], ayy[a][c]);
+          }
+      }
+      if (kt + 1 < KT) stash(cur ^ 1);
+      __syncthreads();
+    }
+    // epilogue of the row block: a_j += sum_i G[i][j] W[i][j], likewise yy and |G_j|^2
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = j0 + 4 * tj + c;
+      if (j < r) {
+        const int i = i0 + 8 * ti;
+        const float4 g0 = (i < N) ? __ldg(reinterpret_cast<const float4*>(G + (int64_t)j * LD + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 g1 = (i + 4 < N) ? __ldg(reinterpret_cast<const float4*>(G + (int64_t)j * LD + i + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          float w0, w1, z0, z1;
+          f2_unpack(axy[a][c], w0, w1);
+          f2_unpack(ayy[a][c], z0, z1);
+          pa[c] = fmaf(w0, gg[2 * a], pa[c]);
+          pa[c] = fmaf(w1, gg[2 * a + 1], pa[c]);
+          pc[c] = fmaf(z0, gg[2 * a], pc[c]);
+          pc[c] = fmaf(z1, gg[2 * a + 1], pc[c]);
+          pl[c] = fmaf(gg[2 * a], gg[2 * a], pl[c]);
+          pl[c] = fmaf(gg[2 * a + 1], gg[2 * a + 1], pl[c]);
+        }
+      }
+    }
+  }
+  // sums over the 16 row groups, then rho and the information of the tile's components
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    s.red[0][4 * tj + c][ti] = pa[c];
+    s.red[1][4 * tj + c][ti] = pc[c];
+    s.red[2][4 * tj + c][ti] = pl[c];
+  }
+  __syncthreads();
+  double info = 0.0;
+  if (tid < BN) {
+    const int j = j0 + tid;
+    double a = 0.0, c = 0.0, l = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      a += (double)s.red[0][tid][q];
+      c += (double)s.red[1][tid][q];
+      l += (double)s.red[2][tid][q];
+    }
+    double rho = 0.0;
+    if (j < r && l > 0.0 && c > 0.0) rho = a / (l * sqrt(c));
+    rho = fmin(1.0, fmax(-1.0, rho));
+    const double pr = 0.75 * rho;
+    info = -0.5 * log2(1.0 - pr * pr);
+    if (j < N) {
+      lam_out[j] = (j < r) ? (float)l : 0.f;
+      rho_out[j] = (float)rho;
+    }
+  }
+  if (tid < 64) {   // two warps, fixed summation order
+    info = warp_sum(info);
+    if (lane == 0) s.wsum[wib] = info;
+  }
+  __syncthreads();
+  if (tid == 0) info_part[(int64_t)pair * 8 + jt] = s.wsum[0] + s.wsum[1];
+}
+
+// score and status of the pairs scored by the quadratic forms (the others: siib_projquad_kernel)
+__global__ void quad_finish_kernel(SiibBuffers b, const double* __restrict__ info_part, int n) {
+  const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lp >= n) return;
+  const int pair = b.pair_lo + lp;
+  int r = 0;
+  if (!pair_scored_here(b, pair, r)) {
+    const int Fa = b.Fa[pair];
+    if (b.M[pair] <= 0 || (double)Fa / 80.0 < 20.0 || Fa - 14 < 2) {  // pysiib: "at least 20 seconds of speech"
+      b.score[pair] = nan("");
+      b.status[pair] = 2;
+    }
+    return;
+  }
+  double sum = 0.0;
+  for (int jt = 0; jt < JT; ++jt) sum += info_part[(int64_t)pair * 8 + jt];
+  const double v = 16000.0 / 200.0 / 15.0 * sum;
+  b.score[pair] = v > 0.0 ? v : 0.0;
+  // bit 8: the null space of a rank-deficient (exactly periodic) covariance was given zero information
+  // (NELE_INFO_SIIB_NULLSPACE).  sweeps: -1 tridiagonal path at full rank, -3 rank deficient, -2 Gram path.
+  const int sw = b.sweeps[pair];
+  b.status[pair] = (sw == -2 || sw == -3 || (sw >= 0 && r < N)) ? 0x100 : 0;
+}
+
+}  // namespace qf
+
+int siib_launch_quadform(const SiibBuffers& b, double* info_part, int n, KernelTimer* kt, cudaStream_t s) {
+  static const bool attr = [] {
+    cudaFuncSetAttribute(qf::quadform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(qf::Smem));
+    return true;
+  }();
+  (void)attr;
+  kt_begin(kt, "siib_quad", s);
+  qf::quadform_kernel<<<dim3(qf::JT, n), qf::NT, sizeof(qf::Smem), s>>>(b, info_part);
+  kt_end(kt, s);
+  kt_begin(kt, "siib_quad_finish", s);
+  qf::quad_finish_kernel<<<(n + 127) / 128, 128, 0, s>>>(b, info_part, n);
+  kt_end(kt, s);
+  return 2;
+}
+
+// ------------------------------------------------------------------ back-transformation
+// u_j = H_0 ... H_{n-3} z_j with the vector in registers (lane = eigenvector, 8 warps = 8 interleaved row parts), as
+// siib_backtf_kernel, but the reflectors are applied four at a time: one pass forms the four dot products
+// d_q = v_q . u, the coefficients follow from the 4 x 4 triangular recurrence
+//   y_0 = tau_0 d_0,  y_q = tau_q (d_q - sum_{p<q} y_p (v_q . v_p))
+// (the Gram values v_q . v_p are computed once per panel while it is staged), and one pass applies
+// u -= sum_q y_q v_q.  Same flops, but one block barrier per four reflectors instead of one per reflector: the
+// old kernel ran at a quarter of its issue rate waiting on that barrier (15.1 ms per 1024 pairs).
+namespace bt {
+
+constexpr int N = 420, LD = 448, VEC = 32, PARTS = 8, NT = PARTS * 32, ROWS = LD / PARTS, PANEL = 16, GRP = 4;
+
+__device__ __forceinline__ void cp_async4(float* smem, const float* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+// The reflectors of the next panel travel global -> shared memory with cp.async (element-wise: the staged layout
+// interleaves the rows over the eight warps) while the current panel is applied; the first version staged a panel
+// through registers between two barriers and spent most of its time on that exposed L2 latency (ncu: 5.6 cycles of
+// long-scoreboard stall per issued instruction, 24.5 ms per 1024 pairs).
+__global__ void __launch_bounds__(NT, 2) backtf4_kernel(SiibBuffers b, SiibEigBuffers eb, int rank_lo) {
+  const int lp = blockIdx.y, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int rk = b.rank[pair];
+  if (rk < rank_lo) return;
+  const int j = blockIdx.x * VEC + lane;
+  const bool live = j < N;
+  extern __shared__ __align__(16) float s_vbuf[];   // [2][PANEL][LD]: reflector kk of a panel, staged as [row part w][m]: row 8 m + w
+  __shared__ float s_tau[PANEL];
+  __shared__ float s_g[PANEL / GRP][8];            // per group: v1.v0, v2.v0, v2.v1, v3.v0, v3.v1, v3.v2
+  __shared__ float s_dot[2][PARTS][GRP][32];
+  const float* __restrict__ R = eb.refl + (int64_t)lp * N * LD;
+  const double* __restrict__ tt = eb.tau + (int64_t)lp * LD;
+  auto stage = [&](int k1, int buf) {
+    const int nk = min(PANEL, k1 + 1);
+    float* dst = s_vbuf + (size_t)buf * PANEL * LD;
+    for (int kk = 0; kk < PANEL; ++kk) {
+      if (kk < nk) {
+        const float* __restrict__ row = R + (int64_t)(k1 - kk) * LD;
+#pragma unroll
+        for (int i = tid; i < LD; i += NT) cp_async4(dst + kk * LD + (i & (PARTS - 1)) * ROWS + (i >> 3), row + i);
+      } else {
+        for (int i = tid; i < LD; i += NT) dst[kk * LD + i] = 0.f;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(N - 3, 0);
+  float u[ROWS];
+#pragma unroll
+  for (int m = 0; m < ROWS; ++m) {
+    const int i = PARTS * m + w;
+    u[m] = (live && i < N) ? eb.zt[((int64_t)lp * N + i) * LD + j] : 0.f;
+  }
+  int par = 0, buf = 0;
+  for (int k1 = N - 3; k1 >= 0; k1 -= PANEL, buf ^= 1) {   // reflectors k1, k1 - 1, ... (descending inside the panel)
+    const int nk = min(PANEL, k1 + 1);
+    __syncthreads();                                        // everyone is done with the other buffer (previous panel)
+    if (k1 - PANEL >= 0) {
+      stage(k1 - PANEL, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    if (tid < PANEL) s_tau[tid] = (tid < nk) ? (float)tt[k1 - tid] : 0.f;
+    __syncthreads();
+    float (*s_v)[LD] = reinterpret_cast<float (*)[LD]>(s_vbuf + (size_t)buf * PANEL * LD);
+    // Gram values inside each group of four: 24 dot products of length 448, three per warp
+    for (int d = w; d < (PANEL / GRP) * 6; d += PARTS) {
+      const int g = d / 6, e = d % 6;
+      const int qa = (e == 0) ? 1 : (e < 3) ? 2 : 3;
+      const int qb = (e == 0) ? 0 : (e == 1) ? 0 : (e == 2) ? 1 : e - 3;
+      const float* va = s_v[GRP * g + qa];
+      const float* vb = s_v[GRP * g + qb];
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < LD / 32; ++i) acc = fmaf(va[lane + 32 * i], vb[lane + 32 * i], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) s_g[g][e] = acc;
+    }
+    __syncthreads();
+    for (int g = 0; g < PANEL / GRP; ++g) {
+      const int kk0 = GRP * g;
+      if (kk0 >= nk) break;
+      // every reflector of the group is zero in rows <= kmin, i.e. in the words q < kmin / 32 of every warp
+      const int kmin = max(k1 - kk0 - (GRP - 1), 0);
+      const int q0 = kmin >> 5;
+      const float4* v0 = reinterpret_cast<const float4*>(s_v[kk0] + w * ROWS);
+      const float4* v1 = reinterpret_cast<const float4*>(s_v[kk0 + 1] + w * ROWS);
+      const float4* v2 = reinterpret_cast<const float4*>(s_v[kk0 + 2] + w * ROWS);
+      const float4* v3 = reinterpret_cast<const float4*>(s_v[kk0 + 3] + w * ROWS);
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+      for (int q = 0; q < ROWS / 4; ++q) {
+        if (q < q0) continue;
+        const float4 a = v0[q], bq = v1[q], c = v2[q], e = v3[q];
+        d0 = fmaf(a.x, u[4 * q], d0); d0 = fmaf(a.y, u[4 * q + 1], d0); d0 = fmaf(a.z, u[4 * q + 2], d0); d0 = fmaf(a.w, u[4 * q + 3], d0);
+        d1 = fmaf(bq.x, u[4 * q], d1); d1 = fmaf(bq.y, u[4 * q + 1], d1); d1 = fmaf(bq.z, u[4 * q + 2], d1); d1 = fmaf(bq.w, u[4 * q + 3], d1);
+        d2 = fmaf(c.x, u[4 * q], d2); d2 = fmaf(c.y, u[4 * q + 1], d2); d2 = fmaf(c.z, u[4 * q + 2], d2); d2 = fmaf(c.w, u[4 * q + 3], d2);
+        d3 = fmaf(e.x, u[4 * q], d3); d3 = fmaf(e.y, u[4 * q + 1], d3); d3 = fmaf(e.z, u[4 * q + 2], d3); d3 = fmaf(e.w, u[4 * q + 3], d3);
+      }
+      s_dot[par][w][0][lane] = d0;
+      s_dot[par][w][1][lane] = d1;
+      s_dot[par][w][2][lane] = d2;
+      s_dot[par][w][3][lane] = d3;
+      __syncthreads();
+      float D0 = 0.f, D1 = 0.f, D2 = 0.f, D3 = 0.f;
+#pragma unroll
+      for (int t = 0; t < PARTS; ++t) {
+        D0 += s_dot[par][t][0][lane];
+        D1 += s_dot[par][t][1][lane];
+        D2 += s_dot[par][t][2][lane];
+        D3 += s_dot[par][t][3][lane];
+      }
+      par ^= 1;
+      const float y0 = s_tau[kk0] * D0;
+      const float y1 = s_tau[kk0 + 1] * (D1 - y0 * s_g[g][0]);
+      const float y2 = s_tau[kk0 + 2] * (D2 - y0 * s_g[g][1] - y1 * s_g[g][2]);
+      const float y3 = s_tau[kk0 + 3] * (D3 - y0 * s_g[g][3] - y1 * s_g[g][4] - y2 * s_g[g][5]);
+#pragma unroll
+      for (int q = 0; q < ROWS / 4; ++q) {
+        if (q < q0) continue;
+        const float4 a = v0[q], bq = v1[q], c = v2[q], e = v3[q];
+        u[4 * q] -= y0 * a.x + y1 * bq.x + y2 * c.x + y3 * e.x;
+        u[4 * q + 1] -= y0 * a.y + y1 * bq.y + y2 * c.y + y3 * e.y;
+        u[4 * q + 2] -= y0 * a.z + y1 * bq.z + y2 * c.z + y3 * e.z;
+        u[4 * q + 3] -= y0 * a.w + y1 * bq.w + y2 * c.w + y3 * e.w;
+      }
+    }
+  }
+  if (!live) return;
+  // column j of G = sqrt(lambda_j) u_j / |z_j|.  Eigenvalues at or below 1e-10 lambda_max carry no information; of a
+  // periodic tiling of rank r < 420 (pivoted Cholesky, FP64) only the r largest are non-zero in exact arithmetic --
+  // the FP32 tridiagonalisation leaves the others at +-1e-7 lambda_max, so there the rank decides, not the value
+  const double lam = eb.lam[(int64_t)lp * LD + j], lmax = eb.lam[(int64_t)lp * LD + N - 1];
+  const double nz = eb.znorm[(int64_t)lp * LD + j];
+  const bool in_range = j >= N - rk;
+  const float sc = (in_range && lam > 1.0e-10 * lmax && nz > 0.0) ? (float)sqrt(lam / nz) : 0.f;
+  float* __restrict__ G = b.G + (int64_t)lp * N * LD + (int64_t)j * LD;
+#pragma unroll
+  for (int m = 0; m < ROWS; ++m) {
+    const int i = PARTS * m + w;
+    G[i] = (i < N) ? sc * u[m] : 0.f;
+  }
+}
+
+}  // namespace bt
+
+int siib_launch_backtf4(const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, cudaStream_t s) {
+  constexpr int smem = 2 * bt::PANEL * bt::LD * (int)sizeof(float);
+  static const bool attr = [] {
+    cudaFuncSetAttribute(bt::backtf4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return true;
+  }();
+  (void)attr;
+  bt::backtf4_kernel<<<dim3((bt::N + bt::VEC - 1) / bt::VEC, n), bt::NT, smem, s>>>(b, eb, rank_lo);
+  return 1;
+}
+
+// tile lists of tridiag32_kernel, one per first row group, in quads of row groups and column-block major inside a quad
+// (neighbouring warps then share row groups of v and columns of the partial vectors); per device
+static void tile_tables_ready(cudaStream_t s) {
+  static bool ready_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && ready_dev[dev]) return;
+  static unsigned char tiles[klt::JMAX + 1][klt::kMaxTiles];
+  static int ntiles[klt::JMAX + 1];
+  for (int jm = 0; jm <= klt::JMAX; ++jm) {
+    int n = 0;
+    const int cmin = jm / 4;
+    for (int Q = jm / 4; Q <= klt::JMAX / 4; ++Q)
+      for (int C = cmin; C <= Q; ++C)
+        for (int J = std::max(4 * Q, jm); J <= std::min(4 * Q + 3, klt::JMAX); ++J) tiles[jm][n++] = (unsigned char)(J << 3 | C);
+    ntiles[jm] = n;
+  }
+  cudaMemcpyToSymbolAsync(klt::c_tiles, tiles, sizeof(tiles), 0, cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(klt::c_ntiles, ntiles, sizeof(ntiles), 0, cudaMemcpyHostToDevice, s);
+  cudaStreamSynchronize(s);
+  if (dev >= 0 && dev < 64) ready_dev[dev] = true;
+}
+
 int siib_launch_tridiag32(const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, cudaStream_t s) {
   static const bool attr = [] {
     cudaFuncSetAttribute(klt::tridiag32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(klt::Smem));
     return true;
   }();
   (void)attr;
+  tile_tables_ready(s);
   klt::tridiag32_kernel<<<n, klt::NT, sizeof(klt::Smem), s>>>(b, eb, rank_lo, n);
   return 1;
 }

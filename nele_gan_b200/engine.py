@@ -25,7 +25,7 @@ COL_SIIB, COL_HASPI, COL_ESTOI = 0, 1, 2
 SYMBOLS = ("nele_abi_version", "nele_create", "nele_destroy", "nele_last_error", "nele_score_batch", "nele_prefetch",
            "nele_prefetch_cancel",
            "nele_get_stage", "nele_last_timing", "nele_set_profiling", "nele_kernel_time", "nele_feature_frames",
-           "nele_features")
+           "nele_features", "nele_resyn")
 FEAT_NOISE, FEAT_DEVICE_IO, FEAT_NO_POWER = 0x1, 0x2, 0x4
 
 
@@ -78,6 +78,9 @@ def load_library(path=None):
         lib.nele_features.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_double,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.nele_features.restype = C.c_int
+        lib.nele_resyn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.nele_resyn.restype = C.c_int
         if path is None:
             _lib = lib
         return lib
@@ -291,6 +294,23 @@ class Engine:
                 item.append(r["psd"][257 * fo:257 * (fo + T)].reshape(257, T))
             out.append(tuple(item))
         return out
+
+    def resyn(self, clean, noise, offs, lens, alpha2, arow=None, enh=None, deg=None, pcm16=True, stream=None):
+        """``nele_resyn``: device pointers (ints) ``clean`` / ``noise`` / ``alpha2`` / ``enh`` / ``deg``; host ``offs``
+        int64[n], ``lens`` int32[n], ``arow`` int64[n] (first row of each utterance in ``alpha2``; None = packed).
+        Returns the valid output lengths ``256 * (lens // 256)`` (int32[n])."""
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        out_lens = np.empty_like(lens)
+        if arow is not None:
+            arow = np.ascontiguousarray(arow, dtype=np.int64)
+        rc = self._lib.nele_resyn(self._h, int(clean), None if noise is None else int(noise), offs.ctypes.data,
+                                  lens.ctypes.data, int(lens.shape[0]), int(alpha2),
+                                  None if arow is None else arow.ctypes.data, 1 if pcm16 else 0,
+                                  None if enh is None else int(enh), None if deg is None else int(deg),
+                                  out_lens.ctypes.data, None if stream is None else int(stream))
+        self._check(rc, "nele_resyn")
+        return out_lens
 
     def last_timing(self):
         """(kernel milliseconds, kernel launches) of the last call."""

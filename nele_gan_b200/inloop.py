@@ -6,9 +6,12 @@ The reference (train_nele.py:286-322) takes the generator's band gains ``mask * 
 (``interp_band_gain``, audio_util.py:98-115), scales the clean complex spectrogram, inverts it
 with ``librosa.istft`` (``Resyn`` / ``ISTFT``, audio_util.py:60-96), writes PCM-16 WAV files,
 and fans the file names out to 32 processes that re-load them, add the noise and compute the
-three metrics.  Here everything up to the degraded waveform is a handful of batched torch ops
-on the device (plumbing), and the waveforms go straight into the scoring engine
-(``api.score_tensors``, device pointers through the C ABI): no files, no process pool.
+three metrics.  Here everything up to the degraded waveform is one kernel of the engine
+(``nele_resyn``, csrc/features.cu) and the waveforms go straight into the scoring kernels
+(device pointers through the C ABI): no files, no process pool, no torch / cuFFT kernels.
+``stft`` / ``resyn`` below are the same two steps as batched torch ops for equally long
+utterances; they are kept as the host-side restatement the CPU tests check against
+``oracle/resyn_np.py`` and are not on the product path.
 """
 import numpy as np
 
@@ -61,27 +64,53 @@ def resyn(X, alpha2):
     return torch.istft(Xn, N_FFT, hop_length=HOP, win_length=N_FFT, window=win, center=True)
 
 
-def label_sampling_round(alpha2, clean_wav, noise_wav, lengths=None, norm=True, pcm16=True, seed=0, **kw):
-    """One sampling round (train_nele.py:286-322) on the device.
+def label_sampling_round(alpha2, clean_wav, noise_wav, lengths=None, norm=True, pcm16=True, seed=0, strict=True,
+                         return_deg=False, **kw):
+    """One sampling round (train_nele.py:286-322) on the device, through the engine's own kernels:
+    ``nele_resyn`` (band gains -> ``interp_band_gain`` -> ``Resyn`` / ``librosa.istft`` -> PCM-16 rounding ->
+    ``+ noise``, one launch for the whole round) and ``nele_score_batch`` on the device buffers.  No torch / cuFFT
+    kernel runs: torch only owns the memory.
 
-    alpha2     [n, T, 64]  generator output after the energy normalisation, ``mask * beta_2``
-    clean_wav  [n, L]      clean waveforms (zero padded to the longest)
-    noise_wav  [n, L]      noise waveforms
-    lengths    [n]         valid samples per utterance (default L)
+    alpha2     [n, Tmax, 64]  generator output after the energy normalisation, ``mask * beta_2`` (CUDA, float32);
+                              utterance i uses its first ``1 + lengths[i] // 256`` rows
+    clean_wav  [n, L]         clean waveforms, zero padded to the longest (CUDA, float32)
+    noise_wav  [n, L]         noise waveforms
+    lengths    [n]            valid samples per utterance (default L)
 
-    Returns float64 ``[n, 3]`` {SIIB, HASPI, ESTOI} like ``api.score_tensors``.  ``pcm16``
-    reproduces the quantisation of ``sf.write(..., 'PCM_16')`` (train_nele.py:313) on the
-    enhanced waveform before the noise is added, as the reference's reload does
-    (audio_util.py:186-196)."""
+    Every utterance is resynthesised at its own length -- reflect padding at its own ends and
+    ``256 * (length // 256)`` output samples, to which the reference trims both signals (audio_util.py:190-193) --
+    exactly as the reference does one file at a time, so ragged rounds give the per-file numbers.
+    Returns float64 ``[n, 3]`` {SIIB, HASPI, ESTOI} like ``api.score_tensors`` (and the degraded waveforms
+    ``[n, L]`` plus their valid lengths when ``return_deg``)."""
     import torch
-    from . import api
+    from . import api, engine as _eng
+    if not (alpha2.is_cuda and clean_wav.is_cuda and noise_wav.is_cuda):
+        raise ValueError("label_sampling_round needs CUDA tensors (the engine has no CPU path)")
     n, L = clean_wav.shape
-    X = stft(clean_wav)
-    enh = resyn(X, alpha2)
-    if pcm16:
-        enh = torch.clamp(torch.round(enh * 32768.0), -32768.0, 32767.0) / 32768.0
-    lens = np.full(n, L, dtype=np.int64) if lengths is None else np.asarray(lengths, dtype=np.int64)
-    m = min(L, enh.shape[1])
-    lens = np.minimum(lens, m)                            # audio_util.py:190-193: trim to the shorter of clean / enhanced
-    deg = enh[:, :m] + noise_wav[:, :m]
-    return api.score_tensors(clean_wav[:, :m], deg, lengths=lens.astype(np.int32), norm=norm, seed=seed, **kw)
+    if noise_wav.shape != clean_wav.shape or alpha2.dim() != 3 or alpha2.shape[0] != n or alpha2.shape[2] != NB_BANDS:
+        raise ValueError("shapes: alpha2 [n, Tmax, 64], clean_wav / noise_wav [n, L]")
+    lens = np.full(n, L, dtype=np.int32) if lengths is None else np.asarray(lengths, dtype=np.int32)
+    if lens.shape != (n,) or lens.min() <= 256 or lens.max() > L:
+        raise ValueError("lengths must be n values in (256, L]")
+    if int((1 + lens // HOP).max()) > alpha2.shape[1]:
+        raise ValueError("alpha2 has %d frames, the longest utterance needs %d" % (alpha2.shape[1], int((1 + lens // HOP).max())))
+    clean = clean_wav.detach().to(torch.float32).contiguous()
+    noise = noise_wav.detach().to(torch.float32).contiguous()
+    if L % 4:                                              # rows must start 16-byte aligned
+        clean = torch.nn.functional.pad(clean, (0, 4 - L % 4))
+        noise = torch.nn.functional.pad(noise, (0, 4 - L % 4))
+    a2 = alpha2.detach().to(torch.float32).contiguous()
+    stride = clean.shape[1]
+    offs = np.arange(n, dtype=np.int64) * stride
+    arow = np.arange(n, dtype=np.int64) * a2.shape[1]
+    deg = torch.zeros_like(clean)
+    eng = _eng.default_engine(clean.device.index)
+    torch.cuda.current_stream(clean.device).synchronize()  # the engine runs on its own stream
+    out_lens = eng.resyn(clean.data_ptr(), noise.data_ptr(), offs, lens, a2.data_ptr(), arow=arow, deg=deg.data_ptr(),
+                         pcm16=pcm16)
+    r = eng.score_packed(clean.data_ptr(), deg.data_ptr(), offs, out_lens, fs=16000, mapped=bool(norm), seed=seed,
+                         device_input=True, **kw)
+    scores = torch.from_numpy(api.check_status(r, strict=strict).scores)
+    if return_deg:
+        return scores, deg[:, :L], out_lens
+    return scores

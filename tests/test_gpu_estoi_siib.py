@@ -207,3 +207,25 @@ def test_siib_klt_dispatch_paths(eng):
             assert rk[1] == marker, (L, rk[:2])
         if marker == -2:
             assert rk[0] == int(nonnull.sum())
+
+
+def test_all_metrics_on_the_toy_corpus_pairs(eng, golden):
+    """BASELINE.json configs[1]: the three labels of every toy_dataset utterance -- Train (Clean, MultiEnh + Noise),
+    Train (Clean, Clean + Noise), Test (Clean, Clean + Noise); 33 536 / 34 048 samples, so the SIIB tiling has full
+    rank -- raw and mapped, against the oracle on the same arrays (HASPI also against the reference's own value)."""
+    from oracle import intel_np
+    names = ("toy_train_multienh", "toy_train_clean", "toy_test_clean")
+    xs, ys = [golden[n]["x"] for n in names], [golden[n]["y"] for n in names]
+    raw = eng.score_batch(xs, ys, mapped=False, no_dither=True, keep_stages=True)
+    mapped = eng.score_batch(xs, ys, mapped=True, no_dither=True)
+    assert raw.ok.all() and not raw.siib_nullspace_dropped.any()
+    for i, n in enumerate(names):
+        want = intel_np.score_pair(xs[i], ys[i], 16000, norm=False, noise=None)
+        assert abs(raw.siib[i] - want[0]) < SIIB_RTOL * want[0], (n, raw.siib[i], want[0])
+        assert abs(raw.siib[i] - want[0]) < 1e-3 * want[0], (n, raw.siib[i], want[0])     # FP32 KLT: measured <= 3e-4
+        assert abs(raw.haspi[i] - want[1]) < 1e-3 and abs(raw.haspi[i] - float(golden[n]["v2_zero"])) < 1e-3
+        assert abs(raw.estoi[i] - want[2]) < ESTOI_TOL
+        wm = intel_np.score_pair(xs[i], ys[i], 16000, norm=True, noise=None)
+        assert np.abs(mapped.scores[i] - wm).max() < 2e-3
+        rk = eng.stage("siib.rank", i)
+        assert rk[0] == 420 and rk[1] == -1                       # tridiagonalisation path at full rank

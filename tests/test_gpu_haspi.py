@@ -99,3 +99,42 @@ def test_bad_rate_status(eng):
     x = np.random.default_rng(0).standard_normal(48000).astype(np.float32)
     r = eng.score_batch([x], [x], fs=48000, metrics=("haspi",), mapped=False)
     assert r.metric_status("haspi")[0] == 3 and np.isnan(r.haspi[0])
+
+
+def _extra():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "haspi_extra.npz"))
+
+
+def test_nonzero_audiogram_matches_the_reference(eng, golden):
+    """HL != 0 (pyhaspi2.py:1160-1171: hearing-loss dependent OHC / IHC attenuation, compression ratio and
+    bandwidth of the processed signal's path).  Golden: the unmodified reference with HL = [20 .. 60] dB on a toy
+    pair, zero dither (tests/golden/make_golden_extra.py); the score drops from 2.69 to 1.11."""
+    z = _extra()
+    g = golden[str(z["hl/case"])]
+    r = eng.score_batch([g["x"]], [g["y"]], fs=16000, metrics=("haspi",), mapped=False, no_dither=True,
+                        hl=z["hl/HL"], keep_stages=True)
+    bw = eng.stage("haspi.bw").reshape(2, 32)
+    assert np.abs(bw[0] - z["hl/bwx"]).max() < 2e-5
+    assert np.abs(bw[1] - z["hl/bwy"]).max() < 2e-5
+    assert abs(int(eng.stage("haspi.nsel")[0]) - int(z["hl/nsel"])) <= 1
+    assert abs(r.haspi[0] - float(z["hl/v2_zero"])) < TOL
+    assert np.abs(r.haspi_raw[0] - z["hl/v2_zero_raw"]).max() < TOL
+    assert abs(float(z["hl/v2_zero"]) - float(g["v2_zero"])) > 1.0      # the audiogram matters: not a no-op
+    # a later call without HL must not inherit the loss tables
+    r0 = eng.score_batch([g["x"]], [g["y"]], fs=16000, metrics=("haspi",), mapped=False, no_dither=True)
+    assert abs(r0.haspi[0] - float(g["v2_zero"])) < TOL
+
+
+def test_philox_dither_reproduces_the_reference_distribution(eng, golden):
+    """The reference's score is a random variable (0.1 dB dither from numpy's global stream).  The engine's
+    own dither (Philox, keyed by seed and pair) must have the same mean: 128 independent engine draws against the
+    reference run as a user runs it under np.random.seed(0 .. 31) -- means within 3e-4 (standard error of the
+    difference 1.3e-4), spreads within a factor 1.5."""
+    z = _extra()
+    g = golden[str(z["seeds/case"])]
+    ref = z["seeds/v2"]
+    r = eng.score_batch([g["x"]] * 128, [g["y"]] * 128, fs=16000, metrics=("haspi",), mapped=False, seed=2024)
+    assert np.unique(r.haspi).size > 100                                  # every copy draws its own dither
+    assert abs(r.haspi.mean() - ref.mean()) < 3e-4, (r.haspi.mean(), ref.mean())
+    assert ref.std() / 1.5 < r.haspi.std() < 1.5 * ref.std(), (r.haspi.std(), ref.std())
