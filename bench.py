@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the NELE-GAN intelligibility-labelling hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config bench|ganround|sweep]
 
 One "step" = one pass of the hot path (HASPI v2 + SIIB^Gauss + ESTOI, the three
 labels train_nele.py:320-322 computes per utterance) over one batch of synthetic
@@ -20,9 +20,20 @@ Metric: audio-seconds scored per second, whole job.
                  duration, against MEASURED_PEAKS.json
   cpu_baseline   the CPU oracle (a port of the reference algorithms, oracle/) on
                  the host cores, bounded sample, rank 0 at N = 1 only
+  general_case   the same step on 4096 pairs of 47 999 samples.  configs[2]'s 48 000 samples are a multiple
+                 of SIIB's 200-sample hop, so the wrapper's tiling (intel.py:71-75) repeats exactly and
+                 every pair takes the rank-96 KLT route; any other length -- the toy data, a GAN round, the
+                 sweep -- has a full-rank 420 x 420 covariance.  This is the number a user sees.
 
 ``--impl reference`` times that CPU path alone, with all host threads, and
 prints the same line with "impl": "reference".
+
+``--config ganround`` (BASELINE.json configs[3]): latency of one GAN sampling round of train_nele.py:36-37,
+205-214, 320-335 -- 600 pairs labelled with norm=True (300 generator outputs + 300 pre-enhanced) and 480
+validation pairs with norm=False, 2 - 3.5 s each -- from band gains on the device to labels on the host
+(nele_resyn + nele_score_batch), pairs dealt over the ranks by length (shard.partition), one gather.
+``--config sweep`` (configs[4]): 65 536 pairs of 16000 * U[3, 10] samples (default_rng(12345)), strong scaling over
+the ranks through the same partition; the CPU arm scores a 256-pair subsample.
 """
 import argparse
 import json
@@ -85,10 +96,10 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def make_workload(pairs, seconds, seed, unique):
+def make_workload(pairs, seconds, seed, unique, samples=None):
     from nele_gan_b200.synth import make_batch
     from nele_gan_b200.engine import pack
-    L = int(round(seconds * FS))
+    L = int(round(seconds * FS)) if samples is None else int(samples)
     refs, degs = make_batch(pairs, L, seed=seed, unique=unique)
     fr, offs, lens = pack(refs)
     fd, _, _ = pack(degs)
@@ -124,6 +135,9 @@ def kernel_bytes_per_pair(name, L16, Nf=1950, rank=420):
         "siib_chol": 420 * 420 * 8 + rank * 448 * 4,
         "siib_jacobi": 2 * rank * 448 * 4,
         "siib_quad": rank * 448 * 4 + 2 * 420 * 420 * 4,
+        "siib_tridiag": 420 * 420 * 8 + 420 * 448 * 4,   # Sxx in (FP64), reflectors out (FP32); the FP32 work matrix stays in L2
+        "siib_trieig": 2 * 420 * 448 * 4,                # eigenvectors of T out, scratch
+        "siib_backtf": 3 * 420 * 448 * 4,                # reflectors + eigenvectors of T in, G out
         "siib_projquad": rank * 448 * 4 + 2 * 128 * F,
     }
     return table.get(name)
@@ -157,6 +171,239 @@ def cpu_reference_run(refs, degs, cores, steps, warmup):
     return sec * steps / dt, dt / steps
 
 
+# ------------------------------------------------- configs[3]: GAN sampling round
+def _dist_setup(world, local_rank):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    return torch, dist, torch.device("cuda", local_rank)
+
+
+def run_ganround(a, rank, world, local_rank, cores):
+    """Latency of one sampling round (train_nele.py:36-37, 205-214, 320-335): 300 generator outputs + 300 pre-enhanced
+    utterances labelled with norm=True and 480 validation utterances with norm=False, 2 - 3.5 s each, from the
+    generator's band gains on the device to the labels on the host.  The generator itself is out of scope
+    (model.py, checkpoint missing): its output is replaced by random band gains in [0.5, 2.5]."""
+    from nele_gan_b200 import inloop, shard
+    from nele_gan_b200.engine import default_engine
+    from nele_gan_b200.synth import make_batch
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        rng = np.random.default_rng(4242)
+        lens = (FS * rng.uniform(2.0, 3.5, size=max(cores, 8))).astype(np.int64)
+        refs, degs = make_batch(len(lens), lens, seed=555_000, unique=64)
+        v, spstep = cpu_reference_run(refs, degs, cores, a.steps, a.warmup)
+        total_s = 1080 * 2.75
+        print(json.dumps({"impl": "reference", "metric": "gan_sampling_round_latency", "value": total_s / v * 1e3, "unit": "ms",
+                          "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "higher_is_better": False,
+                          "note": "extrapolated from %d pairs scored at %.1f audio-s/s on %d host threads (labels only: the "
+                                  "reference also writes and re-reads 1080 WAV files per round)" % (len(lens), v, cores),
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d pairs" % len(lens)}}))
+        return 0
+    torch, dist, dev = _dist_setup(world, local_rank)
+    rng = np.random.default_rng(4242)
+    sets = []                                              # (pairs, norm)
+    for n_pairs, norm, seed in ((600, True, 555_000), (480, False, 556_000)):
+        lens = (FS * rng.uniform(2.0, 3.5, size=n_pairs)).astype(np.int64)
+        mine = shard.partition(lens, world)[rank]
+        refs, degs = make_batch(n_pairs, lens, seed=seed, unique=64)
+        L = int(lens.max())
+        k = len(mine)
+        clean = np.zeros((k, L), np.float32)
+        noise = np.zeros((k, L), np.float32)
+        for r_, i in enumerate(mine):
+            clean[r_, :lens[i]] = refs[i]
+            noise[r_, :lens[i]] = degs[i] - refs[i]
+        alpha2 = np.random.default_rng(seed + rank).uniform(0.5, 2.5, size=(k, 1 + L // 256, 64)).astype(np.float32)
+        sets.append({"n": n_pairs, "norm": norm, "idx": mine, "lens": lens[mine].astype(np.int32),
+                     "clean": torch.from_numpy(clean).to(dev), "noise": torch.from_numpy(noise).to(dev),
+                     "alpha2": torch.from_numpy(alpha2).to(dev), "audio_s": float(lens.sum()) / FS})
+    eng = default_engine(local_rank)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_round():
+        kms, nl, out = 0.0, 0, []
+        for st in sets:
+            if len(st["idx"]):
+                sc = inloop.label_sampling_round(st["alpha2"], st["clean"], st["noise"], lengths=st["lens"], norm=st["norm"],
+                                                 seed=7).numpy()
+                t = eng.last_timing()
+                kms, nl = kms + t[0], nl + t[1]
+            else:
+                sc = np.zeros((0, 3))
+            if dist is not None:
+                rec = np.zeros((len(st["idx"]), shard.RECORD))
+                rec[:, :3] = sc
+                sc = shard.gather_records(rec, st["idx"], st["n"], device=dev)[:, :3]
+            out.append(sc)
+        return out, kms, nl
+
+    for _ in range(a.warmup):
+        one_round()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lat, kms_all, launches = [], [], 0
+    for _ in range(a.steps):
+        barrier()
+        t0 = time.perf_counter()
+        out, kms, nl = one_round()
+        lat.append((time.perf_counter() - t0) * 1e3)
+        kms_all.append(kms)
+        launches += nl
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([lat, kms_all], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    lat, kms_all = t[0].cpu().numpy(), t[1].cpu().numpy()
+    if rank == 0:
+        audio_s = sum(st["audio_s"] for st in sets)
+        ok = all(np.isfinite(o).all() for o in out)
+        print(json.dumps({
+            "metric": "gan_sampling_round_latency", "value": float(np.median(lat)), "unit": "ms", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(np.mean(lat)), "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64",
+            "data": "synthetic speech-shaped pairs; random band gains stand in for the generator's output",
+            "config": {"workload": "GAN sampling round: 600 pairs norm=True + 480 pairs norm=False, 2-3.5 s, band gains -> "
+                                   "nele_resyn (Resyn, PCM-16, + noise) -> HASPI v2 + SIIB^Gauss + ESTOI -> host",
+                       "pairs": 1080, "audio_seconds": audio_s, "pairs_per_rank": [int(len(st["idx"])) for st in sets]},
+            "latency_ms": {"min": float(lat.min()), "median": float(np.median(lat)), "max": float(lat.max())},
+            "kernel_ms_per_round_max_rank": float(np.median(kms_all)),
+            "throughput": {"value": audio_s / (float(np.median(lat)) * 1e-3), "unit": UNIT},
+            "gpu_launches": int(launches), "clocks": clocks, "all_labels_finite": bool(ok)}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------ configs[4]: 3 - 10 s sweep
+def run_sweep(a, rank, world, local_rank, cores):
+    """65 536 pairs of 16000 * U[3, 10] samples (default_rng(12345)), strong scaling: the pairs are dealt over the ranks
+    by length (shard.partition), every rank scores its shard, one gather returns the records in input order.  The
+    waveforms are 64 distinct synthetic pairs of 10 s; pair i is pair i % 64 cut to its own length -- for the
+    device-resident `value` the engine reads all of them from one 82 MB pool through offs / lens (inputs are read
+    only), so 65 536 independent pairs cost no 54 GB of host memory; `e2e` uploads real, distinct host buffers for as
+    many pairs of the shard as fit the stated budget."""
+    from nele_gan_b200 import shard
+    from nele_gan_b200.engine import Engine, pack
+    from nele_gan_b200.synth import make_batch
+    n = a.sweep_pairs
+    lens = (FS * np.random.default_rng(12345).uniform(3.0, 10.0, size=n)).astype(np.int64)
+    audio_total = float(lens.sum()) / FS
+    cfg = {"workload": "sweep %d pairs x U[3,10] s (default_rng(12345)), HASPI v2 + SIIB^Gauss + ESTOI, mapped" % n,
+           "pairs": n, "audio_seconds": audio_total, "fs": FS}
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        sub = 256
+        refs, degs = make_batch(sub, lens[:sub], seed=777_000, unique=64)
+        v, spstep = cpu_reference_run(refs, degs, cores, max(1, min(a.steps, 1)), 1)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": 1,
+                          "warmup": 1, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                           "sample": "first %d pairs of the sweep (%.0f audio-s), one pass, joblib n_jobs=%d; "
+                                                     "the whole sweep extrapolates linearly to %.0f s" % (
+                                                         sub, float(lens[:sub].sum()) / FS, cores, audio_total / v)},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+    torch, dist, dev = _dist_setup(world, local_rank)
+    pool_r, pool_d = make_batch(64, 160000, seed=777_000)
+    fr, poffs, _ = pack(pool_r)
+    fd, _, _ = pack(pool_d)
+    d_ref, d_deg = torch.from_numpy(fr).to(dev), torch.from_numpy(fd).to(dev)
+    mine = shard.partition(lens, world)[rank]
+    offs = poffs[mine % 64].astype(np.int64)
+    mylens = lens[mine].astype(np.int32)
+    eng = Engine(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def device_pass():
+        return eng.score_packed(d_ref.data_ptr(), d_deg.data_ptr(), offs, mylens, fs=FS, mapped=True, seed=1,
+                                device_input=True, stream=stream.cuda_stream)
+
+    # warm-up: one full pass (the grow-only workspace reaches its final size -- cudaMalloc / cudaFree inside a timed pass
+    # cost seconds -- and the tables are uploaded), then the timed passes
+    device_pass()
+    eng.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    steps = max(1, min(a.steps, 2))
+    kms, launches, kt_sum = 0.0, 0, {}
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = device_pass()
+        tm = eng.last_timing()
+        kms += tm[0]
+        launches += tm[1]
+        for k, (ms, nl) in eng.kernel_times().items():
+            kt_sum[k] = kt_sum.get(k, 0.0) + ms
+    barrier()
+    wall_dev = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    eng.set_profiling(False)
+    # e2e: real host buffers for (a prefix of) the shard, records gathered over the ranks
+    budget_pairs = min(len(mine), 8192)
+    sub = mine[:budget_pairs]
+    h_refs = [pool_r[i % 64][:lens[i]] for i in sub]
+    h_degs = [pool_d[i % 64][:lens[i]] for i in sub]
+    hfr, hoffs, hlens = pack(h_refs)
+    hfd, _, _ = pack(h_degs)
+    del h_refs, h_degs
+    h_ref, h_deg = torch.from_numpy(hfr).pin_memory(), torch.from_numpy(hfd).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    rh = eng.score_packed(h_ref.data_ptr(), h_deg.data_ptr(), hoffs, hlens, fs=FS, mapped=True, seed=1, stream=stream.cuda_stream)
+    if dist is not None:
+        cap = budget_pairs * world
+        shard.gather_records(shard.pack_records(rh), np.arange(budget_pairs, dtype=np.int64) * world + rank, cap, device=dev)
+    barrier()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    e2e_audio = float(hlens.sum()) / FS
+    t = torch.tensor([kms / steps, wall_dev / steps, wall_e2e, e2e_audio], dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    tsum = t.clone()
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ms_dev = float(tmax[0])
+        print(json.dumps({
+            "metric": METRIC, "value": audio_total / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": 1, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic", "config": cfg,
+            "wall_ms_per_pass_device_inputs": float(tmax[1]),
+            "e2e": {"value": float(tsum[3]) / (float(tmax[2]) * 1e-3), "unit": UNIT,
+                    "sample": "%d pairs per rank with distinct pinned host buffers (one blocking call + gather)" % budget_pairs,
+                    "h2d_bytes_per_step": int(h_ref.numel() * 8), "d2h_bytes_per_step": int(budget_pairs * 116),
+                    "ms": float(tmax[2])},
+            "gpu_launches": int(launches), "clocks": clocks, "pairs_ok": int(np.sum(r.ok)), "pairs_this_rank": int(len(mine)),
+            "kernels_ms_per_pass_rank0": {k: round(v / steps, 2) for k, v in sorted(kt_sum.items(), key=lambda kv: -kv[1])[:14]}}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 # -------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -168,11 +415,19 @@ def main():
     ap.add_argument("--seconds", type=float, default=3.0)
     ap.add_argument("--unique", type=int, default=0, help="distinct synthetic pairs per GPU (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-general-case", action="store_true", help="skip the 47 999-sample (full-rank SIIB) measurement")
+    ap.add_argument("--config", default="bench", choices=("bench", "ganround", "sweep"),
+                    help="bench = BASELINE.json configs[2] (the driver's line); ganround = configs[3]; sweep = configs[4]")
+    ap.add_argument("--sweep-pairs", type=int, default=65536)
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
+    if a.config == "ganround":
+        return run_ganround(a, rank, world, local_rank, cores)
+    if a.config == "sweep":
+        return run_sweep(a, rank, world, local_rank, cores)
     workload = "synthetic %d x %.1f s 16 kHz RMS=0.03 speech-shaped noisy pairs per GPU, HASPI v2 + SIIB^Gauss + ESTOI" % (
         a.pairs, a.seconds)
     config = {"workload": workload, "pairs_per_gpu": a.pairs, "seconds_per_pair": a.seconds, "fs": FS,
@@ -292,6 +547,64 @@ def main():
     ms_dev, ms_e2e, ms_e2e_blocking = float(t[0]), float(t[1]), float(t[2])
     ok = int(np.sum((r.status & 0xFFFFFF) == 0))
 
+    # ---- general case: the same step on pairs whose length is not a multiple of SIIB's 200-sample hop
+    general = None
+    if not a.no_general_case:
+        g_samples = int(round(a.seconds * FS)) - 1
+        g_steps, g_warm = max(2, min(a.steps, 5)), 2
+        del d_ref, d_deg
+        _, _, gfr, gfd, goffs, glens = make_workload(a.pairs, a.seconds, 666_000 + rank * a.pairs,
+                                                     a.unique if a.unique > 0 else 64, samples=g_samples)
+        gh_ref, gh_deg = torch.from_numpy(gfr).pin_memory(), torch.from_numpy(gfd).pin_memory()
+        gd_ref, gd_deg = gh_ref.to(dev), gh_deg.to(dev)
+        for _ in range(g_warm):
+            eng.score_packed(gd_ref.data_ptr(), gd_deg.data_ptr(), goffs, glens, fs=FS, mapped=True, seed=1,
+                             device_input=True, stream=sptr, out=out)
+        eng.set_profiling(True)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gkt = {}
+        with torch.cuda.stream(stream):
+            g0.record(stream)
+            for _ in range(g_steps):
+                rg = eng.score_packed(gd_ref.data_ptr(), gd_deg.data_ptr(), goffs, glens, fs=FS, mapped=True, seed=1,
+                                      device_input=True, stream=sptr, out=out)
+                for k, (ms, nl) in eng.kernel_times().items():
+                    gkt[k] = gkt.get(k, 0.0) + ms
+            g1.record(stream)
+        barrier()
+        g_ms_dev = g0.elapsed_time(g1)
+        eng.set_profiling(False)
+        g_ok = int(np.sum(rg.ok))
+        g_null = int(np.sum(rg.siib_nullspace_dropped))
+        eng.score_packed(gh_ref.data_ptr(), gh_deg.data_ptr(), goffs, glens, fs=FS, mapped=True, seed=1, stream=sptr, out=out)
+        barrier()
+        t0 = time.perf_counter()
+        eng.prefetch(gh_ref.data_ptr(), gh_deg.data_ptr(), goffs, glens)
+        for k in range(g_steps):
+            if k + 1 < g_steps:
+                eng.prefetch(gh_ref.data_ptr(), gh_deg.data_ptr(), goffs, glens)
+            rg = eng.score_packed(gh_ref.data_ptr(), gh_deg.data_ptr(), goffs, glens, fs=FS, mapped=True, seed=1,
+                                  stream=sptr, out=out)
+            if dist is not None:
+                shard.gather_records(shard.pack_records(rg), np.arange(n, dtype=np.int64) + rank * n, n * world, device=dev)
+        barrier()
+        g_ms_e2e = (time.perf_counter() - t0) * 1e3
+        tg = torch.tensor([g_ms_dev, g_ms_e2e], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        g_audio = float(glens.sum()) / FS
+        general = {
+            "workload": "synthetic %d x %d samples (%.5f s) per GPU: SIIB tiling does not repeat, full-rank KLT" % (
+                a.pairs, g_samples, g_samples / FS),
+            "value": g_audio * world / (float(tg[0]) / g_steps * 1e-3), "unit": UNIT, "ms_per_step": float(tg[0]) / g_steps,
+            "e2e": {"value": g_audio * world / (float(tg[1]) / g_steps * 1e-3), "unit": UNIT,
+                    "ms_per_step": float(tg[1]) / g_steps, "h2d_bytes_per_step": int(gh_ref.numel() * 4 * 2),
+                    "d2h_bytes_per_step": int(n * (14 * 8 + 4))},
+            "steps": g_steps, "warmup": g_warm, "pairs_ok": g_ok, "pairs_siib_nullspace_dropped": g_null,
+            "kernels_ms_per_step": {k: round(v / g_steps, 3) for k, v in sorted(gkt.items(), key=lambda kv: -kv[1])},
+        }
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         L16 = int(round(a.seconds * FS))
@@ -332,7 +645,10 @@ def main():
                          "siib_klt_frames": Nf, "siib_rank": rank_x},
             "kernels_ms_per_step": {k: round(v[0] / a.steps, 3) for k, v in sorted(kt_sum.items(), key=lambda kv: -kv[1][0])},
             "pairs_ok": ok,
+            "pairs_siib_nullspace_dropped": int(np.sum((r.status & 0x01000000) != 0)),
         }
+        if general is not None:
+            line["general_case"] = general
         if world == 1 and not a.no_cpu_baseline:
             sample = max(cores, 8)
             v, spstep = cpu_reference_run(refs[:sample], degs[:sample], cores, 2, 1)

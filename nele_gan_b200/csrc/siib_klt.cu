@@ -47,6 +47,7 @@ struct Smem {
   float pw[NW][LD];    // per-warp partial products
   float Vt[LD][PB];    // V, W transposed for the trailing update (one 32-byte row per matrix row)
   float Wt[LD][PB];
+  float diag[LD];      // diagonal of the matrix as of the start of the panel
   float part[NW][2 * PB];
   float tot[2 * PB];
   float red[NW];
@@ -75,27 +76,21 @@ __constant__ int c_ntiles[JMAX + 1];
 
 // one tile of p = A v (A symmetric, lower triangle stored).  v: shared-memory vector (zero for indices <= k and
 // >= N), pw: this warp's partial result.
-// DIAG: the tile crosses the diagonal (elements right of it are masked, the diagonal counts once).  Other tiles load
-// through one base pointer with immediate row offsets and no predicates at all: rows <= k or >= N and columns <= k
-// that a tile at the edge of the trailing matrix also covers meet v = 0 (their products vanish, their own results
-// are never read) and hold finite numbers -- stale matrix entries, and zeros in the pad rows 420 .. 431.
-template <bool DIAG>
+// Every tile loads through one base pointer with immediate row offsets and no predicates.  What a tile covers
+// beyond the trailing lower triangle is harmless by construction: rows <= k and columns <= k meet v = 0 (their
+// products vanish, their own results are never read) and hold finite stale entries; the pad rows 420 .. 431 are zero;
+// and inside the 64 x 64 diagonal blocks the part right of the diagonal is kept at zero (written once at the start,
+// never by the update), so a diagonal tile is an ordinary tile whose only flaw is that A[j][j] v[j] enters p[j] twice
+// (column part and row part) -- the caller subtracts it once (Smem::diag).  The first version masked every element of
+// the diagonal tiles: 422 instead of 188 instructions for 30 % of the tiles.
 __device__ __forceinline__ void mv_tile(const float* __restrict__ A, const float* __restrict__ v, float* __restrict__ pw, int J, int C,
                                         int lane) {
   const int j0 = RG * J, c0 = CB * C + 2 * lane;
   float2 a[RG];
-  if (!DIAG) {
+  {
     const float2* __restrict__ p = reinterpret_cast<const float2*>(A + (size_t)j0 * LD + c0);
 #pragma unroll
     for (int r = 0; r < RG; ++r) a[r] = __ldcg(p + r * (LD / 2));
-  } else {
-#pragma unroll
-    for (int r = 0; r < RG; ++r) {
-      const int j = j0 + r;
-      const bool ok = j < N && c0 <= j;
-      a[r] = ok ? __ldcg(reinterpret_cast<const float2*>(A + (size_t)j * LD + c0)) : make_float2(0.f, 0.f);
-      if (c0 + 1 > j) a[r].y = 0.f;
-    }
   }
   const float2 vc = *reinterpret_cast<const float2*>(v + c0);
   float acc0 = 0.f, acc1 = 0.f;
@@ -109,13 +104,7 @@ __device__ __forceinline__ void mv_tile(const float* __restrict__ A, const float
       const int r = 4 * q + rr;
       acc0 = fmaf(a[r].x, vj[rr], acc0);
       acc1 = fmaf(a[r].y, vj[rr], acc1);
-      float ax = a[r].x, ay = a[r].y;
-      if (DIAG) {  // the diagonal element belongs to the column part only
-        const int j = j0 + r;
-        if (c0 == j) ax = 0.f;
-        if (c0 + 1 == j) ay = 0.f;
-      }
-      t[r] = fmaf(ax, vc.x, ay * vc.y);
+      t[r] = fmaf(a[r].x, vc.x, a[r].y * vc.y);
     }
   }
   // row sums over the 32 lanes, 16 rows at once: after the exchanges lane l holds the sum of row l >> 1
@@ -197,6 +186,10 @@ __device__ __forceinline__ void up_tile(float* __restrict__ A, Smem& s, int J, i
         const bool both = !DIAG || c0 + 1 <= j;
         if (both) *reinterpret_cast<float2*>(A + (size_t)j * LD + c0) = make_float2(ax, ay);
         else A[(size_t)j * LD + c0] = ax;
+        if (DIAG) {
+          if (c0 == j) s.diag[j] = ax;
+          if (c0 + 1 == j) s.diag[j] = ay;
+        }
         if (tocol) {
           s.col[c0 - kn][j] = ax;
           if (both) s.col[c0 + 1 - kn][j] = ay;
@@ -223,15 +216,22 @@ __global__ void __launch_bounds__(NT, 2) tridiag32_kernel(SiibBuffers b, SiibEig
     double* __restrict__ ee = eb.e + (int64_t)lp * LD;
     double* __restrict__ tt = eb.tau + (int64_t)lp * LD;
     float* __restrict__ R = eb.refl + (int64_t)lp * N * LD;
-    // lower triangle of Sxx as floats (pairs of columns; the element right of the diagonal is never read)
+    // lower triangle of Sxx as floats; the rest of each row up to the end of its 64-column diagonal block is zero
     for (int j = wib; j < N; j += NW) {
       const double2* src = reinterpret_cast<const double2*>(S + (int64_t)j * N);
       float2* dst = reinterpret_cast<float2*>(A + (size_t)j * LD);
-      for (int c2 = lane; 2 * c2 <= j; c2 += 32) {
-        const double2 v = src[c2];
-        dst[c2] = make_float2((float)v.x, (float)v.y);
+      const int cend = CB * (j / CB) + CB;
+      for (int c2 = lane; 2 * c2 < cend; c2 += 32) {
+        float2 o = make_float2(0.f, 0.f);
+        if (2 * c2 <= j) {
+          const double2 v = src[c2];
+          o.x = (float)v.x;
+          if (2 * c2 + 1 <= j) o.y = (float)v.y;
+        }
+        dst[c2] = o;
       }
     }
+    for (int j = tid; j < LD; j += NT) s.diag[j] = (j < N) ? (float)S[(int64_t)j * N + j] : 0.f;
     for (int idx = tid; idx < (RG * (JMAX + 1) - N) * LD; idx += NT) A[(size_t)N * LD + idx] = 0.f;   // pad rows 420 .. 431
     // columns of the first panel = rows of the symmetric input
     for (int idx = tid; idx < PB * LD; idx += NT) {
@@ -323,8 +323,7 @@ __global__ void __launch_bounds__(NT, 2) tridiag32_kernel(SiibBuffers b, SiibEig
           const int jm = (k + 1) / RG, nt = c_ntiles[jm];
           for (int t = wib; t < nt; t += NW) {
             const int code = c_tiles[jm][t], J = code >> 3, C = code & 7;
-            if (CB * C + CB - 1 > RG * J) mv_tile<true>(A, s.V[m], s.pw[wib], J, C, lane);
-            else mv_tile<false>(A, s.V[m], s.pw[wib], J, C, lane);
+            mv_tile(A, s.V[m], s.pw[wib], J, C, lane);
           }
         }
         __syncthreads();
@@ -337,6 +336,7 @@ __global__ void __launch_bounds__(NT, 2) tridiag32_kernel(SiibBuffers b, SiibEig
           if (tau != 0.f && j > k && j < N) {
 #pragma unroll
             for (int w = 0; w < NW; ++w) pj += s.pw[w][j];
+            pj -= s.diag[j] * vi[e];   // counted by the column part and by the row part of its diagonal tile
             for (int mm = 0; mm < m; ++mm) pj -= s.V[mm][j] * s.tot[2 * mm] + s.W[mm][j] * s.tot[2 * mm + 1];
             pj *= tau;
           }
@@ -767,6 +767,228 @@ __global__ void __launch_bounds__(NT, 2) backtf4_kernel(SiibBuffers b, SiibEigBu
 }
 
 }  // namespace bt
+
+// ---- the same back-transformation with a 14-row x 4-vector register tile per lane
+// backtf4 keeps one eigenvector per lane, so every reflector value is a warp-wide broadcast used for a single FMA:
+// 16 bytes x 32 lanes returned per LDS.128 for four FMAs, and ncu shows the shared-memory pipe at 75 % with the FMA
+// pipe at 28 %.  Here a lane owns rows {32 m + rp : m < 14} of four vectors (rp = one of 32 row parts, four per warp;
+// vector group = lane / 4): a loaded reflector value feeds four FMAs, 3.5x fewer shared-memory bytes per flop.  The 16
+// partial dot products of a group (4 reflectors x 4 vectors) are summed over the row parts by two shuffle levels inside
+// the warp and through shared memory across the eight warps.
+namespace bt5 {
+
+constexpr int N = 420, LD = 448, VEC = 32, NW = 8, NT = NW * 32, RP = 32, M = 16, MV = 14, C = 4, PANEL = 16, GRP = 4;
+constexpr int MS = 20;        // shared-memory stride of a row part: with 16 the four parts of a warp fall on two bank groups
+                              // (ncu: 3.6-way conflicts on the reflector loads); 20 spreads them over banks 0, 20, 8, 28
+constexpr int SLD = RP * MS;  // staged length of one reflector
+
+__global__ void __launch_bounds__(NT, 2) backtf5_kernel(SiibBuffers b, SiibEigBuffers eb, int rank_lo) {
+  const int lp = blockIdx.y, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int rk = b.rank[pair];
+  if (rk < rank_lo) return;
+  const int rpl = lane & 3, vg = lane >> 2, rp = 4 * w + rpl;
+  const int j0 = blockIdx.x * VEC + C * vg;
+  extern __shared__ __align__(16) float s_vbuf[];   // [2][PANEL][SLD]: reflector kk staged as [row part][MS]: row 32 m + rp at rp * MS + m
+  __shared__ float s_tau[PANEL];
+  __shared__ float s_g[PANEL / GRP][8];
+  __shared__ __align__(16) float s_dot[2][NW][VEC / C][GRP * C];
+  const float* __restrict__ R = eb.refl + (int64_t)lp * N * LD;
+  const double* __restrict__ tt = eb.tau + (int64_t)lp * LD;
+  for (int i = tid; i < 2 * PANEL * SLD; i += NT) s_vbuf[i] = 0.f;   // the pad rows (m = 14, 15) stay zero for good
+  __syncthreads();
+  auto stage = [&](int k1, int buf) {
+    const int nk = min(PANEL, k1 + 1);
+    float* dst = s_vbuf + (size_t)buf * PANEL * SLD;
+    for (int kk = 0; kk < PANEL; ++kk) {
+      if (kk < nk) {
+        const float* __restrict__ row = R + (int64_t)(k1 - kk) * LD;
+#pragma unroll
+        for (int i = tid; i < LD; i += NT) bt::cp_async4(dst + kk * SLD + (i & (RP - 1)) * MS + (i >> 5), row + i);
+      } else {
+        for (int i = tid; i < LD; i += NT) dst[kk * SLD + (i & (RP - 1)) * MS + (i >> 5)] = 0.f;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(N - 3, 0);
+  // rows in pairs (m, m + 1) packed for fma.rn.f32x2: a float4 of a staged reflector is two such pairs, so every
+  // multiply-add of the two passes is two-wide with no packing moves (only the 16 coefficients y are duplicated)
+  F2 u[MV / 2][C];
+#pragma unroll
+  for (int mp = 0; mp < MV / 2; ++mp) {
+    const int i0 = RP * (2 * mp) + rp, i1 = i0 + RP;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float lo = (i0 < N && j0 + c < N) ? eb.zt[((int64_t)lp * N + i0) * LD + j0 + c] : 0.f;
+      const float hi = (i1 < N && j0 + c < N) ? eb.zt[((int64_t)lp * N + i1) * LD + j0 + c] : 0.f;
+      u[mp][c] = f2_pack(lo, hi);
+    }
+  }
+  int par = 0, buf = 0;
+  for (int k1 = N - 3; k1 >= 0; k1 -= PANEL, buf ^= 1) {
+    const int nk = min(PANEL, k1 + 1);
+    __syncthreads();
+    if (k1 - PANEL >= 0) {
+      stage(k1 - PANEL, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    if (tid < PANEL) s_tau[tid] = (tid < nk) ? (float)tt[k1 - tid] : 0.f;
+    __syncthreads();
+    const float* s_v = s_vbuf + (size_t)buf * PANEL * SLD;
+    // Gram values inside each group of four reflectors: 24 dot products, three per warp
+    for (int d = w; d < (PANEL / GRP) * 6; d += NW) {
+      const int g = d / 6, e = d % 6;
+      const int qa = (e == 0) ? 1 : (e < 3) ? 2 : 3;
+      const int qb = (e == 0) ? 0 : (e == 1) ? 0 : (e == 2) ? 1 : e - 3;
+      const float* va = s_v + (GRP * g + qa) * SLD;
+      const float* vb = s_v + (GRP * g + qb) * SLD;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < SLD / 32; ++i) acc = fmaf(va[lane + 32 * i], vb[lane + 32 * i], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) s_g[g][e] = acc;
+    }
+    __syncthreads();
+    for (int g = 0; g < PANEL / GRP; ++g) {
+      const int kk0 = GRP * g;
+      if (kk0 >= nk) break;
+      // rows 32 m + rp <= kmin are zero in every reflector of the group: row pairs mp < (kmin + 1) / 64 are skipped
+      const int kmin = max(k1 - kk0 - (GRP - 1), 0);
+      const int p0 = (kmin + 1) >> 6;
+      const float4* vq[GRP];
+#pragma unroll
+      for (int q = 0; q < GRP; ++q) vq[q] = reinterpret_cast<const float4*>(s_v + (kk0 + q) * SLD + rp * MS);
+      F2 d2[GRP][C];
+#pragma unroll
+      for (int q = 0; q < GRP; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) d2[q][c] = f2_pack(0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < M / 4; ++t) {
+        if (2 * t + 1 < p0) continue;
+#pragma unroll
+        for (int q = 0; q < GRP; ++q) {
+          const float4 a4 = vq[q][t];
+          const F2 a2[2] = {f2_pack(a4.x, a4.y), f2_pack(a4.z, a4.w)};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int mp = 2 * t + h;
+            if (mp >= MV / 2 || mp < p0) continue;
+#pragma unroll
+            for (int c = 0; c < C; ++c) d2[q][c] = f2_fma(a2[h], u[mp][c], d2[q][c]);
+          }
+        }
+      }
+      float d[GRP][C];
+#pragma unroll
+      for (int q = 0; q < GRP; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          float lo, hi;
+          f2_unpack(d2[q][c], lo, hi);
+          d[q][c] = lo + hi;
+        }
+      // sum over the four row parts of the warp, then over the warps through shared memory
+#pragma unroll
+      for (int q = 0; q < GRP; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          d[q][c] += __shfl_xor_sync(0xffffffffu, d[q][c], 1);
+          d[q][c] += __shfl_xor_sync(0xffffffffu, d[q][c], 2);
+        }
+      if (rpl == 0) {
+#pragma unroll
+        for (int q = 0; q < GRP; ++q) *reinterpret_cast<float4*>(&s_dot[par][w][vg][q * C]) = make_float4(d[q][0], d[q][1], d[q][2], d[q][3]);
+      }
+      __syncthreads();
+      // lane rpl of a vector group adds up reflector q = rpl over the warps; the four lanes then exchange the totals
+      float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int ww = 0; ww < NW; ++ww) {
+        const float4 x = *reinterpret_cast<const float4*>(&s_dot[par][ww][vg][rpl * C]);
+        mine.x += x.x;
+        mine.y += x.y;
+        mine.z += x.z;
+        mine.w += x.w;
+      }
+      par ^= 1;
+      float D[GRP][C];
+#pragma unroll
+      for (int q = 0; q < GRP; ++q) {
+        const int src = (lane & ~3) | q;
+        D[q][0] = __shfl_sync(0xffffffffu, mine.x, src);
+        D[q][1] = __shfl_sync(0xffffffffu, mine.y, src);
+        D[q][2] = __shfl_sync(0xffffffffu, mine.z, src);
+        D[q][3] = __shfl_sync(0xffffffffu, mine.w, src);
+      }
+      float y[GRP][C];
+      const float g10 = s_g[g][0], g20 = s_g[g][1], g21 = s_g[g][2], g30 = s_g[g][3], g31 = s_g[g][4], g32 = s_g[g][5];
+      const float tau0 = s_tau[kk0], tau1 = s_tau[kk0 + 1], tau2 = s_tau[kk0 + 2], tau3 = s_tau[kk0 + 3];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        y[0][c] = tau0 * D[0][c];
+        y[1][c] = tau1 * (D[1][c] - y[0][c] * g10);
+        y[2][c] = tau2 * (D[2][c] - y[0][c] * g20 - y[1][c] * g21);
+        y[3][c] = tau3 * (D[3][c] - y[0][c] * g30 - y[1][c] * g31 - y[2][c] * g32);
+      }
+      F2 ny[GRP][C];
+#pragma unroll
+      for (int q = 0; q < GRP; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) ny[q][c] = f2_pack(-y[q][c], -y[q][c]);
+#pragma unroll
+      for (int t = 0; t < M / 4; ++t) {
+        if (2 * t + 1 < p0) continue;
+#pragma unroll
+        for (int q = 0; q < GRP; ++q) {
+          const float4 a4 = vq[q][t];
+          const F2 a2[2] = {f2_pack(a4.x, a4.y), f2_pack(a4.z, a4.w)};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int mp = 2 * t + h;
+            if (mp >= MV / 2 || mp < p0) continue;
+#pragma unroll
+            for (int c = 0; c < C; ++c) u[mp][c] = f2_fma(ny[q][c], a2[h], u[mp][c]);
+          }
+        }
+      }
+    }
+  }
+  // column j of G = sqrt(lambda_j) u_j / |z_j| (see backtf4_kernel for the thresholds)
+  const double lmax = eb.lam[(int64_t)lp * LD + N - 1];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int j = j0 + c;
+    if (j >= N) continue;
+    const double lam = eb.lam[(int64_t)lp * LD + j], nz = eb.znorm[(int64_t)lp * LD + j];
+    const bool in_range = j >= N - rk;
+    const float sc = (in_range && lam > 1.0e-10 * lmax && nz > 0.0) ? (float)sqrt(lam / nz) : 0.f;
+    float* __restrict__ G = b.G + (int64_t)lp * N * LD + (int64_t)j * LD;
+#pragma unroll
+    for (int mp = 0; mp < MV / 2; ++mp) {
+      float lo, hi;
+      f2_unpack(u[mp][c], lo, hi);
+      const int i0 = RP * (2 * mp) + rp, i1 = i0 + RP;
+      G[i0] = (i0 < N) ? sc * lo : 0.f;
+      G[i1] = (i1 < N) ? sc * hi : 0.f;
+    }
+  }
+}
+
+}  // namespace bt5
+
+int siib_launch_backtf5(const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, cudaStream_t s) {
+  constexpr int smem = 2 * bt5::PANEL * bt5::SLD * (int)sizeof(float);
+  static const bool attr = [] {
+    cudaFuncSetAttribute(bt5::backtf5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return true;
+  }();
+  (void)attr;
+  bt5::backtf5_kernel<<<dim3((bt5::N + bt5::VEC - 1) / bt5::VEC, n), bt5::NT, smem, s>>>(b, eb, rank_lo);
+  return 1;
+}
 
 int siib_launch_backtf4(const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, cudaStream_t s) {
   constexpr int smem = 2 * bt::PANEL * bt::LD * (int)sizeof(float);

@@ -1,0 +1,110 @@
+"""CPU experiments behind the FP32 KLT of round 2 (csrc/siib_klt.cu), all through the SIIB^Gauss score against
+numpy.linalg.eigh in FP64 on the same matrices:
+
+  precision   Householder tridiagonalisation with the trailing matrix stored / the arithmetic done in FP64 or FP32
+              (s64a64, s32a64, s32a32) and LAPACK's own FP32 eigh, on synthetic pairs (condition numbers 2e5 .. 1e9)
+              and on the real speech of tests/golden/haspi_ref.npz.  Measured: s32a32 3e-6 .. 2e-5 on the synthetic
+              pairs, up to 3.1e-4 on the toy corpus (SIIB 7.5 .. 95); eigh in FP32 4e-7 .. 1.5e-5.  Tolerance 5e-3.
+  iterations  bisection steps per eigenvalue of the (FP32-made) tridiagonal.  Measured: SIIB deviation unchanged
+              (2.0e-5, 4.0e-6, 3.8e-6) from 58 down to 38 steps although the orthogonality of the computed basis
+              degrades from 2e-7 to 0.6: the vectors that lose orthogonality belong to clusters of tiny eigenvalues,
+              whose components carry no information.  The kernel uses 46 (orthogonality <= 1e-3).
+
+usage: exp_klt_fp32.py [precision|iterations]"""
+import sys
+
+import numpy as np
+from scipy.linalg import eigh_tridiagonal
+
+sys.path.insert(0, ".")
+sys.path.insert(0, "scripts")
+import exp_tridiag_eig as E  # noqa: E402
+from exp_jacobi_sweeps import sxx_of  # noqa: E402
+
+
+def tridiag_var(A, store=np.float32, arith=np.float64):
+    """Householder tridiagonalisation; trailing matrix stored in `store`, arithmetic in `arith`."""
+    A = A.astype(store).copy()
+    n = A.shape[0]
+    V = np.zeros((n, n))
+    tau = np.zeros(n)
+    d = np.zeros(n)
+    e = np.zeros(n - 1)
+    for k in range(n - 2):
+        d[k] = A[k, k]
+        x = A[k + 1:, k].astype(arith)
+        alpha = x[0]
+        sig = np.dot(x[1:], x[1:])
+        if sig == 0.0:
+            e[k] = alpha
+            continue
+        nrm = np.sqrt(alpha * alpha + sig)
+        beta = -np.copysign(nrm, alpha)
+        v = x.copy()
+        v[0] = alpha - beta
+        t = (beta - alpha) / beta
+        v = v / v[0]
+        V[k + 1:, k] = v
+        tau[k] = t
+        S = A[k + 1:, k + 1:].astype(arith)
+        p = t * (S @ v)
+        w = p - (arith(0.5) * t * np.dot(p, v)) * v
+        A[k + 1:, k + 1:] = (S - (np.outer(v, w) + np.outer(w, v))).astype(store)
+        e[k] = beta
+    d[n - 2], d[n - 1], e[n - 2] = A[n - 2, n - 2], A[n - 1, n - 1], A[n - 1, n - 2]
+    return d, e, V, tau
+
+
+def matrices(x, y):
+    from oracle import intel_np, pysiib_np
+    M, _ = intel_np.siib_tiling_factor(x, 16000)
+    Xs, Ys, _ = pysiib_np.siib_features(np.tile(x.astype(np.float64), M), np.tile(y.astype(np.float64), M))
+    Xc = Xs - Xs.mean(1, keepdims=True)
+    Yc = Ys - Ys.mean(1, keepdims=True)
+    return Xc @ Xc.T, Xc @ Yc.T, Yc @ Yc.T
+
+
+def cases():
+    from nele_gan_b200.synth import make_pair
+    for i, L in ((0, 52345), (1, 47999), (2, 33536), (3, 40111), (5, 70003), (7, 112345)):
+        x, y, _ = make_pair(i, L)
+        yield "synth %d L=%d" % (i, L), x, y
+    z = np.load("tests/golden/haspi_ref.npz")
+    for name in ("bundled_16000", "toy_train_multienh", "toy_train_clean", "toy_test_clean"):
+        yield name, z[name + "/x"], z[name + "/y"]
+
+
+def precision():
+    for name, x, y in cases():
+        A, Sxy, Syy = matrices(x, y)
+        lam0, U0 = np.linalg.eigh(A)
+        s0 = E.siib(lam0, U0, Sxy, Syy)
+        out = []
+        for nm, st, ar in (("s64a64", np.float64, np.float64), ("s32a64", np.float32, np.float64), ("s32a32", np.float32, np.float32)):
+            d, e, V, tau = tridiag_var(A, st, ar)
+            lam, Z = eigh_tridiagonal(d.astype(np.float64), e.astype(np.float64))
+            out.append("%s %.1e" % (nm, abs(E.siib(lam, E.back(V, tau, Z), Sxy, Syy) - s0) / s0))
+        l32, U32 = np.linalg.eigh(A.astype(np.float32))
+        out.append("eigh32 %.1e" % (abs(E.siib(l32.astype(np.float64), U32.astype(np.float64), Sxy, Syy) - s0) / s0))
+        print("%-22s cond %.1e SIIB %9.5f | %s" % (name, lam0[-1] / lam0[0], s0, "  ".join(out)), flush=True)
+
+
+def iterations():
+    from nele_gan_b200.synth import make_pair
+    for i, L in ((1, 47999), (0, 52345), (5, 70003)):
+        x, y, _ = make_pair(i, L)
+        A, Sxy, Syy = matrices(x, y)
+        lam0, U0 = np.linalg.eigh(A)
+        s0 = E.siib(lam0, U0, Sxy, Syy)
+        d, e, V, tau = tridiag_var(A, np.float32, np.float32)
+        sc = max(np.abs(d).max(), np.abs(e).max())
+        for iters in (58, 50, 46, 42, 38):
+            lam = E.bisect_all(d / sc, e / sc, iters=iters) * sc
+            Z = np.stack([E.getvec(d, e, l) for l in lam], axis=1)
+            orth = np.abs(Z.T @ Z - np.eye(len(lam))).max()
+            s1 = E.siib(lam, E.back(V, tau, Z), Sxy, Syy)
+            print("pair %d L=%d iterations %d: orthogonality %.1e  SIIB rel %.1e" % (i, L, iters, orth, abs(s1 - s0) / s0), flush=True)
+
+
+if __name__ == "__main__":
+    (iterations if len(sys.argv) > 1 and sys.argv[1] == "iterations" else precision)()

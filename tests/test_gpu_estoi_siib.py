@@ -216,8 +216,8 @@ def test_all_metrics_on_the_toy_corpus_pairs(eng, golden):
     from oracle import intel_np
     names = ("toy_train_multienh", "toy_train_clean", "toy_test_clean")
     xs, ys = [golden[n]["x"] for n in names], [golden[n]["y"] for n in names]
-    raw = eng.score_batch(xs, ys, mapped=False, no_dither=True, keep_stages=True)
     mapped = eng.score_batch(xs, ys, mapped=True, no_dither=True)
+    raw = eng.score_batch(xs, ys, mapped=False, no_dither=True, keep_stages=True)
     assert raw.ok.all() and not raw.siib_nullspace_dropped.any()
     for i, n in enumerate(names):
         want = intel_np.score_pair(xs[i], ys[i], 16000, norm=False, noise=None)
