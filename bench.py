@@ -115,9 +115,9 @@ def kernel_bytes_per_pair(name, L16, Nf=1950, rank=420):
     nfr = max(n10 // 128 - 2, 1)
     F = Nf + 14
     table = {
-        "haspi_prep": 2 * (4 * L16 + 4 * n24 + 8 * n24),
-        "haspi_control": 2 * 8 * n24,
-        "haspi_ear": 2 * (8 * n24 + 128 * nsub),
+        "haspi_prep": 2 * (4 * L16 + 4 * n24),              # waveform in, middle-ear output (f32) out
+        "haspi_control": 2 * 4 * n24,
+        "haspi_ear": 2 * (4 * n24 + 128 * nsub),
         "haspi_cep": 2 * 128 * nsub + 2 * 5 * 4 * nsub,
         "haspi_modcorr": 2 * 5 * 4 * nsub,
         "estoi_resample": 2 * (4 * L16 + 4 * n10),
@@ -489,13 +489,25 @@ def main():
         return eng.score_packed(d_ref.data_ptr(), d_deg.data_ptr(), offs, lens, fs=FS, mapped=True, seed=1,
                                 device_input=True, stream=sptr, out=out)
 
-    def step_host():
-        r = eng.score_packed(h_ref.data_ptr(), h_deg.data_ptr(), offs, lens, fs=FS, mapped=True, seed=1,
-                             stream=sptr, out=out)
+    # host buffers as the reference holds them: 16-bit PCM of the clean, the enhanced and the noise signal (the corpus
+    # files and the generator outputs written by sf.write(..., 'PCM_16'), train_nele.py:313); here enhanced = clean
+    q16 = lambda v: np.clip(np.round(v * 32768.0), -32768, 32767).astype(np.int16)
+    h_c16 = torch.from_numpy(q16(fr)).pin_memory()
+    h_n16 = torch.from_numpy(q16(fd - fr)).pin_memory()
+
+    def gather(r):
         if dist is not None:   # the one collective of the path: gather of the per-pair records
             rec = shard.pack_records(r)
             shard.gather_records(rec, np.arange(n, dtype=np.int64) + rank * n, n * world, device=dev)
         return r
+
+    def step_host():           # float32 host buffers (8 bytes per sample pair cross PCIe)
+        return gather(eng.score_packed(h_ref.data_ptr(), h_deg.data_ptr(), offs, lens, fs=FS, mapped=True, seed=1,
+                                       stream=sptr, out=out))
+
+    def step_host_pcm():       # int16 host buffers (6 bytes), enhanced + noise formed on the device
+        return gather(eng.score_packed_pcm16(h_c16.data_ptr(), h_c16.data_ptr(), h_n16.data_ptr(), offs, lens, fs=FS,
+                                             mapped=True, seed=1, stream=sptr, out=out))
 
     # ---- value: device-resident inputs
     for _ in range(a.warmup):
@@ -534,17 +546,29 @@ def main():
             eng.prefetch(h_ref.data_ptr(), h_deg.data_ptr(), offs, lens)
         r = step_host()
     barrier()
+    ms_e2e_f32 = (time.perf_counter() - t0) * 1e3
+    # the same with the PCM-16 host buffers: this is what the drop-in read_batch_* path uploads (api._score_files)
+    step_host_pcm()
+    barrier()
+    t0 = time.perf_counter()
+    eng.prefetch_pcm16(h_c16.data_ptr(), h_c16.data_ptr(), h_n16.data_ptr(), offs, lens)
+    for k in range(a.steps):
+        if k + 1 < a.steps:
+            eng.prefetch_pcm16(h_c16.data_ptr(), h_c16.data_ptr(), h_n16.data_ptr(), offs, lens)
+        r = step_host_pcm()
+    barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
+    ok_pcm = int(np.sum(r.ok))
     # the same loop with plain blocking calls (no nele_prefetch): every upload is exposed
     t0 = time.perf_counter()
     for _ in range(a.steps):
         r = step_host()
     barrier()
     ms_e2e_blocking = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([ms_dev, ms_e2e, ms_e2e_blocking], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_dev, ms_e2e, ms_e2e_blocking, ms_e2e_f32], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e, ms_e2e_blocking = float(t[0]), float(t[1]), float(t[2])
+    ms_dev, ms_e2e, ms_e2e_blocking, ms_e2e_f32 = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     ok = int(np.sum((r.status & 0xFFFFFF) == 0))
 
     # ---- general case: the same step on pairs whose length is not a multiple of SIIB's 200-sample hop
@@ -631,10 +655,15 @@ def main():
             "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic", "config": config,
             "e2e": {"value": audio_s * world / (ms_e2e / a.steps * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(h_ref.numel() * 4 * 2), "d2h_bytes_per_step": int(n * (14 * 8 + 4)),
+                    "h2d_bytes_per_step": int(h_c16.numel() * 2 * 2 + h_n16.numel() * 2), "d2h_bytes_per_step": int(n * (14 * 8 + 4)),
                     "ms_per_step": ms_e2e / a.steps,
-                    "ms_per_step_blocking_calls": ms_e2e_blocking / a.steps,
-                    "pipelining": "upload of step k+1 (nele_prefetch) overlaps the kernels of step k; every step's H2D and D2H copies are inside the timed region"},
+                    "host_buffers": "int16 PCM of clean / enhanced / noise (nele_score_batch_pcm16: what the drop-in read_batch_* path "
+                                    "uploads for the reference's 16-bit WAV files); enhanced + noise is formed on the device",
+                    "pairs_ok": ok_pcm,
+                    "float32_host": {"value": audio_s * world / (ms_e2e_f32 / a.steps * 1e-3), "ms_per_step": ms_e2e_f32 / a.steps,
+                                     "h2d_bytes_per_step": int(h_ref.numel() * 4 * 2),
+                                     "ms_per_step_blocking_calls": ms_e2e_blocking / a.steps},
+                    "pipelining": "upload of step k+1 (nele_prefetch[_pcm16]) overlaps the kernels of step k; every step's H2D and D2H copies are inside the timed region"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",

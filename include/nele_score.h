@@ -136,6 +136,21 @@ int nele_score_batch(nele_engine* e, const float* ref, const float* deg, const i
                      double* scores, double* haspi_raw, int32_t* status, void* stream);
 
 /*
+ * The same call for host inputs held as 16-bit PCM, which is what the reference's files are (the corpus, and the
+ * generator's outputs written by sf.write(..., 'PCM_16'), train_nele.py:313): clean, enhanced and noise int16 arrays
+ * with the layout of ref / deg above.  The engine forms ref = clean / 32768 (librosa.load) and
+ * deg = enhanced / 32768 + noise / 32768 (audio_util.py:139) on the device -- both exact in float32, so the scores are
+ * bit-identical to nele_score_batch on the converted arrays -- and 6 instead of 8 bytes per sample cross PCIe.
+ * nele_prefetch_pcm16 is the matching upload-ahead call.
+ */
+int nele_score_batch_pcm16(nele_engine* e, const int16_t* clean, const int16_t* enhanced, const int16_t* noise,
+                           const int64_t* offs, const int32_t* lens, int n, int fs, uint32_t metrics, uint32_t flags,
+                           const float* dither, int64_t dither_rows, uint64_t seed, const double* hl,
+                           double* scores, double* haspi_raw, int32_t* status, void* stream);
+int nele_prefetch_pcm16(nele_engine* e, const int16_t* clean, const int16_t* enhanced, const int16_t* noise,
+                        const int64_t* offs, const int32_t* lens, int n, uint32_t flags);
+
+/*
  * Optional pipelining across calls for host inputs: start the host -> device upload of an upcoming
  * nele_score_batch(e, ref, deg, offs, lens, n, ..., flags, ...) call now, on the engine's copy
  * stream, into the staging slot the current call does not use.  Returns at once; the matching
@@ -157,7 +172,7 @@ int nele_prefetch_cancel(nele_engine* e);
  * call made with NELE_FLAG_KEEP_STAGES.  Copies stage `name` of pair `pair`
  * into dst (capacity cap bytes) and reports its size; dst may be NULL to query
  * the size.  Stages (element type, shape):
- *   "haspi.mid"    f64 [2][n24]        middle-ear output of x and y (pyhaspi2.py:1185-1186)
+ *   "haspi.mid"    f32 [2][n24]        middle-ear output of x and y (pyhaspi2.py:1185-1186), computed in FP64
  *   "haspi.bw"     f64 [2][32]         BWx, BWy                      (pyhaspi2.py:1204-1205)
  *   "haspi.shift"  i32 [32]            group-delay shifts            (pyhaspi2.py:1118-1122)
  *   "haspi.envlp"  f32 [2][nsub][32]   ebm_EnvFilt output            (pyhaspi2.py:412-413)
@@ -238,9 +253,12 @@ int nele_features(nele_engine* e, const float* wav, const int64_t* offs, const i
  *   out_lens       host int32 [n]: 256 * (lens[i] / 256) valid samples -- len(librosa.istft(...)), to which
  *                  audio_util.py:190-193 trims both signals; pass it as `lens` to nele_score_batch
  *                  (NELE_FLAG_DEVICE_INPUT, ref = clean, deg = deg, same offs)
- *   flags          NELE_RESYN_PCM16
+ *   flags          NELE_RESYN_PCM16: round the enhanced signal to 16 bits before the noise is added;
+ *                  NELE_RESYN_ENH_ROUNDED: `enh` receives the rounded signal (what the discriminator's data loader reads
+ *                  back from the WAV file, dataloader.py:59) instead of the unrounded one
  */
-#define NELE_RESYN_PCM16 0x1u
+#define NELE_RESYN_PCM16       0x1u
+#define NELE_RESYN_ENH_ROUNDED 0x2u
 int nele_resyn(nele_engine* e, const float* clean, const float* noise, const int64_t* offs, const int32_t* lens, int n,
                const float* alpha2, const int64_t* arow, uint32_t flags, float* enh, float* deg, int32_t* out_lens,
                void* stream);

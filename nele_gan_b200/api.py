@@ -309,12 +309,49 @@ def _read_pairs(clean_root, noise_root, enhanced_list, drc):
     return refs, degs
 
 
+def _read_pcm16(clean_root, noise_root, enhanced_list, drc):
+    """The three files of every utterance as int16, trimmed like audio_util.py:134-137 and packed for
+    ``nele_score_batch_pcm16`` -- or None when a file is not 16-bit mono PCM at 16 kHz (then the float path runs)."""
+    from scipy.io import wavfile
+    trip = []
+    for en in enhanced_list:
+        name = _wave_name(en, drc)
+        cur = []
+        for path in (clean_root + name, en, noise_root + name):
+            sr, x = wavfile.read(path)
+            if sr != 16000 or x.dtype != np.int16 or x.ndim != 1:
+                return None
+            cur.append(x)
+        m = min(len(cur[0]), len(cur[1]))
+        if len(cur[2]) < m:
+            return None
+        trip.append([a[:m] for a in cur])
+    lens = np.array([len(t[0]) for t in trip], dtype=np.int32)
+    padded = (lens.astype(np.int64) + 7) // 8 * 8
+    offs = np.concatenate(([0], np.cumsum(padded)[:-1])).astype(np.int64)
+    flat = [np.zeros(int(padded.sum()), dtype=np.int16) for _ in range(3)]
+    for t, o, n in zip(trip, offs, lens):
+        for k in range(3):
+            flat[k][o:o + n] = t[k]
+    return flat, offs, lens
+
+
+def _score_files(clean_root, noise_root, enhanced_list, drc, metrics, norm, seed):
+    """One engine call for a list of files: int16 upload with ``enhanced + noise`` formed on the device when the
+    files are 16-bit PCM (what train_nele.py:313 writes), else the float path."""
+    pcm = _read_pcm16(clean_root, noise_root, enhanced_list, drc)
+    if pcm is not None:
+        flat, offs, lens = pcm
+        return _engine().score_packed_pcm16(flat[0], flat[1], flat[2], offs, lens, fs=fs, metrics=metrics, mapped=bool(norm),
+                                            seed=seed)
+    refs, degs = _read_pairs(clean_root, noise_root, enhanced_list, drc)
+    return _engine().score_batch(refs, degs, fs=fs, metrics=metrics, mapped=bool(norm), seed=seed)
+
+
 def _read_batch(metric, col, clean_root, noise_root, enhanced_list, norm, drc, strict=True):
     if not len(enhanced_list):
         return []
-    refs, degs = _read_pairs(clean_root, noise_root, list(enhanced_list), drc)
-    r = _engine().score_batch(refs, degs, fs=fs, metrics=(metric,), mapped=bool(norm),
-                              seed=int(np.random.randint(0, 2 ** 31 - 1)))
+    r = _score_files(clean_root, noise_root, list(enhanced_list), drc, (metric,), norm, int(np.random.randint(0, 2 ** 31 - 1)))
     check_status(r, (metric,), strict)
     return [float(v) for v in r.scores[:, col]]
 
@@ -349,10 +386,10 @@ def read_batch_all(clean_root, noise_root, enhanced_list, norm=True, drc=False, 
     call.  Returns ``(siib, haspi, estoi)`` lists."""
     if not len(enhanced_list):
         return [], [], []
-    refs, degs = _read_pairs(clean_root, noise_root, list(enhanced_list), drc)
     if seed is None:
         seed = int(np.random.randint(0, 2 ** 31 - 1))
-    s = check_status(_engine().score_batch(refs, degs, fs=fs, mapped=bool(norm), seed=seed), strict=strict).scores
+    s = check_status(_score_files(clean_root, noise_root, list(enhanced_list), drc, ("siib", "haspi", "estoi"), norm, seed),
+                     strict=strict).scores
     return [float(v) for v in s[:, 0]], [float(v) for v in s[:, 1]], [float(v) for v in s[:, 2]]
 
 

@@ -57,6 +57,7 @@ struct nele_engine {
     uint64_t seq = 0;
     uint64_t geom_hash = 0;   // FNV-1a of offs[] and lens[]: the same pointers with another layout must not match
     uint64_t born = 0;        // value of `calls` when the prefetch was issued; dropped when two calls old
+    bool pcm = false;         // uploaded by nele_prefetch_pcm16
   } pf[2];
   uint64_t pf_seq = 0;
   uint64_t calls = 0;         // nele_score_batch calls with host inputs so far
@@ -76,6 +77,8 @@ struct nele_engine {
 
   // workspace (grow-only)
   DevBuf in_ref[2], in_deg[2], geom, sgeom, dither;  // inputs double-buffered: chunk k + 1 uploads while chunk k computes
+  DevBuf in_pcm[2][3];                               // int16 staging of nele_score_batch_pcm16 (clean, enhanced, noise)
+  const int16_t* pcm_noise = nullptr;                // set while a PCM-16 call runs: upload_chunk takes (clean, enhanced, noise) int16
   DevBuf x24, mid, bw, shift, envlp, rowsel, nsel, cep, cepmean, modsum;            // HASPI
   DevBuf v1_bm, v1_segsum, v1_cov, v1_msx, v1_xsum, v1_cepcorr, v1_cov3, v1_status, v1_cave, v1_ave, v1_sync5;  // HASPI version 1
   DevBuf x10, st_energy, st_kept, st_nkept, st_tob;                                 // ESTOI
@@ -211,6 +214,7 @@ extern "C" int nele_create(int device, nele_engine** out) {
   p = getenv("NELE_CONCURRENT");
   e->serial = !(p && p[0] == '1');
   e->all_bufs = {&e->bands, &e->rs_taps, &e->st_taps, &e->in_ref[0], &e->in_ref[1], &e->in_deg[0], &e->in_deg[1], &e->geom, &e->sgeom, &e->dither,
+                 &e->in_pcm[0][0], &e->in_pcm[0][1], &e->in_pcm[0][2], &e->in_pcm[1][0], &e->in_pcm[1][1], &e->in_pcm[1][2],
                  &e->x24, &e->mid, &e->bw, &e->shift, &e->envlp, &e->rowsel, &e->nsel, &e->cep, &e->cepmean, &e->modsum,
                  &e->v1_bm, &e->v1_segsum, &e->v1_cov, &e->v1_msx, &e->v1_xsum, &e->v1_cepcorr, &e->v1_cov3, &e->v1_status, &e->v1_cave, &e->v1_ave, &e->v1_sync5,
                  &e->x10, &e->st_energy, &e->st_kept, &e->st_nkept, &e->st_tob,
@@ -445,6 +449,17 @@ static void plan_chunks(const int64_t* offs, const int32_t* lens, int n, bool de
   }
 }
 
+// PCM-16 inputs (what the reference's WAV files hold): ref = clean / 32768 (librosa.load, audio_util.py:128-130),
+// deg = enhanced / 32768 + noise / 32768 (audio_util.py:139) -- both exact in float32
+__global__ void pcm16_to_float_kernel(const int16_t* __restrict__ c, const int16_t* __restrict__ en, const int16_t* __restrict__ nz,
+                                      float* __restrict__ ref, float* __restrict__ deg, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    ref[i] = (float)c[i] * (1.f / 32768.f);
+    deg[i] = (float)en[i] * (1.f / 32768.f) + (float)nz[i] * (1.f / 32768.f);
+  }
+}
+
 // queue the host -> device upload of one chunk's waveforms on the copy stream
 static int upload_chunk(nele_engine* e, const ChunkPlan& c, int slot, const float* ref, const float* deg,
                         const int64_t* offs, const int32_t* lens) {
@@ -452,6 +467,26 @@ static int upload_chunk(nele_engine* e, const ChunkPlan& c, int slot, const floa
   RESERVE(e, e->in_ref[slot], in_elems * sizeof(float));
   RESERVE(e, e->in_deg[slot], in_elems * sizeof(float));
   cudaStream_t sc = e->s_copy;
+  if (e->pcm_noise) {
+    // int16 triple: `ref` / `deg` carry the clean / enhanced int16 pointers; 6 instead of 8 bytes per sample cross PCIe
+    const int16_t* src[3] = {reinterpret_cast<const int16_t*>(ref), reinterpret_cast<const int16_t*>(deg), e->pcm_noise};
+    for (int k = 0; k < 3; ++k) {
+      RESERVE(e, e->in_pcm[slot][k], in_elems * sizeof(int16_t));
+      if (c.span_copy) {
+        CU(e, cudaMemcpyAsync(e->in_pcm[slot][k].p, src[k] + c.lo, in_elems * sizeof(int16_t), cudaMemcpyHostToDevice, sc));
+      } else {
+        for (int i = c.first; i < c.last; ++i)
+          CU(e, cudaMemcpyAsync((int16_t*)e->in_pcm[slot][k].p + c.off16[i - c.first], src[k] + offs[i], sizeof(int16_t) * lens[i],
+                                cudaMemcpyHostToDevice, sc));
+      }
+    }
+    pcm16_to_float_kernel<<<1184, 256, 0, sc>>>((const int16_t*)e->in_pcm[slot][0].p, (const int16_t*)e->in_pcm[slot][1].p,
+                                                (const int16_t*)e->in_pcm[slot][2].p, (float*)e->in_ref[slot].p,
+                                                (float*)e->in_deg[slot].p, in_elems);
+    CU(e, cudaGetLastError());
+    CU(e, cudaEventRecord(e->ev_in[slot], sc));
+    return NELE_OK;
+  }
   if (c.span_copy) {
     CU(e, cudaMemcpyAsync(e->in_ref[slot].p, ref + c.lo, in_elems * sizeof(float), cudaMemcpyHostToDevice, sc));
     CU(e, cudaMemcpyAsync(e->in_deg[slot].p, deg + c.lo, in_elems * sizeof(float), cudaMemcpyHostToDevice, sc));
@@ -480,12 +515,38 @@ static uint64_t geom_hash(const int64_t* offs, const int32_t* lens, int n) {
   return h;
 }
 
+static int score_core(nele_engine* e, const float* ref, const float* deg, const int64_t* offs, const int32_t* lens, int n,
+                      int fs, uint32_t metrics, uint32_t flags, const float* dither, int64_t dither_rows, uint64_t seed,
+                      const double* hl, double* scores, double* haspi_raw, int32_t* status, void* stream);
+
 extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* deg, const int64_t* offs,
                                 const int32_t* lens, int n, int fs, uint32_t metrics, uint32_t flags,
                                 const float* dither, int64_t dither_rows, uint64_t seed, const double* hl,
                                 double* scores, double* haspi_raw, int32_t* status, void* stream) {
   if (!e) return NELE_E_ARG;
   std::lock_guard<std::mutex> lock(e->mu);
+  e->pcm_noise = nullptr;
+  return score_core(e, ref, deg, offs, lens, n, fs, metrics, flags, dither, dither_rows, seed, hl, scores, haspi_raw, status, stream);
+}
+
+extern "C" int nele_score_batch_pcm16(nele_engine* e, const int16_t* clean, const int16_t* enhanced, const int16_t* noise,
+                                      const int64_t* offs, const int32_t* lens, int n, int fs, uint32_t metrics, uint32_t flags,
+                                      const float* dither, int64_t dither_rows, uint64_t seed, const double* hl,
+                                      double* scores, double* haspi_raw, int32_t* status, void* stream) {
+  if (!e) return NELE_E_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (flags & NELE_FLAG_DEVICE_INPUT) return fail(e, NELE_E_ARG, "nele_score_batch_pcm16 takes host buffers");
+  if (n > 0 && !noise) return fail(e, NELE_E_ARG, "nele_score_batch_pcm16: null pointer");
+  e->pcm_noise = noise;
+  const int rc = score_core(e, reinterpret_cast<const float*>(clean), reinterpret_cast<const float*>(enhanced), offs, lens, n, fs,
+                            metrics, flags, dither, dither_rows, seed, hl, scores, haspi_raw, status, stream);
+  e->pcm_noise = nullptr;
+  return rc;
+}
+
+static int score_core(nele_engine* e, const float* ref, const float* deg, const int64_t* offs, const int32_t* lens, int n,
+                      int fs, uint32_t metrics, uint32_t flags, const float* dither, int64_t dither_rows, uint64_t seed,
+                      const double* hl, double* scores, double* haspi_raw, int32_t* status, void* stream) {
   if (n < 0 || (n > 0 && (!ref || !deg || !offs || !lens || !scores)))
     return fail(e, NELE_E_ARG, "nele_score_batch: null pointer or negative n");
   if ((metrics & ~NELE_METRIC_ALL) || metrics == 0) return fail(e, NELE_E_ARG, "nele_score_batch: bad metric mask 0x%x", metrics);
@@ -557,7 +618,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
     int hit = -1;
     for (int k = 0; k < 2; ++k)
       if (e->pf[k].valid && e->pf[k].ref == ref && e->pf[k].deg == deg && e->pf[k].n == n && e->pf[k].tot == plans[0].tot &&
-          e->pf[k].geom_hash == gh && (hit < 0 || e->pf[k].seq < e->pf[hit].seq))
+          e->pf[k].geom_hash == gh && e->pf[k].pcm == (e->pcm_noise != nullptr) && (hit < 0 || e->pf[k].seq < e->pf[hit].seq))
         hit = k;
     if (hit >= 0) {
       slot0 = hit;
@@ -717,7 +778,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
     memset(&hb, 0, sizeof(hb));
     if (run_haspi) {
       RESERVE(e, e->x24, (size_t)2 * t24 * sizeof(float));
-      RESERVE(e, e->mid, (size_t)2 * t24 * sizeof(double));
+      RESERVE(e, e->mid, (size_t)2 * t24 * sizeof(float));
       RESERVE(e, e->bw, (size_t)cn * 2 * kBands * sizeof(double));
       RESERVE(e, e->shift, (size_t)cn * kBands * sizeof(int32_t));
       if (!haspi_v1) {
@@ -743,7 +804,7 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
       hb.ref = d_ref;
       hb.deg = d_deg;
       hb.x24 = (float*)e->x24.p;
-      hb.mid = (double*)e->mid.p;
+      hb.mid = (float*)e->mid.p;
       hb.tot24 = t24;
       hb.bw = (double*)e->bw.p;
       hb.shift = (int32_t*)e->shift.p;
@@ -1027,10 +1088,30 @@ extern "C" int nele_score_batch(nele_engine* e, const float* ref, const float* d
   return NELE_OK;
 }
 
+static int prefetch_core(nele_engine* e, const float* ref, const float* deg, const int64_t* offs, const int32_t* lens, int n,
+                         uint32_t flags);
+
 extern "C" int nele_prefetch(nele_engine* e, const float* ref, const float* deg, const int64_t* offs, const int32_t* lens,
                              int n, uint32_t flags) {
   if (!e) return NELE_E_ARG;
   std::lock_guard<std::mutex> lock(e->mu);
+  e->pcm_noise = nullptr;
+  return prefetch_core(e, ref, deg, offs, lens, n, flags);
+}
+
+extern "C" int nele_prefetch_pcm16(nele_engine* e, const int16_t* clean, const int16_t* enhanced, const int16_t* noise,
+                                   const int64_t* offs, const int32_t* lens, int n, uint32_t flags) {
+  if (!e) return NELE_E_ARG;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!noise) return fail(e, NELE_E_ARG, "nele_prefetch_pcm16: null pointer");
+  e->pcm_noise = noise;
+  const int rc = prefetch_core(e, reinterpret_cast<const float*>(clean), reinterpret_cast<const float*>(enhanced), offs, lens, n, flags);
+  e->pcm_noise = nullptr;
+  return rc;
+}
+
+static int prefetch_core(nele_engine* e, const float* ref, const float* deg, const int64_t* offs, const int32_t* lens, int n,
+                         uint32_t flags) {
   if (n <= 0 || !ref || !deg || !offs || !lens) return fail(e, NELE_E_ARG, "nele_prefetch: null pointer or n <= 0");
   if (flags & NELE_FLAG_DEVICE_INPUT) return NELE_OK;  // nothing to upload
   for (int i = 0; i < n; ++i)
@@ -1058,6 +1139,7 @@ extern "C" int nele_prefetch(nele_engine* e, const float* ref, const float* deg,
   e->pf[slot].seq = ++e->pf_seq;
   e->pf[slot].geom_hash = geom_hash(offs, lens, n);
   e->pf[slot].born = e->calls;
+  e->pf[slot].pcm = e->pcm_noise != nullptr;
   return NELE_OK;
 }
 
@@ -1189,7 +1271,7 @@ extern "C" int nele_resyn(nele_engine* e, const float* clean, const float* noise
   std::lock_guard<std::mutex> lock(e->mu);
   if (n < 0 || (n > 0 && (!clean || !offs || !lens || !alpha2 || (!enh && !deg) || (deg && !noise))))
     return fail(e, NELE_E_ARG, "nele_resyn: null pointer or negative n");
-  if (flags & ~NELE_RESYN_PCM16) return fail(e, NELE_E_ARG, "nele_resyn: bad flags 0x%x", flags);
+  if (flags & ~(NELE_RESYN_PCM16 | NELE_RESYN_ENH_ROUNDED)) return fail(e, NELE_E_ARG, "nele_resyn: bad flags 0x%x", flags);
   for (int i = 0; i < n; ++i)
     if (lens[i] <= 256 || offs[i] < 0)
       return fail(e, NELE_E_ARG, "nele_resyn: waveform %d has length %d / offset %lld (need more than 256 samples)", i, lens[i],
@@ -1227,7 +1309,7 @@ extern "C" int nele_resyn(nele_engine* e, const float* clean, const float* noise
   CU(e, cudaEventRecord(e->ev0, s));
   e->last_launches += resyn_run(clean, noise, (const int64_t*)(gp + g_off), (const int32_t*)(gp + g_len),
                                 (const int64_t*)(gp + g_foff), (const int2*)(gp + g_tiles), (int)h_tiles.size(), alpha2,
-                                flags & NELE_RESYN_PCM16, enh, deg, kt, s);
+                                (int)(flags & (NELE_RESYN_PCM16 | NELE_RESYN_ENH_ROUNDED)), enh, deg, kt, s);
   CU(e, cudaGetLastError());
   CU(e, cudaEventRecord(e->ev1, s));
   CU(e, cudaStreamSynchronize(s));
@@ -1273,7 +1355,7 @@ extern "C" int nele_get_stage(nele_engine* e, const char* name, int pair, void* 
   if (e->stage_v1 && (nm == "haspi.envlp" || nm == "haspi.nsel" || nm == "haspi.cep" || nm == "haspi.cepmean"))
     return fail(e, NELE_E_ARG, "nele_get_stage: '%s' is a HASPI version 2 stage; the last call ran version 1", name);
   if (nm == "haspi.mid") {
-    for (int q = 0; q < 2; ++q) pieces.push_back({(double*)e->mid.p + q * e->tot24 + o24, n24 * sizeof(double)});
+    for (int q = 0; q < 2; ++q) pieces.push_back({(float*)e->mid.p + q * e->tot24 + o24, n24 * sizeof(float)});
   } else if (nm == "haspi.x24") {
     for (int q = 0; q < 2; ++q) pieces.push_back({(float*)e->x24.p + q * e->tot24 + o24, n24 * sizeof(float)});
   } else if (nm == "haspi.bw") {

@@ -531,18 +531,19 @@ __global__ void __launch_bounds__(256) feat_resyn_kernel(const float* __restrict
     const float ss = (float)(wa * wa) + (float)(wb * wb);
     float y = acc / ss;
     const int64_t sidx = (int64_t)h * kHop + p;
-    if (enh) enh[o + sidx] = y;
-    if (pcm16) y = fminf(fmaxf(rintf(y * 32768.f), -32768.f), 32767.f) * (1.f / 32768.f);
+    if (enh && !(pcm16 & 2)) enh[o + sidx] = y;
+    if (pcm16 & 1) y = fminf(fmaxf(rintf(y * 32768.f), -32768.f), 32767.f) * (1.f / 32768.f);
+    if (enh && (pcm16 & 2)) enh[o + sidx] = y;   // what the reference reads back from the PCM-16 file (dataloader.py:59)
     if (deg) deg[o + sidx] = y + noise[o + sidx];
   }
 }
 
 int resyn_run(const float* clean, const float* noise, const int64_t* offs, const int32_t* lens, const int64_t* foff,
-              const int2* tiles, int ntiles, const float* alpha2, bool pcm16, float* enh, float* deg, KernelTimer* kt,
+              const int2* tiles, int ntiles, const float* alpha2, int pcm16, float* enh, float* deg, KernelTimer* kt,
               cudaStream_t s) {
   feat_tables_ready(s);
   kt_begin(kt, "feat_resyn", s);
-  feat_resyn_kernel<<<ntiles, 256, 0, s>>>(clean, noise, offs, lens, foff, tiles, alpha2, pcm16 ? 1 : 0, enh, deg);
+  feat_resyn_kernel<<<ntiles, 256, 0, s>>>(clean, noise, offs, lens, foff, tiles, alpha2, pcm16, enh, deg);
   kt_end(kt, s);
   return 1;
 }

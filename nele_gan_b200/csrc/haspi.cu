@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kPrepThreads, 4) haspi_prep_kernel(PairGeom g,
   const int L = g.len16[pair];
   const int N = g.n24[pair];
   float* __restrict__ x24 = b.x24 + (int64_t)q * b.tot24 + g.off24[pair];
-  double* __restrict__ mid = b.mid + (int64_t)q * b.tot24 + g.off24[pair];
+  float* __restrict__ mid = b.mid + (int64_t)q * b.tot24 + g.off24[pair];
   __shared__ double red[32];
   __shared__ double s_loc[kPrepThreads][3];
   __shared__ double s_M[3][3];
@@ -216,10 +216,10 @@ __global__ void __launch_bounds__(kPrepThreads, 4) haspi_prep_kernel(PairGeom g,
   // per-warp shared-memory tile, eight per lane and round, moved with 32-byte row segments (four
   // chunks per warp instruction) instead of one sector per lane and instruction.
   __shared__ float s_tx[kPrepThreads / 32][32][9];
-  __shared__ double s_tm[kPrepThreads / 32][32][9];
+  __shared__ float s_tm[kPrepThreads / 32][32][9];
   const int lane = tid & 31, wib = tid >> 5;
   float (*tx)[9] = s_tx[wib];
-  double (*tm)[9] = s_tm[wib];
+  float (*tm)[9] = s_tm[wib];
   const int rounds = (Lc + 7) / 8;
   const int crow = lane >> 3, ccol = lane & 7;   // cooperative moves: rows 4 i + crow, column ccol
   MidState st = {0.0, 0.0, 0.0};
@@ -280,19 +280,18 @@ __global__ void __launch_bounds__(kPrepThreads, 4) haspi_prep_kernel(PairGeom g,
     for (int i = 0; i < 8; ++i)
       if (t0 + 8 * r + i < t1) {
         const float v = (float)((double)tx[lane][i] * scale);
-        tx[lane][i] = v;
-        tm[lane][i] = mid_step(st, (double)v);
+        tm[lane][i] = (float)mid_step(st, (double)v);
       }
     __syncwarp();
+    // the middle-ear output leaves as float32: the control and main passes run their recurrences in FP32 and
+    // converted it on load anyway (round 1 kept it as FP64 in HBM: 1.15 MB per 3 s pair written once, read twice --
+    // the largest avoidable stream of the step); the level-matched x24 is not written back (nobody reads it)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = 4 * i + crow;
       const int r0 = min((wib * 32 + row) * Lc, N), r1 = min(r0 + Lc, N);
       const int t = r0 + 8 * r + ccol;
-      if (t < r1) {
-        x24[t] = tx[row][ccol];
-        mid[t] = tm[row][ccol];
-      }
+      if (t < r1) mid[t] = tm[row][ccol];
     }
     __syncwarp();
   }
@@ -310,8 +309,8 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_control_kernel(PairGeom 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int pair = blockIdx.x * kEarWarps + wib;
   if (pair >= n_pairs) return;
-  const double* __restrict__ midx = b.mid + g.off24[pair];
-  const double* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
+  const float* __restrict__ midx = b.mid + g.off24[pair];
+  const float* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
   const int N = g.n24[pair];
   __shared__ T s_buf[kEarWarps][2][kCtlChunk];
   T* bx = s_buf[wib][0];
@@ -377,8 +376,8 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_kernel(PairGeom g, H
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int pair = blockIdx.x * kEarWarps + wib;
   if (pair >= n_pairs) return;
-  const double* __restrict__ midx = b.mid + g.off24[pair];
-  const double* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
+  const float* __restrict__ midx = b.mid + g.off24[pair];
+  const float* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
   const int N = g.n24[pair], nsub = g.nsub[pair];
   float* __restrict__ outx = b.envlp + (g.offsub[pair]) * kBands;
   float* __restrict__ outy = b.envlp + (b.totsub + g.offsub[pair]) * kBands;
@@ -481,8 +480,8 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_x2_kernel(PairGeom g
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int pair = blockIdx.x * kEarWarps + wib;
   if (pair >= n_pairs) return;
-  const double* __restrict__ midx = b.mid + g.off24[pair];
-  const double* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
+  const float* __restrict__ midx = b.mid + g.off24[pair];
+  const float* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
   const int N = g.n24[pair], nsub = g.nsub[pair];
   float* __restrict__ outx = b.envlp + (g.offsub[pair]) * kBands;
   float* __restrict__ outy = b.envlp + (b.totsub + g.offsub[pair]) * kBands;

@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(kEar1Warps * 32) haspi_ear_v1_kernel(PairGeom 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int pair = blockIdx.x * kEar1Warps + wib;
   if (pair >= n_pairs) return;
-  const double* __restrict__ midx = b.mid + g.off24[pair];
-  const double* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
+  const float* __restrict__ midx = b.mid + g.off24[pair];
+  const float* __restrict__ midy = b.mid + b.tot24 + g.off24[pair];
   const int N = g.n24[pair];
   float* __restrict__ bmx = v.bm + g.off24[pair] * kBands;
   float* __restrict__ bmy = v.bm + (b.tot24 + g.off24[pair]) * kBands;

@@ -21,8 +21,8 @@ struct PairGeom {
 struct HaspiBuffers {
   const float* ref;      // device, input rate
   const float* deg;
-  float* x24;            // [2][tot24]
-  double* mid;           // [2][tot24]
+  float* x24;            // [2][tot24] resampled signal before the level match (scratch of haspi_prep)
+  float* mid;            // [2][tot24] middle-ear output
   int64_t tot24;
   double* bw;            // [n][2][32]
   double* cave;          // [n][2][32] RMS of the control envelope (eb_EarModel xcave / ycave), or null
@@ -225,7 +225,7 @@ int features_run(const float* wav, const int64_t* offs, const int32_t* lens, con
 // Resynthesis of a sampling round (audio_util.py:60-115, train_nele.py:303-314): tiles = (utterance, first frame) per CTA,
 // 7 output hops each; alpha2 [sum T][64]; enh / deg written at the clean signal's offsets (either may be null)
 int resyn_run(const float* clean, const float* noise, const int64_t* offs, const int32_t* lens, const int64_t* foff,
-              const int2* tiles, int ntiles, const float* alpha2, bool pcm16, float* enh, float* deg, KernelTimer* kt,
-              cudaStream_t s);
+              const int2* tiles, int ntiles, const float* alpha2, int pcm16 /* NELE_RESYN_* bits */, float* enh, float* deg,
+              KernelTimer* kt, cudaStream_t s);
 
 }  // namespace nele

@@ -23,7 +23,7 @@ _METRIC_BITS = {"haspi": METRIC_HASPI, "siib": METRIC_SIIB, "estoi": METRIC_ESTO
 COL_SIIB, COL_HASPI, COL_ESTOI = 0, 1, 2
 
 SYMBOLS = ("nele_abi_version", "nele_create", "nele_destroy", "nele_last_error", "nele_score_batch", "nele_prefetch",
-           "nele_prefetch_cancel",
+           "nele_prefetch_cancel", "nele_score_batch_pcm16", "nele_prefetch_pcm16",
            "nele_get_stage", "nele_last_timing", "nele_set_profiling", "nele_kernel_time", "nele_feature_frames",
            "nele_features", "nele_resyn")
 FEAT_NOISE, FEAT_DEVICE_IO, FEAT_NO_POWER = 0x1, 0x2, 0x4
@@ -61,6 +61,13 @@ def load_library(path=None):
         lib.nele_score_batch.restype = C.c_int
         lib.nele_prefetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
         lib.nele_prefetch.restype = C.c_int
+        lib.nele_score_batch_pcm16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                               C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int64, C.c_uint64,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.nele_score_batch_pcm16.restype = C.c_int
+        lib.nele_prefetch_pcm16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_uint32]
+        lib.nele_prefetch_pcm16.restype = C.c_int
         lib.nele_prefetch_cancel.argtypes = [C.c_void_p]
         lib.nele_prefetch_cancel.restype = C.c_int
         lib.nele_get_stage.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t,
@@ -217,6 +224,41 @@ class Engine:
                                      FLAG_HASPI_V1 if haspi_v1 else 0)
         self._check(rc, "nele_prefetch")
 
+    def score_packed_pcm16(self, clean, enhanced, noise, offs, lens, fs=16000, metrics=METRIC_ALL, mapped=True, seed=0,
+                           no_dither=False, stream=None, out=None):
+        """``nele_score_batch_pcm16``: host int16 arrays (or raw host pointers) of the clean, enhanced and noise
+        signals in the packed layout of :meth:`score_packed`; ``deg = enhanced + noise`` is formed on the device."""
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        n = int(lens.shape[0])
+        ptrs = []
+        for a in (clean, enhanced, noise):
+            if isinstance(a, np.ndarray):
+                if a.dtype != np.int16 or not a.flags.c_contiguous:
+                    raise ValueError("PCM-16 inputs must be contiguous int16 arrays")
+                ptrs.append(a.ctypes.data)
+            else:
+                ptrs.append(int(a))
+        flags = (FLAG_MAPPED if mapped else 0) | (FLAG_NO_DITHER if no_dither else 0)
+        if out is None:
+            scores, raw, status = np.empty((n, 3)), np.empty((n, 10)), np.empty(n, dtype=np.int32)
+        else:
+            scores, raw, status = out
+        rc = self._lib.nele_score_batch_pcm16(self._h, ptrs[0], ptrs[1], ptrs[2], offs.ctypes.data, lens.ctypes.data, n,
+                                              int(fs), metric_mask(metrics), flags, None, 0, int(seed) & (2 ** 64 - 1), None,
+                                              scores.ctypes.data, raw.ctypes.data, status.ctypes.data,
+                                              None if stream is None else int(stream))
+        self._check(rc, "nele_score_batch_pcm16")
+        return BatchResult(scores, raw, status)
+
+    def prefetch_pcm16(self, clean, enhanced, noise, offs, lens):
+        """Upload-ahead for :meth:`score_packed_pcm16` (``nele_prefetch_pcm16``)."""
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        p = [a.ctypes.data if isinstance(a, np.ndarray) else int(a) for a in (clean, enhanced, noise)]
+        self._check(self._lib.nele_prefetch_pcm16(self._h, p[0], p[1], p[2], offs.ctypes.data, lens.ctypes.data,
+                                                  int(lens.shape[0]), 0), "nele_prefetch_pcm16")
+
     def prefetch_cancel(self):
         """Drop pending prefetches (``nele_prefetch_cancel``)."""
         self._check(self._lib.nele_prefetch_cancel(self._h), "nele_prefetch_cancel")
@@ -295,7 +337,8 @@ class Engine:
             out.append(tuple(item))
         return out
 
-    def resyn(self, clean, noise, offs, lens, alpha2, arow=None, enh=None, deg=None, pcm16=True, stream=None):
+    def resyn(self, clean, noise, offs, lens, alpha2, arow=None, enh=None, deg=None, pcm16=True, enh_rounded=False,
+              stream=None):
         """``nele_resyn``: device pointers (ints) ``clean`` / ``noise`` / ``alpha2`` / ``enh`` / ``deg``; host ``offs``
         int64[n], ``lens`` int32[n], ``arow`` int64[n] (first row of each utterance in ``alpha2``; None = packed).
         Returns the valid output lengths ``256 * (lens // 256)`` (int32[n])."""
@@ -306,7 +349,7 @@ class Engine:
             arow = np.ascontiguousarray(arow, dtype=np.int64)
         rc = self._lib.nele_resyn(self._h, int(clean), None if noise is None else int(noise), offs.ctypes.data,
                                   lens.ctypes.data, int(lens.shape[0]), int(alpha2),
-                                  None if arow is None else arow.ctypes.data, 1 if pcm16 else 0,
+                                  None if arow is None else arow.ctypes.data, (1 if pcm16 else 0) | (2 if enh_rounded else 0),
                                   None if enh is None else int(enh), None if deg is None else int(deg),
                                   out_lens.ctypes.data, None if stream is None else int(stream))
         self._check(rc, "nele_resyn")
@@ -331,7 +374,7 @@ class Engine:
             i += 1
         return out
 
-    _STAGE_DTYPES = {"haspi.mid": np.float64, "haspi.x24": np.float32, "haspi.bw": np.float64,
+    _STAGE_DTYPES = {"haspi.mid": np.float32, "haspi.x24": np.float32, "haspi.bw": np.float64,
                      "haspi.shift": np.int32, "haspi.envlp": np.float32, "haspi.nsel": np.int32,
                      "haspi.cep": np.float32, "haspi.cepmean": np.float64, "estoi.x10": np.float32,
                      "haspi1.segsum": np.float32, "haspi1.cov": np.float32, "haspi1.msx": np.float32,

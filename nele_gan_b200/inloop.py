@@ -65,7 +65,7 @@ def resyn(X, alpha2):
 
 
 def label_sampling_round(alpha2, clean_wav, noise_wav, lengths=None, norm=True, pcm16=True, seed=0, strict=True,
-                         return_deg=False, **kw):
+                         return_deg=False, return_enh=False, **kw):
     """One sampling round (train_nele.py:286-322) on the device, through the engine's own kernels:
     ``nele_resyn`` (band gains -> ``interp_band_gain`` -> ``Resyn`` / ``librosa.istft`` -> PCM-16 rounding ->
     ``+ noise``, one launch for the whole round) and ``nele_score_batch`` on the device buffers.  No torch / cuFFT
@@ -80,8 +80,10 @@ def label_sampling_round(alpha2, clean_wav, noise_wav, lengths=None, norm=True, 
     Every utterance is resynthesised at its own length -- reflect padding at its own ends and
     ``256 * (length // 256)`` output samples, to which the reference trims both signals (audio_util.py:190-193) --
     exactly as the reference does one file at a time, so ragged rounds give the per-file numbers.
-    Returns float64 ``[n, 3]`` {SIIB, HASPI, ESTOI} like ``api.score_tensors`` (and the degraded waveforms
-    ``[n, L]`` plus their valid lengths when ``return_deg``)."""
+    Returns float64 ``[n, 3]`` {SIIB, HASPI, ESTOI} like ``api.score_tensors``; with ``return_deg`` /
+    ``return_enh`` a tuple ``(scores[, deg][, enh], out_lens)``: the degraded waveforms, the (PCM-16 rounded)
+    enhanced waveforms the discriminator's data loader reads back (dataloader.py:59) -- both ``[n, L]`` on the
+    device -- and their valid lengths."""
     import torch
     from . import api, engine as _eng
     if not (alpha2.is_cuda and clean_wav.is_cuda and noise_wav.is_cuda):
@@ -104,13 +106,14 @@ def label_sampling_round(alpha2, clean_wav, noise_wav, lengths=None, norm=True, 
     offs = np.arange(n, dtype=np.int64) * stride
     arow = np.arange(n, dtype=np.int64) * a2.shape[1]
     deg = torch.zeros_like(clean)
+    enh = torch.zeros_like(clean) if return_enh else None
     eng = _eng.default_engine(clean.device.index)
     torch.cuda.current_stream(clean.device).synchronize()  # the engine runs on its own stream
     out_lens = eng.resyn(clean.data_ptr(), noise.data_ptr(), offs, lens, a2.data_ptr(), arow=arow, deg=deg.data_ptr(),
-                         pcm16=pcm16)
+                         enh=None if enh is None else enh.data_ptr(), pcm16=pcm16, enh_rounded=pcm16)
     r = eng.score_packed(clean.data_ptr(), deg.data_ptr(), offs, out_lens, fs=16000, mapped=bool(norm), seed=seed,
                          device_input=True, **kw)
     scores = torch.from_numpy(api.check_status(r, strict=strict).scores)
-    if return_deg:
-        return scores, deg[:, :L], out_lens
+    if return_deg or return_enh:
+        return (scores,) + ((deg[:, :L],) if return_deg else ()) + ((enh[:, :L],) if return_enh else ()) + (out_lens,)
     return scores

@@ -219,3 +219,44 @@ def test_inloop_sampling_round_matches_the_file_based_reference_flow(api):
     # no torch / cuFFT kernel on the path: the round is two engine calls
     eng = __import__("nele_gan_b200.engine", fromlist=["default_engine"]).default_engine(0)
     assert eng.last_timing()[1] > 0
+
+
+def test_device_discriminator_dataset_matches_the_reference_loader_items(api):
+    """dataloader.py:54-84 without files: the items of DiscriminatorRoundDataset (views into three nele_features
+    outputs) against the per-utterance feature calls the reference's __getitem__ makes, and its records against
+    the string format the reference's loader parses."""
+    import torch
+    from nele_gan_b200 import inloop, features, records
+    from nele_gan_b200.dataset import DiscriminatorRoundDataset
+    from nele_gan_b200.synth import make_pair
+    lens = [33536, 40111]
+    n, L = len(lens), max(lens)
+    clean = np.zeros((n, L), np.float32)
+    noise = np.zeros((n, L), np.float32)
+    for i, l in enumerate(lens):
+        p = make_pair(90 + i, l)
+        clean[i, :l], noise[i, :l] = p[0], p[1] - p[0]
+    alpha2 = np.random.default_rng(9).uniform(0.5, 2.5, size=(n, 1 + L // 256, 64)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    tc, tn = torch.from_numpy(clean).to(dev), torch.from_numpy(noise).to(dev)
+    scores, enh, out_lens = inloop.label_sampling_round(torch.from_numpy(alpha2).to(dev), tc, tn, lengths=lens, norm=True,
+                                                        no_dither=True, return_enh=True)
+    ds = DiscriminatorRoundDataset.from_round(enh, tc, tn, lens, out_lens, scores.numpy(), names=["a@3.wav", "b@3.wav"])
+    assert len(ds) == n
+    enh_h = enh.cpu().numpy()
+    for i, l in enumerate(lens):
+        x3, x2, ts, tq = ds[i]
+        T = 1 + l // 256
+        assert x3.shape == (3, 64, T) and x2.shape == (2, 64, T) and x3.is_cuda
+        eb = features.Sp_and_phase_Speech(enh_h[i, :out_lens[i]], features.power_law)[0]
+        nb = features.Sp_and_phase_Noise(noise[i, :l], features.power_law)[0]
+        cb = features.Sp_and_phase_Speech(clean[i, :l], features.power_law)[0]
+        want3 = np.stack((eb.T, nb.T, cb.T))
+        assert np.array_equal(x3.cpu().numpy(), want3)                    # same kernels, batch vs single call
+        assert np.array_equal(x2.cpu().numpy(), np.stack((eb.T, cb.T)))
+        assert np.allclose(ts.cpu().numpy(), scores.numpy()[i].astype(np.float32)) and tq.abs().sum().item() == 0
+        # the enhanced signal the loader sees is what a PCM-16 file would hold
+        assert np.array_equal(np.round(enh_h[i, :out_lens[i]] * 32768.0), enh_h[i, :out_lens[i]] * 32768.0)
+    rec = ds.records()
+    ts, tq, path = records.parse_record(rec[1])
+    assert path == "b@3.wav" and np.allclose(ts, scores.numpy()[1].astype(np.float32))

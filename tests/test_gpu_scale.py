@@ -94,3 +94,89 @@ def test_prefetch_gives_identical_results_and_mismatches_are_ignored(eng):
     assert same(c.scores, base.scores[:3])
     d = eng.score_packed(fr, fd, offs, lens, mapped=False, no_dither=True)
     assert same(d.scores, base.scores)
+
+
+def _sharded_worker(rank, world, port, ngpu, q):
+    """One rank of score_sharded on a real engine: NCCL when every rank has its own GPU, else both ranks share
+    GPU 0 and the records travel over gloo (the data path is the same: partition -> score -> gather -> un-permute)."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from nele_gan_b200 import shard
+    from nele_gan_b200.engine import Engine
+    from nele_gan_b200.synth import make_pair
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    own_gpu = ngpu >= world
+    dev = rank if own_gpu else 0
+    torch.cuda.set_device(dev)
+    if own_gpu:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    lens = [32001, 47999, 56789, 40411, 35555, 61003, 33536]
+    pairs = [make_pair(400 + i, L)[:2] for i, L in enumerate(lens)]
+    refs, degs = [p[0] for p in pairs], [p[1] for p in pairs]
+    eng = Engine(dev)
+    full = shard.score_sharded(lambda a, b: eng.score_batch(a, b, mapped=False, no_dither=True), refs, degs,
+                               device=torch.device("cuda", dev) if own_gpu else None)
+    if rank == 0:
+        want = shard.pack_records(eng.score_batch(refs, degs, mapped=False, no_dither=True))
+        q.put((full.tolist(), want.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_score_sharded_two_ranks_on_real_engines_restores_input_order():
+    """BASELINE configs[4]'s data path at world size 2: the length-sorted deal, one engine per rank, the gather and
+    the un-permute must give exactly what one engine gives for the whole ragged batch, in input order."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ngpu = torch.cuda.device_count()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, ngpu, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full, want = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+    full, want = np.asarray(full), np.asarray(want)
+    assert full.shape == want.shape == (7, 14)
+    assert np.array_equal(full[:, 13], want[:, 13])                            # status words
+    assert np.allclose(full[:, :13], want[:, :13], rtol=1e-6, atol=1e-9)       # batch composition moves FP32 sums by ~1e-9
+
+
+def test_pcm16_host_inputs_are_bit_identical_to_the_float_path(eng):
+    """nele_score_batch_pcm16: clean / enhanced / noise as the int16 samples of the reference's WAV files, deg formed
+    on the device -- the same scores as the float call on librosa-style conversions, with and without a prefetch."""
+    from nele_gan_b200.engine import pack
+    from nele_gan_b200.synth import make_pair
+    lens = [33536, 34048, 40111, 16001]
+    c16, e16, n16 = [], [], []
+    for i, L in enumerate(lens):
+        x, y, _ = make_pair(500 + i, L)
+        c = np.clip(np.round(x * 32768 * 8), -32768, 32767).astype(np.int16)         # RMS 0.03 * 8: uses the 16-bit range
+        nz = np.clip(np.round((y - x) * 32768 * 8), -32768, 32767).astype(np.int16)
+        en = np.clip(np.round(0.8 * x * 32768 * 8), -32768, 32767).astype(np.int16)
+        c16.append(c), e16.append(en), n16.append(nz)
+    refs = [c.astype(np.float32) / 32768.0 for c in c16]
+    degs = [e.astype(np.float32) / 32768.0 + n.astype(np.float32) / 32768.0 for e, n in zip(e16, n16)]
+    want = eng.score_batch(refs, degs, mapped=False, no_dither=True)
+    padded = (np.array(lens, dtype=np.int64) + 7) // 8 * 8
+    offs = np.concatenate(([0], np.cumsum(padded)[:-1])).astype(np.int64)
+    flat = [np.zeros(int(padded.sum()), np.int16) for _ in range(3)]
+    for k, arrs in enumerate((c16, e16, n16)):
+        for a, o in zip(arrs, offs):
+            flat[k][o:o + len(a)] = a
+    got = eng.score_packed_pcm16(flat[0], flat[1], flat[2], offs, np.array(lens, np.int32), mapped=False, no_dither=True)
+    same = lambda u, v: np.allclose(u, v, rtol=1e-7, atol=0, equal_nan=True)     # run-to-run noise of FP32 atomics ~1e-9
+    assert same(got.scores, want.scores) and np.array_equal(got.status, want.status)
+    eng.prefetch_pcm16(flat[0], flat[1], flat[2], offs, np.array(lens, np.int32))
+    again = eng.score_packed_pcm16(flat[0], flat[1], flat[2], offs, np.array(lens, np.int32), mapped=False, no_dither=True)
+    assert same(again.scores, want.scores)
