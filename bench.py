@@ -570,6 +570,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e, ms_e2e_blocking, ms_e2e_f32 = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     ok = int(np.sum((r.status & 0xFFFFFF) == 0))
+    nulldrop = int(np.sum((r.status & 0x01000000) != 0))   # (the general-case runs below reuse the output arrays)
 
     # ---- general case: the same step on pairs whose length is not a multiple of SIIB's 200-sample hop
     general = None
@@ -674,7 +675,7 @@ def main():
                          "siib_klt_frames": Nf, "siib_rank": rank_x},
             "kernels_ms_per_step": {k: round(v[0] / a.steps, 3) for k, v in sorted(kt_sum.items(), key=lambda kv: -kv[1][0])},
             "pairs_ok": ok,
-            "pairs_siib_nullspace_dropped": int(np.sum((r.status & 0x01000000) != 0)),
+            "pairs_siib_nullspace_dropped": nulldrop,
         }
         if general is not None:
             line["general_case"] = general

@@ -204,6 +204,7 @@ int siib_launch_tridiag32(const SiibBuffers& b, const SiibEigBuffers& eb, int n,
 // back-transformation with the reflectors applied four at a time (siib_klt.cu): same inputs / output as siib_backtf_kernel
 int siib_launch_backtf4(const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, cudaStream_t s);
 int siib_launch_backtf5(const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, cudaStream_t s);  // 14 x 4 register tile per lane
+int siib_launch_backtf6(const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, cudaStream_t s);  // warp = 4 vectors over all rows
 // register-tiled quadratic forms + score (siib_klt.cu); info_part: [n_chunk][8] doubles of scratch
 int siib_launch_quadform(const SiibBuffers& b, double* info_part, int n, KernelTimer* kt, cudaStream_t s);
 void siib_upload_tables(const float* win, const float* decay, const float* g2t, const float* tw, cudaStream_t s);

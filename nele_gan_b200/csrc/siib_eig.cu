@@ -502,8 +502,10 @@ int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& 
   if (bt_old) siib_backtf_kernel<<<dim3((kEDim + kBtVec - 1) / kBtVec, n), kBtThreads, 0, s>>>(g, b, eb, rank_lo);
   else {
     static const bool bt4 = [] { const char* p = getenv("NELE_BACKTF4"); return p && p[0] == '1'; }();  // A/B: one vector per lane
+    static const bool bt5 = [] { const char* p = getenv("NELE_BACKTF5"); return p && p[0] == '1'; }();  // A/B: row parts over the CTA
     if (bt4) siib_launch_backtf4(b, eb, n, rank_lo, s);
-    else siib_launch_backtf5(b, eb, n, rank_lo, s);
+    else if (bt5) siib_launch_backtf5(b, eb, n, rank_lo, s);
+    else siib_launch_backtf6(b, eb, n, rank_lo, s);
   }
   kt_end(kt, s);
   kt_begin(kt, "siib_eig_finish", s);

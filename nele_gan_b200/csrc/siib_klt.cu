@@ -37,18 +37,23 @@ namespace nele {
 namespace klt {
 
 constexpr int N = 420, LD = 448, NT = 384, NW = NT / 32, PB = 8, RG = 16, CB = 64;
-constexpr int NE = (LD + NT - 1) / NT;  // vector elements per thread (j = tid, tid + 256)
+constexpr int NE = (LD + NT - 1) / NT;  // vector elements per thread (j = tid, tid + NT)
+constexpr int LC = 424;                 // pitch of the panel-column buffer (rows < N only)
 constexpr int JMAX = (N - 1) / RG;      // last row group
 
 struct Smem {
   float V[PB][LD];     // Householder vectors of the panel
   float W[PB][LD];
-  float col[PB][LD];   // the panel's columns as of the start of the panel (rows >= column index)
+  float col[PB][LC];   // the panel's columns as of the start of the panel (rows >= column index)
   float pw[NW][LD];    // per-warp partial products
-  float Vt[LD][PB];    // V, W transposed for the trailing update (one 32-byte row per matrix row)
-  float Wt[LD][PB];
+  union {
+    struct {
+      float Vt[LD][PB];  // V, W transposed for the trailing update (one 32-byte row per matrix row)
+      float Wt[LD][PB];
+    };
+    float tile[NW][RG][CB];  // matvec phase: the tile each warp has in flight (cp.async), 4 KB per warp
+  };
   float diag[LD];      // diagonal of the matrix as of the start of the panel
-  float part[NW][2 * PB];
   float tot[2 * PB];
   float red[NW];
   float alpha;
@@ -83,15 +88,21 @@ __constant__ int c_ntiles[JMAX + 1];
 // never by the update), so a diagonal tile is an ordinary tile whose only flaw is that A[j][j] v[j] enters p[j] twice
 // (column part and row part) -- the caller subtracts it once (Smem::diag).  The first version masked every element of
 // the diagonal tiles: 422 instead of 188 instructions for 30 % of the tiles.
-__device__ __forceinline__ void mv_tile(const float* __restrict__ A, const float* __restrict__ v, float* __restrict__ pw, int J, int C,
+// start the copy of tile (J, C) into this warp's shared-memory slot: 256 chunks of 16 bytes, eight per lane
+__device__ __forceinline__ void tile_fetch(const float* __restrict__ A, float (*tile)[CB], int J, int C, int lane) {
+  const float* __restrict__ src = A + (size_t)(RG * J) * LD + CB * C;
+#pragma unroll
+  for (int i = 0; i < RG * CB / 4 / 32; ++i) {
+    const int id = lane + 32 * i, row = id >> 4, c4 = id & 15;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(&tile[row][4 * c4]);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + (size_t)row * LD + 4 * c4) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void mv_tile(const float2 (&a)[RG], const float* __restrict__ v, float* __restrict__ pw, int J, int C,
                                         int lane) {
   const int j0 = RG * J, c0 = CB * C + 2 * lane;
-  float2 a[RG];
-  {
-    const float2* __restrict__ p = reinterpret_cast<const float2*>(A + (size_t)j0 * LD + c0);
-#pragma unroll
-    for (int r = 0; r < RG; ++r) a[r] = __ldcg(p + r * (LD / 2));
-  }
   const float2 vc = *reinterpret_cast<const float2*>(v + c0);
   float acc0 = 0.f, acc1 = 0.f;
   float t[RG];
@@ -190,7 +201,7 @@ __device__ __forceinline__ void up_tile(float* __restrict__ A, Smem& s, int J, i
           if (c0 == j) s.diag[j] = ax;
           if (c0 + 1 == j) s.diag[j] = ay;
         }
-        if (tocol) {
+        if (tocol && j < N) {
           s.col[c0 - kn][j] = ax;
           if (both) s.col[c0 + 1 - kn][j] = ay;
         }
@@ -234,8 +245,8 @@ __global__ void __launch_bounds__(NT, 2) tridiag32_kernel(SiibBuffers b, SiibEig
     for (int j = tid; j < LD; j += NT) s.diag[j] = (j < N) ? (float)S[(int64_t)j * N + j] : 0.f;
     for (int idx = tid; idx < (RG * (JMAX + 1) - N) * LD; idx += NT) A[(size_t)N * LD + idx] = 0.f;   // pad rows 420 .. 431
     // columns of the first panel = rows of the symmetric input
-    for (int idx = tid; idx < PB * LD; idx += NT) {
-      const int q = idx / LD, j = idx % LD;
+    for (int idx = tid; idx < PB * LC; idx += NT) {
+      const int q = idx / LC, j = idx % LC;
       s.col[q][j] = (j < N) ? (float)S[(int64_t)q * N + j] : 0.f;
     }
     __syncthreads();
@@ -290,40 +301,54 @@ __global__ void __launch_bounds__(NT, 2) tridiag32_kernel(SiibBuffers b, SiibEig
           ee[k] = (double)beta;
           tt[k] = (double)tau;
         }
-        // dot products of v with the panel's earlier vectors (for the corrections of p below)
-        for (int mm = 0; mm < m; ++mm) {
-          float aw = 0.f, av = 0.f;
-#pragma unroll
-          for (int e = 0; e < NE; ++e) {
-            const int j = tid + e * NT;
-            if (j < LD) {
-              aw = fmaf(s.W[mm][j], vi[e], aw);
-              av = fmaf(s.V[mm][j], vi[e], av);
-            }
-          }
-          aw = warp_sum(aw);
-          av = warp_sum(av);
-          if (lane == 0) {
-            s.part[wib][2 * mm] = aw;
-            s.part[wib][2 * mm + 1] = av;
-          }
-        }
         // this warp's partial product vector starts at zero
 #pragma unroll
         for (int i = 0; i < LD / 32; ++i) s.pw[wib][lane + 32 * i] = 0.f;
         __syncthreads();
         if (tau != 0.f) {
-          if (tid < 2 * m) {
-            float t = 0.f;
+          // dot products of v with the panel's earlier vectors (for the corrections of p below): one warp -- the last,
+          // which gets the fewest tiles -- does all 2 m of them while the others start on their tiles
+          if (wib == NW - 1 && m > 0) {
+            float vm[LD / 32];
 #pragma unroll
-            for (int w = 0; w < NW; ++w) t += s.part[w][tid];
-            s.tot[tid] = t;
+            for (int i = 0; i < LD / 32; ++i) vm[i] = s.V[m][lane + 32 * i];
+            for (int mm = 0; mm < m; ++mm) {
+              float aw = 0.f, av = 0.f;
+#pragma unroll
+              for (int i = 0; i < LD / 32; ++i) {
+                aw = fmaf(s.W[mm][lane + 32 * i], vm[i], aw);
+                av = fmaf(s.V[mm][lane + 32 * i], vm[i], av);
+              }
+              aw = warp_sum(aw);
+              av = warp_sum(av);
+              if (lane == 0) {
+                s.tot[2 * mm] = aw;
+                s.tot[2 * mm + 1] = av;
+              }
+            }
           }
           // ---- p = A v over the trailing lower triangle
+          // Each warp keeps one tile in flight: the copy of its next tile (cp.async, global -> its 4 KB slot) runs while
+          // it multiplies the current one from registers.  Loading a tile straight into registers left the L2 latency
+          // exposed once per tile (ncu: 2.8 of 9.8 stall cycles per instruction on the long scoreboard).
           const int jm = (k + 1) / RG, nt = c_ntiles[jm];
+          if (wib < nt) {
+            const int code = c_tiles[jm][wib];
+            tile_fetch(A, s.tile[wib], code >> 3, code & 7, lane);
+          }
           for (int t = wib; t < nt; t += NW) {
             const int code = c_tiles[jm][t], J = code >> 3, C = code & 7;
-            mv_tile(A, s.V[m], s.pw[wib], J, C, lane);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            float2 a[RG];
+#pragma unroll
+            for (int r = 0; r < RG; ++r) a[r] = *reinterpret_cast<const float2*>(&s.tile[wib][r][2 * lane]);
+            __syncwarp();
+            if (t + NW < nt) {
+              const int nc = c_tiles[jm][t + NW];
+              tile_fetch(A, s.tile[wib], nc >> 3, nc & 7, lane);
+            }
+            mv_tile(a, s.V[m], s.pw[wib], J, C, lane);
           }
         }
         __syncthreads();
@@ -987,6 +1012,208 @@ int siib_launch_backtf5(const SiibBuffers& b, const SiibEigBuffers& eb, int n, i
   }();
   (void)attr;
   bt5::backtf5_kernel<<<dim3((bt5::N + bt5::VEC - 1) / bt5::VEC, n), bt5::NT, smem, s>>>(b, eb, rank_lo);
+  return 1;
+}
+
+// ---- warp-independent form: a warp owns four eigenvectors over ALL rows
+// backtf5 still meets at a block barrier once per group of four reflectors (its 32 row parts are spread over the eight
+// warps), and with 16 warps per SM that barrier and the shared-memory exchange of the partial dot products leave the
+// kernel latency bound (ncu: 54 % issue slots, FMA pipe 33 %, neither the shared-memory nor the FMA pipe saturated).
+// Here lane l of a warp holds rows {64 p + 2 l, 64 p + 2 l + 1 : p < 7} of the warp's four vectors (the same 14 x 4
+// register tile, as f32x2 row pairs): the dot products of a group are reduced inside the warp (a 16-value transposed
+// shuffle reduction and a 16-shuffle all-gather), so warps never wait for each other except when the staged panel
+// is swapped.  The staged reflectors keep their natural order: 16-byte cp.async, 64-bit conflict-free loads.
+namespace bt6 {
+
+constexpr int N = 420, LD = 448, NW = 8, NT = NW * 32, C = 4, VEC = NW * C, NP = 7, PANEL = 16, GRP = 4;
+
+__global__ void __launch_bounds__(NT, 2) backtf6_kernel(SiibBuffers b, SiibEigBuffers eb, int rank_lo) {
+  const int lp = blockIdx.y, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int rk = b.rank[pair];
+  if (rk < rank_lo) return;
+  const int j0 = blockIdx.x * VEC + C * w;
+  extern __shared__ __align__(16) float s_vbuf[];   // [2][PANEL][LD]
+  __shared__ float s_tau[2][PANEL];
+  __shared__ float s_g[2][PANEL / GRP][8];
+  const float* __restrict__ R = eb.refl + (int64_t)lp * N * LD;
+  const double* __restrict__ tt = eb.tau + (int64_t)lp * LD;
+  auto stage = [&](int k1, int buf) {
+    const int nk = min(PANEL, k1 + 1);
+    float* dst = s_vbuf + (size_t)buf * PANEL * LD;
+    for (int idx = tid; idx < PANEL * (LD / 4); idx += NT) {
+      const int kk = idx / (LD / 4), i4 = idx % (LD / 4);
+      float* d = dst + kk * LD + 4 * i4;
+      if (kk < nk) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(R + (int64_t)(k1 - kk) * LD + 4 * i4) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(N - 3, 0);
+  F2 u[NP][C];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int i0 = 64 * p + 2 * lane;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const bool okj = j0 + c < N;
+      const float lo = (okj && i0 < N) ? eb.zt[((int64_t)lp * N + i0) * LD + j0 + c] : 0.f;
+      const float hi = (okj && i0 + 1 < N) ? eb.zt[((int64_t)lp * N + i0 + 1) * LD + j0 + c] : 0.f;
+      u[p][c] = f2_pack(lo, hi);
+    }
+  }
+  const unsigned full = 0xffffffffu;
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+  int buf = 0;
+  for (int k1 = N - 3; k1 >= 0; k1 -= PANEL, buf ^= 1) {
+    const int nk = min(PANEL, k1 + 1);
+    __syncthreads();                                        // every warp is done with the other buffer
+    if (k1 - PANEL >= 0) {
+      stage(k1 - PANEL, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    if (tid < PANEL) s_tau[buf][tid] = (tid < nk) ? (float)tt[k1 - tid] : 0.f;
+    __syncthreads();
+    const float* s_v = s_vbuf + (size_t)buf * PANEL * LD;
+    // Gram values inside each group of four reflectors: 24 dot products, three per warp
+    for (int d = w; d < (PANEL / GRP) * 6; d += NW) {
+      const int g = d / 6, e = d % 6;
+      const int qa = (e == 0) ? 1 : (e < 3) ? 2 : 3;
+      const int qb = (e == 0) ? 0 : (e == 1) ? 0 : (e == 2) ? 1 : e - 3;
+      const float* va = s_v + (GRP * g + qa) * LD;
+      const float* vb = s_v + (GRP * g + qb) * LD;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < LD / 32; ++i) acc = fmaf(va[lane + 32 * i], vb[lane + 32 * i], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) s_g[buf][g][e] = acc;
+    }
+    __syncthreads();
+    for (int g = 0; g < PANEL / GRP; ++g) {
+      const int kk0 = GRP * g;
+      if (kk0 >= nk) break;
+      // rows <= kmin are zero in every reflector of the group: row pairs with 64 p + 63 <= kmin are skipped
+      const int kmin = max(k1 - kk0 - (GRP - 1), 0);
+      const int p0 = (kmin + 1) >> 6;
+      const float2* vq[GRP];
+#pragma unroll
+      for (int q = 0; q < GRP; ++q) vq[q] = reinterpret_cast<const float2*>(s_v + (kk0 + q) * LD) + lane;
+      F2 d2[GRP][C];
+#pragma unroll
+      for (int q = 0; q < GRP; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) d2[q][c] = f2_pack(0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        if (p < p0) continue;
+#pragma unroll
+        for (int q = 0; q < GRP; ++q) {
+          const float2 a = vq[q][32 * p];
+          const F2 a2 = f2_pack(a.x, a.y);
+#pragma unroll
+          for (int c = 0; c < C; ++c) d2[q][c] = f2_fma(a2, u[p][c], d2[q][c]);
+        }
+      }
+      // 16 partial dot products per lane -> totals in every lane: transposed reduction (lane l ends with value
+      // (l >> 1) & 15 summed over the warp), then an all-gather
+      float t[16];
+#pragma unroll
+      for (int q = 0; q < GRP; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          float lo, hi;
+          f2_unpack(d2[q][c], lo, hi);
+          t[q * C + c] = lo + hi;
+        }
+      float u8[8], u4[4], u2[2], u1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float mine = b4 ? t[i + 8] : t[i], other = b4 ? t[i] : t[i + 8];
+        u8[i] = mine + __shfl_xor_sync(full, other, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float mine = b3 ? u8[i + 4] : u8[i], other = b3 ? u8[i] : u8[i + 4];
+        u4[i] = mine + __shfl_xor_sync(full, other, 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float mine = b2 ? u4[i + 2] : u4[i], other = b2 ? u4[i] : u4[i + 2];
+        u2[i] = mine + __shfl_xor_sync(full, other, 4);
+      }
+      {
+        const float mine = b1 ? u2[1] : u2[0], other = b1 ? u2[0] : u2[1];
+        u1 = mine + __shfl_xor_sync(full, other, 2);
+      }
+      u1 += __shfl_xor_sync(full, u1, 1);
+      float D[GRP][C];
+#pragma unroll
+      for (int q = 0; q < GRP; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) D[q][c] = __shfl_sync(full, u1, 2 * (q * C + c));
+      const float g10 = s_g[buf][g][0], g20 = s_g[buf][g][1], g21 = s_g[buf][g][2], g30 = s_g[buf][g][3], g31 = s_g[buf][g][4],
+                  g32 = s_g[buf][g][5];
+      const float tau0 = s_tau[buf][kk0], tau1 = s_tau[buf][kk0 + 1], tau2 = s_tau[buf][kk0 + 2], tau3 = s_tau[buf][kk0 + 3];
+      F2 ny[GRP][C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float y0 = tau0 * D[0][c];
+        const float y1 = tau1 * (D[1][c] - y0 * g10);
+        const float y2 = tau2 * (D[2][c] - y0 * g20 - y1 * g21);
+        const float y3 = tau3 * (D[3][c] - y0 * g30 - y1 * g31 - y2 * g32);
+        ny[0][c] = f2_pack(-y0, -y0);
+        ny[1][c] = f2_pack(-y1, -y1);
+        ny[2][c] = f2_pack(-y2, -y2);
+        ny[3][c] = f2_pack(-y3, -y3);
+      }
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        if (p < p0) continue;
+#pragma unroll
+        for (int q = 0; q < GRP; ++q) {
+          const float2 a = vq[q][32 * p];
+          const F2 a2 = f2_pack(a.x, a.y);
+#pragma unroll
+          for (int c = 0; c < C; ++c) u[p][c] = f2_fma(ny[q][c], a2, u[p][c]);
+        }
+      }
+    }
+  }
+  // column j of G = sqrt(lambda_j) u_j / |z_j| (see backtf4_kernel for the thresholds)
+  const double lmax = eb.lam[(int64_t)lp * LD + N - 1];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int j = j0 + c;
+    if (j >= N) continue;
+    const double lam = eb.lam[(int64_t)lp * LD + j], nz = eb.znorm[(int64_t)lp * LD + j];
+    const bool in_range = j >= N - rk;
+    const float sc = (in_range && lam > 1.0e-10 * lmax && nz > 0.0) ? (float)sqrt(lam / nz) : 0.f;
+    float* __restrict__ G = b.G + (int64_t)lp * N * LD + (int64_t)j * LD;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      float lo, hi;
+      f2_unpack(u[p][c], lo, hi);
+      const int i0 = 64 * p + 2 * lane;
+      *reinterpret_cast<float2*>(G + i0) = make_float2(i0 < N ? sc * lo : 0.f, i0 + 1 < N ? sc * hi : 0.f);
+    }
+  }
+}
+
+}  // namespace bt6
+
+int siib_launch_backtf6(const SiibBuffers& b, const SiibEigBuffers& eb, int n, int rank_lo, cudaStream_t s) {
+  constexpr int smem = 2 * bt6::PANEL * bt6::LD * (int)sizeof(float);
+  static const bool attr = [] {
+    cudaFuncSetAttribute(bt6::backtf6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return true;
+  }();
+  (void)attr;
+  bt6::backtf6_kernel<<<dim3((bt6::N + bt6::VEC - 1) / bt6::VEC, n), bt6::NT, smem, s>>>(b, eb, rank_lo);
   return 1;
 }
 
