@@ -51,14 +51,10 @@ __device__ __forceinline__ void householder(double x, double alpha, double sig, 
   vi = (tid == k + 1) ? 1.0 : (tid > k + 1 && own) ? x / (alpha - beta) : 0.0;
 }
 
-// mv32 (experimental, NELE_TRIDIAG_MV32=1, off by default): from the second panel on the matrix-vector pass reads
-// an FP32 copy of the trailing matrix (written by the panel update next to the FP64 master, in the rows of eb.refl
-// that hold no reflector yet: row j > k is trailing matrix, row <= k is reflector) and accumulates in FP64 -- half
-// the bytes of the pass that bounds this kernel.  Row k itself (the Householder vector) always comes from the FP64
-// master.  CPU prototype (scripts/exp_tridiag_eig.py with the FP32-rounded matvec): SIIB moves by 6e-8 .. 6e-7
-// relative, eigen-residual 4e-10 of lambda_max.
-__global__ void __launch_bounds__(kEThreads, 3) siib_tridiag_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_lo, int n_pairs,
-                                                                     int mv32) {
+// (Round 2 measured a variant whose matrix-vector pass read an FP32 copy of the trailing matrix, NELE_TRIDIAG_MV32:
+// 55.0 -> 49.5 ms per 1024 pairs, SIIB equal to 3e-7.  The all-FP32 lower-triangle kernel of siib_klt.cu -- 13.9 ms --
+// superseded it and it was removed; this FP64 kernel stays as the A/B reference behind NELE_TRIDIAG_F64=1.)
+__global__ void __launch_bounds__(kEThreads, 3) siib_tridiag_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_lo, int n_pairs) {
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   constexpr int NW = kEThreads / 32;
   // persistent CTAs: the grid is sized so that the work matrices of the resident CTAs fit in the L2
@@ -105,27 +101,7 @@ __global__ void __launch_bounds__(kEThreads, 3) siib_tridiag_kernel(SiibGeom g, 
       __syncthreads();
       // p = S_panel v: one coalesced read-only pass over rows j > k
       double p = 0.0;
-      if (own && tid > k && mv32 && k0 > 0) {
-        const float* col = eb.refl + (int64_t)lp * kEDim * kELd + tid;   // FP32 copy of the panel-start matrix, rows > k
-        const double* __restrict__ v = sV + m * kELd;
-        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-        int j = k + 1;
-        for (; j + 8 <= kEDim; j += 8) {
-          float a[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) a[u] = __ldcg(col + (int64_t)(j + u) * kELd);
-          p0 = fma((double)a[0], v[j], p0);
-          p1 = fma((double)a[1], v[j + 1], p1);
-          p2 = fma((double)a[2], v[j + 2], p2);
-          p3 = fma((double)a[3], v[j + 3], p3);
-          p0 = fma((double)a[4], v[j + 4], p0);
-          p1 = fma((double)a[5], v[j + 5], p1);
-          p2 = fma((double)a[6], v[j + 6], p2);
-          p3 = fma((double)a[7], v[j + 7], p3);
-        }
-        for (; j < kEDim; ++j) p0 = fma((double)__ldcg(col + (int64_t)j * kELd), v[j], p0);
-        p = (p0 + p1) + (p2 + p3);
-      } else if (own && tid > k) {
+      if (own && tid > k) {
         const double* col = Ain + tid;
         const double* __restrict__ v = sV + m * kELd;
         double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
@@ -185,17 +161,11 @@ __global__ void __launch_bounds__(kEThreads, 3) siib_tridiag_kernel(SiibGeom g, 
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) A[(int64_t)(j + u) * kEDim + tid] = a[u];
-        if (mv32) {
-          float* Af = eb.refl + (int64_t)lp * kEDim * kELd + tid;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) Af[(int64_t)(j + u) * kELd] = (float)a[u];
-        }
       }
       for (; j < kEDim; ++j) {
         double a = Ain[(int64_t)j * kEDim + tid];
         for (int mm = 0; mm < nb; ++mm) a -= sV[mm * kELd + j] * sW[mm * kELd + tid] + sW[mm * kELd + j] * sV[mm * kELd + tid];
         A[(int64_t)j * kEDim + tid] = a;
-        if (mv32) eb.refl[((int64_t)lp * kEDim + j) * kELd + tid] = (float)a;
       }
     }
     __syncthreads();
@@ -490,8 +460,7 @@ int siib_run_eig(const SiibGeom& g, const SiibBuffers& b, const SiibEigBuffers& 
   }();
   (void)tri_attr;
   static const int tri_grid = [] { const char* p = getenv("NELE_TRIDIAG_GRID"); return p ? atoi(p) : 1 << 30; }();
-  static const int tri_mv32 = [] { const char* p = getenv("NELE_TRIDIAG_MV32"); return (p && p[0] == '1') ? 1 : 0; }();
-  siib_tridiag_kernel<<<std::min(n, tri_grid), kEThreads, 2 * kTriB * kELd * sizeof(double), s>>>(g, b, eb, rank_lo, n, tri_mv32);
+  siib_tridiag_kernel<<<std::min(n, tri_grid), kEThreads, 2 * kTriB * kELd * sizeof(double), s>>>(g, b, eb, rank_lo, n);
   }
   kt_end(kt, s);
   kt_begin(kt, "siib_trieig", s);

@@ -1,4 +1,4 @@
-"""A/B of the experimental switches in one go: for each configuration a fresh process
+"""A/B of the kernel switches in one go: for each configuration a fresh process
 (the switches are read once per process) scores the same batch, prints per-kernel CUDA-event times and the
 largest score deviation from the default configuration.
 usage: ab_switches.py [n] [L]      (needs a B200; e.g. 4096 48000 for the bench workload, 1024 52345 for full rank)"""
@@ -7,9 +7,10 @@ import os
 import subprocess
 import sys
 
-CONFIGS = [("default", {}), ("f32x2", {"NELE_F32X2": "1"}), ("resample_f32", {"NELE_RESAMPLE_F32": "1"}),
-           ("tridiag_mv32", {"NELE_TRIDIAG_MV32": "1"}),
-           ("all", {"NELE_F32X2": "1", "NELE_RESAMPLE_F32": "1", "NELE_TRIDIAG_MV32": "1"})]
+# every configuration is one set of environment switches of DESIGN.md section 9 (A/B references of the round-2 defaults)
+CONFIGS = [("default", {}), ("ear_scalar", {"NELE_F32X2": "0"}), ("resample_f64", {"NELE_RESAMPLE_F32": "0"}),
+           ("tridiag_f64", {"NELE_TRIDIAG_F64": "1"}), ("backtf_old", {"NELE_BACKTF_OLD": "1"}),
+           ("backtf4", {"NELE_BACKTF4": "1"}), ("backtf5", {"NELE_BACKTF5": "1"}), ("quad_old", {"NELE_SIIB_QUAD_OLD": "1"})]
 
 CHILD = r'''
 import json, sys

@@ -15,7 +15,9 @@ def engine_name(fn):
     n = n.split('<')[0]
     if n.endswith('_kernel'):
         n = n[:-7]
-    return {'haspi_modcorr2': 'haspi_modcorr'}.get(n, n)
+    return {'haspi_modcorr2': 'haspi_modcorr', 'haspi_ear_x2': 'haspi_ear', 'estoi_resample58': 'estoi_resample',
+            'klt::tridiag32': 'siib_tridiag', 'bt6::backtf6': 'siib_backtf', 'bt5::backtf5': 'siib_backtf',
+            'bt::backtf4': 'siib_backtf', 'qf::quadform': 'siib_quad', 'qf::quad_finish': 'siib_quad_finish'}.get(n, n)
 
 
 def main(path, pairs, seconds, out):

@@ -260,3 +260,32 @@ def test_device_discriminator_dataset_matches_the_reference_loader_items(api):
     rec = ds.records()
     ts, tq, path = records.parse_record(rec[1])
     assert path == "b@3.wav" and np.allclose(ts, scores.numpy()[1].astype(np.float32))
+
+
+def _pool_task(i, L):
+    """One task of the reference's fan-out (audio_util.py:146): a loky worker process scoring one pair through the
+    zero-edit shims -- `from pystoi.stoi import stoi` etc. resolve to the engine-backed drop-ins."""
+    import sys
+    import nele_gan_b200.api as nele
+    if nele.dropin_path() not in sys.path:
+        sys.path.insert(0, nele.dropin_path())
+    from pyHASPI.pyhaspi2 import haspi_v2
+    from pystoi.stoi import stoi
+    from nele_gan_b200.synth import make_pair
+    x, y, _ = make_pair(600 + i, L)
+    return float(haspi_v2(x, 16000, y, 16000, seed=5)[0]), float(stoi(x, y, 16000, extended=True))
+
+
+def test_dropin_shims_under_the_reference_process_pool(api):
+    """The zero-edit adoption path under the reference's own `Parallel(n_jobs=...)` (audio_util.py:146,174,202): every
+    loky worker builds its own engine (CUDA context + workspace) on the GPU and scores one pair per call; the results
+    must equal what the parent process gets for the same pairs."""
+    from joblib import Parallel, delayed
+    from nele_gan_b200.synth import make_pair
+    Ls = [24000, 31999, 33536, 28001, 40111, 26000]
+    got = Parallel(n_jobs=3)(delayed(_pool_task)(i, L) for i, L in enumerate(Ls))
+    for i, L in enumerate(Ls):
+        x, y, _ = make_pair(600 + i, L)
+        h = api.haspi_v2(x, 16000, y, 16000, seed=5)[0]
+        e = api.stoi(x, y, 16000, extended=True)
+        assert abs(got[i][0] - h) < 1e-9 and abs(got[i][1] - e) < 1e-12
