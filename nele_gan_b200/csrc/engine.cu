@@ -79,6 +79,7 @@ struct nele_engine {
   DevBuf in_ref[2], in_deg[2], geom, sgeom, dither;  // inputs double-buffered: chunk k + 1 uploads while chunk k computes
   DevBuf in_pcm[2][3];                               // int16 staging of nele_score_batch_pcm16 (clean, enhanced, noise)
   const int16_t* pcm_noise = nullptr;                // set while a PCM-16 call runs: upload_chunk takes (clean, enhanced, noise) int16
+  size_t pcm_elems[2] = {0, 0};                      // samples staged as int16 in each slot
   DevBuf x24, mid, bw, shift, envlp, rowsel, nsel, cep, cepmean, modsum;            // HASPI
   DevBuf v1_bm, v1_segsum, v1_cov, v1_msx, v1_xsum, v1_cepcorr, v1_cov3, v1_status, v1_cave, v1_ave, v1_sync5;  // HASPI version 1
   DevBuf x10, st_energy, st_kept, st_nkept, st_tob;                                 // ESTOI
@@ -480,10 +481,9 @@ static int upload_chunk(nele_engine* e, const ChunkPlan& c, int slot, const floa
                                 cudaMemcpyHostToDevice, sc));
       }
     }
-    pcm16_to_float_kernel<<<1184, 256, 0, sc>>>((const int16_t*)e->in_pcm[slot][0].p, (const int16_t*)e->in_pcm[slot][1].p,
-                                                (const int16_t*)e->in_pcm[slot][2].p, (float*)e->in_ref[slot].p,
-                                                (float*)e->in_deg[slot].p, in_elems);
-    CU(e, cudaGetLastError());
+    // the expansion to float32 runs on the compute stream at the start of the chunk (score_core): launched here, on the
+    // copy stream, it queued behind whole compute kernels and delayed the next step by ~5 ms
+    e->pcm_elems[slot] = in_elems;
     CU(e, cudaEventRecord(e->ev_in[slot], sc));
     return NELE_OK;
   }
@@ -687,6 +687,13 @@ static int score_core(nele_engine* e, const float* ref, const float* deg, const 
       CU(e, cudaStreamWaitEvent(s, e->ev_in[slot], 0));
       d_ref = (const float*)e->in_ref[slot].p;
       d_deg = (const float*)e->in_deg[slot].p;
+      if (e->pcm_noise) {
+        pcm16_to_float_kernel<<<1184, 256, 0, s>>>((const int16_t*)e->in_pcm[slot][0].p, (const int16_t*)e->in_pcm[slot][1].p,
+                                                   (const int16_t*)e->in_pcm[slot][2].p, (float*)e->in_ref[slot].p,
+                                                   (float*)e->in_deg[slot].p, e->pcm_elems[slot]);
+        CU(e, cudaGetLastError());
+        ++e->last_launches;
+      }
     }
     // ---- geometry arrays -> device (one blob, one copy)
     GeomPacker gp;

@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(kEThreads) siib_trieig_kernel(SiibGeom g, Siib
   if (b.rank[pair] < rank_lo) return;
   __shared__ double s_d[kEDim], s_e[kEDim], s_e2[kEDim];
   __shared__ __align__(16) double2 s_de[kEDim];
+  __shared__ double s_ie[kEDim];   // 1 / e_i (the divisions by e_i of the vector recurrences are shared by all threads)
   __shared__ double red[32];
   const double* __restrict__ dd = eb.d + (int64_t)lp * kELd;
   const double* __restrict__ ee = eb.e + (int64_t)lp * kELd;
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(kEThreads) siib_trieig_kernel(SiibGeom g, Siib
     const double ev = (tid < kEDim - 1) ? ee[tid] * inv : 0.0;
     s_e[tid] = ev;
     s_e2[tid] = ev * ev;
+    s_ie[tid] = 1.0 / (ev != 0.0 ? ev : 1.0e-300);
     s_de[tid].x = dd[tid] * inv;
     if (tid + 1 < kEDim) s_de[tid + 1].y = ev * ev;
     if (tid == 0) s_de[0].y = 0.0;
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(kEThreads) siib_trieig_kernel(SiibGeom g, Siib
     scr[(int64_t)(kEDim - 1) * kELd] = (float)dm;
     for (int i = kEDim - 2; i >= 0; --i) {
       if (dm == 0.0) dm = tiny;
-      dm = (s_d[i] - lam) - s_e2[i] / dm;
+      dm = (s_d[i] - lam) - s_e2[i] * __drcp_rn(dm);
       scr[(int64_t)i * kELd] = (float)dm;
     }
   }
@@ -285,10 +287,9 @@ __global__ void __launch_bounds__(kEThreads) siib_trieig_kernel(SiibGeom g, Siib
       }
       if (i == kEDim - 1) break;
       if (dp == 0.0) dp = tiny;
-      const double ei = s_e[i] != 0.0 ? s_e[i] : tiny;
-      z.m = -z.m * dp / ei;
+      z.m = -z.m * dp * s_ie[i];
       z.norm();
-      dp = (s_d[i + 1] - lam) - s_e2[i] / dp;
+      dp = (s_d[i + 1] - lam) - s_e2[i] * __drcp_rn(dp);
     }
   }
   // value of the backward recurrence z_i = -z_{i+1} dm_{i+1} / e_i at the twist index
@@ -297,10 +298,9 @@ __global__ void __launch_bounds__(kEThreads) siib_trieig_kernel(SiibGeom g, Siib
     double dm = s_d[kEDim - 1] - lam;
     for (int i = kEDim - 2; i >= kt; --i) {
       if (dm == 0.0) dm = tiny;
-      const double ei = s_e[i] != 0.0 ? s_e[i] : tiny;
-      zb.m = -zb.m * dm / ei;
+      zb.m = -zb.m * dm * s_ie[i];
       zb.norm();
-      dm = (s_d[i] - lam) - s_e2[i] / dm;
+      dm = (s_d[i] - lam) - s_e2[i] * __drcp_rn(dm);
     }
   }
   // write z (z_kt = 1) and its squared norm; entries below 2^-126 flush to zero in FP32
@@ -308,30 +308,30 @@ __global__ void __launch_bounds__(kEThreads) siib_trieig_kernel(SiibGeom g, Siib
   {
     double dp = s_d[0] - lam;
     Scaled z = {1.0, 0};
+    const double izk = 1.0 / zk.m;
     for (int i = 0; i <= kt; ++i) {
-      const double v = ldexp(z.m / zk.m, z.ex - zk.ex);
+      const double v = ldexp(z.m * izk, z.ex - zk.ex);
       eb.zt[((int64_t)lp * kEDim + i) * kELd + tid] = (float)v;
       nrm2 += v * v;
       if (i == kt) break;
       if (dp == 0.0) dp = tiny;
-      const double ei = s_e[i] != 0.0 ? s_e[i] : tiny;
-      z.m = -z.m * dp / ei;
+      z.m = -z.m * dp * s_ie[i];
       z.norm();
-      dp = (s_d[i + 1] - lam) - s_e2[i] / dp;
+      dp = (s_d[i + 1] - lam) - s_e2[i] * __drcp_rn(dp);
     }
   }
   {
     double dm = s_d[kEDim - 1] - lam;
     Scaled z = {1.0, 0};
+    const double izb = 1.0 / zb.m;
     for (int i = kEDim - 1; i > kt; --i) {
-      const double v = ldexp(z.m / zb.m, z.ex - zb.ex);
+      const double v = ldexp(z.m * izb, z.ex - zb.ex);
       eb.zt[((int64_t)lp * kEDim + i) * kELd + tid] = (float)v;
       nrm2 += v * v;
       if (dm == 0.0) dm = tiny;
-      const double ei = s_e[i - 1] != 0.0 ? s_e[i - 1] : tiny;
-      z.m = -z.m * dm / ei;
+      z.m = -z.m * dm * s_ie[i - 1];
       z.norm();
-      dm = (s_d[i - 1] - lam) - s_e2[i - 1] / dm;
+      dm = (s_d[i - 1] - lam) - s_e2[i - 1] * __drcp_rn(dm);
     }
   }
   eb.znorm[(int64_t)lp * kELd + tid] = nrm2;
