@@ -29,27 +29,44 @@ def pack_records(result):
     return rec
 
 
-def gather_records(local_rec, local_idx, n_total, group=None, device=None):
-    """all_gather the per-rank records and put them back in input order.
-    Every rank returns the full ``[n_total, 14]`` array."""
+def gather_records_start(local_rec, local_idx, n_total, group=None, device=None):
+    """Start the all_gather of the per-rank records (asynchronous collective) and return a handle for
+    :func:`gather_records_finish`.  A caller that streams many batches finishes the gather of batch k after it has
+    queued batch k + 1, so the ranks meet in the collective without waiting for each other on the critical path."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     cap = (n_total + world - 1) // world
-    buf = torch.zeros((cap, RECORD + 1), dtype=torch.float64, device=device)
     k = local_rec.shape[0]
+    host = np.full((cap, RECORD + 1), -1.0)
+    host[:, :RECORD] = 0.0
     if k:
-        buf[:k, :RECORD] = torch.from_numpy(local_rec).to(buf.device)
-        buf[:k, RECORD] = torch.from_numpy(local_idx.astype(np.float64)).to(buf.device)
-    buf[k:, RECORD] = -1.0
+        host[:k, :RECORD] = local_rec
+        host[:k, RECORD] = local_idx
+    buf = torch.from_numpy(host)
+    if device is not None:
+        buf = buf.to(device, non_blocking=False)
     out = torch.empty((world * cap, RECORD + 1), dtype=torch.float64, device=device)
-    dist.all_gather_into_tensor(out, buf, group=group)
-    out = out.cpu().numpy()
+    work = dist.all_gather_into_tensor(out, buf, group=group, async_op=True)
+    return {"work": work, "out": out, "buf": buf, "n_total": n_total}
+
+
+def gather_records_finish(handle):
+    """Wait for a gather started by :func:`gather_records_start`; every rank returns the full ``[n_total, 14]``
+    array in input order."""
+    handle["work"].wait()
+    out = handle["out"].cpu().numpy()
     keep = out[:, RECORD] >= 0
-    full = np.full((n_total, RECORD), np.nan)
+    full = np.full((handle["n_total"], RECORD), np.nan)
     full[out[keep, RECORD].astype(np.int64)] = out[keep, :RECORD]
     return full
+
+
+def gather_records(local_rec, local_idx, n_total, group=None, device=None):
+    """all_gather the per-rank records and put them back in input order.
+    Every rank returns the full ``[n_total, 14]`` array."""
+    return gather_records_finish(gather_records_start(local_rec, local_idx, n_total, group=group, device=device))
 
 
 def score_sharded(score_fn, refs, degs, group=None, device=None):
