@@ -516,9 +516,20 @@ def main():
         return gather(eng.score_packed(h_ref.data_ptr(), h_deg.data_ptr(), offs, lens, fs=FS, mapped=True, seed=1,
                                        stream=sptr, out=out))
 
+    trace = os.environ.get("NELE_BENCH_TRACE") == "1"   # per-rank wall time of the pieces of an e2e step, on stderr
+    tr_acc = {"score": 0.0, "gather": 0.0, "n": 0}
+
     def step_host_pcm():       # int16 host buffers (6 bytes), enhanced + noise formed on the device
-        return gather(eng.score_packed_pcm16(h_c16.data_ptr(), h_c16.data_ptr(), h_n16.data_ptr(), offs, lens, fs=FS,
-                                             mapped=True, seed=1, stream=sptr, out=out))
+        t_a = time.perf_counter()
+        r = eng.score_packed_pcm16(h_c16.data_ptr(), h_c16.data_ptr(), h_n16.data_ptr(), offs, lens, fs=FS,
+                                   mapped=True, seed=1, stream=sptr, out=out)
+        t_b = time.perf_counter()
+        gather(r)
+        if trace:
+            tr_acc["score"] += t_b - t_a
+            tr_acc["gather"] += time.perf_counter() - t_b
+            tr_acc["n"] += 1
+        return r
 
     # ---- value: device-resident inputs
     for _ in range(a.warmup):
@@ -574,6 +585,9 @@ def main():
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     ok_pcm = int(np.sum(r.ok))
+    if trace and tr_acc["n"]:
+        sys.stderr.write("[bench trace] rank %d: e2e step %.2f ms = score call %.2f + gather %.2f (+ prefetch call, loop), kernels %.2f ms\n" % (
+            rank, ms_e2e / a.steps, tr_acc["score"] / tr_acc["n"] * 1e3, tr_acc["gather"] / tr_acc["n"] * 1e3, eng.last_timing()[0]))
     # the same loop with plain blocking calls (no nele_prefetch): every upload is exposed
     t0 = time.perf_counter()
     for _ in range(a.steps):
