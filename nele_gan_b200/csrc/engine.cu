@@ -209,10 +209,10 @@ extern "C" int nele_create(int device, nele_engine** out) {
   e->device = device;
   const char* p = getenv("NELE_HASPI_F64");
   e->f64 = (p && p[0] == '1');
-  // One stream by default: every kernel of the three pipelines fills the SMs on its own (register-
-  // or shared-memory-limited occupancy), so running the metrics on concurrent streams measured
-  // 381.7 vs 385.6 ms per 4096-pair step and blurs the per-kernel timings.  NELE_CONCURRENT=1
-  // turns the fork/join on (useful for small batches).
+  // One stream for large chunks: every kernel of the three pipelines fills the SMs on its own (register-
+  // or shared-memory-limited occupancy), so concurrent streams gain nothing there (302 vs 307 ms per 4096
+  // full-rank pairs) and blur the per-kernel timings.  Chunks below 1024 pairs fork / join the three metric
+  // pipelines (see score_core); NELE_CONCURRENT=0 / 1 forces either behaviour.
   p = getenv("NELE_CONCURRENT");
   e->concurrent = (p && (p[0] == '0' || p[0] == '1')) ? p[0] - '0' : -1;
   e->all_bufs = {&e->bands, &e->rs_taps, &e->st_taps, &e->in_ref[0], &e->in_ref[1], &e->in_deg[0], &e->in_deg[1], &e->geom, &e->sgeom, &e->dither,

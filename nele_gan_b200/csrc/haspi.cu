@@ -304,6 +304,8 @@ constexpr int kCtlChunk = 256;
 
 // One warp per pair, lane = band; the clean and the processed signal run side by side in a thread
 // (two independent recurrence chains, one shared carrier), as in the main pass.
+// (Occupancy is not the limit: capping the registers so that 7 instead of 6 CTAs fit per SM -- one wave instead of two at
+// 4096 pairs -- measured 13.8 -> 14.5 ms; the FP32 pipe is saturated either way.)
 template <typename T>
 __global__ void __launch_bounds__(kEarWarps * 32) haspi_control_kernel(PairGeom g, HaspiBuffers b, int n_pairs) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -476,6 +478,8 @@ __global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_kernel(PairGeom g, H
 // 4096 x 3 s, HASPI equal to 2.7e-6; default since then (NELE_F32X2=0 selects the scalar kernel).
 // The control pass was packed the same way and was *slower* (4.15 -> 4.65 ms per 1024 pairs: it
 // has no MUFU / clamp work to overlap, so packing only lengthens the dependency chain): removed.
+// (168 registers, three CTAs per SM.  A cap at 128 registers -- four CTAs, two waves instead of three at 4096 pairs, 16 bytes
+// of spills -- measured 40.7 -> 41.9 ms: the kernel is bound by the FP32 pipe, not by occupancy or the tail of the grid.)
 __global__ void __launch_bounds__(kEarWarps * 32) haspi_ear_x2_kernel(PairGeom g, HaspiBuffers b, int n_pairs) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int pair = blockIdx.x * kEarWarps + wib;
