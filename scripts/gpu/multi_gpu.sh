@@ -1,8 +1,8 @@
 #!/bin/bash
-# round 2, call 10 (8 GPUs): BASELINE configs[3] (GAN round latency) and configs[4] (3-10 s sweep, strong scaling) at N = 1, 2, 4, 8;
+# BASELINE configs[3] (GAN round latency) and configs[4] (3-10 s sweep, strong scaling) at N = 1, 2, 4, 8;
 # the driver's weak-scaling line at N = 8; score_sharded on real engines (pytest -m gpu includes the 2-rank test)
 mkdir -p gpurun_out
-O=gpurun_out/r2c10
+O=gpurun_out/mgpu
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 nvidia-smi topo -m > ${O}_topo.txt 2>&1
 for N in 8 4 2; do

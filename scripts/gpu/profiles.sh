@@ -1,8 +1,8 @@
 #!/bin/bash
-# round 2, call 14: the evidence set for profiles/ -- bench line (driver settings), reference arm, launch list, ncu --set full of a
+# the evidence set for profiles/ -- bench line (driver settings), reference arm, launch list, ncu --set full of a
 # whole step at bench size and of a general-case step, DRAM traffic per kernel
 mkdir -p gpurun_out
-O=gpurun_out/r2c14
+O=gpurun_out/prof
 timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > ${O}_bench_n1.json 2> ${O}_bench_n1.err; echo "bench exit $?"; tail -2 ${O}_bench_n1.err; cut -c1-600 ${O}_bench_n1.json
 timeout 900 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > ${O}_bench_reference_arm.json 2> ${O}_bench_ref.err; echo "ref exit $?"; cut -c1-700 ${O}_bench_reference_arm.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${O}_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > ${O}_launch.log 2>&1; wc -l ${O}_launches_bench.csv
