@@ -710,7 +710,7 @@ def main():
         if general is not None:
             line["general_case"] = general
         if world == 1 and not a.no_cpu_baseline:
-            sample = max(cores, 8)
+            sample = 2 * max(cores, 8)      # two pairs per host thread and pass: halves the run-to-run spread of one-pair passes
             v, spstep = cpu_reference_run(refs[:sample], degs[:sample], cores, 2, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "first %d pairs of the batch, 2 timed passes, joblib n_jobs=%d" % (sample, cores)}
