@@ -28,6 +28,8 @@ Metric: audio-seconds scored per second, whole job.
 ``--impl reference`` times that CPU path alone, with all host threads, and
 prints the same line with "impl": "reference".
 
+``--config toy`` (BASELINE.json configs[1]): the three toy_dataset pairs (arrays of tests/golden/haspi_ref.npz) on one B200
+against the CPU oracle, labels compared.
 ``--config ganround`` (BASELINE.json configs[3]): latency of one GAN sampling round of train_nele.py:36-37,
 205-214, 320-335 -- 600 pairs labelled with norm=True (300 generator outputs + 300 pre-enhanced) and 480
 validation pairs with norm=False, 2 - 3.5 s each -- from band gains on the device to labels on the host
@@ -169,6 +171,54 @@ def cpu_reference_run(refs, degs, cores, steps, warmup):
             pool(delayed(_cpu_score_one)((refs[i], degs[i])) for i in range(n))
         dt = time.perf_counter() - t0
     return sec * steps / dt, dt / steps
+
+
+# ------------------------------------------------- configs[1]: the toy corpus
+def run_toy(a, rank, world, local_rank, cores):
+    """BASELINE.json configs[1]: HASPI + SIIB + ESTOI labels of every toy_dataset utterance -- Train (Clean, MultiEnh +
+    Noise), Train (Clean, Clean + Noise), Test (Clean, Clean + Noise); the arrays are those of tests/golden/haspi_ref.npz
+    (the corpus itself is not on the GPU box) -- one B200 against the CPU oracle on the host, labels compared."""
+    if rank != 0:
+        return 0
+    z = np.load(os.path.join(ROOT, "tests", "golden", "haspi_ref.npz"))
+    names = ("toy_train_multienh", "toy_train_clean", "toy_test_clean")
+    refs = [z[n + "/x"] for n in names]
+    degs = [z[n + "/y"] for n in names]
+    audio_s = sum(len(r) for r in refs) / FS
+    from joblib import Parallel, delayed
+    from oracle import intel_np
+    t0 = time.perf_counter()
+    want = Parallel(n_jobs=min(cores, 3))(delayed(intel_np.score_pair)(refs[i], degs[i], FS, True, None) for i in range(3))
+    t_cpu_first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    want = np.array(Parallel(n_jobs=min(cores, 3))(delayed(intel_np.score_pair)(refs[i], degs[i], FS, True, None) for i in range(3)))
+    t_cpu = time.perf_counter() - t0
+    line = {"metric": "toy_corpus_labelling_latency", "unit": "ms", "higher_is_better": False, "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "config": {"workload": "toy_dataset: 3 (clean, degraded) pairs of 33 536 / 34 048 samples, mapped labels",
+                                           "audio_seconds": audio_s},
+            "cpu_baseline": {"value": t_cpu * 1e3, "unit": "ms", "cores": min(cores, 3), "kind": "port",
+                             "sample": "the three pairs, one per worker process, second pass (first pass incl. imports: %.0f ms)" % (t_cpu_first * 1e3)}}
+    if a.impl == "reference":
+        line.update({"impl": "reference", "value": t_cpu * 1e3})
+        print(json.dumps(line))
+        return 0
+    from nele_gan_b200.engine import Engine
+    eng = Engine(local_rank)
+    for _ in range(max(a.warmup, 1)):
+        r = eng.score_batch(refs, degs, mapped=True, no_dither=True)
+    lat = []
+    for _ in range(max(a.steps, 1)):
+        t0 = time.perf_counter()
+        r = eng.score_batch(refs, degs, mapped=True, no_dither=True)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    dev = np.abs(r.scores - want)
+    line.update({"value": float(np.median(lat)), "ms_per_step": float(np.mean(lat)), "kernel_ms": eng.last_timing()[0],
+                 "gpu_launches": int(eng.last_timing()[1]), "labels": {n: [float(v) for v in r.scores[i]] for i, n in enumerate(names)},
+                 "max_abs_deviation_from_cpu_oracle": {"siib": float(dev[:, 0].max()), "haspi": float(dev[:, 1].max()),
+                                                       "estoi": float(dev[:, 2].max())},
+                 "speedup_vs_cpu": t_cpu * 1e3 / float(np.median(lat))})
+    print(json.dumps(line))
+    return 0
 
 
 # ------------------------------------------------- configs[3]: GAN sampling round
@@ -416,14 +466,16 @@ def main():
     ap.add_argument("--unique", type=int, default=0, help="distinct synthetic pairs per GPU (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-general-case", action="store_true", help="skip the 47 999-sample (full-rank SIIB) measurement")
-    ap.add_argument("--config", default="bench", choices=("bench", "ganround", "sweep"),
-                    help="bench = BASELINE.json configs[2] (the driver's line); ganround = configs[3]; sweep = configs[4]")
+    ap.add_argument("--config", default="bench", choices=("bench", "toy", "ganround", "sweep"),
+                    help="bench = BASELINE.json configs[2] (the driver's line); toy = configs[1]; ganround = configs[3]; sweep = configs[4]")
     ap.add_argument("--sweep-pairs", type=int, default=65536)
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
+    if a.config == "toy":
+        return run_toy(a, rank, world, local_rank, cores)
     if a.config == "ganround":
         return run_ganround(a, rank, world, local_rank, cores)
     if a.config == "sweep":
