@@ -287,13 +287,15 @@ struct SpecSmem {
   cpx tw[kSWin];
   float win[kSWin];
   float g2t[kSBins * kSLanes];
-  cpx z[kSpecWarps][kSWin];
-  cpx t[kSpecWarps][kSWin];
+  cpx z[kSpecWarps][kSWin];  // one buffer per warp: the FFT is in place (fft400.cuh), the power spectra overwrite it
 };
 
 constexpr int kSpecIter = 8;  // frames per warp: the 29 KB of tables are staged once per 64 frames, not once per 8
 
-__global__ void __launch_bounds__(kSpecWarps * 32) siib_spec_kernel(SiibGeom g, SiibBuffers b) {
+// 55 KB of shared memory and <= 80 registers: three CTAs (24 warps) per SM.  The kernel is issue bound (68 % of the
+// issue slots with 16 warps, 2970 instructions per frame of which the band sums were 1300): the band sums now run
+// fully unrolled over constant positions, the 16-point FFTs carry their twiddles as constants.
+__global__ void __launch_bounds__(kSpecWarps * 32, 3) siib_spec_kernel(SiibGeom g, SiibBuffers b) {
   const int pair = b.pair_lo + blockIdx.y, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int Fa = b.Fa[pair];
   const int tbase = blockIdx.x * kSpecWarps * kSpecIter;
@@ -321,38 +323,44 @@ __global__ void __launch_bounds__(kSpecWarps * 32) siib_spec_kernel(SiibGeom g, 
   const int L = g.len16[pair];
   const float mx = (float)b.mean[2 * pair], my = (float)b.mean[2 * pair + 1];
   cpx* z = sm.z[wib];
-  cpx* tt = sm.t[wib];
+  const float* gl = sm.g2t + lane;
   for (int it = 0; it < kSpecIter; ++it) {
     const int t = tbase + it * kSpecWarps + wib;
     if (t >= Fa) break;
     if (b.src[g.offF[pair] + t] != t) continue;  // a copy of an earlier frame (siib_vad_kernel)
     const int64_t f = b.act[g.offF[pair] + t];
-    const int64_t base = (f * kSHop) % L;
+    const int base = (int)((f * kSHop) % L);
     __syncwarp();
+#pragma unroll 1
     for (int i = lane; i < kSWin; i += 32) {
-      int64_t idx = base + i;
-      if (idx >= L) idx %= L;
+      int idx = base + i;  // < 2 L
+      if (idx >= L) {
+        idx -= L;
+        if (idx >= L) idx %= L;  // utterances shorter than a frame
+      }
       const float w = sm.win[i];
       z[i] = {w * (x[idx] - mx), w * (y[idx] - my)};
     }
     __syncwarp();
-    if (lane < 25) fft400_phase_a(lane, z, tt, sm.tw);
+    if (lane < 25) fft400_phase_a(lane, z, sm.tw);
     __syncwarp();
-    if (lane < 16) fft400_phase_b(lane, tt, z, sm.tw);
+    if (lane < 16) fft400_phase_b(lane, z, sm.tw);
     __syncwarp();
-    // power spectra of the two real signals, interleaved (px, py) into tt
-    float2* pw = reinterpret_cast<float2*>(tt);
+    // power spectra of the two real signals, (px, py) of bin k written over X[k]: no other bin reads X[k]
+    // (bin k reads X[k] and X[400 - k], and 400 - k > 200 unless k = 200)
+    float2* pw = reinterpret_cast<float2*>(z);
     for (int k = lane; k < kSBins; k += 32) {
-      const cpx a = z[k], c = z[(kSWin - k) % kSWin];
+      const int pk = fft400_pos(k);
+      const cpx a = z[pk], c = z[fft400_pos((kSWin - k) % kSWin)];
       const float xr = a.x + c.x, xi = a.y - c.y, yr = a.y + c.y, yi = c.x - a.x;
-      pw[k] = make_float2(0.25f * (xr * xr + xi * xi), 0.25f * (yr * yr + yi * yi));
+      pw[pk] = make_float2(0.25f * (xr * xr + xi * xi), 0.25f * (yr * yr + yi * yi));
     }
     __syncwarp();
     float ex = 0.f, ey = 0.f;
-#pragma unroll 4
+#pragma unroll
     for (int k = 0; k < kSBins; ++k) {
-      const float2 p = pw[k];
-      const float gk = sm.g2t[k * kSLanes + lane];
+      const float2 p = pw[(k & 15) * 25 + (k >> 4)];
+      const float gk = gl[k * kSLanes];
       ex = fmaf(gk, p.x, ex);
       ey = fmaf(gk, p.y, ey);
     }
@@ -623,11 +631,13 @@ __global__ void __launch_bounds__(kCov32Warps * 32) siib_cov32_kernel(SiibGeom g
   const int rg = lane >> 3, cg = lane & 7;
   const float* __restrict__ X = b.logspec + (g.offF[pair]) * kSLanes;
   const float* __restrict__ Y = b.logspec + (b.totF + g.offF[pair]) * kSLanes;
-  float tot0[8][4], tot1[8][4];
+  // accumulators as f32x2 pairs of rows (fma.rn.f32x2: the kernel sits at 63 % issue slots and 54 % of the FMA pipe, so
+  // halving the FMA instructions is time; the arithmetic per component is unchanged)
+  F2 tot0[4][4], tot1[4][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) tot0[i][j] = tot1[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) tot0[i][j] = tot1[i][j] = f2_pack(0.f, 0.f);
   for (int t0 = 0; t0 < span.ne; t0 += kCovTile) {
     __syncthreads();
     for (int idx = threadIdx.x; idx < 2 * kCovRows * (kSLanes / 4); idx += kCov32Warps * 32) {
@@ -648,35 +658,35 @@ __global__ void __launch_bounds__(kCov32Warps * 32) siib_cov32_kernel(SiibGeom g
     const int nt = min(kCovTile, span.ne - t0);
     const float* A = &s_x[ta][0][8 * rg];
     const float* B = &s_x[2 + tb][e][4 * cg];
-    float acc0[8][4], acc1[8][4];
+    F2 acc0[4][4], acc1[4][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = f2_pack(0.f, 0.f);
     float4 cc = *reinterpret_cast<const float4*>(B);
 #pragma unroll 2
     for (int t = 0; t < nt; ++t) {
       const float4 a0 = *reinterpret_cast<const float4*>(A + t * kSLanes);
       const float4 a1 = *reinterpret_cast<const float4*>(A + t * kSLanes + 4);
       const float4 nn = *reinterpret_cast<const float4*>(B + (t + 1) * kSLanes);  // lag e + 1 now, lag e next frame
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float c[4] = {cc.x, cc.y, cc.z, cc.w};
-      const float n[4] = {nn.x, nn.y, nn.z, nn.w};
+      const F2 a[4] = {f2_pack(a0.x, a0.y), f2_pack(a0.z, a0.w), f2_pack(a1.x, a1.y), f2_pack(a1.z, a1.w)};
+      const F2 c[4] = {f2_pack(cc.x, cc.x), f2_pack(cc.y, cc.y), f2_pack(cc.z, cc.z), f2_pack(cc.w, cc.w)};
+      const F2 n[4] = {f2_pack(nn.x, nn.x), f2_pack(nn.y, nn.y), f2_pack(nn.z, nn.z), f2_pack(nn.w, nn.w)};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          acc0[i][j] = fmaf(a[i], c[j], acc0[i][j]);
-          acc1[i][j] = fmaf(a[i], n[j], acc1[i][j]);
+          acc0[i][j] = f2_fma(a[i], c[j], acc0[i][j]);
+          acc1[i][j] = f2_fma(a[i], n[j], acc1[i][j]);
         }
       cc = nn;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        tot0[i][j] += acc0[i][j];
-        tot1[i][j] += acc1[i][j];
+        tot0[i][j] = f2_add(tot0[i][j], acc0[i][j]);
+        tot1[i][j] = f2_add(tot1[i][j], acc1[i][j]);
       }
   }
   if (!active) return;
@@ -690,7 +700,9 @@ __global__ void __launch_bounds__(kCov32Warps * 32) siib_cov32_kernel(SiibGeom g
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double v = (double)(l ? tot1[i][j] : tot0[i][j]);
+        float lo, hi;
+        f2_unpack(l ? tot1[i >> 1][j] : tot0[i >> 1][j], lo, hi);
+        const double v = (double)((i & 1) ? hi : lo);
         const int ra = 8 * rg + i, cb = 4 * cg + j;
         if (tr) out[cb * kSLanes + ra] = v;
         else out[ra * kSLanes + cb] = v;

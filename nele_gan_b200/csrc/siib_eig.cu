@@ -181,27 +181,35 @@ __global__ void __launch_bounds__(kEThreads, 3) siib_tridiag_kernel(SiibGeom g, 
 
 // --------------------------------------------------- eigenpairs of the tridiagonal
 // number of eigenvalues of T (scaled so that |entries| <= 1) below x: sign changes of the
-// three-term recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}, rescaled every 8 steps.
-// de[i] = {d_i, e_{i-1}^2} (de[0].y unused): one 128-bit shared-memory load per step, broadcast to the whole CTA.  The
-// sign changes are counted on the sign bits of the high words (two integer instructions instead of two FP64 compares
-// and their logic): the kernel is issue bound (ncu: 80 % issue slots, FP64 pipe 55 %), so instructions are time.
+// three-term recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}.
+// de[i] = {d_i, e_{i-1}^2} (de[0].y unused), padded to kSturmLen entries with {1000, 0} (p keeps its sign there, |x| <= 3):
+// one 128-bit shared-memory load per step, broadcast to the whole CTA, and blocks of 16 steps with a compile-time trip
+// count.  The kernel is issue bound (ncu: 71 % issue slots, FP64 pipe 39 %; 15 instructions per step before this form,
+// of which 3 are the FP64 arithmetic), so instructions are time:
+//   * the sign of every p_i is shifted into a bit mask (one funnel shift per step) and the changes of a block counted
+//     with one xor + popc, instead of an xor + shift + add per step;
+//   * the range check that guards the recurrence against overflow looks at the exponent fields of the high words and
+//     rescales by an exact power of two: |p| grows by at most 7 per step (2^45 per block), the window is 2^+-128.
+constexpr int kSturmBlk = 16;
+constexpr int kSturmLen = 1 + ((kEDim - 1 + kSturmBlk - 1) / kSturmBlk) * kSturmBlk;  // 433
 __device__ __forceinline__ int sturm_count(const double2* __restrict__ de, double x) {
   double pm = 1.0, p = de[0].x - x;
-  int cnt = __double2hiint(p) >> 31;   // -1 for a negative start: subtracted below
-  cnt = -cnt;
-  for (int i0 = 1; i0 < kEDim; i0 += 8) {
-    const int i1 = min(i0 + 8, kEDim);
-#pragma unroll 8
-    for (int i = i0; i < i1; ++i) {
-      const double2 c = de[i];
+  unsigned sg = (unsigned)__double2hiint(p) >> 31;  // bit 0: sign of the newest p; p_{-1} = 1 is positive
+  int cnt = (int)sg;
+#pragma unroll 1
+  for (int i0 = 1; i0 < kSturmLen; i0 += kSturmBlk) {
+#pragma unroll
+    for (int i = 0; i < kSturmBlk; ++i) {
+      const double2 c = de[i0 + i];
       const double pn = fma(c.x - x, p, -c.y * pm);
-      cnt += (unsigned)(__double2hiint(pn) ^ __double2hiint(p)) >> 31;  // a sign change = one more eigenvalue below x
+      sg = __funnelshift_l((unsigned)__double2hiint(pn), sg, 1);  // (sg << 1) | sign(pn)
       pm = p;
       p = pn;
     }
-    const double m = fmax(fabs(p), fabs(pm));
-    if (m > 1.0e100 || (m < 1.0e-100 && m > 0.0)) {
-      const double sc = 1.0 / m;
+    cnt += __popc((sg ^ (sg >> 1)) & 0xffffu);  // a sign change = one more eigenvalue below x
+    const int e = max(__double2hiint(p) & 0x7ff00000, __double2hiint(pm) & 0x7ff00000);  // exponent field of max(|p|, |pm|)
+    if ((unsigned)(e - ((1023 - 128) << 20)) > (unsigned)(256 << 20)) {
+      const double sc = __hiloint2double(0x7fe00000 - e, 0);  // 2^-(exponent): exact, the signs stay
       p *= sc;
       pm *= sc;
     }
@@ -224,7 +232,8 @@ __global__ void __launch_bounds__(kEThreads) siib_trieig_kernel(SiibGeom g, Siib
   const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x;
   if (b.rank[pair] < rank_lo) return;
   __shared__ double s_d[kEDim], s_e[kEDim], s_e2[kEDim];
-  __shared__ __align__(16) double2 s_de[kEDim];
+  __shared__ __align__(16) double2 s_de[kSturmLen];
+  __shared__ int s_grid[kEDim + 1];
   __shared__ double s_ie[kEDim];   // 1 / e_i (the divisions by e_i of the vector recurrences are shared by all threads)
   __shared__ double red[32];
   const double* __restrict__ dd = eb.d + (int64_t)lp * kELd;
@@ -243,15 +252,30 @@ __global__ void __launch_bounds__(kEThreads) siib_trieig_kernel(SiibGeom g, Siib
     s_de[tid].x = dd[tid] * inv;
     if (tid + 1 < kEDim) s_de[tid + 1].y = ev * ev;
     if (tid == 0) s_de[0].y = 0.0;
+  } else if (tid < kSturmLen) {
+    s_de[tid] = make_double2(1000.0, 0.0);
   }
   __syncthreads();
+  // ---- eigenvalue number tid (ascending) inside the Gershgorin interval [-3, 3].
+  // One Sturm count per thread on a uniform grid of 420 cells first: every thread then finds its own cell by a binary
+  // search of the counts (9 shared-memory reads instead of 8.7 bisection steps of 420 recurrence steps each) ...
+  const double cell = 6.0 / kEDim;
+  if (tid < kEDim) s_grid[tid] = tid ? sturm_count(s_de, -3.0 + cell * tid) : 0;
+  if (tid == 0) s_grid[kEDim] = kEDim;
+  __syncthreads();
   if (tid >= kEDim) return;  // no block-wide barrier below
-  // ---- bisection: eigenvalue number tid (ascending) inside the Gershgorin interval [-3, 3]
-  // 46 steps: 6 * 2^-46 = 8.5e-14 of max|T|.  T comes from an FP32 tridiagonalisation (entries known to 1e-7), and the
-  // score does not react to what fewer steps cost -- orthogonality inside clusters of tiny eigenvalues, whose components
-  // carry no information: SIIB deviation unchanged from 58 down to 38 steps (scripts/exp_klt_fp32.py iterations)
-  double lo = -3.0, hi = 3.0;
-  for (int it = 0; it < 46; ++it) {
+  int klo = 0, khi = kEDim;  // count(grid[klo]) <= tid < count(grid[khi])
+  while (khi - klo > 1) {
+    const int km = (klo + khi) >> 1;
+    if (s_grid[km] > tid) khi = km;
+    else klo = km;
+  }
+  // ... then 38 bisection steps: 6 / 420 * 2^-38 = 5.2e-14 of max|T| (46 steps from the whole interval gave 8.5e-14).
+  // T comes from an FP32 tridiagonalisation (entries known to 1e-7), and the score does not react to what fewer steps
+  // cost -- orthogonality inside clusters of tiny eigenvalues, whose components carry no information: SIIB deviation
+  // unchanged from 58 down to 38 steps from the whole interval (scripts/exp_klt_fp32.py iterations)
+  double lo = -3.0 + cell * klo, hi = -3.0 + cell * khi;
+  for (int it = 0; it < 38; ++it) {
     const double mid = 0.5 * (lo + hi);
     if (sturm_count(s_de, mid) > tid) hi = mid;
     else lo = mid;

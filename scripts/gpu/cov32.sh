@@ -1,0 +1,5 @@
+#!/bin/bash
+# SIIB suite + per-kernel times of the general case after a change to one SIIB kernel
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_estoi_siib.py -q -x > gpurun_out/cov32_pytest.log 2>&1; echo "pytest exit $? $(tail -1 gpurun_out/cov32_pytest.log)"
+timeout 200 python scripts/kernel_times.py 1024 47999 siib 2>&1 | tee gpurun_out/cov32_times.txt | head -16

@@ -1,4 +1,4 @@
-"""Host emulation of device band arithmetic (tests/host_emul, g++): the two-wide main-pass lane EarLane2
+"""Host emulation of device arithmetic (tests/host_emul, g++).  The two-wide main-pass lane EarLane2
 (the experimental f32x2 kernels, NELE_F32X2=1) must agree with two scalar EarLane<float> lanes.  The
 device build runs the same source with fma.rn.f32x2 in place of the component-wise fmaf."""
 import os
@@ -23,3 +23,17 @@ def test_two_wide_lane_matches_the_scalar_lanes(tmp_path):
     # the scalar lanes round a * r + x twice with contraction off, the two-wide lane once (fmaf): the
     # recurrences differ by rounding only -- far below the model's own 0.1 dB dither
     assert worst < 2e-3, out
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_in_place_fft400_matches_a_direct_dft(tmp_path):
+    """fft400.cuh (SIIB's 400-point STFT, intel.py:52-54): both phases run in place on one buffer and leave
+    X[k] at fft400_pos(k).  Against a float64 DFT, and independent of the order the lanes run in."""
+    exe = str(tmp_path / "fft400_emul")
+    src = os.path.join(ROOT, "tests", "host_emul", "fft400_emul.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, src], check=True)
+    out = subprocess.run([exe], check=True, stdout=subprocess.PIPE, text=True).stdout
+    err = float(re.search(r"MAXERR ([0-9.eE+-]+)", out).group(1))
+    order = float(re.search(r"ORDER ([0-9.eE+-]+)", out).group(1))
+    assert err < 1e-6, out          # float32 butterflies: about 1.5e-7 of the largest bin
+    assert order == 0.0, out        # no lane reads what another lane of the same phase writes
