@@ -150,6 +150,8 @@ struct SiibBuffers {
   int32_t* Pact;         // [n] active frames per period of the tiled signal (0 = no repetition)
   int32_t* perflag;      // [n][2] masked features of x / y verified periodic from the second period on
   int no_proj;           // 1: never take the projection route for periodic pairs (NELE_SIIB_QUADFORM=1, A/B runs)
+  int xx32;              // 1: pairs whose x features do not repeat take the xx lag products in FP32 too (set by siib_run when the
+                         // tridiagonalisation path follows, which rounds Sxx to FP32 anyway; NELE_COV_XX64=1 keeps FP64, A/B runs)
   float* lograw;         // [2][totF][32] log band energies of the distinct active frames
   float* logspec;        // [2][totF][32] after forward masking and mean removal
   int64_t totF;

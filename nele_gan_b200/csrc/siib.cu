@@ -59,17 +59,29 @@ __device__ float g_siib_g2t[kSBins * kSLanes];  // squared gammatone responses, 
 __device__ cpx g_siib_tw[kSWin];
 
 // ---------------------------------------------------------------- VAD helpers
-// power (dB) of Hann frame f of (x - mean); wrap = tiled signal, else zero padded
-__device__ __forceinline__ double frame_power_db(const float* __restrict__ x, int L, double mean, int64_t f,
-                                                 bool wrap, int lane, const float* __restrict__ win) {
+// energy of Hann frame f of (x - mean), summed over the warp; wrap = tiled signal, else zero padded.  win = the window
+// as doubles in shared memory.  A frame that neither wraps nor runs past the end (all but one per tile) takes the loop
+// without per-sample index checks; the dB conversion is left to the caller, one frame per thread (frame_db) instead of
+// one per warp: the VAD kernels are issue bound and log10 in FP64 was a fifth of their instructions.
+__device__ __forceinline__ double frame_energy(const float* __restrict__ x, int L, double mean, int64_t f, bool wrap,
+                                               int lane, const double* __restrict__ win) {
   // f * 200 < 2^31 for every frame count the engine admits (F <= 400 000)
   const int s0 = (int)f * kSHop;
   const int base = wrap ? (s0 % L) : s0;
   double ss = 0.0;
+  if (base + kSWin <= L) {
+    const float* __restrict__ xf = x + base;
 #pragma unroll
-  for (int k = 0; k < (kSWin + 31) / 32; ++k) {
-    const int i = k * 32 + lane;
-    if (i < kSWin) {
+    for (int k = 0; k < (kSWin + 31) / 32; ++k) {
+      const int i = k * 32 + lane;
+      if (i < kSWin) {
+        const double v = ((double)xf[i] - mean) * win[i];
+        ss = fma(v, v, ss);
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int i = lane; i < kSWin; i += 32) {
       int idx = base + i;
       double v;
       if (wrap) {
@@ -78,13 +90,13 @@ __device__ __forceinline__ double frame_power_db(const float* __restrict__ x, in
       } else {
         v = (idx < L) ? (double)x[idx] - mean : 0.0;
       }
-      v *= (double)win[i];
+      v *= win[i];
       ss = fma(v, v, ss);
     }
   }
-  ss = warp_sum(ss);
-  return 10.0 * log10(ss / (double)kSWin + kEps);
+  return warp_sum(ss);
 }
+__device__ __forceinline__ double frame_db(double ss) { return 10.0 * log10(ss / (double)kSWin + kEps); }
 
 // k-th largest (counting multiplicity) of v[0..n), k >= 1: k rounds of arg-max in the
 // total order (value descending, index ascending).  All threads get the result.
@@ -157,13 +169,15 @@ __global__ void __launch_bounds__(kVadThreads) siib_wrapvad_kernel(SiibGeom g, S
   double* __restrict__ db = b.wrapdb + g.offW[pair];
   __shared__ double red[32];
   __shared__ int64_t redi[32];
-  __shared__ float s_win[kSWin];
-  for (int i = tid; i < kSWin; i += kVadThreads) s_win[i] = g_siib_win[i];
+  __shared__ double s_win[kSWin];
+  for (int i = tid; i < kSWin; i += kVadThreads) s_win[i] = (double)g_siib_win[i];
   __syncthreads();
   for (int f = wib; f < F1; f += NW) {
-    const double d = frame_power_db(x, L, 0.0, f, false, lane, s_win);
+    const double d = frame_energy(x, L, 0.0, f, false, lane, s_win);
     if (lane == 0) db[f] = d;
   }
+  __syncthreads();
+  for (int f = tid; f < F1; f += kVadThreads) db[f] = frame_db(db[f]);
   __syncthreads();
   const double sel = kth_largest(db, F1, percentile_rank(F1), red, redi);
   const double thr = sel - 40.0;
@@ -193,12 +207,12 @@ __global__ void __launch_bounds__(kVad2Threads) siib_vad_kernel(SiibGeom g, Siib
   __shared__ int64_t redi[32];
   __shared__ int s_cnt[NW];
   __shared__ int s_base;
-  __shared__ float s_win[kSWin];
+  __shared__ double s_win[kSWin];
   if (F <= 0) {
     if (tid == 0) b.Fa[pair] = 0;
     return;
   }
-  for (int i = tid; i < kSWin; i += kVad2Threads) s_win[i] = g_siib_win[i];
+  for (int i = tid; i < kSWin; i += kVad2Threads) s_win[i] = (double)g_siib_win[i];
   double sx = 0.0, sy = 0.0;
   for (int i = tid; i < L; i += kVad2Threads) {
     sx += (double)x[i];
@@ -224,9 +238,11 @@ __global__ void __launch_bounds__(kVad2Threads) siib_vad_kernel(SiibGeom g, Siib
   const int64_t per = L / gcd;
   const int64_t Fu = (per < F) ? per : F;
   for (int64_t f = wib; f < Fu; f += NW) {
-    const double d = frame_power_db(x, L, mx, f, true, lane, s_win);
+    const double d = frame_energy(x, L, mx, f, true, lane, s_win);
     if (lane == 0) db[f] = d;
   }
+  __syncthreads();
+  for (int64_t f = tid; f < Fu; f += kVad2Threads) db[f] = frame_db(db[f]);
   __syncthreads();
   for (int64_t f = Fu + tid; f < F; f += kVad2Threads) db[f] = db[f % per];
   __syncthreads();
@@ -522,6 +538,11 @@ __device__ __forceinline__ void cov_task(int task, int& ta, int& tb, int& e, int
   }
 }
 
+// Pairs whose x features do not repeat (siib_mask_kernel's check) skip the Cholesky rank decision and go to the FP32
+// tridiagonalisation of Sxx: their xx lag products need no more than FP32 either and join the FP32 kernel (the FP64
+// kernel runs at the FP64 pipe's rate: 2.8 ms per 1024 pairs for 8 of the 31 tasks, the FP32 one 4.5 ms for 23).
+__device__ __forceinline__ bool cov_xx32(const SiibBuffers& b, int pair) { return b.xx32 && !b.perflag[2 * pair]; }
+
 // The eight warps of a CTA walk the time axis together: each tile of frames is converted to
 // FP64 once into shared memory and every warp accumulates two 32 x 32 lag blocks (28 x 28 used)
 // that share their A rows; the B rows of lag e + 1 at frame t are the B rows of lag e at frame
@@ -531,7 +552,7 @@ __global__ void __launch_bounds__(kCovWarps * 32) siib_cov_kernel(SiibGeom g, Si
   const int task = blockIdx.x * kCovWarps + wib;
   const int Fa = b.Fa[pair];
   const int Nf = Fa - (kSStack - 1);
-  if (Nf < 1) return;
+  if (Nf < 1 || cov_xx32(b, pair)) return;
   __shared__ __align__(16) double s_x[2][kCovRows][kSLanes];  // [0] rows weighted (A side), [1] plain (B side)
   const CovSpan span = cov_span(b, pair, Nf, false);
   const bool active = task < kCovTasks64;
@@ -618,7 +639,10 @@ __global__ void __launch_bounds__(kCovWarps * 32) siib_cov_kernel(SiibGeom g, Si
 // what moves the score by 1e-4).
 __global__ void __launch_bounds__(kCov32Warps * 32) siib_cov32_kernel(SiibGeom g, SiibBuffers b) {
   const int lp = blockIdx.y, pair = b.pair_lo + lp, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int task = kCovTasks64 + blockIdx.x * kCov32Warps + wib;
+  // tasks 8..30 in two CTAs, or 0..30 in three when the xx products are taken here as well
+  const bool xx = cov_xx32(b, pair);
+  if (!xx && blockIdx.x == 2) return;
+  const int task = (xx ? 0 : kCovTasks64) + blockIdx.x * kCov32Warps + wib;
   const int Fa = b.Fa[pair];
   const int Nf = Fa - (kSStack - 1);
   if (Nf < 1 || siib_projected(b, pair, Nf)) return;
@@ -694,7 +718,7 @@ __global__ void __launch_bounds__(kCov32Warps * 32) siib_cov32_kernel(SiibGeom g
   for (int l = 0; l < 2; ++l) {
     if (l >= nl) break;
     const int lag = e + l;
-    const int blk = tr ? (44 - lag) : (ta == 1 && tb == 1) ? 15 + lag : 44 + lag;
+    const int blk = tr ? (44 - lag) : (ta == 0 && tb == 0) ? lag : (ta == 1 && tb == 1) ? 15 + lag : 44 + lag;
     double* __restrict__ out = b.base + ((int64_t)lp * kSBlocks + blk) * (kSLanes * kSLanes);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -1643,9 +1667,18 @@ int siib_run_wrapvad(const SiibGeom& g, const SiibBuffers& b, int n, bool no_til
   return 1;
 }
 
-int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, const SiibEigBuffers* eb, int n, int64_t max_F,
+int siib_run(const SiibGeom& g, const SiibBuffers& b_in, const SiibKnnBuffers* kb, const SiibEigBuffers* eb, int n, int64_t max_F,
              int64_t max_unique, KernelTimer* kt, cudaStream_t s) {
   int launches = 0;
+  // FP32 xx lag products for the pairs that skip the Cholesky below (same condition: eb, x features not periodic), unless
+  // an A/B run asks for the FP64 ones (NELE_COV_XX64=1) or for the FP64 tridiagonalisation (NELE_TRIDIAG_F64=1)
+  static const bool xx64 = [] {
+    const char* p = getenv("NELE_COV_XX64");
+    const char* q = getenv("NELE_TRIDIAG_F64");
+    return (p && p[0] == '1') || (q && q[0] == '1');
+  }();
+  SiibBuffers b = b_in;
+  b.xx32 = (eb && !xx64) ? 1 : 0;
   kt_begin(kt, "siib_vad", s);
   siib_vad_kernel<<<n, kVad2Threads, 0, s>>>(g, b);
   kt_end(kt, s);
@@ -1666,7 +1699,7 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b, const SiibKnnBuffers* kb, 
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "siib_cov32", s);
-  siib_cov32_kernel<<<dim3((kCovTasks - kCovTasks64 + kCov32Warps - 1) / kCov32Warps, n), kCov32Warps * 32, 0, s>>>(g, b);
+  siib_cov32_kernel<<<dim3(b.xx32 ? 3 : 2, n), kCov32Warps * 32, 0, s>>>(g, b);
   kt_end(kt, s);
   ++launches;
   kt_begin(kt, "siib_expand", s);

@@ -191,13 +191,16 @@ __global__ void __launch_bounds__(kEThreads, 3) siib_tridiag_kernel(SiibGeom g, 
 //   * the range check that guards the recurrence against overflow looks at the exponent fields of the high words and
 //     rescales by an exact power of two: |p| grows by at most 7 per step (2^45 per block), the window is 2^+-128.
 constexpr int kSturmBlk = 16;
-constexpr int kSturmLen = 1 + ((kEDim - 1 + kSturmBlk - 1) / kSturmBlk) * kSturmBlk;  // 433
+constexpr int sturm_len(int n) { return 1 + ((n - 1 + kSturmBlk - 1) / kSturmBlk) * kSturmBlk; }
+constexpr int kSturmLen = sturm_len(kEDim);  // 433
+constexpr int kSturmLenSmall = sturm_len(112);  // 113: the Gram path (kSN below)
+template <int LEN>
 __device__ __forceinline__ int sturm_count(const double2* __restrict__ de, double x) {
   double pm = 1.0, p = de[0].x - x;
   unsigned sg = (unsigned)__double2hiint(p) >> 31;  // bit 0: sign of the newest p; p_{-1} = 1 is positive
   int cnt = (int)sg;
 #pragma unroll 1
-  for (int i0 = 1; i0 < kSturmLen; i0 += kSturmBlk) {
+  for (int i0 = 1; i0 < LEN; i0 += kSturmBlk) {
 #pragma unroll
     for (int i = 0; i < kSturmBlk; ++i) {
       const double2 c = de[i0 + i];
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(kEThreads) siib_trieig_kernel(SiibGeom g, Siib
   // One Sturm count per thread on a uniform grid of 420 cells first: every thread then finds its own cell by a binary
   // search of the counts (9 shared-memory reads instead of 8.7 bisection steps of 420 recurrence steps each) ...
   const double cell = 6.0 / kEDim;
-  if (tid < kEDim) s_grid[tid] = tid ? sturm_count(s_de, -3.0 + cell * tid) : 0;
+  if (tid < kEDim) s_grid[tid] = tid ? sturm_count<kSturmLen>(s_de, -3.0 + cell * tid) : 0;
   if (tid == 0) s_grid[kEDim] = kEDim;
   __syncthreads();
   if (tid >= kEDim) return;  // no block-wide barrier below
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(kEThreads) siib_trieig_kernel(SiibGeom g, Siib
   double lo = -3.0 + cell * klo, hi = -3.0 + cell * khi;
   for (int it = 0; it < 38; ++it) {
     const double mid = 0.5 * (lo + hi);
-    if (sturm_count(s_de, mid) > tid) hi = mid;
+    if (sturm_count<kSturmLen>(s_de, mid) > tid) hi = mid;
     else lo = mid;
   }
   const double lam = 0.5 * (lo + hi);
@@ -579,27 +582,6 @@ __global__ void __launch_bounds__(kGramThreads) siib_gram_kernel(SiibGeom g, Sii
     }
 }
 
-__device__ __forceinline__ int sturm_count_n(const double* __restrict__ d, const double* __restrict__ e2, int n, double x) {
-  double pm = 1.0, p = d[0] - x;
-  int cnt = (p < 0.0) ? 1 : 0;
-  for (int i0 = 1; i0 < n; i0 += 8) {
-    const int i1 = min(i0 + 8, n);
-    for (int i = i0; i < i1; ++i) {
-      const double pn = fma(d[i] - x, p, -e2[i - 1] * pm);
-      cnt += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
-      pm = p;
-      p = pn;
-    }
-    const double m = fmax(fabs(p), fabs(pm));
-    if (m > 1.0e100 || (m < 1.0e-100 && m > 0.0)) {
-      const double sc = 1.0 / m;
-      p *= sc;
-      pm *= sc;
-    }
-  }
-  return cnt;
-}
-
 // unblocked Householder tridiagonalisation of the padded Gram matrix in shared memory
 // (thread = row = column); d, e, tau and the reflectors (in the eliminated rows) go back to global
 __global__ void __launch_bounds__(128) siib_smalltri_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_hi) {
@@ -675,7 +657,11 @@ __global__ void __launch_bounds__(128) siib_smallvec_kernel(SiibGeom g, SiibBuff
   const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x;
   const int r = b.rank[pair];
   if (r < 2 || r > rank_hi) return;
+  constexpr int kLen = kSturmLenSmall;
+  static_assert(kSturmLenSmall == 1 + ((kSN - 1 + kSturmBlk - 1) / kSturmBlk) * kSturmBlk, "padded length follows kSN");
   __shared__ double s_d[kSN], s_e[kSN], s_e2[kSN];
+  __shared__ __align__(16) double2 s_de[kLen];
+  __shared__ int s_grid[kSN + 1];
   __shared__ double red[32];
   const double* __restrict__ dd = eb.d + (int64_t)lp * kELd;
   const double* __restrict__ ee = eb.e + (int64_t)lp * kELd;
@@ -688,14 +674,32 @@ __global__ void __launch_bounds__(128) siib_smallvec_kernel(SiibGeom g, SiibBuff
     const double ev = (tid < kSN - 1) ? ee[tid] * inv : 0.0;
     s_e[tid] = ev;
     s_e2[tid] = ev * ev;
+    s_de[tid].x = dd[tid] * inv;
+    if (tid + 1 < kSN) s_de[tid + 1].y = ev * ev;
+    if (tid == 0) s_de[0].y = 0.0;
+  } else if (tid < kLen) {
+    s_de[tid] = make_double2(1000.0, 0.0);
   }
+  __syncthreads();
+  // grid start and bisection as in siib_trieig_kernel: 52 steps from a cell of 6 / 112 end below the 6 * 2^-58 of the
+  // 58 steps from the whole interval that this (FP64) path has always taken
+  const double cell = 6.0 / kSN;
+  if (own) s_grid[tid] = tid ? sturm_count<kLen>(s_de, -3.0 + cell * tid) : 0;
+  if (tid == 0) s_grid[kSN] = kSN;
   __syncthreads();
   if (!own) return;
   float* __restrict__ scr = eb.zt + (int64_t)lp * kEDim * kELd;  // [i][128] D- sequence, then [i][128] z
-  double lo = -3.0, hi = 3.0;
-  for (int it = 0; it < 58; ++it) {
+  const int want = kSN - 1 - tid;  // ascending index of this thread's eigenvalue
+  int klo = 0, khi = kSN;
+  while (khi - klo > 1) {
+    const int km = (klo + khi) >> 1;
+    if (s_grid[km] > want) khi = km;
+    else klo = km;
+  }
+  double lo = -3.0 + cell * klo, hi = -3.0 + cell * khi;
+  for (int it = 0; it < 52; ++it) {
     const double mid = 0.5 * (lo + hi);
-    if (sturm_count_n(s_d, s_e2, kSN, mid) > kSN - 1 - tid) hi = mid;
+    if (sturm_count<kLen>(s_de, mid) > want) hi = mid;
     else lo = mid;
   }
   const double lam = 0.5 * (lo + hi);
