@@ -190,7 +190,9 @@ int nele_prefetch_cancel(nele_engine* e);
  *   "siib.tile"    i32 [4]             {M, active frames (wrapper VAD), frames of the tiled signal, active frames}
  *   "siib.logspec" f32 [2][Fa][32]     masked, de-meaned log band energies (28 bands + 4 zero lanes)
  *   "siib.sxx"     f64 [420][420]      centred scatter matrix of the stacked clean features
- *   "siib.sxy" / "siib.syy"  f32 [420][420]
+ *   "siib.sxy" / "siib.syy"  f32 [420][420]  cross / degraded scatter matrices FOLDED onto the lower triangle, the form the
+ *                                     quadratic forms read: F[c][a] = S[c][a] + S[a][c] (c > a), F[a][a] = S[a][a]; the
+ *                                     upper triangle is not written (nor any of it for pairs on the projection route)
  *   "siib.rank"    i32 [2]             {numerical rank of Sxx, Jacobi sweeps}
  *   "siib.lambda"  f32 [420]           eigenvalues of Sxx (order of the Jacobi columns; 0 beyond the rank)
  *   "siib.rho"     f32 [420]           per-component correlation

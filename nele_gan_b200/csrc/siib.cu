@@ -19,14 +19,14 @@
 //                        three 420 x 420 x Nf products (8x fewer flops, exact).
 //   siib_expand_kernel   per pair CTA: walks every block diagonal with the one-term-out,
 //                        one-term-in recurrence -> centred scatter matrices Sxx (FP64),
-//                        Sxy, Syy (FP32)
+//                        Sxy, Syy (FP32, folded onto the lower triangle: only u^T S u is ever needed)
 //   siib_chol_kernel     per pair CTA: diagonally pivoted left-looking Cholesky of Sxx in
 //                        FP64, stops at the numerical rank r -> L (FP32 copy, r columns)
 //   siib_jacobi_kernel   per pair CTA: one-sided (Hestenes) Jacobi on the r columns of L;
 //                        at convergence column j = sqrt(lambda_j) u_j, i.e. the KLT basis of
 //                        cov(X) without accumulating rotations.  Column blocks of 4 are held
 //                        in registers and paired by a round-robin tournament.
-//   siib_quad_kernel     per pair CTA: rho_j = u^T Sxy u / sqrt(lambda_j u^T Syy u), the
+//   qf::quadform_kernel  (siib_klt.cu) rho_j = u^T Sxy u / sqrt(lambda_j u^T Syy u), the
 //                        Gaussian channel capacity sum and the final score
 //
 // Rank-deficient inputs (a tiled signal whose length is a multiple of the 200-sample hop
@@ -793,42 +793,77 @@ __global__ void __launch_bounds__(kExpThreads) siib_expand_kernel(SiibGeom g, Si
   float* __restrict__ Sxy = b.Sxy + (int64_t)lp * kSDim * kSDim;
   float* __restrict__ Syy = b.Syy + (int64_t)lp * kSDim * kSDim;
   const double* __restrict__ base = b.base + (int64_t)lp * kSBlocks * (kSLanes * kSLanes);
-  // Every (block, j1, j2) diagonal is walked twice for the symmetric matrices: once with the lanes along j2,
-  // writing row segments of the upper block triangle, once with the lanes along j1, writing the mirrored
-  // element into the lower one -- so both stores are 28 consecutive values of a row (a lane-transposed store
-  // costs one L1 wavefront per element, which bound this kernel).
-  const bool proj = siib_projected(b, pair, Nf);
-  const int ndiag = (proj ? 15 : kSBlocks) * kSBands * kSBands;  // xx blocks only / all 59
-  const int nmir = (proj ? 15 : 30) * kSBands * kSBands;         // xx (and yy) blocks have a mirror image
-  for (int it = tid; it < ndiag + nmir; it += kExpThreads) {
-    const bool mirror = it >= ndiag;
-    const int idx = mirror ? it - ndiag : it;
-    const int blk = idx / (kSBands * kSBands), rem = idx % (kSBands * kSBands);
+  // Sxx (FP64, full): every (block, j1, j2) diagonal is walked twice, once with the lanes along j2, writing row
+  // segments of the upper block triangle, once with the lanes along j1, writing the mirrored element into the lower
+  // one -- so both stores are 28 consecutive values of a row (a lane-transposed store costs one L1 wavefront per
+  // element, which bound this kernel).
+  for (int it = tid; it < 2 * 15 * kSBands * kSBands; it += kExpThreads) {
+    const bool mirror = it >= 15 * kSBands * kSBands;
+    const int idx = mirror ? it - 15 * kSBands * kSBands : it;
+    const int d = idx / (kSBands * kSBands), rem = idx % (kSBands * kSBands);
     const int j1 = mirror ? rem % kSBands : rem / kSBands, j2 = mirror ? rem / kSBands : rem % kSBands;
-    int ta, tb, d;
-    block_desc(blk, ta, tb, d);
     if (mirror && d == 0) continue;   // a diagonal block is its own mirror image
-    const float (*A)[kSLanes] = s_edge[ta];
-    const float (*B)[kSLanes] = s_edge[tb];
-    int k1 = max(0, -d), k2 = max(0, d);
-    double r = base[blk * (kSLanes * kSLanes) + j1 * kSLanes + j2];
-    const int steps = kSStack - (d < 0 ? -d : d);
+    const float (*A)[kSLanes] = s_edge[0];
+    int k1 = 0, k2 = d;
+    double r = base[d * (kSLanes * kSLanes) + j1 * kSLanes + j2];
+    const int steps = kSStack - d;
     for (int m = 0; m < steps; ++m) {
       const int a = k1 * kSBands + j1, c = k2 * kSBands + j2;
-      const double v = r - s_rs[ta][a] * s_rs[tb][c] * inv_nf;
-      if (!mirror) {
-        if (blk < 15) Sxx[(int64_t)a * kSDim + c] = v;
-        else if (blk < 30) Syy[(int64_t)a * kSDim + c] = (float)v;
-        else Sxy[(int64_t)a * kSDim + c] = (float)v;
-      } else {
-        if (blk < 15) Sxx[(int64_t)c * kSDim + a] = v;
-        else Syy[(int64_t)c * kSDim + a] = (float)v;
-      }
+      const double v = r - s_rs[0][a] * s_rs[0][c] * inv_nf;
+      if (!mirror) Sxx[(int64_t)a * kSDim + c] = v;
+      else Sxx[(int64_t)c * kSDim + a] = v;
       if (m + 1 == steps) break;
       // slide the summation window by one frame
-      r += (double)A[kSStack + k1][j1] * (double)B[kSStack + k2][j2] - (double)A[k1][j1] * (double)B[k2][j2];
+      r += (double)A[kSStack + k1][j1] * (double)A[kSStack + k2][j2] - (double)A[k1][j1] * (double)A[k2][j2];
       ++k1;
       ++k2;
+    }
+  }
+  if (siib_projected(b, pair, Nf)) return;  // siib_projquad_kernel needs neither Syy nor Sxy
+  // Syy and Sxy enter the score only through the quadratic forms u^T S u (qf::quadform_kernel), which see the symmetric
+  // part of S: they are stored FOLDED onto the lower triangle -- F[c][a] = S[c][a] + S[a][c] for c > a, F[a][a] = S[a][a],
+  // the upper triangle is never written nor read -- so the products visit half the matrix.  Element a = (k1, j1),
+  // c = (k1 + d, j2), d >= 0 (d = 0: j2 >= j1): Syy[a][c] = Syy[c][a] comes from the yy block of lag d; Sxy[a][c] from
+  // the xy block of lag d and Sxy[c][a] from the one of lag -d, each with its own sliding window.  Lanes along j1: the
+  // stores are consecutive values of row c.
+  for (int it = tid; it < 2 * 15 * kSBands * kSBands; it += kExpThreads) {
+    const bool xy = it >= 15 * kSBands * kSBands;
+    const int idx = xy ? it - 15 * kSBands * kSBands : it;
+    const int d = idx / (kSBands * kSBands), rem = idx % (kSBands * kSBands);
+    const int j1 = rem % kSBands, j2 = rem / kSBands;
+    if (d == 0 && j2 < j1) continue;
+    const bool diag = d == 0 && j1 == j2;
+    int k1 = 0, k2 = d;
+    const int steps = kSStack - d;
+    if (!xy) {
+      const float (*B)[kSLanes] = s_edge[1];
+      double r = base[(15 + d) * (kSLanes * kSLanes) + j1 * kSLanes + j2];
+      for (int m = 0; m < steps; ++m) {
+        const int a = k1 * kSBands + j1, c = k2 * kSBands + j2;
+        const double v = r - s_rs[1][a] * s_rs[1][c] * inv_nf;
+        Syy[(int64_t)c * kSDim + a] = (float)(diag ? v : 2.0 * v);
+        if (m + 1 == steps) break;
+        r += (double)B[kSStack + k1][j1] * (double)B[kSStack + k2][j2] - (double)B[k1][j1] * (double)B[k2][j2];
+        ++k1;
+        ++k2;
+      }
+    } else {
+      const float (*A)[kSLanes] = s_edge[0];
+      const float (*B)[kSLanes] = s_edge[1];
+      // r1: x_a y_c (x stack k1, band j1; y stack k2, band j2), r2: x_c y_a (x stack k2, band j2; y stack k1, band j1)
+      double r1 = base[(44 + d) * (kSLanes * kSLanes) + j1 * kSLanes + j2];
+      double r2 = base[(44 - d) * (kSLanes * kSLanes) + j2 * kSLanes + j1];
+      for (int m = 0; m < steps; ++m) {
+        const int a = k1 * kSBands + j1, c = k2 * kSBands + j2;
+        const double v1 = r1 - s_rs[0][a] * s_rs[1][c] * inv_nf;
+        const double v2 = r2 - s_rs[0][c] * s_rs[1][a] * inv_nf;
+        Sxy[(int64_t)c * kSDim + a] = (float)(diag ? v1 : v1 + v2);
+        if (m + 1 == steps) break;
+        r1 += (double)A[kSStack + k1][j1] * (double)B[kSStack + k2][j2] - (double)A[k1][j1] * (double)B[k2][j2];
+        r2 += (double)A[kSStack + k2][j2] * (double)B[kSStack + k1][j1] - (double)A[k2][j2] * (double)B[k1][j1];
+        ++k1;
+        ++k2;
+      }
     }
   }
 }
@@ -1356,125 +1391,6 @@ __global__ void __launch_bounds__(NWARP * 32) siib_jacobi2_kernel(SiibGeom g, Si
   if (threadIdx.x == 0 && crank == 0) b.sweeps[pair] = sweeps;
 }
 
-// ------------------------------------------------------- quadratic forms + score
-constexpr int kQuadThreads = 448;
-constexpr int kQuadJ = 16;  // eigenvectors per pass over Sxy / Syy (each pass re-reads 1.4 MB); 24 per pass was slower (104 registers, one CTA per SM)
-
-__global__ void __launch_bounds__(kQuadThreads) siib_quad_kernel(SiibGeom g, SiibBuffers b) {
-  const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-  constexpr int NW = kQuadThreads / 32;
-  const int Fa = b.Fa[pair];
-  const int Nf = Fa - (kSStack - 1);
-  const int M = b.M[pair];
-  if (M <= 0 || (double)Fa / 80.0 < 20.0 || Nf < 2) {  // pysiib: "at least 20 seconds of speech"
-    if (tid == 0) {
-      b.score[pair] = nan("");
-      b.status[pair] = 2;
-    }
-    return;
-  }
-  if (siib_projected(b, pair, Nf)) return;  // siib_projquad_kernel scores this pair
-  const int r = b.rank[pair];
-  const float* __restrict__ G = b.G + (int64_t)lp * kSDim * kSLd;
-  const float* __restrict__ Sxy = b.Sxy + (int64_t)lp * kSDim * kSDim;
-  const float* __restrict__ Syy = b.Syy + (int64_t)lp * kSDim * kSDim;
-  __shared__ __align__(16) float s_u[kSDim][kQuadJ];  // unit eigenvectors in original coordinates
-  __shared__ float s_lam[kQuadJ];
-  __shared__ float s_part[NW][2 * kQuadJ];
-  __shared__ double s_info;
-  if (tid == 0) s_info = 0.0;
-  float* __restrict__ lam_out = b.lambda + (int64_t)pair * kSDim;
-  float* __restrict__ rho_out = b.rho + (int64_t)pair * kSDim;
-  for (int j0 = 0; j0 < r; j0 += kQuadJ) {
-    __syncthreads();
-    // norms of the columns j0..j0+7 (one warp per column), then scatter the unit vectors
-    for (int jj = wib; jj < kQuadJ; jj += NW) {
-      float s = 0.f;
-      if (j0 + jj < r) {
-        const float* col = G + (int64_t)(j0 + jj) * kSLd;
-        for (int i = lane; i < kSDim; i += 32) s = fmaf(col[i], col[i], s);
-      }
-      s = warp_sum(s);
-      if (lane == 0) s_lam[jj] = s;
-    }
-    __syncthreads();
-    if (tid < kSDim) {
-      const int orig = tid;  // the factor keeps the original row order
-#pragma unroll
-      for (int jj = 0; jj < kQuadJ; ++jj) {
-        const float lam = s_lam[jj];
-        s_u[orig][jj] = (j0 + jj < r && lam > 0.f) ? G[(int64_t)(j0 + jj) * kSLd + tid] * rsqrtf(lam) : 0.f;
-      }
-    }
-    __syncthreads();
-    float axy[kQuadJ], ayy[kQuadJ];
-#pragma unroll
-    for (int jj = 0; jj < kQuadJ; ++jj) axy[jj] = ayy[jj] = 0.f;
-    if (tid < kSDim) {
-#pragma unroll 4
-      for (int c = 0; c < kSDim; ++c) {
-        const float sxy = __ldg(Sxy + (int64_t)c * kSDim + tid), syy = __ldg(Syy + (int64_t)c * kSDim + tid);
-        const float4 u0 = *reinterpret_cast<const float4*>(&s_u[c][0]);
-        const float4 u1 = *reinterpret_cast<const float4*>(&s_u[c][4]);
-        const float4 u2 = *reinterpret_cast<const float4*>(&s_u[c][8]);
-        const float4 u3 = *reinterpret_cast<const float4*>(&s_u[c][12]);
-        const float uu[kQuadJ] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w,
-                                  u2.x, u2.y, u2.z, u2.w, u3.x, u3.y, u3.z, u3.w};
-#pragma unroll
-        for (int jj = 0; jj < kQuadJ; ++jj) {
-          axy[jj] = fmaf(sxy, uu[jj], axy[jj]);
-          ayy[jj] = fmaf(syy, uu[jj], ayy[jj]);
-        }
-      }
-      // (u^T S)_i u_i
-#pragma unroll
-      for (int jj = 0; jj < kQuadJ; ++jj) {
-        axy[jj] *= s_u[tid][jj];
-        ayy[jj] *= s_u[tid][jj];
-      }
-    }
-#pragma unroll
-    for (int jj = 0; jj < kQuadJ; ++jj) {
-      const float a = warp_sum(axy[jj]), c = warp_sum(ayy[jj]);
-      if (lane == 0) {
-        s_part[wib][jj] = a;
-        s_part[wib][kQuadJ + jj] = c;
-      }
-    }
-    __syncthreads();
-    if (tid < kQuadJ && j0 + tid < r) {
-      double a = 0.0, c = 0.0;
-      for (int w = 0; w < NW; ++w) {
-        a += (double)s_part[w][tid];
-        c += (double)s_part[w][kQuadJ + tid];
-      }
-      const double lam = (double)s_lam[tid];
-      double rho = 0.0;
-      if (lam > 0.0 && c > 0.0) rho = a / sqrt(lam * c);
-      if (rho > 1.0) rho = 1.0;
-      if (rho < -1.0) rho = -1.0;
-      const double pr = 0.75 * rho;
-      atomicAdd(&s_info, -0.5 * log2(1.0 - pr * pr));
-      lam_out[j0 + tid] = (float)lam;
-      rho_out[j0 + tid] = (float)rho;
-    }
-  }
-  __syncthreads();
-  for (int j = r + tid; j < kSDim; j += kQuadThreads) {
-    lam_out[j] = 0.f;
-    rho_out[j] = 0.f;
-  }
-  if (tid == 0) {
-    const double R = 1.0 / 200.0 * 16000.0;
-    const double v = R / (double)kSStack * s_info;
-    b.score[pair] = v > 0.0 ? v : 0.0;
-    // bit 8: the null space of a rank-deficient (exactly periodic) covariance was given zero information
-    // (NELE_INFO_SIIB_NULLSPACE).  sweeps: -1 tridiagonal path at full rank, -3 rank deficient, -2 Gram path.
-    const int sw = b.sweeps[pair];
-    b.status[pair] = (sw == -2 || sw == -3 || (sw >= 0 && r < kSDim)) ? 0x100 : 0;
-  }
-}
-
 // -------------------------------------------------- projection route (periodic pairs)
 // rho_j of a pair whose stacked frames repeat (siib_projected): with the summation plan of
 // cov_span only the first 2 P stacked frames are distinct, so
@@ -1497,7 +1413,7 @@ __global__ void __launch_bounds__(kPqThreads) siib_projquad_kernel(SiibGeom g, S
   const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   const int Fa = b.Fa[pair];
   const int Nf = Fa - (kSStack - 1);
-  if (b.M[pair] <= 0 || (double)Fa / 80.0 < 20.0 || Nf < 2) return;  // siib_quad_kernel reports these
+  if (b.M[pair] <= 0 || (double)Fa / 80.0 < 20.0 || Nf < 2) return;  // quad_finish_kernel reports these
   if (!siib_projected(b, pair, Nf)) return;
   const CovSpan span = cov_span(b, pair, Nf, true);
   const int r = b.rank[pair];
@@ -1743,16 +1659,8 @@ int siib_run(const SiibGeom& g, const SiibBuffers& b_in, const SiibKnnBuffers* k
     }
   }
   if (kb) return launches + siib_run_knn(g, b, *kb, n, max_F, kt, s);
-  // default: register-tiled quadratic forms (siib_klt.cu); NELE_SIIB_QUAD_OLD=1 selects the thread-per-row kernel (A/B)
-  static const bool quad_old = [] { const char* p = getenv("NELE_SIIB_QUAD_OLD"); return p && p[0] == '1'; }();
-  if (quad_old) {
-    kt_begin(kt, "siib_quad", s);
-    siib_quad_kernel<<<n, kQuadThreads, 0, s>>>(g, b);
-    kt_end(kt, s);
-    ++launches;
-  } else {
-    launches += siib_launch_quadform(b, b.info_part, n, kt, s);
-  }
+  // register-tiled quadratic forms over the folded Sxy / Syy (siib_klt.cu)
+  launches += siib_launch_quadform(b, b.info_part, n, kt, s);
   if (!b.no_proj) {
     kt_begin(kt, "siib_projquad", s);
     siib_projquad_kernel<<<n, kPqThreads, kPqSmem, s>>>(g, b);

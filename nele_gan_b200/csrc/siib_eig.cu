@@ -17,7 +17,7 @@
 //                        an explicit exponent, so no O(n) per-thread storage is needed
 //   siib_backtf_kernel   per (pair, 64 eigenvectors) CTA, 4 lanes per vector: u = H_0 ... H_{n-3} z
 //                        with the vector in registers, reflectors staged through shared memory;
-//                        writes G[j] = sqrt(lambda_j) u_j, the format siib_quad_kernel reads
+//                        writes G[j] = sqrt(lambda_j) u_j, the format qf::quadform_kernel reads
 #include <stdlib.h>
 
 #include <algorithm>
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(kBtThreads, 2) siib_backtf_kernel(SiibGeom g, 
   }
 }
 
-// rank <- 420 for the pairs that took this path (siib_quad_kernel loops over `rank` columns)
+// rank <- 420 for the pairs that took this path (qf::quadform_kernel loops over `rank` columns)
 __global__ void siib_eig_finish_kernel(SiibBuffers b, int n, int rank_lo) {
   const int lp = blockIdx.x * blockDim.x + threadIdx.x;
   if (lp >= n) return;
@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(128) siib_smalltri_kernel(SiibGeom g, SiibBuff
 }
 
 // eigenpairs of the 112 x 112 tridiagonal (as siib_trieig_kernel): thread = eigenvalue, descending,
-// so that the <= r non-zero ones fill the first columns (siib_quad_kernel reads `rank` of them)
+// so that the <= r non-zero ones fill the first columns (qf::quadform_kernel reads `rank` of them)
 __global__ void __launch_bounds__(128) siib_smallvec_kernel(SiibGeom g, SiibBuffers b, SiibEigBuffers eb, int rank_hi) {
   const int lp = blockIdx.x, pair = b.pair_lo + lp, tid = threadIdx.x;
   const int r = b.rank[pair];

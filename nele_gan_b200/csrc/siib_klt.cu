@@ -429,8 +429,9 @@ __global__ void __launch_bounds__(NT, 2) tridiag32_kernel(SiibBuffers b, SiibEig
 // FP32 product per 64 eigenvectors: W = S^T G (420 x 420 x 64, Sxy and Syy side by side sharing the G
 // fragments) with the epilogue a_j = sum_i G[i][j] W[i][j] fused, so W never exists.  G[j] = sqrt(lambda_j) u_j
 // is what every KLT route leaves in b.G (column j contiguous); lambda_j = |G_j|^2 comes out of the same epilogue.
-// Replaces siib_quad_kernel (thread = row, 16 eigenvectors per pass: Sxy / Syy re-read 27 times per pair, 36 GB
-// of L2 traffic per 1024 pairs, 14.9 ms) -- here they are read 7 times by CTAs that run 64 FMAs per 5 shared loads.
+// Replaced round 1's siib_quad_kernel (thread = row, 16 eigenvectors per pass: Sxy / Syy re-read 27 times per pair,
+// 36 GB of L2 traffic per 1024 pairs, 14.9 ms) -- here they are read 7 times by CTAs that run 64 FMAs per 5 shared
+// loads, and only their folded lower triangles (u^T S u = u^T F u, F[c][i] = S[c][i] + S[i][c] for c > i).
 //   CTA = (64-eigenvector tile, pair), 256 threads = 16 (rows) x 16 (columns), thread tile 8 x 4 x 2 matrices,
 //   k-steps of 16 through double-buffered shared memory, next tile prefetched into registers.
 namespace qf {
@@ -483,14 +484,23 @@ __global__ void __launch_bounds__(NT, 2) quadform_kernel(SiibBuffers b, double* 
   const int bj = tid >> 2, bc = 4 * (tid & 3);
   const bool bj_ok = j0 + bj < r;
   float4 rxy[2], ryy[2], rb;
+  // Sxy and Syy arrive folded onto the lower triangle (siib_expand_kernel: F[c][i] = S[c][i] + S[i][c], c > i), so a
+  // row block only visits the k-tiles from its own first row on, and in the eight tiles that cross the diagonal the
+  // elements above it (never written) are replaced by zeros
   auto fetch = [&](int i0, int kt) {
     const int c0 = kt * BK;
+    const bool crosses = c0 < i0 + BM;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int c = c0 + arow + 8 * h, i = i0 + acol;
-      const bool ok = c < N && i < N;
+      const bool ok = c < N && i < N && c >= i;
       rxy[h] = ok ? __ldg(reinterpret_cast<const float4*>(Sxy + (int64_t)c * N + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
       ryy[h] = ok ? __ldg(reinterpret_cast<const float4*>(Syy + (int64_t)c * N + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (crosses) {
+        if (c < i + 1) rxy[h].y = ryy[h].y = 0.f;
+        if (c < i + 2) rxy[h].z = ryy[h].z = 0.f;
+        if (c < i + 3) rxy[h].w = ryy[h].w = 0.f;
+      }
     }
     const int c = c0 + bc;
     rb = (bj_ok && c < N) ? __ldg(reinterpret_cast<const float4*>(G + (int64_t)(j0 + bj) * LD + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -517,10 +527,11 @@ __global__ void __launch_bounds__(NT, 2) quadform_kernel(SiibBuffers b, double* 
 #pragma unroll
       for (int c = 0; c < 4; ++c) axy[a][c] = ayy[a][c] = f2_pack(0.f, 0.f);
     __syncthreads();
-    fetch(i0, 0);
-    stash(0);
+    const int kt0 = i0 / BK;   // BM is a multiple of BK
+    fetch(i0, kt0);
+    stash(kt0 & 1);
     __syncthreads();
-    for (int kt = 0; kt < KT; ++kt) {
+    for (int kt = kt0; kt < KT; ++kt) {
       const int cur = kt & 1;
       if (kt + 1 < KT) fetch(i0, kt + 1);
 #pragma unroll

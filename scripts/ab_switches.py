@@ -10,7 +10,7 @@ import sys
 # every configuration is one set of environment switches of DESIGN.md section 9 (A/B references of the round-2 defaults)
 CONFIGS = [("default", {}), ("ear_scalar", {"NELE_F32X2": "0"}), ("resample_f64", {"NELE_RESAMPLE_F32": "0"}),
            ("tridiag_f64", {"NELE_TRIDIAG_F64": "1"}), ("backtf_old", {"NELE_BACKTF_OLD": "1"}),
-           ("backtf4", {"NELE_BACKTF4": "1"}), ("backtf5", {"NELE_BACKTF5": "1"}), ("quad_old", {"NELE_SIIB_QUAD_OLD": "1"})]
+           ("backtf4", {"NELE_BACKTF4": "1"}), ("backtf5", {"NELE_BACKTF5": "1"}), ("cov_xx64", {"NELE_COV_XX64": "1"})]
 
 CHILD = r'''
 import json, sys

@@ -102,6 +102,15 @@ def test_siib_scores_and_stages_full_rank(eng):
         xm = Xs - Xs.mean(1, keepdims=True)
         sxx = eng.stage("siib.sxx", i).reshape(420, 420)
         assert np.abs(sxx - xm @ xm.T).max() < 1e-5 * np.abs(sxx).max()
+        # Sxy / Syy are kept folded onto the lower triangle (u^T S u only sees the symmetric part of S)
+        Ys = pysiib_np.stack_frames(st["Y"], 15)
+        ym = Ys - Ys.mean(1, keepdims=True)
+        low = np.tril_indices(420)
+        for name, S in (("siib.sxy", xm @ ym.T), ("siib.syy", ym @ ym.T)):
+            F = S + S.T
+            F[np.diag_indices(420)] = np.diag(S)
+            got = eng.stage(name, i).reshape(420, 420)
+            assert np.abs(got[low] - F[low]).max() < 2e-5 * np.abs(F).max(), name
         rk = eng.stage("siib.rank", i)
         assert rk[0] == 420 and (rk[1] == -1 or 0 < rk[1] < 14)      # -1: tridiagonalisation path (no sweeps)
         lam = np.sort(eng.stage("siib.lambda", i))[::-1]
