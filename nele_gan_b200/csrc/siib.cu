@@ -347,15 +347,29 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 3) siib_spec_kernel(SiibGeom 
     const int64_t f = b.act[g.offF[pair] + t];
     const int base = (int)((f * kSHop) % L);
     __syncwarp();
+    if (base + kSWin <= L) {
+      // all but one frame per tile: no wrap, constant offsets from one pointer per signal
+      const float* __restrict__ xf = x + base + lane;
+      const float* __restrict__ yf = y + base + lane;
+      const float* wl = sm.win + lane;
+      cpx* zl = z + lane;
+#pragma unroll
+      for (int k = 0; k < (kSWin + 31) / 32; ++k)
+        if (k * 32 + 32 <= kSWin || lane < kSWin - k * 32) {
+          const float w = wl[k * 32];
+          zl[k * 32] = {w * (xf[k * 32] - mx), w * (yf[k * 32] - my)};
+        }
+    } else {
 #pragma unroll 1
-    for (int i = lane; i < kSWin; i += 32) {
-      int idx = base + i;  // < 2 L
-      if (idx >= L) {
-        idx -= L;
-        if (idx >= L) idx %= L;  // utterances shorter than a frame
+      for (int i = lane; i < kSWin; i += 32) {
+        int idx = base + i;  // < 2 L
+        if (idx >= L) {
+          idx -= L;
+          if (idx >= L) idx %= L;  // utterances shorter than a frame
+        }
+        const float w = sm.win[i];
+        z[i] = {w * (x[idx] - mx), w * (y[idx] - my)};
       }
-      const float w = sm.win[i];
-      z[i] = {w * (x[idx] - mx), w * (y[idx] - my)};
     }
     __syncwarp();
     if (lane < 25) fft400_phase_a(lane, z, sm.tw);
@@ -364,12 +378,21 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 3) siib_spec_kernel(SiibGeom 
     __syncwarp();
     // power spectra of the two real signals, (px, py) of bin k written over X[k]: no other bin reads X[k]
     // (bin k reads X[k] and X[400 - k], and 400 - k > 200 unless k = 200)
+    // k = lane + 32 it: fft400_pos(k) = pos(lane) + 2 it and fft400_pos(400 - k) = pos(400 - lane) - 2 it (k > 0), so
+    // the unrolled loop addresses both with constant offsets
     float2* pw = reinterpret_cast<float2*>(z);
-    for (int k = lane; k < kSBins; k += 32) {
-      const int pk = fft400_pos(k);
-      const cpx a = z[pk], c = z[fft400_pos((kSWin - k) % kSWin)];
-      const float xr = a.x + c.x, xi = a.y - c.y, yr = a.y + c.y, yi = c.x - a.x;
-      pw[pk] = make_float2(0.25f * (xr * xr + xi * xi), 0.25f * (yr * yr + yi * yi));
+    {
+      const cpx* za = z + fft400_pos(lane);
+      const cpx* zc = z + fft400_pos(kSWin - lane);  // lane 0: position of "bin 400", replaced by bin 0 below
+      float2* pa = pw + fft400_pos(lane);
+#pragma unroll
+      for (int it = 0; it < (kSBins + 31) / 32; ++it)
+        if (it * 32 + 32 <= kSBins || lane < kSBins - it * 32) {
+          const cpx a = za[2 * it];
+          const cpx c = (it == 0 && lane == 0) ? a : zc[-2 * it];
+          const float xr = a.x + c.x, xi = a.y - c.y, yr = a.y + c.y, yi = c.x - a.x;
+          pa[2 * it] = make_float2(0.25f * (xr * xr + xi * xi), 0.25f * (yr * yr + yi * yi));
+        }
     }
     __syncwarp();
     float ex = 0.f, ey = 0.f;
