@@ -77,9 +77,13 @@ NELE_HD void fft16_stage(cpx (&a)[16]) {
   fft16_butterfly<S, 7>(a);
 }
 
-// tw400[k] = exp(-2 pi i k / 400), k = 0..399 (shared or global memory)
+// Twiddle tables (shared memory), both cut from w[k] = exp(-2 pi i k / 400):
+//   twa[25 k1 + n2] = w[n2 k1]   phase A: lane n2 reads consecutive words for a fixed k1 (indexing w[n2 k1] directly
+//                                 costs up to 13 shared-memory wavefronts per load: the stride 2 k1 words folds the 25
+//                                 lanes onto few banks; siib_spec_kernel is bound by the shared-memory pipe)
+//   tw25[m]         = w[16 m]     phase B: the 25th roots of unity, one broadcast read each
 // phase A for lane n2 (< 25), in place on z[400]
-NELE_HD void fft400_phase_a(int n2, cpx* z, const cpx* tw400) {
+NELE_HD void fft400_phase_a(int n2, cpx* z, const cpx* twa) {
   cpx a[16];
   // bit-reversed load for radix-2 decimation in time
 #pragma unroll
@@ -93,11 +97,11 @@ NELE_HD void fft400_phase_a(int n2, cpx* z, const cpx* tw400) {
   fft16_stage<3>(a);
   z[n2] = a[0];
 #pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) z[k1 * 25 + n2] = cmulc(a[k1], tw400[n2 * k1]);  // n2 k1 <= 360
+  for (int k1 = 1; k1 < 16; ++k1) z[k1 * 25 + n2] = cmulc(a[k1], twa[k1 * 25 + n2]);
 }
 
 // phase B for lane k1 (< 16), in place on row k1 of z: X[k1 + 16 k2] ends at z[25 k1 + k2]
-NELE_HD void fft400_phase_b(int k1, cpx* z, const cpx* tw400) {
+NELE_HD void fft400_phase_b(int k1, cpx* z, const cpx* tw25) {
   cpx v[25];
   cpx* row = z + k1 * 25;
 #pragma unroll
@@ -108,7 +112,7 @@ NELE_HD void fft400_phase_b(int k1, cpx* z, const cpx* tw400) {
     dft5(v[nb], v[5 + nb], v[10 + nb], v[15 + nb], v[20 + nb]);  // index 5 ka + nb now holds ka
     if (nb > 0) {
 #pragma unroll
-      for (int ka = 1; ka < 5; ++ka) v[5 * ka + nb] = cmulc(v[5 * ka + nb], tw400[16 * ((nb * ka) % 25)]);
+      for (int ka = 1; ka < 5; ++ka) v[5 * ka + nb] = cmulc(v[5 * ka + nb], tw25[(nb * ka) % 25]);
     }
   }
 #pragma unroll

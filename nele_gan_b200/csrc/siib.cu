@@ -300,17 +300,20 @@ __global__ void __launch_bounds__(kVad2Threads) siib_vad_kernel(SiibGeom g, Siib
 // ------------------------------------------------------------- spectra
 constexpr int kSpecWarps = 8;
 struct SpecSmem {
-  cpx tw[kSWin];
+  cpx twa[kSWin];            // fft400.cuh: phase-A twiddles [k1][n2]
+  cpx tw25[32];              // phase-B twiddles (25 used)
   float win[kSWin];
   float g2t[kSBins * kSLanes];
-  cpx z[kSpecWarps][kSWin];  // one buffer per warp: the FFT is in place (fft400.cuh), the power spectra overwrite it
+  cpx z[kSpecWarps][kSWin];  // one buffer per warp: the FFT is in place (fft400.cuh)
+  float2 pw[kSpecWarps][kSBins + 1];  // power spectra (px, py) in bin order: two bins per 128-bit broadcast read
 };
 
 constexpr int kSpecIter = 8;  // frames per warp: the 29 KB of tables are staged once per 64 frames, not once per 8
 
-// 55 KB of shared memory and <= 80 registers: three CTAs (24 warps) per SM.  The kernel is issue bound (68 % of the
-// issue slots with 16 warps, 2970 instructions per frame of which the band sums were 1300): the band sums now run
-// fully unrolled over constant positions, the 16-point FFTs carry their twiddles as constants.
+// 68 KB of shared memory and <= 80 registers: three CTAs (24 warps) per SM.  Round 2 started from 2970 instructions
+// per frame at 68 % of the issue slots with 16 warps; unrolled band sums, constant FFT twiddles and constant offsets
+// brought that to 1985, at which point the shared-memory pipe became the limit (ncu: 93 % busy) -- hence the
+// conflict-free twiddle table and the 128-bit reads of the power spectra.
 __global__ void __launch_bounds__(kSpecWarps * 32, 3) siib_spec_kernel(SiibGeom g, SiibBuffers b) {
   const int pair = b.pair_lo + blockIdx.y, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int Fa = b.Fa[pair];
@@ -329,9 +332,10 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 3) siib_spec_kernel(SiibGeom 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SpecSmem& sm = *reinterpret_cast<SpecSmem*>(smem_raw);
   for (int k = threadIdx.x; k < kSWin; k += kSpecWarps * 32) {
-    sm.tw[k] = g_siib_tw[k];
+    sm.twa[k] = g_siib_tw[(k % 25) * (k / 25)];   // n2 k1 <= 360
     sm.win[k] = g_siib_win[k];
   }
+  if (threadIdx.x < 25) sm.tw25[threadIdx.x] = g_siib_tw[16 * threadIdx.x];
   for (int k = threadIdx.x; k < kSBins * kSLanes; k += kSpecWarps * 32) sm.g2t[k] = g_siib_g2t[k];
   __syncthreads();
   const float* __restrict__ x = b.ref + g.off16[pair];
@@ -372,34 +376,42 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 3) siib_spec_kernel(SiibGeom 
       }
     }
     __syncwarp();
-    if (lane < 25) fft400_phase_a(lane, z, sm.tw);
+    if (lane < 25) fft400_phase_a(lane, z, sm.twa);
     __syncwarp();
-    if (lane < 16) fft400_phase_b(lane, z, sm.tw);
+    if (lane < 16) fft400_phase_b(lane, z, sm.tw25);
     __syncwarp();
-    // power spectra of the two real signals, (px, py) of bin k written over X[k]: no other bin reads X[k]
-    // (bin k reads X[k] and X[400 - k], and 400 - k > 200 unless k = 200)
-    // k = lane + 32 it: fft400_pos(k) = pos(lane) + 2 it and fft400_pos(400 - k) = pos(400 - lane) - 2 it (k > 0), so
-    // the unrolled loop addresses both with constant offsets
-    float2* pw = reinterpret_cast<float2*>(z);
+    // power spectra of the two real signals.  k = lane + 32 it: fft400_pos(k) = pos(lane) + 2 it and
+    // fft400_pos(400 - k) = pos(400 - lane) - 2 it (k > 0), so the unrolled loop reads both with constant offsets
+    float2* pw = sm.pw[wib];
     {
       const cpx* za = z + fft400_pos(lane);
       const cpx* zc = z + fft400_pos(kSWin - lane);  // lane 0: position of "bin 400", replaced by bin 0 below
-      float2* pa = pw + fft400_pos(lane);
 #pragma unroll
       for (int it = 0; it < (kSBins + 31) / 32; ++it)
         if (it * 32 + 32 <= kSBins || lane < kSBins - it * 32) {
           const cpx a = za[2 * it];
           const cpx c = (it == 0 && lane == 0) ? a : zc[-2 * it];
           const float xr = a.x + c.x, xi = a.y - c.y, yr = a.y + c.y, yi = c.x - a.x;
-          pa[2 * it] = make_float2(0.25f * (xr * xr + xi * xi), 0.25f * (yr * yr + yi * yi));
+          pw[it * 32 + lane] = make_float2(0.25f * (xr * xr + xi * xi), 0.25f * (yr * yr + yi * yi));
         }
     }
     __syncwarp();
+    // band energies: the kernel is bound by the shared-memory pipe (93 % busy), and these sums are most of its
+    // wavefronts -- one per lane-indexed filter weight, one per TWO bins of the broadcast power spectra
     float ex = 0.f, ey = 0.f;
+    const float4* pw4 = reinterpret_cast<const float4*>(pw);
 #pragma unroll
-    for (int k = 0; k < kSBins; ++k) {
-      const float2 p = pw[(k & 15) * 25 + (k >> 4)];
-      const float gk = gl[k * kSLanes];
+    for (int k2 = 0; k2 < kSBins / 2; ++k2) {
+      const float4 p = pw4[k2];
+      const float g0 = gl[(2 * k2) * kSLanes], g1 = gl[(2 * k2 + 1) * kSLanes];
+      ex = fmaf(g0, p.x, ex);
+      ey = fmaf(g0, p.y, ey);
+      ex = fmaf(g1, p.z, ex);
+      ey = fmaf(g1, p.w, ey);
+    }
+    {
+      const float2 p = pw[kSBins - 1];
+      const float gk = gl[(kSBins - 1) * kSLanes];
       ex = fmaf(gk, p.x, ex);
       ey = fmaf(gk, p.y, ey);
     }

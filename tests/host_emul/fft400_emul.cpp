@@ -16,8 +16,13 @@
 using namespace nele;
 
 static void run(std::vector<cpx>& z, const cpx* tw, bool reverse) {
-  for (int i = 0; i < 25; ++i) fft400_phase_a(reverse ? 24 - i : i, z.data(), tw);
-  for (int i = 0; i < 16; ++i) fft400_phase_b(reverse ? 15 - i : i, z.data(), tw);
+  // the two tables siib_spec_kernel cuts from w[k] = exp(-2 pi i k / 400)
+  std::vector<cpx> twa(400), tw25(25);
+  for (int k1 = 0; k1 < 16; ++k1)
+    for (int n2 = 0; n2 < 25; ++n2) twa[k1 * 25 + n2] = tw[n2 * k1];
+  for (int m = 0; m < 25; ++m) tw25[m] = tw[16 * m];
+  for (int i = 0; i < 25; ++i) fft400_phase_a(reverse ? 24 - i : i, z.data(), twa.data());
+  for (int i = 0; i < 16; ++i) fft400_phase_b(reverse ? 15 - i : i, z.data(), tw25.data());
 }
 
 int main() {
