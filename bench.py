@@ -569,7 +569,7 @@ def main():
                                        stream=sptr, out=out))
 
     trace = os.environ.get("NELE_BENCH_TRACE") == "1"   # per-rank wall time of the pieces of an e2e step, on stderr
-    tr_acc = {"score": 0.0, "gather": 0.0, "n": 0}
+    tr_acc = {"score": 0.0, "gather": 0.0, "prefetch": 0.0, "n": 0}
 
     def step_host_pcm():       # int16 host buffers (6 bytes), enhanced + noise formed on the device
         t_a = time.perf_counter()
@@ -631,15 +631,18 @@ def main():
     eng.prefetch_pcm16(h_c16.data_ptr(), h_c16.data_ptr(), h_n16.data_ptr(), offs, lens)
     for k in range(a.steps):
         if k + 1 < a.steps:
+            t_p = time.perf_counter()
             eng.prefetch_pcm16(h_c16.data_ptr(), h_c16.data_ptr(), h_n16.data_ptr(), offs, lens)
+            tr_acc["prefetch"] += time.perf_counter() - t_p
         r = step_host_pcm()
     drain()
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     ok_pcm = int(np.sum(r.ok))
     if trace and tr_acc["n"]:
-        sys.stderr.write("[bench trace] rank %d: e2e step %.2f ms = score call %.2f + gather %.2f (+ prefetch call, loop), kernels %.2f ms\n" % (
-            rank, ms_e2e / a.steps, tr_acc["score"] / tr_acc["n"] * 1e3, tr_acc["gather"] / tr_acc["n"] * 1e3, eng.last_timing()[0]))
+        sys.stderr.write("[bench trace] rank %d: e2e step %.2f ms = score call %.2f + gather %.2f + prefetch call %.2f (+ loop), kernels %.2f ms\n" % (
+            rank, ms_e2e / a.steps, tr_acc["score"] / tr_acc["n"] * 1e3, tr_acc["gather"] / tr_acc["n"] * 1e3,
+            tr_acc["prefetch"] / tr_acc["n"] * 1e3, eng.last_timing()[0]))
     # the same loop with plain blocking calls (no nele_prefetch): every upload is exposed
     t0 = time.perf_counter()
     for _ in range(a.steps):

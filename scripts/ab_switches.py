@@ -34,8 +34,9 @@ print(json.dumps({"ms": ms, "launches": nl, "kernels": {k: v[0] for k, v in e.ke
 if __name__ == "__main__":
     n = sys.argv[1] if len(sys.argv) > 1 else "4096"
     L = sys.argv[2] if len(sys.argv) > 2 else "48000"
+    only = sys.argv[3:]   # optional: names of the configurations to run ("default" first)
     base = None
-    for name, env in CONFIGS:
+    for name, env in [c for c in CONFIGS if not only or c[0] in only]:
         p = subprocess.run([sys.executable, "-c", CHILD, n, L], env={**os.environ, **env}, stdout=subprocess.PIPE,
                            stderr=subprocess.PIPE, text=True)
         if p.returncode != 0:
