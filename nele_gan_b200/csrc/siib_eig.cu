@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "kernels.h"
+#include "sturm.cuh"
 
 namespace nele {
 
@@ -180,45 +181,9 @@ __global__ void __launch_bounds__(kEThreads, 3) siib_tridiag_kernel(SiibGeom g, 
 }
 
 // --------------------------------------------------- eigenpairs of the tridiagonal
-// number of eigenvalues of T (scaled so that |entries| <= 1) below x: sign changes of the
-// three-term recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}.
-// de[i] = {d_i, e_{i-1}^2} (de[0].y unused), padded to kSturmLen entries with {1000, 0} (p keeps its sign there, |x| <= 3):
-// one 128-bit shared-memory load per step, broadcast to the whole CTA, and blocks of 16 steps with a compile-time trip
-// count.  The kernel is issue bound (ncu: 71 % issue slots, FP64 pipe 39 %; 15 instructions per step before this form,
-// of which 3 are the FP64 arithmetic), so instructions are time:
-//   * the sign of every p_i is shifted into a bit mask (one funnel shift per step) and the changes of a block counted
-//     with one xor + popc, instead of an xor + shift + add per step;
-//   * the range check that guards the recurrence against overflow looks at the exponent fields of the high words and
-//     rescales by an exact power of two: |p| grows by at most 7 per step (2^45 per block), the window is 2^+-128.
-constexpr int kSturmBlk = 16;
-constexpr int sturm_len(int n) { return 1 + ((n - 1 + kSturmBlk - 1) / kSturmBlk) * kSturmBlk; }
+// Sturm counts: sturm.cuh (sign masks + popc, blocks of 16 steps, exponent-field overflow guard)
 constexpr int kSturmLen = sturm_len(kEDim);  // 433
 constexpr int kSturmLenSmall = sturm_len(112);  // 113: the Gram path (kSN below)
-template <int LEN>
-__device__ __forceinline__ int sturm_count(const double2* __restrict__ de, double x) {
-  double pm = 1.0, p = de[0].x - x;
-  unsigned sg = (unsigned)__double2hiint(p) >> 31;  // bit 0: sign of the newest p; p_{-1} = 1 is positive
-  int cnt = (int)sg;
-#pragma unroll 1
-  for (int i0 = 1; i0 < LEN; i0 += kSturmBlk) {
-#pragma unroll
-    for (int i = 0; i < kSturmBlk; ++i) {
-      const double2 c = de[i0 + i];
-      const double pn = fma(c.x - x, p, -c.y * pm);
-      sg = __funnelshift_l((unsigned)__double2hiint(pn), sg, 1);  // (sg << 1) | sign(pn)
-      pm = p;
-      p = pn;
-    }
-    cnt += __popc((sg ^ (sg >> 1)) & 0xffffu);  // a sign change = one more eigenvalue below x
-    const int e = max(__double2hiint(p) & 0x7ff00000, __double2hiint(pm) & 0x7ff00000);  // exponent field of max(|p|, |pm|)
-    if ((unsigned)(e - ((1023 - 128) << 20)) > (unsigned)(256 << 20)) {
-      const double sc = __hiloint2double(0x7fe00000 - e, 0);  // 2^-(exponent): exact, the signs stay
-      p *= sc;
-      pm *= sc;
-    }
-  }
-  return cnt;
-}
 
 // value with an explicit binary exponent, kept near 1
 struct Scaled {

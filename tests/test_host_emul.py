@@ -37,3 +37,23 @@ def test_in_place_fft400_matches_a_direct_dft(tmp_path):
     order = float(re.search(r"ORDER ([0-9.eE+-]+)", out).group(1))
     assert err < 1e-6, out          # float32 butterflies: about 1.5e-7 of the largest bin
     assert order == 0.0, out        # no lane reads what another lane of the same phase writes
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_sturm_count_and_bisection_plan_match_the_ratio_form(tmp_path):
+    """sturm.cuh (the eigenvalue bisection of siib_trieig_kernel / siib_smallvec_kernel, pysiib's KLT): sign masks,
+    16-step blocks over the padded table and the exponent-field range guard give the same counts as the ratio-form
+    Sturm count in long double -- on dense, graded (14 decades), numerically rank-deficient, Toeplitz, decoupled
+    (underflow side) and growing (overflow side) tridiagonals of both kernel sizes -- and the grid start + k steps
+    land on the eigenvalues of plain bisection."""
+    exe = str(tmp_path / "sturm_emul")
+    src = os.path.join(ROOT, "tests", "host_emul", "sturm_emul.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, src], check=True)
+    out = subprocess.run([exe], check=True, stdout=subprocess.PIPE, text=True).stdout
+    rows = re.findall(r"(\S+) n=(\d+) points=(\d+) skipped=(\d+) MISMATCH=(\d+) EIGERR=([0-9.eE+-]+)", out)
+    assert len(rows) == 12, out
+    for name, n, points, skipped, mismatch, eigerr in rows:
+        assert int(points) > 700 and int(skipped) < 10, out
+        assert int(mismatch) == 0, out
+        # half the final interval: 6 / 420 * 2^-38 / 2 = 2.6e-14 (n = 420), 6 / 112 * 2^-52 / 2 = 6e-18 (+ rounding of mid)
+        assert float(eigerr) < (3e-14 if n == "420" else 1e-15), out
